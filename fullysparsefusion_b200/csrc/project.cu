@@ -1,0 +1,221 @@
+// project.cu — LiDAR→camera projection fused with nearest sampling of the 2D instance-id planes
+// (a7 + a8 + the camera selection of a9).
+//
+// Reference semantics, op for op: FSF.prj_points_2d + FSF.points_in_mask
+// (projects/mmdet3d_plugin/models/detectors/FSF.py:169-226) and the camera selection of
+// FSF.img_cross_attn (:714-718) / FSF.extract_fg_pts (:299-308):
+//   pts_2d = [x,y,z,1] @ lidar2img^T;  depth_valid = z' > 1e-3;  z' = clip(z', 1e-5, 1e5)
+//   u = x'/z' / W;  v = y'/z' / H;  g = (uv - 0.5) * 2;  valid = depth_valid & g in (-1,1)^2
+//   invalid → g = -2;  id = grid_sample(mask.float(), g, mode='nearest', align_corners=False)
+// grid_sample(nearest): ix = ((g+1)*W - 1)/2 (the CUDA kernel's form, with the multiply-subtract
+// contracted to one FMA as nvcc compiles ATen), texel = nearbyint(ix) (half to even), zeros
+// outside.  The reference first casts the whole [cams,classes,H,W] u8 tensor to f32 (346 MB
+// written per call at nuScenes size); here the u8 / i32 planes are sampled as stored.
+//
+// HBM-bound.  Algorithmic bytes per point: 12 (xyz) + cams*classes*1 (texels) +
+// cams*classes*8 (i64 ids) = 552 B for the drop-in contract at 6x10; 12 + 60 + 4*classes + 3
+// for the fused contract.  Drop-in kernel: ids are staged in shared memory per warp and the
+// [32 pts x cams x classes] i64 block is written as one contiguous run of 16-byte stores.
+#include "common.cuh"
+
+namespace fsfb {
+
+constexpr int kMaxCams = 8;
+constexpr int kMaxClasses = 16;
+
+struct CamSet {
+  float P[kMaxCams][12];  // first three rows of each 4x4 lidar2img
+};
+
+__device__ __forceinline__ void load_cams(CamSet& s, const float* __restrict__ lidar2img, int cams) {
+  for (int t = threadIdx.x; t < cams * 12; t += blockDim.x)
+    s.P[t / 12][t % 12] = __ldg(lidar2img + (t / 12) * 16 + (t % 12));
+  __syncthreads();
+}
+
+// Returns texel offset (iy*W+ix) or -1 when the point does not sample this camera.
+__device__ __forceinline__ int project_texel(const float* __restrict__ P, float x, float y, float z,
+                                             int W, int H) {
+  // [x y z 1] . row_j — sequential FMA accumulation over k (K = 4 GEMM)
+  float xc = __fadd_rn(fmaf(z, P[2], fmaf(y, P[1], __fmul_rn(x, P[0]))), P[3]);
+  float yc = __fadd_rn(fmaf(z, P[6], fmaf(y, P[5], __fmul_rn(x, P[4]))), P[7]);
+  float zc = __fadd_rn(fmaf(z, P[10], fmaf(y, P[9], __fmul_rn(x, P[8]))), P[11]);
+  const bool depth_ok = zc > 1e-3f;
+  zc = fminf(fmaxf(zc, 1e-5f), 1e5f);
+  float u = __fdiv_rn(__fdiv_rn(xc, zc), (float)W);
+  float v = __fdiv_rn(__fdiv_rn(yc, zc), (float)H);
+  float gx = __fmul_rn(__fsub_rn(u, 0.5f), 2.f);
+  float gy = __fmul_rn(__fsub_rn(v, 0.5f), 2.f);
+  const bool ok = depth_ok & (gx > -1.f) & (gx < 1.f) & (gy > -1.f) & (gy < 1.f);
+  if (!ok) return -1;
+  // grid_sampler_unnormalize (align_corners = False) + nearbyint
+  float ix = __fdiv_rn(fmaf(__fadd_rn(gx, 1.f), (float)W, -1.f), 2.f);
+  float iy = __fdiv_rn(fmaf(__fadd_rn(gy, 1.f), (float)H, -1.f), 2.f);
+  int ixn = __float2int_rn(ix), iyn = __float2int_rn(iy);
+  if (ixn < 0 || ixn >= W || iyn < 0 || iyn >= H) return -1;
+  return iyn * W + ixn;
+}
+
+// ---- drop-in contract: out_ids [n, cams, classes] i64 ----------------------------------
+template <typename MaskT>
+__global__ void __launch_bounds__(256)
+    k_project_sample(const float* __restrict__ xyz, int64_t n, int64_t stride,
+                     const float* __restrict__ lidar2img, int cams, const MaskT* __restrict__ mask,
+                     int classes, int H, int W, long long* __restrict__ out) {
+  extern __shared__ unsigned char s_raw[];
+  __shared__ CamSet s_cams;
+  load_cams(s_cams, lidar2img, cams);
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int per_pt = cams * classes;
+  MaskT* s_ids = reinterpret_cast<MaskT*>(s_raw) + (size_t)warp * 32 * per_pt;
+  const int64_t plane = (int64_t)H * W;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32; base < n;
+       base += n_warps * 32) {
+    const int64_t i = base + lane;
+    if (i < n) {
+      const float* p = xyz + i * stride;
+      const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+      MaskT* mine = s_ids + lane * per_pt;
+      for (int cam = 0; cam < cams; ++cam) {
+        const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
+        if (tex >= 0) {
+          const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
+#pragma unroll 10
+          for (int k = 0; k < classes; ++k) mine[cam * classes + k] = __ldg(m0 + k * plane);
+        } else {
+          for (int k = 0; k < classes; ++k) mine[cam * classes + k] = 0;
+        }
+      }
+    }
+    __syncwarp();
+    // coalesced i64 write of the warp's contiguous block
+    const int64_t pts_here = min((int64_t)32, n - base);
+    const int64_t total = pts_here * per_pt;  // i64 elements
+    long long* o = out + base * per_pt;
+    if ((total & 1) == 0 && ((uintptr_t)o & 15) == 0) {
+      for (int64_t e = (int64_t)lane * 2; e < total; e += 64) {
+        longlong2 v = make_longlong2((long long)s_ids[e], (long long)s_ids[e + 1]);
+        *reinterpret_cast<longlong2*>(o + e) = v;
+      }
+    } else {
+      for (int64_t e = lane; e < total; e += 32) o[e] = (long long)s_ids[e];
+    }
+    __syncwarp();
+  }
+}
+
+// ---- fused contract: camera-selected ids + fg flag --------------------------------------
+template <typename MaskT>
+__global__ void __launch_bounds__(256)
+    k_project_sample_select(const float* __restrict__ xyz, int64_t n, int64_t stride,
+                            const float* __restrict__ lidar2img, int cams,
+                            const MaskT* __restrict__ mask, int classes, int H, int W,
+                            int32_t* __restrict__ ids_sel, uint8_t* __restrict__ cam_sel,
+                            uint8_t* __restrict__ fg, uint8_t* __restrict__ overlap) {
+  __shared__ CamSet s_cams;
+  load_cams(s_cams, lidar2img, cams);
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float* p = xyz + i * stride;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    int best_ids[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) best_ids[k] = 0;
+    long long best_sum = 0;  // an all-zero camera 0 wins ties, as torch.max returns the first maximum
+    int best_cam = 0, n_pos = 0;
+    for (int cam = 0; cam < cams; ++cam) {
+      const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
+      if (tex < 0) continue;
+      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
+      int ids[kMaxClasses];
+      long long sum = 0;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        ids[k] = (k < classes) ? (int)__ldg(m0 + k * plane) : 0;
+        sum += ids[k];
+        n_pos += ids[k] > 0;
+      }
+      if (sum > best_sum) {
+        best_sum = sum;
+        best_cam = cam;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) best_ids[k] = ids[k];
+      }
+    }
+    int32_t* o = ids_sel + i * classes;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < classes) o[k] = best_ids[k];
+    cam_sel[i] = (uint8_t)best_cam;
+    fg[i] = (uint8_t)(best_sum > 0 || n_pos > 0);
+    if (overlap) overlap[i] = (uint8_t)min(n_pos, 255);
+  }
+}
+
+static int check_common(const float* xyz, int64_t n, int64_t xyz_stride, const float* lidar2img,
+                        int cams, const void* mask, int classes, int H, int W, const char* who) {
+  FSFB_CHECK_ARG(n >= 0 && xyz_stride >= 3, "%s: bad n/stride", who);
+  FSFB_CHECK_ARG(cams >= 1 && cams <= kMaxCams, "%s: cams=%d unsupported (1..%d)", who, cams, kMaxCams);
+  FSFB_CHECK_ARG(classes >= 1 && classes <= kMaxClasses, "%s: classes=%d unsupported (1..%d)", who,
+                 classes, kMaxClasses);
+  FSFB_CHECK_ARG(H >= 1 && W >= 1 && (int64_t)H * W < (1ll << 31), "%s: bad H/W", who);
+  FSFB_CHECK_ARG(n == 0 || (xyz && lidar2img && mask), "%s: null pointer", who);
+  return FSFB_OK;
+}
+
+}  // namespace fsfb
+
+extern "C" {
+
+int fsfb_project_sample(const float* xyz, int64_t n, int64_t xyz_stride, const float* lidar2img,
+                        int cams, const void* mask, int mask_i32, int classes, int H, int W,
+                        int64_t* out_ids, void* stream) {
+  using namespace fsfb;
+  int rc = check_common(xyz, n, xyz_stride, lidar2img, cams, mask, classes, H, W, "project_sample");
+  if (rc != FSFB_OK) return rc;
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(out_ids, "project_sample: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = 256;
+  const size_t smem = (size_t)(threads / 32) * 32 * cams * classes * (mask_i32 ? 4 : 1);
+  const int grid = (int)std::min<int64_t>(ceil_div(n, threads), (int64_t)kNumSMs * 8);
+  if (mask_i32) {
+    static bool attr = false;
+    if (!attr) {
+      FSFB_CUDA(cudaFuncSetAttribute(k_project_sample<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+      attr = true;
+    }
+    FSFB_LAUNCH(k_project_sample<int>, grid, threads, smem, st, xyz, n, xyz_stride, lidar2img, cams,
+                (const int*)mask, classes, H, W, (long long*)out_ids);
+  } else {
+    FSFB_LAUNCH(k_project_sample<unsigned char>, grid, threads, smem, st, xyz, n, xyz_stride, lidar2img, cams,
+                (const unsigned char*)mask, classes, H, W, (long long*)out_ids);
+  }
+  return FSFB_OK;
+}
+
+int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
+                               const float* lidar2img, int cams, const void* mask, int mask_i32,
+                               int classes, int H, int W, int32_t* ids_sel, uint8_t* cam_sel,
+                               uint8_t* fg, uint8_t* overlap, void* stream) {
+  using namespace fsfb;
+  int rc = check_common(xyz, n, xyz_stride, lidar2img, cams, mask, classes, H, W,
+                        "project_sample_select");
+  if (rc != FSFB_OK) return rc;
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(ids_sel && cam_sel && fg, "project_sample_select: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
+  if (mask_i32) {
+    FSFB_LAUNCH(k_project_sample_select<int>, grid, 256, 0, st, xyz, n, xyz_stride, lidar2img, cams,
+                (const int*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap);
+  } else {
+    FSFB_LAUNCH(k_project_sample_select<unsigned char>, grid, 256, 0, st, xyz, n, xyz_stride, lidar2img, cams,
+                (const unsigned char*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap);
+  }
+  return FSFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// segment_reduce.cu — segmented max(+argmax) / mean / sum over rows grouped by a CSR (a2, a12, a13)
+// and the row gather that undoes it (a6).
+//
+// Reference semantics: torch_scatter.scatter_max(feat, inv, dim=0) and
+// torch_scatter.scatter(feat, inv, dim=0, reduce='mean'|'sum') as called from scatter_v2,
+// projects/mmdet3d_plugin/ops/sst_ops.py:168,170.  argmax = lowest source row attaining the max
+// (torch_scatter's sequential CPU rule); empty segment → value 0, argmax = n.
+//
+// B200 design (HBM-bound; algorithmic bytes 4NC + 8N + 4MC): no atomics on features.  Rows are
+// visited in CSR order; a warp owns 32 consecutive sorted positions, lanes own channels
+// (128-bit loads when C % 4 == 0), rows stream through registers 4 at a time, and a segment
+// that begins and ends inside the warp's chunk is written once with plain stores.  Segments
+// that cross a chunk boundary leave at most two partial rows per chunk in a scratch buffer;
+// a second small kernel folds those (and zero-fills empty segments).
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace fsfb {
+
+constexpr int kSrChunk = 32;    // sorted positions per warp
+constexpr int kSrWarps = 8;     // warps per CTA
+constexpr int kSrUnroll = 4;    // rows in flight per warp
+
+template <int VEC>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, bool ok, float (&v)[VEC]) {
+  if (VEC == 4) {
+    float4 t = ok ? ldg_stream_f4(reinterpret_cast<const float4*>(p)) : make_float4(0, 0, 0, 0);
+    v[0] = t.x;
+    v[VEC > 1 ? 1 : 0] = t.y;
+    v[VEC > 2 ? 2 : 0] = t.z;
+    v[VEC > 3 ? 3 : 0] = t.w;
+  } else {
+    v[0] = ok ? ldg_stream_f1(p) : 0.f;
+  }
+}
+
+template <int VEC, int K, bool IS_MAX, bool HAS_ARG>
+struct Acc {
+  float val[K][VEC];
+  int arg[HAS_ARG ? K : 1][HAS_ARG ? VEC : 1];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        val[k][e] = IS_MAX ? -INFINITY : 0.f;
+        if (HAS_ARG) arg[k][e] = INT_MAX;
+      }
+  }
+  __device__ __forceinline__ void add(int k, const float (&v)[VEC], int row) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      if (IS_MAX) {
+        if (HAS_ARG) {
+          bool take = (v[e] > val[k][e]) | ((v[e] == val[k][e]) & (row < arg[k][e]));
+          arg[k][e] = take ? row : arg[k][e];
+          val[k][e] = take ? v[e] : val[k][e];
+        } else {
+          val[k][e] = fmaxf(val[k][e], v[e]);
+        }
+      } else {
+        val[k][e] += v[e];
+      }
+    }
+  }
+};
+
+// Channel owned by (lane, k, e) inside the channel block starting at c0.
+template <int VEC>
+__device__ __forceinline__ int chan(int c0, int lane, int k, int e) {
+  return c0 + (k * 32 + lane) * VEC + e;
+}
+
+template <int VEC, int K, bool IS_MAX, bool HAS_ARG>
+__global__ void __launch_bounds__(kSrWarps * 32)
+    k_segreduce(const float* __restrict__ feat, int64_t stride, int C,
+                const int32_t* __restrict__ perm, const int32_t* __restrict__ seg,
+                const int32_t* __restrict__ offsets, int m, int mean, float* __restrict__ out,
+                long long* __restrict__ argout, int32_t* __restrict__ part_seg,
+                float* __restrict__ part_val, int32_t* __restrict__ part_arg, int64_t n_chunks) {
+  const int lane = lane_id();
+  const int64_t gw = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  if (gw >= n_chunks) return;  // warp-uniform
+  const int c0 = blockIdx.y * (32 * VEC * K);
+  const int64_t n_valid = offsets[m];
+  const int64_t p0 = gw * kSrChunk;
+  const int cnt = (int)max((int64_t)0, min((int64_t)kSrChunk, n_valid - p0));
+  int head_seg = -1, tail_seg = -1;  // what lands in the two partial slots
+  if (cnt > 0) {
+    const int64_t p = p0 + lane;
+    const int my_seg = lane < cnt ? seg[p] : -1;
+    const int my_row = lane < cnt ? (perm ? perm[p] : (int)p) : 0;
+    const int seg_prev = p0 > 0 ? seg[p0 - 1] : -1;
+    const int seg_next = (p0 + kSrChunk < n_valid) ? seg[p0 + kSrChunk] : -2;
+
+    Acc<VEC, K, IS_MAX, HAS_ARG> acc;
+    acc.reset();
+    int cur = __shfl_sync(0xffffffffu, my_seg, 0);
+
+    auto flush = [&](int s) {
+      const bool partial = (s == seg_prev) | (s == seg_next);
+      if (!partial) {
+        const float denom = mean ? (float)max(1, offsets[s + 1] - offsets[s]) : 1.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = chan<VEC>(c0, lane, k, 0);
+          if (c < C) {
+            float r[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) r[e] = mean ? acc.val[k][e] / denom : acc.val[k][e];
+            float* o = out + (int64_t)s * C + c;
+            if (VEC == 4) {
+              stg_stream_f4(reinterpret_cast<float4*>(o),
+                            make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]));
+            } else {
+              o[0] = r[0];
+            }
+            if (HAS_ARG) {
+#pragma unroll
+              for (int e = 0; e < VEC; ++e) argout[(int64_t)s * C + c + e] = (long long)acc.arg[k][e];
+            }
+          }
+        }
+      } else {
+        const int64_t slot = 2 * gw + ((s == seg_prev) ? 0 : 1);
+        if (s == seg_prev) head_seg = s; else tail_seg = s;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = chan<VEC>(c0, lane, k, 0);
+          if (c < C) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+              part_val[slot * C + c + e] = acc.val[k][e];
+              if (HAS_ARG) part_arg[slot * C + c + e] = acc.arg[k][e];
+            }
+          }
+        }
+      }
+      acc.reset();
+    };
+
+    for (int r0 = 0; r0 < cnt; r0 += kSrUnroll) {
+      float v[kSrUnroll][K][VEC];
+      int rows[kSrUnroll], segs[kSrUnroll];
+#pragma unroll
+      for (int u = 0; u < kSrUnroll; ++u) {
+        const int r = min(r0 + u, kSrChunk - 1);
+        rows[u] = __shfl_sync(0xffffffffu, my_row, r);
+        segs[u] = __shfl_sync(0xffffffffu, my_seg, r);
+        const bool live = (r0 + u) < cnt;
+        const float* base = feat + (int64_t)rows[u] * stride;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = chan<VEC>(c0, lane, k, 0);
+          load_row<VEC>(base + c, live && c < C, v[u][k]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kSrUnroll; ++u) {
+        if (r0 + u < cnt) {
+          if (segs[u] != cur) {
+            flush(cur);
+            cur = segs[u];
+          }
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc.add(k, v[u][k], rows[u]);
+        }
+      }
+    }
+    flush(cur);
+  }
+  if (lane == 0 && blockIdx.y == 0) {
+    part_seg[2 * gw] = head_seg;
+    part_seg[2 * gw + 1] = tail_seg;
+  }
+}
+
+// Fold partial rows of segments that cross chunk boundaries; zero-fill empty segments.
+template <bool IS_MAX, bool HAS_ARG>
+__global__ void __launch_bounds__(kSrWarps * 32)
+    k_segreduce_fixup(int C, const int32_t* __restrict__ offsets, int m, int mean, int64_t n,
+                      float* __restrict__ out, long long* __restrict__ argout,
+                      const int32_t* __restrict__ part_seg, const float* __restrict__ part_val,
+                      const int32_t* __restrict__ part_arg, int64_t n_chunks) {
+  const int lane = lane_id();
+  const int64_t gw = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  // part 1: owner = chunk whose tail slot holds a segment that started inside it
+  if (gw < n_chunks) {
+    const int s = part_seg[2 * gw + 1];
+    if (s >= 0) {
+      const int64_t last_chunk = ((int64_t)offsets[s + 1] - 1) / kSrChunk;
+      const int count = offsets[s + 1] - offsets[s];
+      for (int c = lane; c < C; c += 32) {
+        float best = part_val[(2 * gw + 1) * C + c];
+        int arg = HAS_ARG ? part_arg[(2 * gw + 1) * C + c] : 0;
+        for (int64_t w = gw + 1; w <= last_chunk; ++w) {
+          const float v = part_val[(2 * w) * C + c];
+          if (IS_MAX) {
+            if (HAS_ARG) {
+              const int a = part_arg[(2 * w) * C + c];
+              const bool take = (v > best) | ((v == best) & (a < arg));
+              arg = take ? a : arg;
+              best = take ? v : best;
+            } else {
+              best = fmaxf(best, v);
+            }
+          } else {
+            best += v;
+          }
+        }
+        if (mean) best = best / (float)max(1, count);
+        out[(int64_t)s * C + c] = best;
+        if (HAS_ARG) argout[(int64_t)s * C + c] = (long long)arg;
+      }
+    }
+  }
+  // part 2: empty segments (only possible when the index does not come from a ranking)
+  for (int64_t s = gw; s < m; s += (int64_t)gridDim.x * kSrWarps) {
+    if (offsets[s + 1] == offsets[s]) {
+      for (int c = lane; c < C; c += 32) {
+        out[s * C + c] = 0.f;
+        if (HAS_ARG) argout[s * C + c] = (long long)n;
+      }
+    }
+  }
+}
+
+// ---- row gather ------------------------------------------------------------------------
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256)
+    k_gather_rows(const float* __restrict__ src, int64_t m, int C, const IdxT* __restrict__ idx,
+                  int64_t n, float fill, float* __restrict__ out, int64_t out_stride) {
+  // one warp per output row, lanes over channels; several rows in flight per warp
+  const int lane = lane_id();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const long long s = (long long)idx[i];
+    const bool ok = s >= 0 && s < m;
+    const float* p = src + (ok ? s : 0) * C;
+    float* o = out + i * out_stride;
+    for (int c = lane * VEC; c < C; c += 32 * VEC) {
+      if (VEC == 4) {
+        float4 v = ok ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(fill, fill, fill, fill);
+        stg_stream_f4(reinterpret_cast<float4*>(o + c), v);
+      } else {
+        o[c] = ok ? __ldg(p + c) : fill;
+      }
+    }
+  }
+}
+
+template <int VEC, int K>
+static int launch_segreduce(const float* feat, int64_t stride, int C, const int32_t* perm,
+                            const int32_t* seg, const int32_t* offsets, int m, int mode, float* out,
+                            long long* argout, int32_t* part_seg, float* part_val,
+                            int32_t* part_arg, int64_t n_chunks, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(n_chunks, kSrWarps), (unsigned)ceil_div(C, 32 * VEC * K));
+  const int mean = mode == FSFB_REDUCE_MEAN;
+  auto kern = (mode == FSFB_REDUCE_MAX)
+                  ? (argout ? k_segreduce<VEC, K, true, true> : k_segreduce<VEC, K, true, false>)
+                  : k_segreduce<VEC, K, false, false>;
+  FSFB_LAUNCH(kern, grid, kSrWarps * 32, 0, st, feat, stride, C, perm, seg, offsets, m, mean, out,
+              argout, part_seg, part_val, part_arg, n_chunks);
+  return FSFB_OK;
+}
+
+}  // namespace fsfb
+
+extern "C" {
+
+int fsfb_segment_reduce_workspace_bytes(int64_t n, int c, int with_arg, size_t* bytes) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(bytes && n >= 0 && c >= 1, "segment_reduce_workspace_bytes: bad argument");
+  const int64_t n_chunks = std::max<int64_t>(1, ceil_div(n, kSrChunk));
+  Workspace ws(nullptr, 0);
+  ws.take<int32_t>(2 * n_chunks);
+  ws.take<float>((size_t)2 * n_chunks * c);
+  if (with_arg) ws.take<int32_t>((size_t)2 * n_chunks * c);
+  *bytes = ws.used;
+  return FSFB_OK;
+}
+
+int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride,
+                        const int32_t* perm, const int32_t* seg, const int32_t* offsets, int64_t m,
+                        int mode, float* out, int64_t* argmax, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(n >= 0 && n < (1ll << 31) && m >= 0 && m < (1ll << 31) && c >= 1 && feat_stride >= c,
+                 "segment_reduce: bad n=%lld m=%lld c=%d stride=%lld", (long long)n, (long long)m, c,
+                 (long long)feat_stride);
+  FSFB_CHECK_ARG(mode == FSFB_REDUCE_SUM || mode == FSFB_REDUCE_MEAN || mode == FSFB_REDUCE_MAX,
+                 "segment_reduce: bad mode %d", mode);
+  FSFB_CHECK_ARG(argmax == nullptr || mode == FSFB_REDUCE_MAX, "segment_reduce: argmax needs MAX");
+  if (m == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(offsets && out && (n == 0 || (feat && seg)), "segment_reduce: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_chunks = std::max<int64_t>(1, ceil_div(n, kSrChunk));
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* part_seg = ws.take<int32_t>(2 * n_chunks);
+  float* part_val = ws.take<float>((size_t)2 * n_chunks * c);
+  int32_t* part_arg = argmax ? ws.take<int32_t>((size_t)2 * n_chunks * c) : nullptr;
+  if (!ws.ok()) {
+    set_error("segment_reduce: workspace too small (%zu given, %zu needed)", workspace_bytes, ws.used);
+    return FSFB_ERR_CAPACITY;
+  }
+  const bool vec4 = (c % 4 == 0) && (feat_stride % 4 == 0) && ((uintptr_t)feat % 16 == 0) &&
+                    ((uintptr_t)out % 16 == 0);
+  long long* argout = (long long*)argmax;
+  int rc;
+#define SR_DISPATCH(VEC, K)                                                                     \
+  rc = launch_segreduce<VEC, K>(feat, feat_stride, c, perm, seg, offsets, (int)m, mode, out,     \
+                                argout, part_seg, part_val, part_arg, n_chunks, st)
+  if (vec4) {
+    const int lanes_groups = (int)ceil_div(c, 128);
+    if (lanes_groups <= 1) SR_DISPATCH(4, 1);
+    else if (lanes_groups <= 2) SR_DISPATCH(4, 2);
+    else SR_DISPATCH(4, 4);
+  } else {
+    const int lanes_groups = (int)ceil_div(c, 32);
+    if (lanes_groups <= 1) SR_DISPATCH(1, 1);
+    else if (lanes_groups <= 2) SR_DISPATCH(1, 2);
+    else if (lanes_groups <= 4) SR_DISPATCH(1, 4);
+    else SR_DISPATCH(1, 8);
+  }
+#undef SR_DISPATCH
+  if (rc != FSFB_OK) return rc;
+  const int64_t items = std::max<int64_t>(n_chunks, std::min<int64_t>(m, (int64_t)kNumSMs * 64));
+  const int grid = (int)ceil_div(items, kSrWarps);
+  const int mean = mode == FSFB_REDUCE_MEAN;
+  auto fix = (mode == FSFB_REDUCE_MAX)
+                 ? (argmax ? k_segreduce_fixup<true, true> : k_segreduce_fixup<true, false>)
+                 : k_segreduce_fixup<false, false>;
+  FSFB_LAUNCH(fix, grid, kSrWarps * 32, 0, st, c, offsets, (int)m, mean, n, out, argout, part_seg,
+              part_val, part_arg, n_chunks);
+  return FSFB_OK;
+}
+
+int fsfb_gather_rows(const float* src, int64_t m, int c, const void* idx, int idx_i64, int64_t n,
+                     float fill, float* out, int64_t out_stride, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(n >= 0 && m >= 0 && c >= 1 && out_stride >= c, "gather_rows: bad argument");
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(idx && out && (m == 0 || src), "gather_rows: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec4 = (c % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
+                    ((uintptr_t)out % 16 == 0);
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 8), (int64_t)kNumSMs * 32);
+  if (idx_i64) {
+    auto kern = vec4 ? k_gather_rows<long long, 4> : k_gather_rows<long long, 1>;
+    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, (const long long*)idx, n, fill, out, out_stride);
+  } else {
+    auto kern = vec4 ? k_gather_rows<int, 4> : k_gather_rows<int, 1>;
+    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, (const int*)idx, n, fill, out, out_stride);
+  }
+  return FSFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+"""Torch-tensor front end of the C-ABI kernels.
+
+PyTorch is used here for device memory (the caching allocator), streams and dtype bookkeeping
+only; all arithmetic on the hot path happens in libfsf_b200.so.  Every function raises if a
+tensor is not on a CUDA device — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _capi
+from ._capi import REDUCE_MAX, REDUCE_MEAN, REDUCE_SUM, check, load
+
+_MODES = {"sum": REDUCE_SUM, "add": REDUCE_SUM, "mean": REDUCE_MEAN, "avg": REDUCE_MEAN, "max": REDUCE_MAX}
+
+
+def _need_cuda(*ts: torch.Tensor) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _capi.FsfbError(
+                "fullysparsefusion_b200 ops run on CUDA tensors only (no CPU fallback); got a "
+                f"{t.device} tensor"
+            )
+        dev = dev or t.device
+    return dev
+
+
+def _stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ws(nbytes: int, dev: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def _host_f32(vals: Sequence[float]):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+def _host_i64(vals: Sequence[int]):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _host_i32(vals: Sequence[int]):
+    return (C.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+# ------------------------------------------------------------------------------------------
+# a1 voxelize
+# ------------------------------------------------------------------------------------------
+def grid_shape(point_cloud_range: Sequence[float], voxel_size: Sequence[float]) -> Tuple[int, int, int]:
+    """(gx, gy, gz) = round((max - min) / voxel) as mmdet3d's Voxelization computes it."""
+    r, v = point_cloud_range, voxel_size
+    return tuple(int(round((r[i + 3] - r[i]) / v[i])) for i in range(3))
+
+
+def voxelize(points: torch.Tensor, voxel_size: Sequence[float], point_cloud_range: Sequence[float],
+             floor_mode: int = 0, grid: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Dynamic voxelization → coors [N,3] int32 (z,y,x); out-of-range → -1.
+
+    Mirrors mmdet3d.ops.Voxelization(max_num_points=-1)(points)
+    (reference call: projects/mmdet3d_plugin/models/detectors/single_stage_fsd.py:217-219).
+    floor_mode=1 reproduces torch.div(..., rounding_mode='floor') (single_stage_fsd.py:270,591).
+    """
+    dev = _need_cuda(points)
+    assert points.dim() == 2 and points.size(1) >= 3 and points.dtype == torch.float32
+    if points.stride(1) != 1:
+        points = points.contiguous()
+    n = points.size(0)
+    g = tuple(grid) if grid is not None else grid_shape(point_cloud_range, voxel_size)
+    coors = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    rc = load().fsfb_voxelize(_ptr(points), n, points.stride(0) if n else 3, _host_f32(point_cloud_range[:3]),
+                              _host_f32(voxel_size), _host_i32(g), int(floor_mode), _ptr(coors), _stream(dev))
+    check(rc, "fsfb_voxelize")
+    return coors
+
+
+# ------------------------------------------------------------------------------------------
+# a2 row ranking (torch.unique(dim=0))
+# ------------------------------------------------------------------------------------------
+MAX_CELLS = (1 << 32) - 2
+
+
+def rows_minmax(rows: torch.Tensor) -> Tuple[list, list]:
+    """Per-column (min, max) of an integer [N,D] tensor; one device→host sync."""
+    dev = _need_cuda(rows)
+    n, d = rows.shape
+    out = torch.empty(2 * d, dtype=torch.int64, device=dev)
+    rc = load().fsfb_rows_minmax(_ptr(rows), int(rows.dtype == torch.int64), n, d, _ptr(out), _stream(dev))
+    check(rc, "fsfb_rows_minmax")
+    h = out.tolist()
+    return h[:d], h[d:]
+
+
+def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Optional[Sequence[int]] = None,
+                return_counts: bool = False, return_unique: bool = True, inv_dtype: torch.dtype = torch.int64):
+    """torch.unique(rows, dim=0, return_inverse=True[, return_counts=True]) for bounded integer rows.
+
+    Returns (unique_rows [M,D], inverse [N], counts [M] | None).  `lo`/`ext` give the per-column
+    bounds when the caller knows them (a voxel grid); otherwise one extra min/max pass runs.
+    Reference call sites: sst_ops.py:156,165; sir.py:68; single_stage_fsd.py:595.
+    """
+    dev = _need_cuda(rows)
+    assert rows.dim() == 2 and rows.dtype in (torch.int64, torch.int32), (rows.shape, rows.dtype)
+    rows = rows.contiguous()
+    n, d = rows.shape
+    if n == 0:
+        return (rows.new_empty((0, d)), torch.empty(0, dtype=inv_dtype, device=dev),
+                torch.empty(0, dtype=torch.int64, device=dev) if return_counts else None)
+    if lo is None or ext is None:
+        mn, mx = rows_minmax(rows)
+        lo = mn
+        ext = [b - a + 1 for a, b in zip(mn, mx)]
+    cells = 1
+    for e in ext:
+        cells *= int(e)
+    if cells > MAX_CELLS:
+        raise _capi.FsfbError(
+            f"unique_rows: key space of {cells} cells exceeds the bitmap ranker's 2^32-2 limit")
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_rank_workspace_bytes(n, cells, C.byref(need)), "fsfb_rank_workspace_bytes")
+    ws = _ws(need.value, dev)
+    inv32 = torch.empty(n, dtype=torch.int32, device=dev) if inv_dtype == torch.int32 else None
+    inv64 = torch.empty(n, dtype=torch.int64, device=dev) if inv_dtype == torch.int64 else None
+    uniq = torch.empty((n, d), dtype=rows.dtype, device=dev) if return_unique else None
+    counts = torch.empty(n, dtype=torch.int32, device=dev) if return_counts else None
+    meta = torch.empty(2, dtype=torch.int32, device=dev)  # [num_unique, status]
+    rc = lib.fsfb_rank_rows(_ptr(rows), int(rows.dtype == torch.int64), n, d, _host_i64(lo), _host_i64(ext),
+                            _ptr(ws), ws.numel(), _ptr(inv32), _ptr(inv64), _ptr(uniq), n, _ptr(counts),
+                            C.c_void_p(meta.data_ptr()), C.c_void_p(meta.data_ptr() + 4), _stream(dev))
+    check(rc, "fsfb_rank_rows")
+    m, status = meta.tolist()  # the one sync torch.unique also pays (output size)
+    if status & 1:
+        raise _capi.FsfbError("unique_rows: a row lies outside the given lo/ext bounds")
+    inv = inv64 if inv64 is not None else inv32
+    return (uniq[:m] if uniq is not None else None, inv, counts[:m].long() if counts is not None else None)
+
+
+# ------------------------------------------------------------------------------------------
+# segment CSR + reductions (torch_scatter)
+# ------------------------------------------------------------------------------------------
+@dataclass
+class SegmentCSR:
+    """The "scatter rulebook": rows grouped by segment id, stable inside a segment."""
+    offsets: torch.Tensor  # [m+1] int32
+    perm: torch.Tensor     # [n] int32 source row of each sorted position
+    seg: torch.Tensor      # [n] int32 segment of each sorted position
+    n: int
+    m: int
+
+
+def build_csr(index: torch.Tensor, m: int) -> SegmentCSR:
+    dev = _need_cuda(index)
+    assert index.dim() == 1 and index.dtype in (torch.int64, torch.int32)
+    index = index.contiguous()
+    n = index.numel()
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_csr_workspace_bytes(n, m, C.byref(need)), "fsfb_csr_workspace_bytes")
+    ws = _ws(need.value, dev)
+    offsets = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    seg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    rc = lib.fsfb_csr_build(_ptr(index), int(index.dtype == torch.int64), n, m, _ptr(offsets), _ptr(perm),
+                            _ptr(seg), _ptr(ws), ws.numel(), _stream(dev))
+    check(rc, "fsfb_csr_build")
+    return SegmentCSR(offsets, perm[:n], seg[:n], n, m)
+
+
+def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax: bool = False):
+    """out[s] = reduce(feat[rows of segment s]); mode in {'sum','mean','max'}.
+
+    Equals torch_scatter.scatter(feat, index, 0, reduce=mode) / scatter_max (sst_ops.py:168,170);
+    argmax ties resolve to the lowest source row; empty segments give 0 / argmax == N.
+    """
+    dev = _need_cuda(feat, csr.offsets)
+    assert feat.dim() == 2 and feat.dtype == torch.float32 and feat.size(0) == csr.n
+    if feat.stride(1) != 1 and feat.numel():
+        feat = feat.contiguous()
+    n, c = feat.shape
+    mode_id = _MODES[mode]
+    want_arg = return_argmax and mode_id == REDUCE_MAX
+    out = torch.empty((csr.m, c), dtype=torch.float32, device=dev)
+    arg = torch.empty((csr.m, c), dtype=torch.int64, device=dev) if want_arg else None
+    if c == 0 or csr.m == 0:
+        return (out, arg) if return_argmax else out
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_segment_reduce_workspace_bytes(n, c, int(want_arg), C.byref(need)),
+          "fsfb_segment_reduce_workspace_bytes")
+    ws = _ws(need.value, dev)
+    rc = lib.fsfb_segment_reduce(_ptr(feat), n, c, feat.stride(0) if n else c, _ptr(csr.perm), _ptr(csr.seg),
+                                 _ptr(csr.offsets), csr.m, mode_id, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
+                                 _stream(dev))
+    check(rc, "fsfb_segment_reduce")
+    return (out, arg) if return_argmax else out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0, out: Optional[torch.Tensor] = None):
+    """out[i] = src[idx[i]] (idx < 0 → fill).  voxel2point_neck.py:42-50, FSF.py:310-311."""
+    dev = _need_cuda(src, idx)
+    assert src.dim() == 2 and src.dtype == torch.float32
+    assert idx.dim() == 1 and idx.dtype in (torch.int64, torch.int32)
+    src = src.contiguous()
+    idx = idx.contiguous()
+    n, c = idx.numel(), src.size(1)
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    assert out.size(0) == n and out.size(1) >= c and out.stride(1) == 1
+    if n == 0 or c == 0:
+        return out
+    rc = load().fsfb_gather_rows(_ptr(src), src.size(0), c, _ptr(idx), int(idx.dtype == torch.int64), n,
+                                 float(fill), _ptr(out), out.stride(0), _stream(dev))
+    check(rc, "fsfb_gather_rows")
+    return out
+
+
+def ingroup_indices(group: torch.Tensor, num_groups: Optional[int] = None) -> torch.Tensor:
+    """Stable in-group index (ingroup_indices.forward, sst_ops.py:246-248)."""
+    dev = _need_cuda(group)
+    assert group.dim() == 1 and group.dtype == torch.int64
+    group = group.contiguous()
+    n = group.numel()
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out
+    m = int(num_groups) if num_groups is not None else int(group.max().item()) + 1
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_ingroup_workspace_bytes(n, m, C.byref(need)), "fsfb_ingroup_workspace_bytes")
+    ws = _ws(need.value, dev)
+    rc = lib.fsfb_ingroup_indices(_ptr(group), n, m, _ptr(out), _ptr(ws), ws.numel(), _stream(dev))
+    check(rc, "fsfb_ingroup_indices")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# a7+a8 projection + nearest sampling
+# ------------------------------------------------------------------------------------------
+def _mask_args(mask: torch.Tensor):
+    assert mask.dim() == 4 and mask.dtype in (torch.uint8, torch.int32), (mask.shape, mask.dtype)
+    return mask.contiguous(), int(mask.dtype == torch.int32)
+
+
+def project_sample(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """FSF.points_in_mask (FSF.py:202-226): ids [N, cams, classes] int64."""
+    dev = _need_cuda(xyz, lidar2img, mask)
+    assert xyz.dim() == 2 and xyz.size(1) >= 3 and xyz.dtype == torch.float32
+    if xyz.stride(1) != 1:
+        xyz = xyz.contiguous()
+    mask, is_i32 = _mask_args(mask)
+    cams, classes, H, W = mask.shape
+    l2i = lidar2img.to(torch.float32).contiguous()
+    assert l2i.shape == (cams, 4, 4)
+    n = xyz.size(0)
+    out = torch.empty((n, cams, classes), dtype=torch.int64, device=dev)
+    rc = load().fsfb_project_sample(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask), is_i32,
+                                    classes, H, W, _ptr(out), _stream(dev))
+    check(rc, "fsfb_project_sample")
+    return out
+
+
+def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torch.Tensor, want_overlap: bool = False):
+    """Fused contract: (ids_sel [N,classes] i32, cam_sel [N] u8, fg [N] u8[, overlap [N] u8])."""
+    dev = _need_cuda(xyz, lidar2img, mask)
+    assert xyz.dim() == 2 and xyz.size(1) >= 3 and xyz.dtype == torch.float32
+    if xyz.stride(1) != 1:
+        xyz = xyz.contiguous()
+    mask, is_i32 = _mask_args(mask)
+    cams, classes, H, W = mask.shape
+    l2i = lidar2img.to(torch.float32).contiguous()
+    n = xyz.size(0)
+    ids = torch.empty((n, classes), dtype=torch.int32, device=dev)
+    cam = torch.empty(n, dtype=torch.uint8, device=dev)
+    fg = torch.empty(n, dtype=torch.uint8, device=dev)
+    ov = torch.empty(n, dtype=torch.uint8, device=dev) if want_overlap else None
+    rc = load().fsfb_project_sample_select(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask),
+                                           is_i32, classes, H, W, _ptr(ids), _ptr(cam), _ptr(fg), _ptr(ov),
+                                           _stream(dev))
+    check(rc, "fsfb_project_sample_select")
+    return (ids, cam, fg, ov) if want_overlap else (ids, cam, fg)

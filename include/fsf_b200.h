@@ -1,0 +1,177 @@
+/*
+ * fsf_b200.h — C-ABI of the B200-native FSF hot path (libfsf_b200.so).
+ *
+ * Plain pointers + sizes, no torch types.  Every pointer marked "dev" is a CUDA
+ * device pointer owned by the caller; every pointer marked "host" is host memory
+ * read synchronously during the call.  All kernels are enqueued on `stream`
+ * (a cudaStream_t passed as void*); no call synchronises the device or the
+ * stream unless it says so.  Return value: FSFB_OK (0) or a negative status;
+ * fsfb_last_error() gives a thread-local message for the last failure.
+ *
+ * The reference (BraveGroup/FullySparseFusion) has no C FFI of its own: its hot
+ * path calls Python extension modules (torch_scatter, spconv, TorchEx,
+ * ingroup_indices, mmdet3d.ops.Voxelization) and ATen.  Each entry point below
+ * cites the reference call site (file:line under /root/reference) whose
+ * arithmetic it replaces; INTEGRATION.md shows the ctypes stub per symbol.
+ */
+#ifndef FSF_B200_H_
+#define FSF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSFB_OK 0
+#define FSFB_ERR_BADARG (-1)   /* null pointer, negative size, unsupported width */
+#define FSFB_ERR_CAPACITY (-2) /* workspace / key space / output buffer too small */
+#define FSFB_ERR_CUDA (-3)     /* a CUDA runtime call or launch failed */
+
+#define FSFB_REDUCE_SUM 0
+#define FSFB_REDUCE_MEAN 1
+#define FSFB_REDUCE_MAX 2
+
+#define FSFB_ACT_NONE 0
+#define FSFB_ACT_RELU 1
+#define FSFB_ACT_GELU 2
+
+#define FSFB_NORM_NONE 0
+#define FSFB_NORM_LAYERNORM 1 /* per-row LN over channels (mmcv 'LN')            */
+#define FSFB_NORM_AFFINE 2    /* per-channel scale/shift (eval-mode BN folded)  */
+
+/* ABI version (bumped on any signature change). */
+int fsfb_version(void);
+/* Thread-local text of the last error on this thread ("" if none). */
+const char* fsfb_last_error(void);
+/* Number of kernel launches issued through this library since process start
+ * (bench.py's gpu_launches counter). */
+int64_t fsfb_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * a1  Dynamic voxelization.
+ * Replaces mmdet3d.ops.Voxelization(max_num_points=-1) as called at
+ * projects/mmdet3d_plugin/models/detectors/single_stage_fsd.py:217-219 and the
+ * in-tree formula torch.div(p - min, vs, rounding_mode='floor') at :270, :444,
+ * :591-593, :948.  Evaluated in IEEE fp32 with no contraction;
+ *   floor_mode 0: c = floor((p - range_min) / voxel)        (the Voxelization kernel)
+ *   floor_mode 1: c = torch.div(p - range_min, voxel, rounding_mode='floor')
+ *                 (ATen div_floor_floating: exact fmod first — the in-tree formula)
+ * a point with any coordinate outside [0, grid) (or NaN) gets (-1,-1,-1).
+ *   pts      dev  [n, row_stride] f32, xyz in columns 0..2
+ *   range_min, voxel  host [3] f32 (x,y,z);  grid host [3] i32 (x,y,z)
+ *   coors_zyx dev [n,3] i32 (z,y,x) — written
+ * ------------------------------------------------------------------------- */
+int fsfb_voxelize(const float* pts, int64_t n, int64_t row_stride,
+                  const float* range_min, const float* voxel, const int32_t* grid,
+                  int floor_mode, int32_t* coors_zyx, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a2  Row ranking = torch.unique(rows, dim=0, return_inverse, return_counts)
+ * as called by scatter_v2 (projects/mmdet3d_plugin/ops/sst_ops.py:156,165),
+ * SIR (models/backbones/sir.py:68), pre_voxelize (single_stage_fsd.py:595).
+ * Sort-free: rows are linearised into a bounded key space (per-column lo/extent),
+ * marked in an L2-resident bitmap, and ranked by a popcount prefix, which yields
+ * exactly the lexicographic-ascending ranks torch.unique(dim=0) returns.
+ * ------------------------------------------------------------------------- */
+
+/* Per-column min and max of integer rows.  minmax dev [2*d] i64 = {min[d], max[d]}.
+ * rows_i64: 1 → rows are int64, 0 → int32.  n == 0 leaves {INT64_MAX, INT64_MIN}. */
+int fsfb_rows_minmax(const void* rows, int rows_i64, int64_t n, int d,
+                     int64_t* minmax, void* stream);
+
+/* Workspace bytes fsfb_rank_rows needs for n rows over `cells` key cells. */
+int fsfb_rank_workspace_bytes(int64_t n, int64_t cells, size_t* bytes);
+
+/* Rank rows.  lo/ext host [d]: column j must lie in [lo[j], lo[j]+ext[j]); rows
+ * outside raise *status (dev i32, bit0) and get inv = -1.  prod(ext) <= 2^32-1.
+ *   inv32     dev [n] i32 (nullable)   rank of each row
+ *   inv64     dev [n] i64 (nullable)   same, torch dtype
+ *   uniq      dev [cap_unique, d] same dtype as rows (nullable) — unique rows ascending
+ *   counts    dev [cap_unique] i32 (nullable) — rows per unique row
+ *   num_unique dev [1] i32 — M (read it after syncing the stream)
+ *   status    dev [1] i32 — 0 ok; bit0 row out of bounds; bit1 cap_unique exceeded
+ */
+int fsfb_rank_rows(const void* rows, int rows_i64, int64_t n, int d,
+                   const int64_t* lo, const int64_t* ext,
+                   void* workspace, size_t workspace_bytes,
+                   int32_t* inv32, int64_t* inv64,
+                   void* uniq, int64_t cap_unique, int32_t* counts,
+                   int32_t* num_unique, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a2/a12/a13  Segment CSR ("scatter rulebook") and segmented reductions =
+ * torch_scatter.scatter_max / scatter(reduce='mean'|'sum') over dim 0 as called
+ * at projects/mmdet3d_plugin/ops/sst_ops.py:168,170.
+ * ------------------------------------------------------------------------- */
+
+int fsfb_csr_workspace_bytes(int64_t n, int64_t m, size_t* bytes);
+
+/* Build the CSR of `index` (values in [0,m), or <0 = dropped row):
+ *   offsets dev [m+1] i32, perm dev [n] i32 (source rows grouped by segment,
+ *   ascending source row inside a segment — stable), seg dev [n] i32 (segment of
+ *   each sorted position).  Rows with index<0 are placed after offsets[m].
+ * index_i64: 1 → int64 index, 0 → int32. */
+int fsfb_csr_build(const void* index, int index_i64, int64_t n, int64_t m,
+                   int32_t* offsets, int32_t* perm, int32_t* seg,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+int fsfb_segment_reduce_workspace_bytes(int64_t n, int c, int with_arg, size_t* bytes);
+
+/* out[s, :] = reduce over rows r with index[r]==s of feat[r, :].
+ * mode FSFB_REDUCE_{SUM,MEAN,MAX}.  MAX: ties → lowest source row (torch_scatter's
+ * sequential CPU rule); argmax (nullable) dev [m,c] i64.  Empty segment → 0 and
+ * argmax = n.  perm == NULL means rows are already grouped (perm = identity).
+ *   feat dev [n, feat_stride] f32 (c <= feat_stride), out dev [m, c] f32 */
+int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride,
+                        const int32_t* perm, const int32_t* seg, const int32_t* offsets,
+                        int64_t m, int mode, float* out, int64_t* argmax,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i, :] = idx[i] >= 0 ? src[idx[i], :] : fill.  Voxel→point gather of
+ * models/necks/voxel2point_neck.py:42-50 and voxel_center[unq_inv]
+ * (models/detectors/FSF.py:310-311).  idx_i64 selects the index dtype. */
+int fsfb_gather_rows(const float* src, int64_t m, int c, const void* idx, int idx_i64,
+                     int64_t n, float fill, float* out, int64_t out_stride, void* stream);
+
+/* In-group index: out[i] = number of j < i with group[j] == group[i]  (stable
+ * variant of ingroup_indices.forward, projects/mmdet3d_plugin/ops/sst_ops.py:246-248;
+ * oracle = get_inner_win_inds_slow, models/middle_encoders/sst_input_layer.py:200-208).
+ * group dev [n] i64 values in [0, m); out dev [n] i64. */
+int fsfb_ingroup_workspace_bytes(int64_t n, int64_t m, size_t* bytes);
+int fsfb_ingroup_indices(const int64_t* group, int64_t n, int64_t m, int64_t* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a7+a8  LiDAR→camera projection fused with nearest sampling of the instance-id
+ * planes = FSF.prj_points_2d + FSF.points_in_mask
+ * (projects/mmdet3d_plugin/models/detectors/FSF.py:169-226): homogeneous
+ * projection by lidar2img, depth > 1e-3, clip to [1e-5,1e5], normalise to (-1,1),
+ * invalid → -2, then F.grid_sample(mode='nearest', align_corners=False, zeros).
+ * The id planes are sampled as stored (u8 or i32): no float copy is made.
+ *   xyz       dev [n, xyz_stride] f32
+ *   lidar2img dev [cams,4,4] f32 row-major
+ *   mask      dev [cams, classes, H, W]  (mask_i32: 0 → uint8, 1 → int32)
+ *   out_ids   dev [n, cams, classes] i64  — the reference's obj_id_tensor
+ * ------------------------------------------------------------------------- */
+int fsfb_project_sample(const float* xyz, int64_t n, int64_t xyz_stride,
+                        const float* lidar2img, int cams,
+                        const void* mask, int mask_i32, int classes, int H, int W,
+                        int64_t* out_ids, void* stream);
+
+/* Fused contract (a9: FSF.img_cross_attn, FSF.py:714-718): same sampling, but only
+ * the camera with the largest id sum is kept (first maximal camera on ties):
+ *   ids_sel dev [n, classes] i32 (i32 so AV2 ids fit), cam_sel dev [n] u8,
+ *   fg dev [n] u8 = any id > 0 over all cams/classes (FSF.extract_fg_pts, :299-308);
+ *   overlap dev [n] u8 (nullable) = number of (cam,class) slots with id > 0. */
+int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
+                               const float* lidar2img, int cams,
+                               const void* mask, int mask_i32, int classes, int H, int W,
+                               int32_t* ids_sel, uint8_t* cam_sel, uint8_t* fg,
+                               uint8_t* overlap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSF_B200_H_ */

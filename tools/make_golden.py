@@ -1,0 +1,337 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python on seeded inputs.
+
+Runs only in the build container (needs /root/reference).  The reference imports mmcv / mmdet /
+mmdet3d / mmseg / torch_scatter / ingroup_indices / dynamic_point_pool_ext, none of which are
+installable here, so those names are served by inert import stubs: registries whose
+register_module() is the identity, base classes that are plain nn.Module, decorators that pass
+through.  Three stubs carry behaviour, each a documented stand-in:
+  * mmcv.cnn.build_norm_layer  → nn.LayerNorm / nn.BatchNorm1d (what mmcv builds for 'LN'/'BN1d')
+  * torch_scatter.scatter_max / scatter → torch scatter_reduce_/index_add_ on CPU with the
+    sequential first-max-wins argmax of torch-scatter's CPU kernel
+  * mmdet3d.ops.Voxelization  → not called (the goldens use the in-tree torch.div formula)
+Everything else that executes is the reference's code, unmodified, imported from
+/root/reference: FSF.prj_points_2d / points_in_mask / frustum_gather / extract_fg_pts /
+double_overlap_pts / get_cluster_delta_weighted / img_cross_attn's selection,
+single_stage_fsd.find_connected_componets[_single_batch] (scipy), sst_ops.scatter_v2 /
+build_mlp, Voxel2PointScatterNeck.forward, SSTInputLayer.get_inner_win_inds_slow,
+VoteSegHead.decode_vote_targets.
+
+Usage:  python tools/make_golden.py        (writes tests/golden/, prints a manifest)
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+from torch import nn
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+
+STUB_ROOTS = ("mmcv", "mmdet", "mmdet3d", "mmseg", "torch_scatter", "ingroup_indices",
+              "dynamic_point_pool_ext", "torchex", "nuscenes", "shapely", "av2", "pyquaternion",
+              "trimesh", "open3d", "numba", "lyft_dataset_sdk", "plyfile", "skimage", "ipdb", "terminaltables",
+              "pycocotools", "tensorboard")
+
+
+import abc
+
+
+class _StubMeta(abc.ABCMeta):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _make_stub(name)
+
+    def register_module(cls, *a, **k):  # REGISTRY.register_module() on the class itself
+        return lambda c: c
+
+
+class _Stub(nn.Module, metaclass=_StubMeta):
+    """Subclassable, callable as a decorator factory, usable as a registry."""
+
+    def __init__(self, *a, **k):
+        super().__init__()
+
+    def forward(self, *a, **k):
+        if len(a) == 1 and (isinstance(a[0], type) or callable(a[0])):
+            return a[0]  # decorator use
+        raise RuntimeError("stub called")
+
+    @classmethod
+    def register_module(cls, *a, **k):  # REGISTRY.register_module() → identity decorator
+        return lambda c: c
+
+def _make_stub(name):
+    return _StubMeta(name, (_Stub,), {})
+
+
+class _StubModule(types.ModuleType):
+    __path__: list = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        obj = _SPECIAL.get((self.__name__, name))
+        if obj is None:
+            obj = _make_stub(name)
+        setattr(self, name, obj)
+        return obj
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path, target=None):
+        if fullname.split(".")[0] in STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+# ---- behavioural stand-ins ---------------------------------------------------------------
+def _build_norm_layer(cfg, num_features, postfix=""):
+    t = cfg["type"]
+    if t == "LN":
+        return "ln", nn.LayerNorm(num_features, eps=cfg.get("eps", 1e-5))
+    if t in ("BN1d", "naiveSyncBN1d", "BN"):
+        return "bn", nn.BatchNorm1d(num_features, eps=cfg.get("eps", 1e-5), momentum=cfg.get("momentum", 0.1))
+    raise NotImplementedError(t)
+
+
+def _ts_scatter_max(src, index, dim=0, out=None, dim_size=None):
+    assert dim == 0 and src.dim() == 2
+    n, c = src.shape
+    m = int(index.max()) + 1 if dim_size is None else dim_size
+    res = torch.full((m, c), float("-inf"), dtype=src.dtype)
+    arg = torch.full((m, c), n, dtype=torch.long)
+    for i in range(n):  # torch-scatter CPU kernel: sequential, strict '>' keeps the first max
+        s = int(index[i])
+        upd = src[i] > res[s]
+        res[s] = torch.where(upd, src[i], res[s])
+        arg[s] = torch.where(upd, torch.full_like(arg[s], i), arg[s])
+    res[arg == n] = 0
+    return res, arg
+
+
+def _ts_scatter(src, index, dim=0, out=None, dim_size=None, reduce="sum"):
+    assert dim == 0 and src.dim() == 2
+    m = int(index.max()) + 1 if dim_size is None else dim_size
+    res = torch.zeros((m, src.size(1)), dtype=src.dtype).index_add_(0, index, src)
+    if reduce in ("sum", "add"):
+        return res
+    if reduce == "mean":
+        cnt = torch.zeros(m, dtype=src.dtype).index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
+        return res / cnt.clamp(min=1)[:, None]
+    raise NotImplementedError(reduce)
+
+
+def _multi_apply(func, *args, **kwargs):
+    from functools import partial
+    pfunc = partial(func, **kwargs) if kwargs else func
+    return tuple(map(list, zip(*map(pfunc, *args))))
+
+
+_SPECIAL = {
+    ("mmcv.cnn", "build_norm_layer"): _build_norm_layer,
+    ("torch_scatter", "scatter_max"): _ts_scatter_max,
+    ("torch_scatter", "scatter"): _ts_scatter,
+    ("mmdet.core", "multi_apply"): _multi_apply,
+}
+
+
+def import_reference():
+    assert os.path.isdir(REF), "tools/make_golden.py needs /root/reference (build container only)"
+    sys.meta_path.insert(0, _Finder())
+    sys.path.insert(0, REF)
+    sst_ops = importlib.import_module("projects.mmdet3d_plugin.ops.sst_ops")
+    fsd = importlib.import_module("projects.mmdet3d_plugin.models.detectors.single_stage_fsd")
+    fsf = importlib.import_module("projects.mmdet3d_plugin.models.detectors.FSF")
+    neck = importlib.import_module("projects.mmdet3d_plugin.models.necks.voxel2point_neck")
+    sst_in = importlib.import_module("projects.mmdet3d_plugin.models.middle_encoders.sst_input_layer")
+    seg_head = importlib.import_module("projects.mmdet3d_plugin.models.decode_heads.segmentation_head")
+    return dict(sst_ops=sst_ops, fsd=fsd, fsf=fsf, neck=neck, sst_in=sst_in, seg_head=seg_head)
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.1f} KiB  keys={sorted(arrays)}")
+
+
+def main():
+    from fullysparsefusion_b200 import synth  # shared seeded generators (also used by the GPU parity tests)
+
+    ref = import_reference()
+    torch.manual_seed(0)
+    FSF = ref["fsf"].FSF
+    fsf_self = types.SimpleNamespace()
+    fsf_self.prj_points_2d = lambda *a: FSF.prj_points_2d(fsf_self, *a)
+    fsf_self.points_in_mask = lambda *a: FSF.points_in_mask(fsf_self, *a)
+
+    # ---- projection + nearest sampling (FSF.py:169-258) ------------------------------------
+    for tag, (n, H, W, cams, classes, seed) in {
+        "projection_small": (4000, 90, 160, 6, 10, 1),
+        "projection_nusc": (3000, 900, 1600, 6, 10, 2),
+    }.items():
+        pts = synth.ring_points(n, sweeps=1, seed=seed)[:, :3]
+        l2i = synth.lidar2img(cams, H, W)
+        mask = synth.mask_planes(cams, classes, H, W, seed=seed)
+        tp, tm, tl = torch.from_numpy(pts), torch.from_numpy(mask), torch.from_numpy(l2i)
+        pts2d = FSF.prj_points_2d(fsf_self, tp, tl, H, W)
+        ids = FSF.points_in_mask(fsf_self, tp, tm, tl)
+        bidx = torch.zeros(n, dtype=torch.long)
+        ids_fg = FSF.frustum_gather(fsf_self, bidx, tp, tm[None], None, [dict(lidar2img=l2i)])
+        assert torch.equal(ids, ids_fg)
+        # camera selection exactly as FSF.img_cross_attn (:714-718)
+        cam_sel = ids.sum(-1).max(-1)[1]
+        sel_mask = torch.nn.functional.one_hot(cam_sel, cams).bool().unsqueeze(-1)
+        ids_sel = ids.masked_select(sel_mask).reshape(-1, classes)
+        fg = ids.sum((-2, -1)) > 0
+        extra = {} if tag == "projection_small" else {}
+        save(tag, points=pts, lidar2img=l2i, mask_seed=seed, mask_shape=np.array(mask.shape),
+             mask=mask if tag == "projection_small" else np.zeros(0, np.uint8),
+             pts_2d=pts2d, ids=ids.to(torch.int16), cam_sel=cam_sel, ids_sel=ids_sel.to(torch.int16), fg=fg, **extra)
+
+    # ---- frustum helpers: extract_fg_pts / double_overlap_pts / get_cluster_delta_weighted --
+    n = 1500
+    pts = synth.ring_points(n, sweeps=1, seed=5)[:, :3]
+    l2i = synth.lidar2img(6, 90, 160)
+    mask = synth.mask_planes(6, 10, 90, 160, seed=5, overlap=True)
+    ids = FSF.points_in_mask(fsf_self, torch.from_numpy(pts), torch.from_numpy(mask), torch.from_numpy(l2i))
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(n, 8, generator=g)
+    w = torch.rand(n, generator=g)
+    bz = torch.zeros(n, 1, dtype=torch.long)
+    f1, b1, p1, o1, w1 = FSF.extract_fg_pts(fsf_self, feat, bz, torch.from_numpy(pts), ids, w)
+    f2, b2, p2, o2, w2 = FSF.double_overlap_pts(fsf_self, f1, b1, p1, o1, w1)
+    fsf_self.map_voxel_center_to_point = lambda a, b: FSF.map_voxel_center_to_point(fsf_self, a, b)
+    sir_coors, _ = FSF.get_sir_coors(fsf_self, b2, o2, w2)
+    delta, center, ccoors = FSF.get_cluster_delta_weighted(fsf_self, p2, sir_coors, w2.unsqueeze(-1))
+    save("frustum_pool", points=pts, lidar2img=l2i, mask=mask, feat=feat, weights=w, ids=ids.to(torch.int16),
+         fg_feat=f1, fg_points=p1, fg_ids=o1.to(torch.int16), fg_w=w1,
+         dup_feat=f2, dup_points=p2, dup_obj=o2, dup_w=w2, sir_coors=sir_coors,
+         f_cluster=delta, center=center, center_coors=ccoors)
+
+    # ---- CCL (single_stage_fsd.py:45-82) -----------------------------------------------------
+    fsd = ref["fsd"]
+    for tag, (m, dist, seed, nb) in {"ccl_small": (300, 0.6, 3, 1), "ccl_mid": (2500, 0.5, 4, 1),
+                                      "ccl_batch": (900, 0.7, 6, 3)}.items():
+        cp, cb = synth.cluster_points(m, seed=seed, batches=nb)
+        tp, tb = torch.from_numpy(cp), torch.from_numpy(cb)
+        if nb == 1:
+            lab = fsd.find_connected_componets_single_batch(tp, tb, dist)
+            lab2 = fsd.find_connected_componets(tp, tb, dist)
+            assert torch.equal(lab, lab2)
+        else:
+            lab = fsd.find_connected_componets(tp, tb, dist)
+        save(tag, points=cp, batch_idx=cb, dist=np.float32(dist), labels=lab)
+
+    # ---- scatter_v2 (sst_ops.py:150-177) ------------------------------------------------------
+    sst_ops = ref["sst_ops"]
+    g = torch.Generator().manual_seed(7)
+    for tag, (n, c, spec) in {"scatter_c1": (10000, 128, ("ids", 32)), "scatter_vox": (6000, 16, ("vox", None)),
+                              "scatter_odd": (3000, 5, ("vox", None)), "scatter_ties": (2000, 33, ("ids", 40))}.items():
+        feat = torch.randn(n, c, generator=g)
+        if tag == "scatter_c1":  # 5 MB of features: regenerate from a dedicated seed instead of storing
+            feat = torch.randn(n, c, generator=torch.Generator().manual_seed(107))
+        if tag == "scatter_ties":
+            feat = torch.round(feat * 2) / 2  # many exact ties → argmax rule is exercised
+        if spec[0] == "ids":
+            coors = torch.stack([torch.zeros(n, dtype=torch.long), torch.zeros(n, dtype=torch.long),
+                                 torch.randint(0, spec[1], (n,), generator=g)], 1)
+        else:
+            pts = torch.from_numpy(synth.ring_points(n, sweeps=1, seed=11)[:, :3])
+            pc_range = torch.tensor([-51.2, -51.2, -5.0])
+            vs = torch.tensor([0.2, 0.2, 0.2])
+            cz = torch.div(pts - pc_range[None], vs[None], rounding_mode="floor").long()[:, [2, 1, 0]]
+            coors = torch.cat([torch.zeros(n, 1, dtype=torch.long), cz], 1)
+        out = {}
+        for mode in ("max", "avg", "sum"):
+            nf, nc, inv = sst_ops.scatter_v2(feat, coors, mode)
+            out[f"out_{mode}"] = nf
+        _, arg = _ts_scatter_max(feat, inv)
+        import hashlib
+        sha = np.frombuffer(hashlib.sha256(feat.numpy().tobytes()).digest(), dtype=np.uint8)
+        save(tag, feat=feat if tag != "scatter_c1" else np.zeros(0, np.float32), feat_seed=107, feat_sha=sha,
+             feat_shape=np.array(feat.shape), coors=coors.to(torch.int32), new_coors=nc.to(torch.int32),
+             unq_inv=inv.to(torch.int32), argmax=arg.to(torch.int32), **out)
+
+    # ---- voxel coordinates: the in-tree torch.div formula (single_stage_fsd.py:270,591-593) ----
+    pts = synth.ring_points(20000, sweeps=2, seed=13)
+    # add points that sit exactly on voxel boundaries (where floor(a/b) and div_floor can differ)
+    edge = torch.arange(-250, 250, dtype=torch.float32)[:, None] * 0.2 + torch.zeros(1, 3)
+    edge[:, 2] = (torch.arange(500, dtype=torch.float32) % 38) * 0.2 - 4.8
+    allp = torch.cat([torch.from_numpy(pts[:, :3]), edge], 0)
+    for tag, (rng, vs) in {"voxel_nusc": ([-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], [0.2, 0.2, 0.2]),
+                           "voxel_pre": ([-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], [0.1, 0.1, 0.1])}.items():
+        pc = torch.tensor(rng[:3])
+        v = torch.tensor(vs)
+        c1 = torch.div(allp - pc[None], v[None], rounding_mode="floor").long()[:, [2, 1, 0]]
+        c0 = torch.floor((allp - pc[None]) / v[None]).long()[:, [2, 1, 0]]  # Voxelization kernel's rule
+        save(tag, points=allp, pc_range=np.array(rng, np.float32), voxel_size=np.array(vs, np.float32),
+             coors_divfloor=c1, coors_floor=c0)
+
+    # ---- build_mlp (sst_ops.py:808-833) --------------------------------------------------------
+    torch.manual_seed(3)
+    for tag, (cin, dims, norm, act, is_head, rows) in {
+        "mlp_ln_gelu": (48, [64, 64], dict(type="LN", eps=1e-3), "gelu", False, 257),
+        "mlp_head": (64, [32, 32, 10], dict(type="LN", eps=1e-3), "gelu", True, 100),
+        "mlp_bn_relu": (131, [128, 128], dict(type="naiveSyncBN1d", eps=1e-3, momentum=0.01), "relu", False, 300),
+    }.items():
+        mlp = sst_ops.build_mlp(cin, dims, norm, is_head=is_head, act=act)
+        for mod in mlp.modules():  # non-trivial norm statistics / affine
+            if isinstance(mod, nn.BatchNorm1d):
+                mod.running_mean.normal_(0, 0.5)
+                mod.running_var.uniform_(0.5, 2.0)
+            if isinstance(mod, (nn.BatchNorm1d, nn.LayerNorm)):
+                mod.weight.data.uniform_(0.5, 1.5)
+                mod.bias.data.normal_(0, 0.2)
+        mlp.eval()
+        x = torch.randn(rows, cin)
+        with torch.no_grad():
+            y = mlp(x)
+        sd = {k.replace(".", "__"): v for k, v in mlp.state_dict().items()}
+        save(tag, x=x, y=y, **sd)
+
+    # ---- Voxel2PointScatterNeck.forward (voxel2point_neck.py:27-70) --------------------------
+    Neck = ref["neck"].Voxel2PointScatterNeck
+    neck = Neck(point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], voxel_size=[0.2, 0.2, 0.2])
+    neck.eval()
+    pts = torch.from_numpy(synth.ring_points(2000, sweeps=1, seed=17)[:, :5])
+    pc = torch.tensor([-51.2, -51.2, -5.0])
+    cz = torch.div(pts[:, :3] - pc[None], torch.tensor([0.2, 0.2, 0.2])[None], rounding_mode="floor").long()[:, [2, 1, 0]]
+    coors = torch.cat([torch.zeros(len(pts), 1, dtype=torch.long), cz], 1)
+    vc, inv = torch.unique(coors, return_inverse=True, dim=0)
+    vfeat = torch.randn(len(vc), 32)
+    vfeat[::17] = -1  # padded (dropped) voxels, voxel_padding = -1
+    res, pmask = neck(pts, coors, vfeat, inv, -1)
+    save("neck", points=pts, coors=coors, voxel_feats=vfeat, voxel2point_inds=inv, out=res, mask=pmask)
+
+    # ---- in-group indices slow oracle (sst_input_layer.py:200-208) ----------------------------
+    L = ref["sst_in"].SSTInputLayer
+    grp = torch.randint(0, 50, (4000,), generator=g)
+    inner = L.get_inner_win_inds_slow(types.SimpleNamespace(), grp)
+    save("ingroup", group=grp, inner=inner)
+
+    # ---- vote decode (segmentation_head.py:265-266) ---------------------------------------------
+    H = ref["seg_head"].VoteSegHead
+    v = torch.randn(500, 33, generator=g)
+    save("vote_decode", preds=v, offsets=H.decode_vote_targets(types.SimpleNamespace(), v))
+
+
+if __name__ == "__main__":
+    main()
