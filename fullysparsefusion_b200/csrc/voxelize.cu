@@ -42,13 +42,15 @@ __global__ void __launch_bounds__(256) k_voxelize(const float* __restrict__ pts,
   for (; i < n; i += step) {
     const float* p = pts + i * stride;
     float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    // __float2int_rd saturates for huge/NaN inputs, which the range test then rejects
-    // (NaN converts to 0: reject it explicitly).
+    // __float2int_rd saturates for huge inputs, which the range test then rejects; NaN converts
+    // to 0 (and mode 1 turns +-inf into NaN through fmod), so non-finite inputs are rejected
+    // explicitly.
     int cx = voxel_coord(x, P.min_x, P.vs_x, mode);
     int cy = voxel_coord(y, P.min_y, P.vs_y, mode);
     int cz = voxel_coord(z, P.min_z, P.vs_z, mode);
     bool ok = (cx >= 0) & (cx < P.gx) & (cy >= 0) & (cy < P.gy) & (cz >= 0) & (cz < P.gz) &
-              (x == x) & (y == y) & (z == z);
+              (fabsf(x) <= 3.402823466e38f) & (fabsf(y) <= 3.402823466e38f) &
+              (fabsf(z) <= 3.402823466e38f);
     int32_t* o = coors + i * 3;
     o[0] = ok ? cz : -1;
     o[1] = ok ? cy : -1;

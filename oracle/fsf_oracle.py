@@ -283,3 +283,140 @@ def cam_select(obj_id_tensor: np.ndarray):
     fg = obj_id_tensor.sum((-2, -1)) > 0
     overlap = (obj_id_tensor.reshape(obj_id_tensor.shape[0], -1) > 0).sum(-1)
     return ids, cam, fg, overlap
+
+
+# ------------------------------------------------------------------------------------------
+# a14 connected components (the stock config's live path: scipy on a dense xy-distance graph)
+# ------------------------------------------------------------------------------------------
+def _ccl_pairs(xy: np.ndarray, dist: float):
+    """All (i<j) with fp32 sqrt(dx^2+dy^2) < fp32(dist), evaluated exactly as
+    single_stage_fsd.py:75-78 does: (this_points[:,None,:2]-this_points[None,:,:2])**2 summed in
+    fp32, ** 0.5, compared with the Python scalar cast to fp32."""
+    from scipy.spatial import cKDTree
+
+    xy = np.asarray(xy, dtype=F32)
+    d32 = F32(dist)
+    if xy.shape[0] < 2:
+        return np.zeros((0, 2), np.int64)
+    cand = cKDTree(xy.astype(np.float64)).query_pairs(float(d32) * 1.001 + 1e-6, output_type="ndarray")
+    if cand.shape[0] == 0:
+        return cand.astype(np.int64)
+    dx = (xy[cand[:, 0], 0] - xy[cand[:, 1], 0]).astype(F32)
+    dy = (xy[cand[:, 0], 1] - xy[cand[:, 1], 1]).astype(F32)
+    d = np.sqrt(((dx * dx).astype(F32) + (dy * dy).astype(F32)).astype(F32)).astype(F32)
+    return cand[d < d32].astype(np.int64)
+
+
+def connected_components_single_batch(points: np.ndarray, dist: float) -> np.ndarray:
+    """find_connected_componets_single_batch (single_stage_fsd.py:69-82): batch_idx is ignored;
+    labels int32, numbered in order of each component's lowest member index (scipy's
+    connected_components numbers components in order of first visit, scanning nodes 0..m-1)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components as cc
+
+    m = np.asarray(points).shape[0]
+    if m == 0:
+        return np.zeros(0, np.int32)
+    pairs = _ccl_pairs(np.asarray(points)[:, :2], dist)
+    adj = coo_matrix((np.ones(len(pairs), bool), (pairs[:, 0], pairs[:, 1])), shape=(m, m))
+    return cc(adj, directed=False)[1].astype(np.int32)
+
+
+def connected_components(points: np.ndarray, batch_idx: np.ndarray, dist: float) -> np.ndarray:
+    """find_connected_componets (single_stage_fsd.py:45-67): per-sample clustering, labels of
+    sample b offset by the number of components in samples < b."""
+    points = np.asarray(points, dtype=F32)
+    batch_idx = np.asarray(batch_idx).astype(np.int64)
+    out = -np.ones(points.shape[0], np.int32)
+    base = 0
+    for b in range(int(batch_idx.max()) + 1 if len(batch_idx) else 0):
+        sel = np.flatnonzero(batch_idx == b)
+        if len(sel) == 0:
+            continue
+        lab = connected_components_single_batch(points[sel], dist) + base
+        base = int(lab.max()) + 1
+        out[sel] = lab
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# a9/a10/a16/a17 build_mlp stacks
+# ------------------------------------------------------------------------------------------
+def gelu(x: np.ndarray) -> np.ndarray:
+    """nn.GELU() (exact erf form), sst_ops.py:851."""
+    from scipy.special import erf
+
+    x64 = x.astype(np.float64)
+    return (0.5 * x64 * (1.0 + erf(x64 / np.sqrt(2.0)))).astype(F32)
+
+
+def mlp_layer(x, weight, bias=None, norm=None, norm_w=None, norm_b=None, mean=None, var=None, eps=1e-5, act=None):
+    """One block of build_mlp (sst_ops.py:808-833): Linear(bias) → norm → act.
+    norm 'ln' = nn.LayerNorm(c, eps) over channels; 'bn' = eval-mode BatchNorm1d with running
+    stats (naiveSyncBN1d falls back to plain BN in eval).  Accumulation in float64, rounded to
+    fp32 after the Linear, after the norm and after the activation (tolerance 1e-4 rel in tests)."""
+    y = (x.astype(np.float64) @ np.asarray(weight, np.float64).T)
+    if bias is not None:
+        y = y + np.asarray(bias, np.float64)
+    y = y.astype(F32)
+    if norm == "ln":
+        y64 = y.astype(np.float64)
+        mu = y64.mean(-1, keepdims=True)
+        v = ((y64 - mu) ** 2).mean(-1, keepdims=True)
+        y = ((y64 - mu) / np.sqrt(v + eps) * np.asarray(norm_w, np.float64) + np.asarray(norm_b, np.float64)).astype(F32)
+    elif norm == "bn":
+        y64 = y.astype(np.float64)
+        y = ((y64 - np.asarray(mean, np.float64)) / np.sqrt(np.asarray(var, np.float64) + eps)
+             * np.asarray(norm_w, np.float64) + np.asarray(norm_b, np.float64)).astype(F32)
+    elif norm is not None:
+        raise NotImplementedError(norm)
+    if act == "relu":
+        y = np.maximum(y, F32(0))
+    elif act == "gelu":
+        y = gelu(y)
+    elif act is not None:
+        raise NotImplementedError(act)
+    return y
+
+
+def mlp_from_state_dict(x, sd: dict, norm: str, act: str, eps: float, prefix: str = ""):
+    """Run a build_mlp nn.Sequential from its state_dict layout (`{i}.0.weight` Linear,
+    `{i}.1.*` norm; a head's last layer is `{i}.weight`/`{i}.bias`; sst_ops.py:808-833)."""
+    i = 0
+    while True:
+        k_seq, k_head = f"{prefix}{i}.0.weight", f"{prefix}{i}.weight"
+        if k_seq in sd:
+            kw = dict(weight=sd[k_seq], bias=sd.get(f"{prefix}{i}.0.bias"), norm=norm, act=act, eps=eps,
+                      norm_w=sd[f"{prefix}{i}.1.weight"], norm_b=sd[f"{prefix}{i}.1.bias"])
+            if norm == "bn":
+                kw.update(mean=sd[f"{prefix}{i}.1.running_mean"], var=sd[f"{prefix}{i}.1.running_var"])
+            x = mlp_layer(x, **kw)
+        elif k_head in sd:
+            x = mlp_layer(x, sd[k_head], sd.get(f"{prefix}{i}.bias"))
+        else:
+            return x
+        i += 1
+
+
+# ------------------------------------------------------------------------------------------
+# a6 voxel → point neck,  a10 vote decode
+# ------------------------------------------------------------------------------------------
+def voxel2point_neck(points, pts_coors, voxel_feats, voxel2point_inds, voxel_size, point_cloud_range,
+                     voxel_padding: float = -1.0):
+    """Voxel2PointScatterNeck.forward (models/necks/voxel2point_neck.py:42-70), with_xyz=True,
+    normalize_local_xyz=False: returns (results [N_kept, C+3], pts_mask [N] bool)."""
+    points = np.asarray(points, F32)
+    feats = np.asarray(voxel_feats, F32)[np.asarray(voxel2point_inds, np.int64)]          # :47
+    mask = ~np.all(feats == F32(voxel_padding), axis=1)                                  # :48
+    vs = np.asarray(voxel_size, F32).reshape(1, 3)
+    lo = np.asarray(point_cloud_range[:3], F32).reshape(1, 3)
+    c_xyz = np.asarray(pts_coors)[:, [3, 2, 1]].astype(F32)
+    centre = (((c_xyz + F32(0.5)).astype(F32) * vs).astype(F32) + lo).astype(F32)        # :56
+    local = (points[:, :3] - centre).astype(F32)                                          # :57
+    return np.concatenate([feats, local], 1)[mask], mask
+
+
+def decode_vote_targets(preds: np.ndarray) -> np.ndarray:
+    """VoteSegHead.decode_vote_targets (decode_heads/segmentation_head.py:265-266): v * |v|."""
+    preds = np.asarray(preds, F32)
+    return (preds * np.abs(preds)).astype(F32)

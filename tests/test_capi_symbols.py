@@ -1,0 +1,55 @@
+"""The C-ABI library builds, loads and exports every symbol include/fsf_b200.h declares (no GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+REPO = Path(__file__).resolve().parents[1]
+
+
+def _declared():
+    text = (REPO / "include" / "fsf_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsfb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_symbols():
+    names = _declared()
+    assert "fsfb_segment_reduce" in names and "fsfb_project_sample" in names and len(names) >= 12
+
+
+def test_library_exports_every_declared_symbol():
+    from fullysparsefusion_b200 import _capi
+
+    lib = _capi.load()
+    raw = ctypes.CDLL(str(_capi.LIB_PATH))
+    for name in _declared():
+        assert hasattr(raw, name), f"{name} declared in fsf_b200.h but not exported"
+        assert name in _capi.SIGNATURES, f"{name} has no ctypes signature in _capi.py"
+    for name in _capi.SIGNATURES:
+        assert name in _declared(), f"{name} bound in _capi.py but not declared in the header"
+    assert lib.fsfb_version() >= 1
+    assert lib.fsfb_launch_count() >= 0
+
+
+def test_bad_arguments_fail_without_gpu():
+    from fullysparsefusion_b200 import _capi
+
+    lib = _capi.load()
+    need = ctypes.c_size_t(0)
+    assert lib.fsfb_rank_workspace_bytes(10, 1 << 40, ctypes.byref(need)) == _capi.ERR_BADARG
+    assert b"2^32" in lib.fsfb_last_error()
+    assert lib.fsfb_voxelize(None, -1, 3, None, None, None, 0, None, None) == _capi.ERR_BADARG
+    assert lib.fsfb_csr_workspace_bytes(100, 10, ctypes.byref(need)) == 0 and need.value > 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+
+    from fullysparsefusion_b200 import _capi, ops
+
+    with pytest.raises(_capi.FsfbError):
+        ops.voxelize(torch.zeros(4, 5), [0.2] * 3, [-1, -1, -1, 1, 1, 1])
+    with pytest.raises(_capi.FsfbError):
+        ops.unique_rows(torch.zeros(4, 3, dtype=torch.int64))
