@@ -1,0 +1,118 @@
+// gemm_common.cuh — packed-weight layout and the fused epilogue shared by the tensor-core
+// gather-GEMM (gemm_tc.cu), its CUDA-core cross-check (gemm_simt.cu) and fsfb_rownorm_act.
+#pragma once
+#include "common.cuh"
+
+namespace fsfb {
+
+// ---- packed weight layout (written by fsfb_gemm_prepack, read by the tcgen05 kernel) -------
+// w[koff][cout][cin] is cut into column tiles of kGemmNTile output channels (the last one
+// narrower, widths rounded up to 16 = UMMA N granularity at M=128) and K chunks of 32 floats
+// (= one 128-byte swizzle row of tf32).  Block (nt, k, kc) holds [hi|lo][n_w][32] floats:
+// hi = w rounded to nearest tf32, lo = tf32(w - hi).
+// Inside a block, row n lives at byte n*128 and its 16-byte chunk j at position j ^ (n & 7)
+// (the SWIZZLE_128B K-major canonical layout UMMA shared-memory descriptors expect), so a
+// block is moved to shared memory with one linear bulk copy.
+constexpr int kGemmNTile = 256;
+constexpr int kGemmKChunk = 32;
+
+struct GemmShape {
+  int koff, cin, cout;
+  __host__ __device__ int kc() const { return (cin + kGemmKChunk - 1) / kGemmKChunk; }
+  __host__ __device__ int n_pad() const { return (cout + 15) / 16 * 16; }
+  __host__ __device__ int n_tiles() const { return (n_pad() + kGemmNTile - 1) / kGemmNTile; }
+  __host__ __device__ int n_w(int nt) const { return min(kGemmNTile, n_pad() - nt * kGemmNTile); }
+  // bytes of one (nt,k,kc) block: hi + lo
+  __host__ __device__ size_t block_bytes(int nt) const { return (size_t)2 * n_w(nt) * 128; }
+  __host__ __device__ size_t tile_base(int nt) const {
+    return (size_t)nt * koff * kc() * 2 * kGemmNTile * 128;
+  }
+  __host__ __device__ size_t block_offset(int nt, int k, int kchunk) const {
+    return tile_base(nt) + ((size_t)k * kc() + kchunk) * block_bytes(nt);
+  }
+  __host__ __device__ size_t total_bytes() const {
+    return tile_base(n_tiles() - 1) + (size_t)koff * kc() * block_bytes(n_tiles() - 1);
+  }
+};
+
+// byte offset of element (n, j) inside a [rows][32 float] SWIZZLE_128B K-major block
+__host__ __device__ inline uint32_t sw128_offset(int n, int j) {
+  return (uint32_t)n * 128u + (uint32_t)((((j >> 2) ^ (n & 7)) << 4) | ((j & 3) << 2));
+}
+
+// Round-to-nearest tf32 (low 13 mantissa bits zero afterwards), so the tensor core's own
+// operand truncation is a no-op and the split is unbiased: x = hi + lo + O(2^-23 |x|).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
+
+// ---- epilogue ------------------------------------------------------------------------------
+struct Epilogue {
+  const float* bias;      // [cout] or null
+  int norm;               // FSFB_NORM_*
+  const float* norm_w;    // [cout]
+  const float* norm_b;    // [cout]
+  float eps;
+  const float* residual;  // [rows, residual_stride] or null
+  int64_t residual_stride;
+  int act;                // FSFB_ACT_*
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == FSFB_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == FSFB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  return x;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp finishes one row: x (pre-bias accumulators, row-major in global or anywhere
+// addressable) → out.  x and out may alias.
+__device__ __forceinline__ void warp_row_epilogue(const float* x, int c, const Epilogue& E,
+                                                  int64_t row, float* out) {
+  const int lane = lane_id();
+  float mean = 0.f, rstd = 1.f;
+  if (E.norm == FSFB_NORM_LAYERNORM) {
+    float s = 0.f;
+    for (int j = lane; j < c; j += 32) s += x[j] + (E.bias ? __ldg(E.bias + j) : 0.f);
+    mean = warp_sum(s) / (float)c;
+    float q = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float d = x[j] + (E.bias ? __ldg(E.bias + j) : 0.f) - mean;
+      q += d * d;
+    }
+    rstd = 1.f / sqrtf(warp_sum(q) / (float)c + E.eps);
+  }
+  for (int j = lane; j < c; j += 32) {
+    float v = x[j] + (E.bias ? __ldg(E.bias + j) : 0.f);
+    if (E.norm == FSFB_NORM_LAYERNORM) {
+      v = (v - mean) * rstd * __ldg(E.norm_w + j) + __ldg(E.norm_b + j);
+    } else if (E.norm == FSFB_NORM_AFFINE) {
+      v = fmaf(v, __ldg(E.norm_w + j), __ldg(E.norm_b + j));
+    }
+    if (E.residual) v += __ldg(E.residual + row * E.residual_stride + j);
+    out[j] = apply_act(v, E.act);
+  }
+}
+
+inline int check_epilogue(int cout, const float* bias, int norm, const float* norm_w,
+                          const float* norm_b, int act, const char* who) {
+  (void)bias;
+  FSFB_CHECK_ARG(norm == FSFB_NORM_NONE || norm == FSFB_NORM_LAYERNORM || norm == FSFB_NORM_AFFINE,
+                 "%s: bad norm %d", who, norm);
+  FSFB_CHECK_ARG(norm == FSFB_NORM_NONE || (norm_w && norm_b), "%s: norm needs norm_w and norm_b", who);
+  FSFB_CHECK_ARG(act == FSFB_ACT_NONE || act == FSFB_ACT_RELU || act == FSFB_ACT_GELU, "%s: bad act %d",
+                 who, act);
+  FSFB_CHECK_ARG(cout >= 1, "%s: cout must be >= 1", who);
+  return FSFB_OK;
+}
+
+}  // namespace fsfb

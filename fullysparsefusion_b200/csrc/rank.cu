@@ -274,6 +274,95 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- 5. sparse-convolution rulebook (a5) --------------------------------------------------
+// Output-stationary neighbour table over the ranked bitmap: the bitmap doubles as a perfect
+// hash of the active-site set (test bit + popcount prefix = row of a coordinate), so the
+// rulebook needs no separate hash table and no sort.
+struct ConvGeom {
+  int k[3], s[3], p[3];  // kernel / stride / padding in (z, y, x)
+  int transposed;        // 1: SparseInverseConv3d (pairs of the forward conv, reversed)
+  int koff;
+};
+
+// out_coors [m_out,4] i32 (b,z,y,x).  nbr[k][o] = row (in the INPUT index) that offset k of
+// output o reads, or -1.
+//   forward   : in = o*s - p + k                      (SubMConv3d: s=1; SparseConv3d: s=2)
+//   transposed: in = (o + p - k) / s when divisible   (SparseInverseConv3d)
+__global__ void __launch_bounds__(256)
+    k_conv_rulebook(const int* __restrict__ out_coors, int64_t m_out, const uint4* __restrict__ blocks,
+                    RowSpec S, ConvGeom G, int32_t* __restrict__ nbr) {
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < m_out;
+       o += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(out_coors) + o);  // b,z,y,x
+    const long long vb = (long long)c.x - S.lo[0];
+    const bool b_ok = vb >= 0 && vb < (long long)S.ext[0];
+    int k = 0;
+    for (int kz = 0; kz < G.k[0]; ++kz)
+      for (int ky = 0; ky < G.k[1]; ++ky)
+        for (int kx = 0; kx < G.k[2]; ++kx, ++k) {
+          const int kk[3] = {kz, ky, kx};
+          const int oc[3] = {c.y, c.z, c.w};
+          bool ok = b_ok;
+          uint32_t key = (uint32_t)vb;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            long long v;
+            if (!G.transposed) {
+              v = (long long)oc[a] * G.s[a] - G.p[a] + kk[a];
+            } else {
+              const int t = oc[a] + G.p[a] - kk[a];
+              ok &= (t >= 0) && (t % G.s[a] == 0);
+              v = t / G.s[a];
+            }
+            v -= S.lo[a + 1];
+            ok &= (v >= 0) & (v < (long long)S.ext[a + 1]);
+            key = key * S.ext[a + 1] + (uint32_t)v;
+          }
+          int32_t r = -1;
+          if (ok) {
+            const uint32_t blk = key / kCellsPerBlock, bit = key - blk * kCellsPerBlock;
+            const uint4 b = __ldg(blocks + blk);
+            const uint32_t word = bit >> 5 == 0 ? b.x : (bit >> 5 == 1 ? b.y : b.z);
+            if ((word >> (bit & 31)) & 1u) r = (int32_t)rank_of(b, bit);
+          }
+          nbr[(int64_t)k * m_out + o] = r;
+        }
+  }
+}
+
+// Mark the output sites of a strided SparseConv3d: every (input site, kernel offset) with
+// (i + p - k) divisible by s and inside the output grid activates output (i + p - k) / s.
+__global__ void __launch_bounds__(256)
+    k_conv_mark_outputs(const int* __restrict__ in_coors, int64_t m_in, RowSpec S /* OUTPUT grid */,
+                        ConvGeom G, uint32_t* __restrict__ bitmap) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_in;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(in_coors) + i);
+    const long long vb = (long long)c.x - S.lo[0];
+    if (vb < 0 || vb >= (long long)S.ext[0]) continue;
+    const int ic[3] = {c.y, c.z, c.w};
+    for (int kz = 0; kz < G.k[0]; ++kz)
+      for (int ky = 0; ky < G.k[1]; ++ky)
+        for (int kx = 0; kx < G.k[2]; ++kx) {
+          const int kk[3] = {kz, ky, kx};
+          bool ok = true;
+          uint32_t key = (uint32_t)vb;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const int t = ic[a] + G.p[a] - kk[a];
+            ok &= (t >= 0) && (t % G.s[a] == 0);
+            const long long v = (long long)(t / G.s[a]) - S.lo[a + 1];
+            ok &= (v >= 0) & (v < (long long)S.ext[a + 1]);
+            key = key * S.ext[a + 1] + (uint32_t)v;
+          }
+          if (ok) {
+            const uint32_t blk = key / kCellsPerBlock, bit = key - blk * kCellsPerBlock;
+            atomicOr(bitmap + (size_t)blk * 4 + (bit >> 5), 1u << (bit & 31));
+          }
+        }
+  }
+}
+
 static int grid_for(int64_t n, int threads, int per_sm) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, threads), (int64_t)kNumSMs * per_sm));
 }
@@ -385,6 +474,93 @@ int fsfb_rank_rows(const void* rows, int rows_i64, int64_t n, int d, const int64
       FSFB_LAUNCH(k_rank_unique_rows<int>, grid, 256, 0, st, blocks, nblocks, S, (int*)uniq,
                   cap_unique);
     }
+  }
+  return FSFB_OK;
+}
+
+int fsfb_conv_rulebook(const int32_t* out_coors, int64_t m_out, const void* in_index,
+                       const int64_t* in_lo, const int64_t* in_ext, const int32_t* ksize,
+                       const int32_t* stride, const int32_t* pad, int transposed, int32_t* nbr,
+                       void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(m_out >= 0 && in_lo && in_ext && ksize && stride && pad, "conv_rulebook: bad argument");
+  RowSpec S;
+  S.d = 4;
+  unsigned long long cells = 1;
+  for (int j = 0; j < kMaxCols; ++j) { S.lo[j] = 0; S.ext[j] = 1; }
+  for (int j = 0; j < 4; ++j) {
+    FSFB_CHECK_ARG(in_ext[j] >= 1 && in_ext[j] <= 0xFFFFFFFFll, "conv_rulebook: bad extent");
+    S.lo[j] = in_lo[j];
+    S.ext[j] = (unsigned)in_ext[j];
+    cells *= (unsigned long long)in_ext[j];
+    FSFB_CHECK_ARG(cells <= 0xFFFFFFFEull, "conv_rulebook: key space exceeds 2^32-2 cells");
+  }
+  ConvGeom G;
+  G.koff = 1;
+  for (int a = 0; a < 3; ++a) {
+    FSFB_CHECK_ARG(ksize[a] >= 1 && ksize[a] <= 3 && stride[a] >= 1 && pad[a] >= 0, "conv_rulebook: bad geometry");
+    G.k[a] = ksize[a]; G.s[a] = stride[a]; G.p[a] = pad[a];
+    G.koff *= ksize[a];
+  }
+  G.transposed = transposed ? 1 : 0;
+  if (m_out == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(out_coors && in_index && nbr, "conv_rulebook: null pointer");
+  FSFB_CHECK_ARG(((uintptr_t)out_coors & 15) == 0, "conv_rulebook: out_coors must be 16-byte aligned");
+  FSFB_LAUNCH(k_conv_rulebook, grid_for(m_out, 256, 8), 256, 0, (cudaStream_t)stream, (const int*)out_coors,
+              m_out, (const uint4*)in_index, S, G, nbr);
+  return FSFB_OK;
+}
+
+int fsfb_conv_out_index(const int32_t* in_coors, int64_t m_in, const int64_t* out_lo,
+                        const int64_t* out_ext, const int32_t* ksize, const int32_t* stride,
+                        const int32_t* pad, void* workspace, size_t workspace_bytes,
+                        int32_t* out_coors, int64_t cap_out, int32_t* num_out, int32_t* status,
+                        void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(m_in >= 0 && out_lo && out_ext && ksize && stride && pad && num_out && status,
+                 "conv_out_index: bad argument");
+  RowSpec S;
+  S.d = 4;
+  unsigned long long cells = 1;
+  for (int j = 0; j < kMaxCols; ++j) { S.lo[j] = 0; S.ext[j] = 1; }
+  for (int j = 0; j < 4; ++j) {
+    FSFB_CHECK_ARG(out_ext[j] >= 1 && out_ext[j] <= 0xFFFFFFFFll, "conv_out_index: bad extent");
+    S.lo[j] = out_lo[j];
+    S.ext[j] = (unsigned)out_ext[j];
+    cells *= (unsigned long long)out_ext[j];
+    FSFB_CHECK_ARG(cells <= 0xFFFFFFFEull, "conv_out_index: key space exceeds 2^32-2 cells");
+  }
+  ConvGeom G;
+  G.koff = 1; G.transposed = 0;
+  for (int a = 0; a < 3; ++a) {
+    FSFB_CHECK_ARG(ksize[a] >= 1 && ksize[a] <= 3 && stride[a] >= 1 && pad[a] >= 0, "conv_out_index: bad geometry");
+    G.k[a] = ksize[a]; G.s[a] = stride[a]; G.p[a] = pad[a];
+    G.koff *= ksize[a];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nblocks = ceil_div((int64_t)cells, kCellsPerBlock);
+  const int64_t ntiles = ceil_div(nblocks, kScanTile);
+  Workspace ws(workspace, workspace_bytes);
+  uint4* blocks = ws.take<uint4>(nblocks);
+  uint32_t* tile_sums = ws.take<uint32_t>(ntiles);
+  if (!ws.ok()) {
+    set_error("conv_out_index: workspace too small (%zu given, %zu needed)", workspace_bytes, ws.used);
+    return FSFB_ERR_CAPACITY;
+  }
+  FSFB_CUDA(cudaMemsetAsync(blocks, 0, (size_t)nblocks * sizeof(uint4), st));
+  FSFB_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+  if (m_in > 0) {
+    FSFB_CHECK_ARG(in_coors && ((uintptr_t)in_coors & 15) == 0, "conv_out_index: in_coors null or unaligned");
+    FSFB_LAUNCH(k_conv_mark_outputs, grid_for(m_in, 256, 8), 256, 0, st, (const int*)in_coors, m_in, S, G,
+                (uint32_t*)blocks);
+  }
+  FSFB_LAUNCH(k_rank_tile_sums, (int)ntiles, kScanThreads, 0, st, blocks, nblocks, tile_sums);
+  FSFB_LAUNCH(k_rank_scan_tiles, 1, 1024, 0, st, tile_sums, ntiles, num_out, out_coors ? cap_out : (int64_t)-1,
+              status);
+  FSFB_LAUNCH(k_rank_apply, (int)ntiles, kScanThreads, 0, st, blocks, nblocks, tile_sums);
+  if (out_coors && cap_out > 0) {
+    FSFB_LAUNCH(k_rank_unique_rows<int>, grid_for(nblocks, 256, 8), 256, 0, st, blocks, nblocks, S, (int*)out_coors,
+                cap_out);
   }
   return FSFB_OK;
 }

@@ -103,8 +103,19 @@ def rows_minmax(rows: torch.Tensor) -> Tuple[list, list]:
     return h[:d], h[d:]
 
 
+@dataclass
+class VoxelIndex:
+    """The ranked bitmap of an active-site set: coordinate → row by bit test + popcount prefix.
+    `ws` is the workspace fsfb_rank_rows / fsfb_conv_out_index filled (bitmap at offset 0)."""
+    ws: torch.Tensor
+    lo: Tuple[int, ...]
+    ext: Tuple[int, ...]
+    m: int
+
+
 def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Optional[Sequence[int]] = None,
-                return_counts: bool = False, return_unique: bool = True, inv_dtype: torch.dtype = torch.int64):
+                return_counts: bool = False, return_unique: bool = True, inv_dtype: torch.dtype = torch.int64,
+                return_index: bool = False):
     """torch.unique(rows, dim=0, return_inverse=True[, return_counts=True]) for bounded integer rows.
 
     Returns (unique_rows [M,D], inverse [N], counts [M] | None).  `lo`/`ext` give the per-column
@@ -145,7 +156,10 @@ def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Opt
     if status & 1:
         raise _capi.FsfbError("unique_rows: a row lies outside the given lo/ext bounds")
     inv = inv64 if inv64 is not None else inv32
-    return (uniq[:m] if uniq is not None else None, inv, counts[:m].long() if counts is not None else None)
+    res = (uniq[:m] if uniq is not None else None, inv, counts[:m].long() if counts is not None else None)
+    if return_index:
+        return res + (VoxelIndex(ws, tuple(int(v) for v in lo), tuple(int(v) for v in ext), m),)
+    return res
 
 
 # ------------------------------------------------------------------------------------------
@@ -291,3 +305,144 @@ def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torc
                                            _stream(dev))
     check(rc, "fsfb_project_sample_select")
     return (ids, cam, fg, ov) if want_overlap else (ids, cam, fg)
+
+
+# ------------------------------------------------------------------------------------------
+# gather-GEMM (sparse conv / Linear) with fused epilogue
+# ------------------------------------------------------------------------------------------
+_NORMS = {None: _capi.NORM_NONE, "none": _capi.NORM_NONE, "ln": _capi.NORM_LAYERNORM, "affine": _capi.NORM_AFFINE}
+_ACTS = {None: _capi.ACT_NONE, "none": _capi.ACT_NONE, "relu": _capi.ACT_RELU, "gelu": _capi.ACT_GELU}
+
+
+@dataclass
+class PackedWeight:
+    """nn.Linear / sparse-conv weights [koff, cout, cin] in the tensor-core tile layout."""
+    data: torch.Tensor  # uint8 blob written by fsfb_gemm_prepack
+    koff: int
+    cin: int
+    cout: int
+    raw: Optional[torch.Tensor] = None  # the fp32 [koff,cout,cin] tensor it was packed from
+
+
+def gemm_prepack(w: torch.Tensor, keep_raw: bool = False) -> PackedWeight:
+    """w: [cout,cin] (nn.Linear.weight) or [koff,cout,cin] f32 → PackedWeight."""
+    dev = _need_cuda(w)
+    assert w.dtype == torch.float32 and w.dim() in (2, 3)
+    w3 = (w if w.dim() == 3 else w[None]).contiguous()
+    koff, cout, cin = w3.shape
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_gemm_prepack_bytes(koff, cin, cout, C.byref(need)), "fsfb_gemm_prepack_bytes")
+    data = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    check(lib.fsfb_gemm_prepack(_ptr(w3), koff, cin, cout, _ptr(data), _stream(dev)), "fsfb_gemm_prepack")
+    return PackedWeight(data, koff, cin, cout, w3 if keep_raw else None)
+
+
+def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
+    for t in (bias, norm_w, norm_b):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.numel() == cout and t.is_contiguous())
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.dim() == 2 and residual.size(1) == cout and residual.stride(1) == 1
+    return (_ptr(bias), _NORMS[norm], _ptr(norm_w), _ptr(norm_b))
+
+
+def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
+                bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
+                out: Optional[torch.Tensor] = None, simt: bool = False) -> torch.Tensor:
+    """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual)  (include/fsf_b200.h).
+
+    nbr: int32 [koff, rows] neighbour table (< 0 = none) or None for a plain Linear over rows of `a`.
+    simt=True runs the CUDA-core cross-check (tests only; needs w.raw).
+    """
+    dev = _need_cuda(a, w.data)
+    assert a.dim() == 2 and a.dtype == torch.float32 and a.size(1) == w.cin, (a.shape, w.cin)
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if nbr is not None:
+        assert nbr.dtype == torch.int32 and nbr.dim() == 2 and nbr.size(0) == w.koff and nbr.is_contiguous()
+        rows = nbr.size(1)
+    else:
+        assert w.koff == 1
+        rows = a.size(0) if rows is None else rows
+    if out is None:
+        out = torch.empty((rows, w.cout), dtype=torch.float32, device=dev)
+    assert out.size(0) == rows and out.size(1) == w.cout and out.stride(1) == 1
+    if rows == 0:
+        return out
+    b, nid, nw, nb = _epilogue_args(w.cout, bias, norm, norm_w, norm_b, residual, act, dev)
+    lib = load()
+    args = (_ptr(a), a.size(0), w.cin, a.stride(0), _ptr(nbr), w.koff, rows)
+    tail = (w.cout, b, nid, nw, nb, float(eps), _ptr(residual), residual.stride(0) if residual is not None else 0,
+            _ACTS[act], _ptr(out), out.stride(0), _stream(dev))
+    if simt:
+        assert w.raw is not None, "gemm_prepack(..., keep_raw=True) needed for the SIMT cross-check"
+        check(lib.fsfb_gather_gemm_simt(*args, _ptr(w.raw), *tail), "fsfb_gather_gemm_simt")
+    else:
+        check(lib.fsfb_gather_gemm(*args, _ptr(w.data), *tail), "fsfb_gather_gemm")
+    return out
+
+
+def rownorm_act(x: torch.Tensor, bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None,
+                act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(norm(x + bias) + residual) row-wise (wide LayerNorms of the cluster heads)."""
+    dev = _need_cuda(x)
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    b, nid, nw, nb = _epilogue_args(c, bias, norm, norm_w, norm_b, residual, act, dev)
+    check(load().fsfb_rownorm_act(_ptr(x), rows, c, x.stride(0), b, nid, nw, nb, float(eps), _ptr(residual),
+                                  residual.stride(0) if residual is not None else 0, _ACTS[act], _ptr(out),
+                                  out.stride(0), _stream(dev)), "fsfb_rownorm_act")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# sparse-convolution rulebook
+# ------------------------------------------------------------------------------------------
+def _triple(v):
+    return [int(v)] * 3 if isinstance(v, int) else [int(x) for x in v]
+
+
+def conv_rulebook(out_coors: torch.Tensor, index: VoxelIndex, ksize=3, stride=1, pad=1, transposed: bool = False):
+    """nbr [koff, m_out] int32 neighbour table (include/fsf_b200.h: fsfb_conv_rulebook).
+    out_coors: int32 [m_out,4] (b,z,y,x); index: VoxelIndex of the INPUT site set."""
+    dev = _need_cuda(out_coors, index.ws)
+    assert out_coors.dtype == torch.int32 and out_coors.dim() == 2 and out_coors.size(1) == 4
+    out_coors = out_coors.contiguous()
+    k, s_, p = _triple(ksize), _triple(stride), _triple(pad)
+    koff = k[0] * k[1] * k[2]
+    m_out = out_coors.size(0)
+    nbr = torch.empty((koff, m_out), dtype=torch.int32, device=dev)
+    rc = load().fsfb_conv_rulebook(_ptr(out_coors), m_out, _ptr(index.ws), _host_i64(index.lo), _host_i64(index.ext),
+                                   _host_i32(k), _host_i32(s_), _host_i32(p), int(transposed), _ptr(nbr), _stream(dev))
+    check(rc, "fsfb_conv_rulebook")
+    return nbr
+
+
+def conv_out_index(in_coors: torch.Tensor, out_shape_bzyx: Sequence[int], ksize=3, stride=2, pad=1):
+    """Active output sites of a strided SparseConv3d: (out_coors int32 [m_out,4] ascending, VoxelIndex)."""
+    dev = _need_cuda(in_coors)
+    assert in_coors.dtype == torch.int32 and in_coors.dim() == 2 and in_coors.size(1) == 4
+    in_coors = in_coors.contiguous()
+    k, s_, p = _triple(ksize), _triple(stride), _triple(pad)
+    ext = [int(v) for v in out_shape_bzyx]
+    lo = [0, 0, 0, 0]
+    cells = ext[0] * ext[1] * ext[2] * ext[3]
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_rank_workspace_bytes(0, cells, C.byref(need)), "fsfb_rank_workspace_bytes")
+    ws = _ws(need.value, dev)
+    m_in = in_coors.size(0)
+    koff = k[0] * k[1] * k[2]
+    cap = max(1, min(cells, m_in * koff))
+    out = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    meta = torch.empty(2, dtype=torch.int32, device=dev)
+    rc = lib.fsfb_conv_out_index(_ptr(in_coors), m_in, _host_i64(lo), _host_i64(ext), _host_i32(k), _host_i32(s_),
+                                 _host_i32(p), _ptr(ws), ws.numel(), _ptr(out), cap, C.c_void_p(meta.data_ptr()),
+                                 C.c_void_p(meta.data_ptr() + 4), _stream(dev))
+    check(rc, "fsfb_conv_out_index")
+    m, status = meta.tolist()
+    if status:
+        raise _capi.FsfbError(f"conv_out_index: status {status}")
+    return out[:m], VoxelIndex(ws, tuple(lo), tuple(ext), m)

@@ -171,6 +171,91 @@ int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
                                int32_t* ids_sel, uint8_t* cam_sel, uint8_t* fg,
                                uint8_t* overlap, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * a5 / a9 / a10 / a16 / a17  Gather-GEMM with fused epilogue — the one dense
+ * contraction of the path.  It serves nn.Linear stacks built by build_mlp
+ * (projects/mmdet3d_plugin/ops/sst_ops.py:808-833: Linear → norm → act), and the
+ * sparse convolutions of SimpleSparseUNet (config
+ * projects/configs/nuScenes/FSF_nuScenes_config.py:58-70; spconv SubMConv3d /
+ * SparseConv3d / SparseInverseConv3d) in output-stationary form:
+ *
+ *   out[r, :] = epilogue( sum_k  a[nbr[k][r], :] @ w[k]^T )        r in [0, rows)
+ *
+ * nbr[k][r] < 0 means "no input row for offset k" (contributes zero); nbr == NULL
+ * with koff == 1 is a plain Linear over rows of `a`.  w is [koff][cout][cin]
+ * (nn.Linear's [out,in] per offset), pre-packed once by fsfb_gemm_prepack into the
+ * tensor-core tile layout (tf32 hi/lo split, 128 B swizzle).  Arithmetic: tcgen05
+ * kind::tf32 MMAs in 3xTF32 split form (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, fp32
+ * accumulation in TMEM): |error| ~ 1e-6 relative, inside the 1e-4 parity budget
+ * that plain TF32 (5e-4) would break.
+ *
+ * epilogue(x) = act( norm(x + bias) + residual ):
+ *   norm FSFB_NORM_LAYERNORM: nn.LayerNorm(cout, eps) with norm_w/norm_b   (cout <= 256)
+ *   norm FSFB_NORM_AFFINE   : x * norm_w[c] + norm_b[c]  (eval-mode BatchNorm1d /
+ *                             naiveSyncBN1d folded: w = gamma/sqrt(var+eps), b = beta - mean*w)
+ *   act  FSFB_ACT_RELU | FSFB_ACT_GELU (exact erf form, nn.GELU()) | NONE
+ * ------------------------------------------------------------------------- */
+int fsfb_gemm_prepack_bytes(int koff, int cin, int cout, size_t* bytes);
+/* w dev [koff, cout, cin] f32 row-major → packed dev (bytes from the call above). */
+int fsfb_gemm_prepack(const float* w, int koff, int cin, int cout, void* packed, void* stream);
+
+int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t a_stride,
+                     const int32_t* nbr, int koff, int64_t rows,
+                     const void* w_packed, int cout,
+                     const float* bias, int norm, const float* norm_w, const float* norm_b,
+                     float eps, const float* residual, int64_t residual_stride, int act,
+                     float* out, int64_t out_stride, void* stream);
+
+/* Same contract evaluated with plain fp32 FMAs on CUDA cores from the UNPACKED weights
+ * (w dev [koff,cout,cin]).  Independent cross-check of the tensor-core path at sizes the
+ * CPU oracle cannot reach; tests only — nothing in the product path calls it. */
+int fsfb_gather_gemm_simt(const float* a, int64_t a_rows, int cin, int64_t a_stride,
+                          const int32_t* nbr, int koff, int64_t rows,
+                          const float* w, int cout,
+                          const float* bias, int norm, const float* norm_w, const float* norm_b,
+                          float eps, const float* residual, int64_t residual_stride, int act,
+                          float* out, int64_t out_stride, void* stream);
+
+/* Row-wise norm + activation in place-or-out: y = act(norm(x + bias) + residual) for
+ * rows wider than the fused epilogue handles (the 1024-wide LN of the cluster heads,
+ * dense_heads/sparse_cluster_head.py:75-77). */
+int fsfb_rownorm_act(const float* x, int64_t rows, int c, int64_t x_stride, const float* bias,
+                     int norm, const float* norm_w, const float* norm_b, float eps,
+                     const float* residual, int64_t residual_stride, int act,
+                     float* out, int64_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a5  Sparse-convolution rulebook (spconv's indice pairs) in output-stationary form.
+ * Replaces the hash → rulebook step inside spconv.SubMConv3d / SparseConv3d /
+ * SparseInverseConv3d as used by SimpleSparseUNet (config
+ * projects/configs/nuScenes/FSF_nuScenes_config.py:58-70; import
+ * projects/mmdet3d_plugin/ops/sst_ops.py:5).  The voxel index is the bitmap that
+ * fsfb_rank_rows / fsfb_conv_out_index leave at the START of their workspace (keep that
+ * buffer alive): a coordinate's row is found by bit test + popcount prefix, so there is no
+ * hash table.  Offsets are numbered k = (kz*K_y + ky)*K_x + kx.
+ *   nbr dev [koff, m_out] i32:  nbr[k][o] = input row read by offset k of output o, or -1
+ *     forward    (transposed=0): in = o*stride - pad + k      (SubM: stride 1, in set == out set)
+ *     transposed (transposed=1): in = (o + pad - k)/stride when divisible  (inverse conv:
+ *                                the pairs of the forward strided conv with the same geometry)
+ *   The reference's (in_row, out_row) pair lists per offset are {(nbr[k][o], o) : nbr[k][o] >= 0},
+ *   already sorted by out_row.
+ * coors are int32 [m,4] rows (b,z,y,x), 16-byte aligned.
+ * ------------------------------------------------------------------------- */
+int fsfb_conv_rulebook(const int32_t* out_coors, int64_t m_out, const void* in_index,
+                       const int64_t* in_lo, const int64_t* in_ext, const int32_t* ksize,
+                       const int32_t* stride, const int32_t* pad, int transposed, int32_t* nbr,
+                       void* stream);
+
+/* Output site set of a strided SparseConv3d + its voxel index: every output cell reached by at
+ * least one (input site, offset).  workspace (fsfb_rank_workspace_bytes(0, cells)) receives
+ * the index of the OUTPUT set; out_coors dev [cap_out,4] i32 receives its rows in
+ * lexicographic (b,z,y,x) order (== their row numbers); num_out/status as in fsfb_rank_rows. */
+int fsfb_conv_out_index(const int32_t* in_coors, int64_t m_in, const int64_t* out_lo,
+                        const int64_t* out_ext, const int32_t* ksize, const int32_t* stride,
+                        const int32_t* pad, void* workspace, size_t workspace_bytes,
+                        int32_t* out_coors, int64_t cap_out, int32_t* num_out, int32_t* status,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

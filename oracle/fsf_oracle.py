@@ -281,7 +281,7 @@ def cam_select(obj_id_tensor: np.ndarray):
     cam = np.argmax(s, axis=1)  # first maximal camera
     ids = np.take_along_axis(obj_id_tensor, cam[:, None, None], axis=1)[:, 0, :]
     fg = obj_id_tensor.sum((-2, -1)) > 0
-    overlap = (obj_id_tensor.reshape(obj_id_tensor.shape[0], -1) > 0).sum(-1)
+    overlap = (obj_id_tensor > 0).sum((-2, -1))
     return ids, cam, fg, overlap
 
 
@@ -420,3 +420,113 @@ def decode_vote_targets(preds: np.ndarray) -> np.ndarray:
     """VoteSegHead.decode_vote_targets (decode_heads/segmentation_head.py:265-266): v * |v|."""
     preds = np.asarray(preds, F32)
     return (preds * np.abs(preds)).astype(F32)
+
+
+# ------------------------------------------------------------------------------------------
+# a5 gather-GEMM contract (sparse convolution in output-stationary form; Linear when koff == 1)
+# ------------------------------------------------------------------------------------------
+def gather_gemm(a, w, nbr=None, bias=None, norm=None, norm_w=None, norm_b=None, eps=1e-5, residual=None, act=None):
+    """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual); nbr < 0 contributes 0.
+
+    Restates spconv's gather → GEMM → scatter-add of SubMConv3d/SparseConv3d/SparseInverseConv3d
+    (used by SimpleSparseUNet, config FSF_nuScenes_config.py:58-70; un-vendored, published
+    algorithm) per OUTPUT row, followed by the Linear→norm→act epilogue of build_mlp
+    (sst_ops.py:808-833) / the conv→BN→ReLU(+residual) order of the backbone's blocks
+    (order=('conv','norm','act'), FSF_nuScenes_config.py:61).  float64 accumulation."""
+    a = np.asarray(a, F32)
+    w = np.asarray(w, F32)
+    if w.ndim == 2:
+        w = w[None]
+    koff, cout, cin = w.shape
+    rows = a.shape[0] if nbr is None else nbr.shape[1]
+    acc = np.zeros((rows, cout), np.float64)
+    for k in range(koff):
+        if nbr is None:
+            acc += a.astype(np.float64) @ w[k].astype(np.float64).T
+        else:
+            src = np.asarray(nbr[k], np.int64)
+            ok = (src >= 0) & (src < a.shape[0])
+            acc[ok] += a[src[ok]].astype(np.float64) @ w[k].astype(np.float64).T
+    if bias is not None:
+        acc = acc + np.asarray(bias, np.float64)
+    if norm == "ln":
+        mu = acc.mean(-1, keepdims=True)
+        var = ((acc - mu) ** 2).mean(-1, keepdims=True)
+        acc = (acc - mu) / np.sqrt(var + eps) * np.asarray(norm_w, np.float64) + np.asarray(norm_b, np.float64)
+    elif norm == "affine":
+        acc = acc * np.asarray(norm_w, np.float64) + np.asarray(norm_b, np.float64)
+    if residual is not None:
+        acc = acc + np.asarray(residual, np.float64)
+    y = acc.astype(F32)
+    if act == "relu":
+        y = np.maximum(y, F32(0))
+    elif act == "gelu":
+        y = gelu(y)
+    return y
+
+
+# ------------------------------------------------------------------------------------------
+# a5 sparse-convolution rulebook (spconv indice pairs) and the SimpleSparseUNet building blocks
+# ------------------------------------------------------------------------------------------
+def _coor_keys(coors, lo, ext):
+    c = np.asarray(coors, np.int64) - np.asarray(lo, np.int64)[None]
+    ok = np.all((c >= 0) & (c < np.asarray(ext, np.int64)[None]), axis=1)
+    key = np.zeros(len(c), np.int64)
+    for j in range(c.shape[1]):
+        key = key * int(ext[j]) + np.where(ok, c[:, j], 0)
+    return np.where(ok, key, -1)
+
+
+def conv_out_coors(in_coors, out_shape_bzyx, ksize, stride, pad):
+    """Active output sites of spconv.SparseConv3d (published spconv algorithm get_indice_pairs:
+    an output site is active iff some (input site, kernel offset) maps onto it), returned in
+    lexicographic (b,z,y,x) order — this framework's canonical row order."""
+    in_coors = np.asarray(in_coors, np.int64)
+    outs = []
+    for kz in range(ksize[0]):
+        for ky in range(ksize[1]):
+            for kx in range(ksize[2]):
+                k = np.array([kz, ky, kx])
+                t = in_coors[:, 1:] + np.asarray(pad)[None] - k[None]
+                ok = np.all((t >= 0) & (t % np.asarray(stride)[None] == 0), axis=1)
+                o = t // np.asarray(stride)[None]
+                ok &= np.all(o < np.asarray(out_shape_bzyx[1:])[None], axis=1)
+                outs.append(np.concatenate([in_coors[ok, :1], o[ok]], 1))
+    allo = np.concatenate(outs, 0) if outs else np.zeros((0, 4), np.int64)
+    return unique_rows(allo)[0].astype(np.int32)
+
+
+def conv_rulebook(out_coors, in_coors, in_shape_bzyx, ksize, stride, pad, transposed=False):
+    """nbr [koff, m_out] int32: input row feeding offset k of output o, or -1.
+    forward: in = o*stride - pad + k  (SubMConv3d / SparseConv3d);  transposed: the forward
+    pairs reversed (SparseInverseConv3d): in = (o + pad - k)/stride when divisible.
+    The reference's per-offset pair lists are {(nbr[k][o], o)}, sorted by o."""
+    out_coors = np.asarray(out_coors, np.int64)
+    in_coors = np.asarray(in_coors, np.int64)
+    lo = [0, 0, 0, 0]
+    in_keys = _coor_keys(in_coors, lo, in_shape_bzyx)
+    order = np.argsort(in_keys, kind="stable")
+    sk = in_keys[order]
+    koff = ksize[0] * ksize[1] * ksize[2]
+    nbr = -np.ones((koff, len(out_coors)), np.int32)
+    k = 0
+    for kz in range(ksize[0]):
+        for ky in range(ksize[1]):
+            for kx in range(ksize[2]):
+                kk = np.array([kz, ky, kx])
+                if not transposed:
+                    c = out_coors[:, 1:] * np.asarray(stride)[None] - np.asarray(pad)[None] + kk[None]
+                    ok = np.ones(len(c), bool)
+                else:
+                    t = out_coors[:, 1:] + np.asarray(pad)[None] - kk[None]
+                    ok = np.all((t >= 0) & (t % np.asarray(stride)[None] == 0), axis=1)
+                    c = t // np.asarray(stride)[None]
+                q = _coor_keys(np.concatenate([out_coors[:, :1], c], 1), lo, in_shape_bzyx)
+                pos = np.searchsorted(sk, q)
+                pos = np.clip(pos, 0, max(len(sk) - 1, 0))
+                hit = ok & (q >= 0) & (len(sk) > 0)
+                if len(sk):
+                    hit &= sk[pos] == q
+                nbr[k, hit] = order[pos[hit]].astype(np.int32)
+                k += 1
+    return nbr

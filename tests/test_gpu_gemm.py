@@ -1,0 +1,130 @@
+"""GPU parity of the gather-GEMM (tcgen05 3xTF32) and its fused epilogue against the CPU oracle,
+the reference-generated build_mlp goldens, and the CUDA-core fp32 cross-check.  Tolerance: 1e-4
+relative (north_star) — the 3xTF32 split lands near 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from fullysparsefusion_b200 import ops
+from oracle import fsf_oracle as O
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 2e-5
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _rel_err(got, want):
+    scale = np.maximum(np.abs(want), 1e-2 * np.abs(want).max() + 1e-12)
+    return float(np.max(np.abs(got - want) / scale))
+
+
+@pytest.mark.parametrize("rows,cin,cout", [(1, 8, 16), (128, 32, 128), (300, 5, 64), (1000, 131, 128), (257, 64, 11),
+                                           (513, 180, 128), (200, 768, 1024), (129, 133, 256), (64, 3, 16),
+                                           (5000, 128, 33), (333, 10, 131), (100, 896, 1024), (77, 1024, 3)])
+def test_linear_plain(cuda, rows, cin, cout):
+    rng = np.random.default_rng(rows + cin + cout)
+    a = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    pw = ops.gemm_prepack(T(w, cuda), keep_raw=True)
+    want = O.gather_gemm(a, w, bias=b)
+    got = ops.gather_gemm(T(a, cuda), pw, bias=T(b, cuda)).cpu().numpy()
+    simt = ops.gather_gemm(T(a, cuda), pw, bias=T(b, cuda), simt=True).cpu().numpy()
+    np.testing.assert_allclose(simt, want, rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    # 3xTF32 with split accumulators: error relative to the output scale stays ~1e-5 even at K=1024
+    # (plain TF32 would sit at ~5e-4)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-5, np.abs(got - want).max() / np.abs(want).max()
+
+
+@pytest.mark.parametrize("norm,act", [("ln", "gelu"), ("affine", "relu"), (None, "gelu"), ("ln", None)])
+@pytest.mark.parametrize("rows,cin,cout", [(700, 48, 64), (300, 131, 128), (1000, 64, 256), (90, 16, 32)])
+def test_linear_epilogue(cuda, norm, act, rows, cin, cout):
+    rng = np.random.default_rng(cin * cout)
+    a = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    nw = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    nb = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((rows, cout)).astype(np.float32)
+    want = O.gather_gemm(a, w, bias=b, norm=norm, norm_w=nw, norm_b=nb, eps=1e-3, residual=res, act=act)
+    pw = ops.gemm_prepack(T(w, cuda), keep_raw=True)
+    kw = dict(bias=T(b, cuda), norm=norm, norm_w=T(nw, cuda) if norm else None, norm_b=T(nb, cuda) if norm else None,
+              eps=1e-3, residual=T(res, cuda), act=act)
+    got = ops.gather_gemm(T(a, cuda), pw, **kw).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    simt = ops.gather_gemm(T(a, cuda), pw, simt=True, **kw).cpu().numpy()
+    np.testing.assert_allclose(simt, want, rtol=RTOL, atol=ATOL)
+    # standalone row epilogue on the pre-norm sums
+    pre = ops.gather_gemm(T(a, cuda), pw)
+    kw2 = dict(kw)
+    got2 = ops.rownorm_act(pre, **kw2).cpu().numpy()
+    np.testing.assert_allclose(got2, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("tag,norm,act", [("mlp_ln_gelu", "ln", "gelu"), ("mlp_head", "ln", "gelu"), ("mlp_bn_relu", "bn", "relu")])
+def test_build_mlp_golden(cuda, tag, norm, act):
+    """The reference's own build_mlp (sst_ops.py:808-833) outputs, layer by layer through the C-ABI."""
+    g = load_golden(tag)
+    sd = {k.replace("__", "."): v for k, v in g.items() if k not in ("x", "y")}
+    x = T(g["x"], cuda)
+    i = 0
+    while True:
+        if f"{i}.0.weight" in sd:
+            pw = ops.gemm_prepack(T(sd[f"{i}.0.weight"], cuda))
+            if norm == "ln":
+                x = ops.gather_gemm(x, pw, norm="ln", norm_w=T(sd[f"{i}.1.weight"], cuda), norm_b=T(sd[f"{i}.1.bias"], cuda),
+                                    eps=1e-3, act=act)
+            else:  # eval-mode BN folded to an affine
+                scale = sd[f"{i}.1.weight"] / np.sqrt(sd[f"{i}.1.running_var"] + np.float32(1e-3))
+                shift = sd[f"{i}.1.bias"] - sd[f"{i}.1.running_mean"] * scale
+                x = ops.gather_gemm(x, pw, norm="affine", norm_w=T(scale.astype(np.float32), cuda),
+                                    norm_b=T(shift.astype(np.float32), cuda), act=act)
+        elif f"{i}.weight" in sd:
+            x = ops.gather_gemm(x, ops.gemm_prepack(T(sd[f"{i}.weight"], cuda)), bias=T(sd[f"{i}.bias"], cuda))
+        else:
+            break
+        i += 1
+    np.testing.assert_allclose(x.cpu().numpy(), g["y"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("rows,a_rows,koff,cin,cout,density", [(500, 400, 27, 16, 32, 0.4), (1000, 1000, 27, 64, 64, 0.3),
+                                                                (130, 90, 8, 128, 256, 0.5), (2000, 2500, 27, 128, 128, 0.05),
+                                                                (256, 256, 27, 5, 16, 1.0)])
+def test_gather_gemm_oracle(cuda, rows, a_rows, koff, cin, cout, density):
+    rng = np.random.default_rng(rows + koff)
+    a = rng.standard_normal((a_rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((koff, cout, cin)) / np.sqrt(cin * koff * density)).astype(np.float32)
+    nbr = rng.integers(0, a_rows, (koff, rows)).astype(np.int32)
+    nbr[rng.random((koff, rows)) > density] = -1
+    if density < 0.1:
+        nbr[3] = -1          # a whole offset with no pairs (skipped by the kernel)
+        nbr[:, 128:256] = -1  # a whole tile with no input at all → zeros + epilogue
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    want = O.gather_gemm(a, w, nbr, norm="affine", norm_w=scale, norm_b=shift, act="relu")
+    pw = ops.gemm_prepack(T(w, cuda), keep_raw=True)
+    kw = dict(nbr=T(nbr, cuda), norm="affine", norm_w=T(scale, cuda), norm_b=T(shift, cuda), act="relu")
+    got = ops.gather_gemm(T(a, cuda), pw, **kw).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    simt = ops.gather_gemm(T(a, cuda), pw, simt=True, **kw).cpu().numpy()
+    np.testing.assert_allclose(simt, want, rtol=RTOL, atol=ATOL)
+
+
+def test_gather_gemm_large_vs_simt(cuda):
+    """Full-size layer (160k voxels x 27 offsets x 128→128) against the fp32 CUDA-core path."""
+    g = torch.Generator(device=cuda).manual_seed(0)
+    m, koff, c = 160_000, 27, 128
+    a = torch.randn(m, c, device=cuda, generator=g)
+    w = torch.randn(koff, c, c, device=cuda, generator=g) / (c * 10) ** 0.5
+    nbr = torch.randint(0, m, (koff, m), device=cuda, generator=g, dtype=torch.int32)
+    nbr[torch.rand(koff, m, device=cuda, generator=g) > 0.37] = -1
+    nbr[13] = torch.arange(m, device=cuda, dtype=torch.int32)
+    pw = ops.gemm_prepack(w, keep_raw=True)
+    got = ops.gather_gemm(a, pw, nbr=nbr, act="relu")
+    want = ops.gather_gemm(a, pw, nbr=nbr, act="relu", simt=True)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
