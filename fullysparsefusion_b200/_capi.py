@@ -44,6 +44,8 @@ SIGNATURES = {
     "fsfb_gather_gemm_simt": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_conv_rulebook": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),
+    "fsfb_ccl_workspace_bytes": (_i, [_i64, _psz]),
+    "fsfb_connected_components": (_i, [_p, _i64, _i64, _p, _f, _p, _p, _p, _sz, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

@@ -1,0 +1,239 @@
+// ccl.cu — connected-components clustering of voted centres (a14).
+//
+// Reference semantics (the stock config's live path): find_connected_componets /
+// find_connected_componets_single_batch,
+// projects/mmdet3d_plugin/models/detectors/single_stage_fsd.py:45-82 — adjacency
+// sqrt(dx^2 + dy^2) < dist over xy in fp32 (self-loops included), components labelled by
+// scipy.sparse.csgraph.connected_components, i.e. numbered in order of their lowest member index
+// (per sample, samples in ascending order, for the batched variant).  The reference builds a dense
+// m x m matrix on the GPU, copies it to the host and runs scipy; torchex.connected_components
+// (:37-43) is the optional GPU path with the same output contract (labels contiguous from 0).
+//
+// B200 design: no m x m matrix and no host round trip.  Tile pairs of 256 x 256 points are
+// tested in registers/shared memory (compute-bound, fp32 CUDA cores: m^2/2 distance tests;
+// m <= 1e4 per class group in practice); adjacent pairs are merged in a lock-free union-find whose
+// roots are always the smallest index of their set, so the labelling is deterministic and equals
+// scipy's first-visit order after one prefix sum over the root flags.
+// Algorithmic bytes: 12 m read + 4 m written (+ 4 m batch ids).
+#include "common.cuh"
+
+namespace fsfb {
+
+constexpr int kCclTile = 256;
+
+__device__ __forceinline__ int uf_find(int* __restrict__ parent, int i) {
+  int p = parent[i];
+  while (p != i) {
+    const int gp = parent[p];
+    if (gp != p) parent[i] = gp;  // path halving (benign race: only ever points closer to the root)
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(int* __restrict__ parent, int a, int b) {
+  int ra = uf_find(parent, a), rb = uf_find(parent, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      const int t = ra;
+      ra = rb;
+      rb = t;
+    }  // ra is the larger root: hook it under the smaller one
+    const int old = atomicCAS(parent + ra, ra, rb);
+    if (old == ra) return;
+    ra = uf_find(parent, old);
+    rb = uf_find(parent, rb);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_init(int* __restrict__ parent, int m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) parent[i] = i;
+}
+
+// One CTA per tile pair (I <= J).  pts: [m, stride] f32 (x, y first).
+__global__ void __launch_bounds__(kCclTile)
+    k_ccl_pairs(const float* __restrict__ pts, int64_t stride, const int* __restrict__ batch, int m, float dist,
+                int n_tiles, int* __restrict__ parent) {
+  // linear block id → (I, J) with I <= J, row-major over the upper triangle
+  int b = blockIdx.x, I = 0;
+  while (b >= n_tiles - I) {
+    b -= n_tiles - I;
+    ++I;
+  }
+  const int J = I + b;
+  __shared__ float sx[kCclTile], sy[kCclTile];
+  __shared__ int sb[kCclTile];
+  const int t = threadIdx.x;
+  const int j0 = J * kCclTile;
+  {
+    const int j = j0 + t;
+    sx[t] = j < m ? __ldg(pts + (int64_t)j * stride) : 0.f;
+    sy[t] = j < m ? __ldg(pts + (int64_t)j * stride + 1) : 0.f;
+    sb[t] = (j < m && batch) ? __ldg(batch + j) : 0;
+  }
+  __syncthreads();
+  const int i = I * kCclTile + t;
+  if (i >= m) return;
+  const float xi = __ldg(pts + (int64_t)i * stride), yi = __ldg(pts + (int64_t)i * stride + 1);
+  const int bi = batch ? __ldg(batch + i) : 0;
+  const int jn = min(kCclTile, m - j0);
+  for (int jj = 0; jj < jn; ++jj) {
+    const int j = j0 + jj;
+    if (j <= i) continue;  // each unordered pair once (self-loops never merge anything)
+    // (a - b)**2 summed in fp32, ** 0.5, < dist — no FMA contraction, as torch evaluates it
+    const float dx = __fsub_rn(xi, sx[jj]), dy = __fsub_rn(yi, sy[jj]);
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    if (d < dist && bi == sb[jj]) uf_union(parent, i, j);
+  }
+}
+
+// root[i] = representative (smallest index of the component); flag[i] = i is a root.
+__global__ void __launch_bounds__(256)
+    k_ccl_flatten(int* __restrict__ parent, int m, int* __restrict__ flag, const int* __restrict__ batch,
+                  int* __restrict__ unsorted) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const int r = uf_find(parent, i);
+    parent[i] = r;
+    flag[i] = (r == i);
+    if (batch && i > 0 && __ldg(batch + i) < __ldg(batch + i - 1)) *unsorted = 1;
+  }
+}
+
+// Single-CTA exclusive scan of flag → rank (m is at most a few 1e5 here).
+__global__ void __launch_bounds__(1024) k_ccl_scan(const int* __restrict__ flag, int m, int* __restrict__ rank) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  constexpr int kRun = 4;
+  for (int base = 0; base < m; base += 1024 * kRun) {
+    const int i0 = base + threadIdx.x * kRun;
+    int v[kRun], s = 0;
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+      v[k] = (i0 + k < m) ? flag[i0 + k] : 0;
+      s += v[k];
+    }
+    int x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane_id() >= o) x += y;
+    }
+    const int w = threadIdx.x >> 5;
+    const int carry = s_carry;
+    if (lane_id() == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      const int tsum = s_warp[lane_id()];
+      int u = tsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, u, o);
+        if ((int)lane_id() >= o) u += y;
+      }
+      s_warp[lane_id()] = u - tsum;
+      if (lane_id() == 31) s_carry = carry + u;
+    }
+    __syncthreads();
+    int ex = carry + s_warp[w] + x - s;
+#pragma unroll
+    for (int k = 0; k < kRun; ++k) {
+      if (i0 + k < m) rank[i0 + k] = ex;
+      ex += v[k];
+    }
+    __syncthreads();
+  }
+}
+
+// Batched variant with batch ids that are not non-decreasing: components are ordered by
+// (batch, lowest member index).  rank[r] for roots = number of roots that precede r in that order.
+__global__ void __launch_bounds__(256)
+    k_ccl_rank_by_batch(const int* __restrict__ flag, const int* __restrict__ batch, int m,
+                        const int* __restrict__ unsorted, int* __restrict__ rank) {
+  if (*unsorted == 0) return;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+    if (!flag[r]) continue;
+    const int br = batch[r];
+    int c = 0;
+    for (int i = 0; i < m; ++i)
+      if (flag[i]) {
+        const int bi = batch[i];
+        c += (bi < br) | ((bi == br) & (i < r));
+      }
+    rank[r] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_ccl_labels(const int* __restrict__ root, const int* __restrict__ rank, int m, int* __restrict__ labels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    labels[i] = rank[root[i]];
+}
+
+__global__ void k_ccl_count(const int* __restrict__ flag, int m, int* __restrict__ num_components) {
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) c += flag[i];
+  atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *num_components = s;
+}
+
+}  // namespace fsfb
+
+extern "C" {
+
+int fsfb_ccl_workspace_bytes(int64_t m, size_t* bytes) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(bytes && m >= 0 && m < (1ll << 31), "ccl_workspace_bytes: bad argument");
+  Workspace ws(nullptr, 0);
+  ws.take<int>(std::max<int64_t>(m, 1));  // parent / root
+  ws.take<int>(std::max<int64_t>(m, 1));  // flag
+  ws.take<int>(std::max<int64_t>(m, 1));  // rank
+  ws.take<int>(1);                        // unsorted flag
+  *bytes = ws.used;
+  return FSFB_OK;
+}
+
+int fsfb_connected_components(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx,
+                              float dist, int32_t* labels, int32_t* num_components, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(m >= 0 && m < (1ll << 31) && stride >= 2, "connected_components: bad m/stride");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) {
+    if (num_components) FSFB_CUDA(cudaMemsetAsync(num_components, 0, 4, st));
+    return FSFB_OK;
+  }
+  FSFB_CHECK_ARG(points && labels, "connected_components: null pointer");
+  Workspace ws(workspace, workspace_bytes);
+  int* parent = ws.take<int>(m);
+  int* flag = ws.take<int>(m);
+  int* rank = ws.take<int>(m);
+  int* unsorted = ws.take<int>(1);
+  if (!ws.ok()) {
+    set_error("connected_components: workspace too small (%zu given, %zu needed)", workspace_bytes, ws.used);
+    return FSFB_ERR_CAPACITY;
+  }
+  const int mi = (int)m;
+  const int grid = (int)std::min<int64_t>(ceil_div(m, 256), (int64_t)kNumSMs * 8);
+  FSFB_CUDA(cudaMemsetAsync(unsorted, 0, 4, st));
+  FSFB_LAUNCH(k_ccl_init, grid, 256, 0, st, parent, mi);
+  const int n_tiles = (int)ceil_div(m, kCclTile);
+  const int64_t n_pairs = (int64_t)n_tiles * (n_tiles + 1) / 2;
+  FSFB_CHECK_ARG(n_pairs < (1ll << 31), "connected_components: m too large for the tile-pair grid");
+  FSFB_LAUNCH(k_ccl_pairs, (int)n_pairs, kCclTile, 0, st, points, stride, (const int*)batch_idx, mi, dist, n_tiles,
+              parent);
+  FSFB_LAUNCH(k_ccl_flatten, grid, 256, 0, st, parent, mi, flag, (const int*)batch_idx, unsorted);
+  FSFB_LAUNCH(k_ccl_scan, 1, 1024, 0, st, flag, mi, rank);
+  if (batch_idx) FSFB_LAUNCH(k_ccl_rank_by_batch, grid, 256, 0, st, flag, (const int*)batch_idx, mi, unsorted, rank);
+  FSFB_LAUNCH(k_ccl_labels, grid, 256, 0, st, parent, rank, mi, (int*)labels);
+  if (num_components) FSFB_LAUNCH(k_ccl_count, 1, 256, 0, st, flag, mi, (int*)num_components);
+  return FSFB_OK;
+}
+
+}  // extern "C"

@@ -446,3 +446,29 @@ def conv_out_index(in_coors: torch.Tensor, out_shape_bzyx: Sequence[int], ksize=
     if status:
         raise _capi.FsfbError(f"conv_out_index: status {status}")
     return out[:m], VoxelIndex(ws, tuple(lo), tuple(ext), m)
+
+
+# ------------------------------------------------------------------------------------------
+# a14 connected components
+# ------------------------------------------------------------------------------------------
+def connected_components(points: torch.Tensor, batch_idx: Optional[torch.Tensor], dist: float,
+                         return_count: bool = False):
+    """Labels [m] int32 (single_stage_fsd.py:45-82 semantics; batch_idx=None → single-batch variant)."""
+    dev = _need_cuda(points, batch_idx)
+    assert points.dim() == 2 and points.size(1) >= 2 and points.dtype == torch.float32
+    if points.stride(1) != 1:
+        points = points.contiguous()
+    m = points.size(0)
+    if batch_idx is not None:
+        assert batch_idx.numel() == m
+        batch_idx = batch_idx.to(torch.int32).contiguous()
+    labels = torch.empty(m, dtype=torch.int32, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_ccl_workspace_bytes(m, C.byref(need)), "fsfb_ccl_workspace_bytes")
+    ws = _ws(need.value, dev)
+    rc = lib.fsfb_connected_components(_ptr(points), m, points.stride(0) if m else 3, _ptr(batch_idx), float(dist),
+                                       _ptr(labels), _ptr(count), _ptr(ws), ws.numel(), _stream(dev))
+    check(rc, "fsfb_connected_components")
+    return (labels, count) if return_count else labels

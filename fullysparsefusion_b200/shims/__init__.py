@@ -1,0 +1,32 @@
+"""Drop-in modules under the names the reference plugin imports.
+
+    import fullysparsefusion_b200.shims as shims
+    shims.install()          # registers torch_scatter, ingroup_indices, torchex in sys.modules
+    import projects.mmdet3d_plugin   # the plugin's `import torch_scatter` etc. now bind to the B200 path
+
+Every function is a thin wrapper over the C-ABI ops (no torch arithmetic on the hot path, no CPU
+fallback: CPU tensors raise).  Forward/inference only in this round — tensors that require grad raise
+NotImplementedError (training backward is SURVEY.md §8f row 4).
+"""
+from __future__ import annotations
+
+import sys
+
+from . import ingroup_indices, mmdet3d_ops, torch_scatter, torchex  # noqa: F401
+
+
+def install(force: bool = False) -> None:
+    """Register the shims under the import names used by projects/mmdet3d_plugin
+    (ops/sst_ops.py:5-6,239; models/detectors/single_stage_fsd.py:13,20-23)."""
+    for name, mod in (("torch_scatter", torch_scatter), ("ingroup_indices", ingroup_indices), ("torchex", torchex)):
+        if force or name not in sys.modules:
+            sys.modules[name] = mod
+
+
+def patch_ccl(single_stage_fsd_module) -> None:
+    """Route the stock config's live CCL path (scipy on the host, single_stage_fsd.py:45-82) to the
+    CUDA kernel by replacing the module-level functions ClusterAssigner looks up at call time
+    (dispatch at single_stage_fsd.py:971-977)."""
+    single_stage_fsd_module.find_connected_componets = torchex.find_connected_componets
+    single_stage_fsd_module.find_connected_componets_single_batch = torchex.find_connected_componets_single_batch
+    single_stage_fsd_module.cc_gpu = torchex.connected_components

@@ -256,6 +256,25 @@ int fsfb_conv_out_index(const int32_t* in_coors, int64_t m_in, const int64_t* ou
                         int32_t* out_coors, int64_t cap_out, int32_t* num_out, int32_t* status,
                         void* stream);
 
+/* ---------------------------------------------------------------------------
+ * a14  Connected-components clustering of voted centres.
+ * Replaces find_connected_componets / find_connected_componets_single_batch
+ * (projects/mmdet3d_plugin/models/detectors/single_stage_fsd.py:45-82: dense m x m
+ * distance matrix on the GPU → host → scipy.sparse.csgraph.connected_components → device)
+ * and torchex.connected_components(points, batch_idx, dist, 100, 2, False) (:37-43).
+ * Adjacency: fp32 sqrt(dx^2 + dy^2) < dist over columns 0,1 of `points`.
+ *   batch_idx dev [m] i32 or NULL.  NULL = the single-batch variant (:69-82, what the stock
+ *   config runs at inference; batch ids ignored).  Non-NULL = per-sample clustering (:45-67):
+ *   points of different samples are never adjacent and components are numbered sample by sample.
+ *   labels dev [m] i32: component id, contiguous from 0, numbered in order of each component's
+ *   lowest member index (scipy's first-visit order) — bit-exact with the reference.
+ *   num_components dev [1] i32 (nullable).
+ * ------------------------------------------------------------------------- */
+int fsfb_ccl_workspace_bytes(int64_t m, size_t* bytes);
+int fsfb_connected_components(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx,
+                              float dist, int32_t* labels, int32_t* num_components, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

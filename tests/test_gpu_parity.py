@@ -234,3 +234,28 @@ def test_projection_oracle(cuda, n, sweeps, dtype):
     assert np.array_equal(ov.cpu().numpy(), w_ov)
     if n:
         assert w_fg.mean() > 0.01  # the synthetic scene does hit masks
+
+
+# ---- a14 connected components -------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["ccl_small", "ccl_mid", "ccl_batch"])
+def test_ccl_golden(cuda, tag):
+    g = load_golden(tag)
+    pts, b = T(g["points"], cuda), T(g["batch_idx"], cuda)
+    lab, cnt = ops.connected_components(pts, b if tag == "ccl_batch" else None, float(g["dist"]), return_count=True)
+    assert np.array_equal(lab.cpu().numpy(), g["labels"])          # bit-exact vs the reference's scipy path
+    assert int(cnt) == int(g["labels"].max()) + 1
+
+
+@pytest.mark.parametrize("m,batches,dist", [(0, 1, 0.5), (1, 1, 0.5), (257, 1, 0.3), (10000, 1, 0.6), (30000, 4, 0.4),
+                                            (5000, 3, 2.0)])
+def test_ccl_oracle(cuda, m, batches, dist):
+    pts, b = synth.cluster_points(max(m, 1), seed=m, batches=batches)
+    pts, b = pts[:m], b[:m]
+    single = ops.connected_components(T(pts.reshape(-1, 3), cuda), None, dist).cpu().numpy()
+    assert np.array_equal(single, O.connected_components_single_batch(pts, dist))
+    if m:
+        # batch ids in arbitrary (unsorted) order and sorted order
+        for bb in (b, np.sort(b)):
+            got = ops.connected_components(T(pts, cuda), T(bb, cuda), dist).cpu().numpy()
+            assert np.array_equal(got, O.connected_components(pts, bb, dist))
+        assert len(np.unique(single)) == single.max() + 1              # the reference's own assert (:42)
