@@ -46,6 +46,15 @@ SIGNATURES = {
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),
     "fsfb_ccl_workspace_bytes": (_i, [_i64, _psz]),
     "fsfb_connected_components": (_i, [_p, _i64, _i64, _p, _f, _p, _p, _p, _sz, _p]),
+    "fsfb_vfe_decorate": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _p, _p, _i, _i, _p, _p]),
+    "fsfb_sir_input": (_i, [_p, _i64, _i, _i64, _p, _p, _i64, _p, _i64, _p]),
+    "fsfb_div_cols": (_i, [_p, _i64, _i, _i64, _p, _p, _i64, _p]),
+    "fsfb_add_inplace": (_i, [_p, _i64, _i, _i64, _p, _i64, _p]),
+    "fsfb_reduce_channel": (_i, [_p, _i64, _i, _i64, _i, _p, _p]),
+    "fsfb_neck_points": (_i, [_p, _i64, _i64, _p, _i, _p, _i64, _i, _p, _i, _p, _p, _f, _p, _p, _p, _p]),
+    "fsfb_vote_decode": (_i, [_p, _i64, _p, _p]),
+    "fsfb_compact_workspace_bytes": (_i, [_i64, _psz]),
+    "fsfb_compact_indices": (_i, [_p, _i64, _p, _p, _p, _sz, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

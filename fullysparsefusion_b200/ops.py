@@ -472,3 +472,130 @@ def connected_components(points: torch.Tensor, batch_idx: Optional[torch.Tensor]
                                        _ptr(labels), _ptr(count), _ptr(ws), ws.numel(), _stream(dev))
     check(rc, "fsfb_connected_components")
     return (labels, count) if return_count else labels
+
+
+# ------------------------------------------------------------------------------------------
+# per-point fused passes
+# ------------------------------------------------------------------------------------------
+def _rowmajor(x: torch.Tensor) -> torch.Tensor:
+    return x if x.stride(-1) == 1 else x.contiguous()
+
+
+def vfe_decorate(features, coors, inv32, voxel_mean, voxel_size, point_cloud_range, with_cluster_center, with_voxel_center,
+                 out: Optional[torch.Tensor] = None):
+    dev = _need_cuda(features, coors)
+    features = _rowmajor(features)
+    n, cin = features.shape
+    cout = cin + 3 * int(with_cluster_center) + 3 * int(with_voxel_center)
+    if out is None:
+        out = torch.empty((n, cout), dtype=torch.float32, device=dev)
+    assert out.shape == (n, cout) and out.is_contiguous()
+    coors = coors.contiguous()
+    assert coors.dtype in (torch.int32, torch.int64) and coors.size(1) == 4
+    if with_cluster_center:
+        assert inv32.dtype == torch.int32 and voxel_mean.is_contiguous() and voxel_mean.size(1) == cin
+    rc = load().fsfb_vfe_decorate(_ptr(features), n, cin, features.stride(0) if n else cin, _ptr(coors),
+                                  int(coors.dtype == torch.int64), _ptr(inv32), _ptr(voxel_mean), _host_f32(voxel_size),
+                                  _host_f32(point_cloud_range[:3]), int(with_cluster_center), int(with_voxel_center),
+                                  _ptr(out), _stream(dev))
+    check(rc, "fsfb_vfe_decorate")
+    return out
+
+
+def sir_input(features, xyz_normalizer, gate=None, out=None):
+    dev = _need_cuda(features, gate)
+    features = _rowmajor(features)
+    n, c = features.shape
+    if gate is not None:
+        gate = _rowmajor(gate)
+        assert gate.shape == (n, c)
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    rc = load().fsfb_sir_input(_ptr(features), n, c, features.stride(0) if n else c, _host_f32(xyz_normalizer), _ptr(gate),
+                               gate.stride(0) if gate is not None and n else c, _ptr(out), out.stride(0) if n else c,
+                               _stream(dev))
+    check(rc, "fsfb_sir_input")
+    return out
+
+
+_DIVISORS: dict = {}
+
+
+def scale_cols(x, inv_scales):
+    """x[:, c] / (1 / inv_scales[c]) — i.e. division by the scaler (f_cluster / rel_dist_scaler)."""
+    dev = _need_cuda(x)
+    x = _rowmajor(x)
+    n, c = x.shape
+    key = (dev, tuple(float(1.0 / s) for s in inv_scales))
+    if key not in _DIVISORS:
+        _DIVISORS[key] = torch.tensor(key[1], dtype=torch.float32, device=dev)
+    out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    rc = load().fsfb_div_cols(_ptr(x), n, c, x.stride(0) if n else c, _ptr(_DIVISORS[key]), _ptr(out), c, _stream(dev))
+    check(rc, "fsfb_div_cols")
+    return out
+
+
+def add_(x, y):
+    dev = _need_cuda(x, y)
+    assert x.shape == y.shape and x.dim() == 2 and x.stride(1) == 1 and y.stride(1) == 1
+    n, c = x.shape
+    rc = load().fsfb_add_inplace(_ptr(x), n, c, x.stride(0) if n else c, _ptr(y), y.stride(0) if n else c, _stream(dev))
+    check(rc, "fsfb_add_inplace")
+    return x
+
+
+def reduce_channel(x, out_channels: int):
+    dev = _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    n, cin = x.shape
+    out = torch.empty((n, out_channels), dtype=torch.float32, device=dev)
+    rc = load().fsfb_reduce_channel(_ptr(x), n, cin, x.stride(0) if n else cin, out_channels, _ptr(out), _stream(dev))
+    check(rc, "fsfb_reduce_channel")
+    return out
+
+
+def compact_indices(mask: torch.Tensor) -> torch.Tensor:
+    """Indices (int32, ascending) of the non-zero entries of a bool/uint8 mask; one D2H sync for the count."""
+    dev = _need_cuda(mask)
+    assert mask.dim() == 1 and mask.dtype in (torch.bool, torch.uint8)
+    mask = mask.contiguous()
+    n = mask.numel()
+    idx = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_compact_workspace_bytes(n, C.byref(need)), "fsfb_compact_workspace_bytes")
+    ws = _ws(need.value, dev)
+    check(lib.fsfb_compact_indices(_ptr(mask), n, _ptr(idx), _ptr(count), _ptr(ws), ws.numel(), _stream(dev)),
+          "fsfb_compact_indices")
+    return idx[: int(count.item())]
+
+
+def voxel2point_neck(points, pts_coors, voxel_feats, voxel2point_inds, voxel_size, point_cloud_range, voxel_padding=-1.0):
+    """Voxel2PointScatterNeck.forward → (results [N_kept, C+3], pts_mask [N] bool)."""
+    dev = _need_cuda(points, pts_coors, voxel_feats, voxel2point_inds)
+    points = _rowmajor(points)
+    pts_coors = pts_coors.contiguous()
+    voxel_feats = voxel_feats.contiguous()
+    inv = voxel2point_inds.contiguous()
+    n, (m, c) = points.size(0), voxel_feats.shape
+    out = torch.empty((n, c + 3), dtype=torch.float32, device=dev)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    dropped = torch.empty(1, dtype=torch.int32, device=dev)
+    rc = load().fsfb_neck_points(_ptr(points), n, points.stride(0) if n else 3, _ptr(pts_coors),
+                                 int(pts_coors.dtype == torch.int64), _ptr(voxel_feats), m, c, _ptr(inv),
+                                 int(inv.dtype == torch.int64), _host_f32(voxel_size), _host_f32(point_cloud_range[:3]),
+                                 float(voxel_padding), _ptr(out), _ptr(mask), _ptr(dropped), _stream(dev))
+    check(rc, "fsfb_neck_points")
+    if int(dropped.item()):  # padded voxels present: compact exactly as the boolean indexing at :50-52 does
+        keep = compact_indices(mask)
+        out = gather_rows(out, keep)
+    return out, mask.bool()
+
+
+def vote_decode(preds: torch.Tensor) -> torch.Tensor:
+    dev = _need_cuda(preds)
+    preds = preds.contiguous()
+    out = torch.empty_like(preds)
+    check(load().fsfb_vote_decode(_ptr(preds), preds.numel(), _ptr(out), _stream(dev)), "fsfb_vote_decode")
+    return out

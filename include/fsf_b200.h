@@ -275,6 +275,53 @@ int fsfb_connected_components(const float* points, int64_t m, int64_t stride, co
                               float dist, int32_t* labels, int32_t* num_components, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Per-point fused passes between the scatters and the GEMMs (one HBM pass each).
+ * ------------------------------------------------------------------------- */
+
+/* a3  DynamicScatterVFE point decoration (registry type named at
+ * projects/configs/nuScenes/FSF_nuScenes_config.py:42-52, called at
+ * models/detectors/single_stage_fsd.py:232):
+ *   out[i] = [ feats[i, 0:cin] | xyz - voxel_mean[inv[i], 0:3] | xyz - (coor*vs + vs/2 + min) ]
+ * coors dev [n,4] (b,z,y,x) i32/i64; inv dev [n] i32; voxel_mean dev [m,cin]; out dev [n, cin+3+3]. */
+int fsfb_vfe_decorate(const float* feats, int64_t n, int cin, int64_t feat_stride, const void* coors,
+                      int coors_i64, const int32_t* inv, const float* voxel_mean, const float* voxel_size,
+                      const float* range_min, int with_cluster_center, int with_voxel_center, float* out,
+                      void* stream);
+
+/* a12  SIRLayer input (models/backbones/sir.py:41-62 builds it with xyz_normalizer and rel_mlp):
+ *   out[i,c] = (c < 3 ? feats[i,c] / xyz_normalizer[c] : feats[i,c]) * (gate ? gate[i,c] : 1) */
+int fsfb_sir_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* xyz_normalizer,
+                   const float* gate, int64_t gate_stride, float* out, int64_t out_stride, void* stream);
+
+/* out[i,c] = x[i,c] / divisors[c]   (f_cluster / rel_dist_scaler, sir.py:57; divisors on device) */
+int fsfb_div_cols(const float* x, int64_t n, int c, int64_t x_stride, const float* divisors_dev, float* out,
+                  int64_t out_stride, void* stream);
+
+/* x[i,c] += y[i,c]   (SIRLayer shortcut; x_merge.features + x.features in the U-Net decoder) */
+int fsfb_add_inplace(float* x, int64_t n, int c, int64_t x_stride, const float* y, int64_t y_stride, void* stream);
+
+/* SparseUNet.reduce_channel: out[i,c] = sum_j x[i, c*(cin/cout) + j]  (features.view(n,cout,-1).sum(2)) */
+int fsfb_reduce_channel(const float* x, int64_t n, int cin, int64_t x_stride, int cout, float* out, void* stream);
+
+/* a6  Voxel2PointScatterNeck.forward (projects/mmdet3d_plugin/models/necks/voxel2point_neck.py:42-67):
+ *   out[i] = [ voxel_feats[inv[i], :] | xyz - ((coor + 0.5)*vs + min) ],  mask[i] = !(gathered row == padding everywhere)
+ * out dev [n, c+3]; mask dev [n] u8; dropped dev [1] i32 = number of masked-out points (the caller compacts
+ * only when it is non-zero, as the reference's boolean indexing would). */
+int fsfb_neck_points(const float* points, int64_t n, int64_t pts_stride, const void* coors, int coors_i64,
+                     const float* voxel_feats, int64_t m, int c, const void* inv, int inv_i64,
+                     const float* voxel_size, const float* range_min, float padding, float* out, uint8_t* mask,
+                     int32_t* dropped, void* stream);
+
+/* a10  VoteSegHead.decode_vote_targets (models/decode_heads/segmentation_head.py:265-266): v * |v| */
+int fsfb_vote_decode(const float* preds, int64_t total, float* out, void* stream);
+
+/* Stable boolean-mask compaction: idx[k] = position of the k-th non-zero mask byte; *count = how many.
+ * (points[mask] of FSF.extract_fg_pts, FSF.py:299-308; group_sample, single_stage_fsd.py:828-850) */
+int fsfb_compact_workspace_bytes(int64_t n, size_t* bytes);
+int fsfb_compact_indices(const uint8_t* mask, int64_t n, int32_t* idx, int32_t* count, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
