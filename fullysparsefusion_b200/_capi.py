@@ -25,7 +25,7 @@ SIGNATURES = {
     "fsfb_version": (_i, []),
     "fsfb_last_error": (C.c_char_p, []),
     "fsfb_launch_count": (_i64, []),
-    "fsfb_voxelize": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _p, _p]),
+    "fsfb_voxelize": (_i, [_p, _i64, _i64, _p, _p, _p, _i, _i, _i, _p, _p]),
     "fsfb_rows_minmax": (_i, [_p, _i, _i64, _i, _p, _p]),
     "fsfb_rank_workspace_bytes": (_i, [_i64, _i64, _psz]),
     "fsfb_rank_rows": (_i, [_p, _i, _i64, _i, _p, _p, _p, _sz, _p, _p, _p, _i64, _p, _p, _p, _p]),
@@ -37,7 +37,7 @@ SIGNATURES = {
     "fsfb_ingroup_workspace_bytes": (_i, [_i64, _i64, _psz]),
     "fsfb_ingroup_indices": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),
     "fsfb_project_sample": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p]),
-    "fsfb_project_sample_select": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "fsfb_project_sample_select": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "fsfb_gemm_prepack_bytes": (_i, [_i, _i, _i, _psz]),
     "fsfb_gemm_prepack": (_i, [_p, _i, _i, _i, _p, _p]),
     "fsfb_gather_gemm": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
@@ -55,6 +55,14 @@ SIGNATURES = {
     "fsfb_vote_decode": (_i, [_p, _i64, _p, _p]),
     "fsfb_compact_workspace_bytes": (_i, [_i64, _psz]),
     "fsfb_compact_indices": (_i, [_p, _i64, _p, _p, _p, _sz, _p]),
+    "fsfb_group_sample": (_i, [_p, _i64, _i, _p, _i64, _p, _p, _p, _i, _p, _p, _p, _p]),
+    "fsfb_gather_overlap": (_i, [_p, _p, _i64, _p, _p]),
+    "fsfb_frustum_expand": (_i, [_p, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fsfb_weighted_xyz": (_i, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "fsfb_cluster_delta": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _p, _p, _p, _p]),
+    "fsfb_encode_preds_2d": (_i, [_p, _i, _i, _p, _i, _i, _i64, _f, _f, _i, _p, _p, _p]),
+    "fsfb_threshold_mask": (_i, [_p, _i64, _i64, _i, _f, _p, _p]),
+    "fsfb_count_mask": (_i, [_p, _p, _i64, _i, _p, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

@@ -23,7 +23,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 extern "C" {
 
-int fsfb_version(void) { return 1; }
+int fsfb_version(void) { return 2; }
 
 const char* fsfb_last_error(void) { return fsfb::g_err; }
 

@@ -220,6 +220,21 @@ __global__ void __launch_bounds__(kCpThreads)
     if (f[k]) idx[ex++] = (int32_t)(base + k);
 }
 
+// mask[i] = x[i*stride + col] > thr     (fg_mask = seg_scores > cls_score_thr, single_stage_fsd.py:756)
+__global__ void __launch_bounds__(256)
+    k_threshold_mask(const float* __restrict__ x, int64_t n, int64_t stride, int col, float thr, uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = __ldg(x + i * stride + col) > thr ? 1 : 0;
+}
+
+// mask[i] = counts[inv[i]] >= min_count   (filter_almost_empty, single_stage_fsd.py:31-35)
+__global__ void __launch_bounds__(256)
+    k_count_mask(const int32_t* __restrict__ counts, const int32_t* __restrict__ inv, int64_t n, int min_count,
+                 uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mask[i] = __ldg(counts + __ldg(inv + i)) >= min_count ? 1 : 0;
+}
+
 static int grid1d(int64_t total, int per_sm = 16) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * per_sm));
 }
@@ -322,6 +337,24 @@ int fsfb_vote_decode(const float* preds, int64_t total, float* out, void* stream
   if (total == 0) return FSFB_OK;
   FSFB_CHECK_ARG(preds && out, "vote_decode: null pointer");
   FSFB_LAUNCH(k_vote_decode, grid1d(total), 256, 0, (cudaStream_t)stream, preds, total, out);
+  return FSFB_OK;
+}
+
+int fsfb_threshold_mask(const float* x, int64_t n, int64_t stride, int col, float thr, uint8_t* mask, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(n >= 0 && col >= 0 && col < stride, "threshold_mask: bad argument");
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(x && mask, "threshold_mask: null pointer");
+  FSFB_LAUNCH(k_threshold_mask, grid1d(n), 256, 0, (cudaStream_t)stream, x, n, stride, col, thr, mask);
+  return FSFB_OK;
+}
+
+int fsfb_count_mask(const int32_t* counts, const int32_t* inv, int64_t n, int min_count, uint8_t* mask, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(n >= 0, "count_mask: bad argument");
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(counts && inv && mask, "count_mask: null pointer");
+  FSFB_LAUNCH(k_count_mask, grid1d(n), 256, 0, (cudaStream_t)stream, counts, inv, n, min_count, mask);
   return FSFB_OK;
 }
 

@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(256)
                             const float* __restrict__ lidar2img, int cams,
                             const MaskT* __restrict__ mask, int classes, int H, int W,
                             int32_t* __restrict__ ids_sel, uint8_t* __restrict__ cam_sel,
-                            uint8_t* __restrict__ fg, uint8_t* __restrict__ overlap) {
+                            uint8_t* __restrict__ fg, uint8_t* __restrict__ overlap,
+                            const float* __restrict__ anno, int anno_rows, int anno_cols, int anno_col,
+                            float* __restrict__ scores) {
   __shared__ CamSet s_cams;
   load_cams(s_cams, lidar2img, cams);
   const int64_t plane = (int64_t)H * W;
@@ -144,13 +146,26 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < kMaxClasses; ++k) best_ids[k] = ids[k];
       }
     }
-    int32_t* o = ids_sel + i * classes;
+    if (ids_sel) {
+      int32_t* o = ids_sel + i * classes;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < classes) o[k] = best_ids[k];
-    cam_sel[i] = (uint8_t)best_cam;
-    fg[i] = (uint8_t)(best_sum > 0 || n_pos > 0);
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < classes) o[k] = best_ids[k];
+    }
+    if (cam_sel) cam_sel[i] = (uint8_t)best_cam;
+    if (fg) fg[i] = (uint8_t)(best_sum > 0 || n_pos > 0);
     if (overlap) overlap[i] = (uint8_t)min(n_pos, 255);
+    if (scores) {
+      // get_all_cls_preds_2d + encode_preds_2d(encode_single_cls=False) (FSF.py:506-535, 449-474):
+      // column `anno_col` (the 2D score) of mask_anno[id - 1]; id == 0 → 0
+      float* so = scores + i * classes;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < classes) {
+          const int id = best_ids[k];
+          so[k] = (id >= 1 && id <= anno_rows) ? __ldg(anno + (int64_t)(id - 1) * anno_cols + anno_col) : 0.f;
+        }
+    }
   }
 }
 
@@ -199,21 +214,148 @@ int fsfb_project_sample(const float* xyz, int64_t n, int64_t xyz_stride, const f
 int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
                                const float* lidar2img, int cams, const void* mask, int mask_i32,
                                int classes, int H, int W, int32_t* ids_sel, uint8_t* cam_sel,
-                               uint8_t* fg, uint8_t* overlap, void* stream) {
+                               uint8_t* fg, uint8_t* overlap, const float* anno, int anno_rows,
+                               int anno_cols, int anno_col, float* scores, void* stream) {
   using namespace fsfb;
   int rc = check_common(xyz, n, xyz_stride, lidar2img, cams, mask, classes, H, W,
                         "project_sample_select");
   if (rc != FSFB_OK) return rc;
   if (n == 0) return FSFB_OK;
-  FSFB_CHECK_ARG(ids_sel && cam_sel && fg, "project_sample_select: null output");
+  FSFB_CHECK_ARG(ids_sel || cam_sel || fg || overlap || scores, "project_sample_select: no output requested");
+  FSFB_CHECK_ARG(!scores || (anno && anno_rows >= 0 && anno_col >= 0 && anno_col < anno_cols),
+                 "project_sample_select: scores need a valid annotation table");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
   if (mask_i32) {
     FSFB_LAUNCH(k_project_sample_select<int>, grid, 256, 0, st, xyz, n, xyz_stride, lidar2img, cams,
-                (const int*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap);
+                (const int*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows, anno_cols,
+                anno_col, scores);
   } else {
     FSFB_LAUNCH(k_project_sample_select<unsigned char>, grid, 256, 0, st, xyz, n, xyz_stride, lidar2img, cams,
-                (const unsigned char*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap);
+                (const unsigned char*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows,
+                anno_cols, anno_col, scores);
+  }
+  return FSFB_OK;
+}
+
+}  // extern "C"
+
+// ---- a11 frustum point expansion (FSF.extract_fg_pts + double_overlap_pts + get_sir_coors) ----------
+// Reference: projects/mmdet3d_plugin/models/detectors/FSF.py:260-308, 357-365.  A foreground point seen
+// by k >= 1 (camera, class) masks yields k rows: row `fg position` carries its largest object id; the
+// remaining k-1 rows are appended after all n_fg first rows, grouped by k ascending, then by rank
+// (2nd, 3rd ... largest id), then by foreground order — the order the reference's cat/repeat/topk
+// sequence produces.  The ids are recovered by re-sampling the planes for foreground points only.
+namespace fsfb {
+
+constexpr int kMaxOverlap = 16;
+
+// sorted position j over the CSR of overlap counts (groups k = 0..kMaxOverlap)
+template <typename MaskT>
+__global__ void __launch_bounds__(256)
+    k_frustum_expand(const float* __restrict__ xyz, int64_t stride, const float* __restrict__ lidar2img, int cams,
+                     const MaskT* __restrict__ mask, int classes, int H, int W, const int32_t* __restrict__ idx_fg,
+                     int64_t n_fg, const int32_t* __restrict__ perm, const int32_t* __restrict__ seg,
+                     const int32_t* __restrict__ offsets, const int32_t* __restrict__ batch,
+                     int32_t* __restrict__ rows_point, int32_t* __restrict__ sir_coors, int32_t* __restrict__ status) {
+  __shared__ CamSet s_cams;
+  __shared__ int s_extra_base[kMaxOverlap + 2];
+  load_cams(s_cams, lidar2img, cams);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k <= kMaxOverlap; ++k) {
+      s_extra_base[k] = acc;
+      const int cnt = offsets[k + 1] - offsets[k];
+      if (k >= 2) acc += cnt * (k - 1);
+    }
+  }
+  __syncthreads();
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_fg; j += (int64_t)gridDim.x * blockDim.x) {
+    const int k = seg[j];
+    const int f = perm[j];          // position among foreground points
+    const int p = idx_fg[f];        // position among all points
+    const float* q = xyz + (int64_t)p * stride;
+    const float x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+    int ids[kMaxOverlap];
+    int cnt = 0;
+    for (int cam = 0; cam < cams; ++cam) {
+      const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
+      if (tex < 0) continue;
+      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
+      for (int c = 0; c < classes; ++c) {
+        const int id = (int)__ldg(m0 + c * plane);
+        if (id > 0) {
+          // insertion into a descending list (topk order)
+          int pos = min(cnt, kMaxOverlap - 1);
+          if (cnt >= kMaxOverlap && id <= ids[kMaxOverlap - 1]) continue;
+          while (pos > 0 && ids[pos - 1] < id) {
+            ids[pos] = ids[pos - 1];
+            --pos;
+          }
+          ids[pos] = id;
+          cnt = min(cnt + 1, kMaxOverlap);
+        }
+      }
+    }
+    if (cnt != k || k < 1) atomicOr(status, 4);  // inconsistent with the overlap count given (or > kMaxOverlap)
+    const int b = batch ? __ldg(batch + p) : 0;
+    // first row: foreground order, largest id
+    rows_point[f] = p;
+    sir_coors[(int64_t)f * 3 + 0] = b;
+    sir_coors[(int64_t)f * 3 + 1] = 0;
+    sir_coors[(int64_t)f * 3 + 2] = cnt > 0 ? ids[0] : 0;
+    const int rank = (int)(j - offsets[k]);
+    const int cnt_k = offsets[k + 1] - offsets[k];
+    for (int pad = 1; pad < k && pad < cnt; ++pad) {
+      const int64_t r = n_fg + s_extra_base[k] + (int64_t)(pad - 1) * cnt_k + rank;
+      rows_point[r] = p;
+      sir_coors[r * 3 + 0] = b;
+      sir_coors[r * 3 + 1] = 0;
+      sir_coors[r * 3 + 2] = ids[pad];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_gather_overlap(const uint8_t* __restrict__ overlap, const int32_t* __restrict__ idx_fg, int64_t n_fg,
+                     int32_t* __restrict__ ov32) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_fg; j += (int64_t)gridDim.x * blockDim.x)
+    ov32[j] = min((int)overlap[idx_fg[j]], kMaxOverlap);
+}
+
+}  // namespace fsfb
+
+extern "C" {
+
+int fsfb_gather_overlap(const uint8_t* overlap, const int32_t* idx_fg, int64_t n_fg, int32_t* ov32, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(n_fg >= 0, "gather_overlap: bad n");
+  if (n_fg == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(overlap && idx_fg && ov32, "gather_overlap: null pointer");
+  const int grid = (int)std::min<int64_t>(ceil_div(n_fg, 256), (int64_t)kNumSMs * 8);
+  FSFB_LAUNCH(k_gather_overlap, grid, 256, 0, (cudaStream_t)stream, overlap, idx_fg, n_fg, ov32);
+  return FSFB_OK;
+}
+
+int fsfb_frustum_expand(const float* xyz, int64_t xyz_stride, const float* lidar2img, int cams, const void* mask,
+                        int mask_i32, int classes, int H, int W, const int32_t* idx_fg, int64_t n_fg,
+                        const int32_t* perm, const int32_t* seg, const int32_t* offsets, const int32_t* batch_idx,
+                        int32_t* rows_point, int32_t* sir_coors, int32_t* status, void* stream) {
+  using namespace fsfb;
+  int rc = check_common(xyz, n_fg, xyz_stride, lidar2img, cams, mask, classes, H, W, "frustum_expand");
+  if (rc != FSFB_OK) return rc;
+  if (n_fg == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(idx_fg && perm && seg && offsets && rows_point && sir_coors && status, "frustum_expand: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<int64_t>(ceil_div(n_fg, 256), (int64_t)kNumSMs * 8);
+  if (mask_i32) {
+    FSFB_LAUNCH(k_frustum_expand<int>, grid, 256, 0, st, xyz, xyz_stride, lidar2img, cams, (const int*)mask, classes, H,
+                W, idx_fg, n_fg, perm, seg, offsets, batch_idx, rows_point, sir_coors, status);
+  } else {
+    FSFB_LAUNCH(k_frustum_expand<unsigned char>, grid, 256, 0, st, xyz, xyz_stride, lidar2img, cams,
+                (const unsigned char*)mask, classes, H, W, idx_fg, n_fg, perm, seg, offsets, batch_idx, rows_point,
+                sir_coors, status);
   }
   return FSFB_OK;
 }

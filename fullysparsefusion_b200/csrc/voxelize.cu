@@ -36,6 +36,7 @@ __device__ __forceinline__ int voxel_coord(float p, float lo, float vs, int mode
 
 __global__ void __launch_bounds__(256) k_voxelize(const float* __restrict__ pts, int64_t n,
                                                   int64_t stride, VoxelParams P, int mode,
+                                                  int order_xyz, int check_range,
                                                   int32_t* __restrict__ coors) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -48,13 +49,13 @@ __global__ void __launch_bounds__(256) k_voxelize(const float* __restrict__ pts,
     int cx = voxel_coord(x, P.min_x, P.vs_x, mode);
     int cy = voxel_coord(y, P.min_y, P.vs_y, mode);
     int cz = voxel_coord(z, P.min_z, P.vs_z, mode);
-    bool ok = (cx >= 0) & (cx < P.gx) & (cy >= 0) & (cy < P.gy) & (cz >= 0) & (cz < P.gz) &
-              (fabsf(x) <= 3.402823466e38f) & (fabsf(y) <= 3.402823466e38f) &
+    bool ok = (fabsf(x) <= 3.402823466e38f) & (fabsf(y) <= 3.402823466e38f) &
               (fabsf(z) <= 3.402823466e38f);
+    if (check_range) ok &= (cx >= 0) & (cx < P.gx) & (cy >= 0) & (cy < P.gy) & (cz >= 0) & (cz < P.gz);
     int32_t* o = coors + i * 3;
-    o[0] = ok ? cz : -1;
+    o[0] = ok ? (order_xyz ? cx : cz) : -1;
     o[1] = ok ? cy : -1;
-    o[2] = ok ? cx : -1;
+    o[2] = ok ? (order_xyz ? cz : cx) : -1;
   }
 }
 
@@ -62,19 +63,20 @@ __global__ void __launch_bounds__(256) k_voxelize(const float* __restrict__ pts,
 
 extern "C" int fsfb_voxelize(const float* pts, int64_t n, int64_t row_stride,
                              const float* range_min, const float* voxel, const int32_t* grid,
-                             int floor_mode, int32_t* coors_zyx, void* stream) {
+                             int floor_mode, int order_xyz, int check_range, int32_t* coors_zyx,
+                             void* stream) {
   using namespace fsfb;
   FSFB_CHECK_ARG(n >= 0 && row_stride >= 3, "voxelize: bad n=%lld stride=%lld", (long long)n,
                  (long long)row_stride);
-  FSFB_CHECK_ARG(range_min && voxel && grid, "voxelize: null host parameter");
+  FSFB_CHECK_ARG(range_min && voxel && (grid || !check_range), "voxelize: null host parameter");
   FSFB_CHECK_ARG(floor_mode == 0 || floor_mode == 1, "voxelize: floor_mode must be 0 or 1");
   if (n == 0) return FSFB_OK;
   FSFB_CHECK_ARG(pts && coors_zyx, "voxelize: null device pointer");
   VoxelParams P{range_min[0], range_min[1], range_min[2], voxel[0], voxel[1], voxel[2],
-                grid[0],      grid[1],      grid[2]};
+                grid ? grid[0] : 0, grid ? grid[1] : 0, grid ? grid[2] : 0};
   FSFB_CHECK_ARG(P.vs_x > 0 && P.vs_y > 0 && P.vs_z > 0, "voxelize: voxel size must be > 0");
   int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 16);
   FSFB_LAUNCH(k_voxelize, blocks, 256, 0, (cudaStream_t)stream, pts, n, row_stride, P,
-              floor_mode, coors_zyx);
+              floor_mode, order_xyz, check_range, coors_zyx);
   return FSFB_OK;
 }

@@ -1,0 +1,276 @@
+"""FSF inference forward (one frame per call) on the B200 hot path.
+
+Mirrors projects/mmdet3d_plugin/models/detectors/FSF.py::simple_test (:1114-1176) up to and including
+combine_frustum_and_fsd (:657-692), with the segmentor of single_stage_fsd.py (VoteSegmentor.extract_feat
+:228-245) inlined:
+
+  segment      voxelize → DynamicScatterVFE → SimpleSparseUNet → Voxel2PointScatterNeck
+  enhance      img_cross_attn (projection ⊕ sampling ⊕ camera select ⊕ score lookup → MLP) + VoteSegHead
+  frustum      camera queries: fg extraction, overlap duplication, weighted centroids, SIR, FrustumClusterHead
+  fsd          LiDAR queries: pre_voxelize, group_sample, ClusterAssigner (CCL), SIR, SparseClusterHeadV2
+  combine      the two 1024-wide fusion MLPs
+
+The refine stage (dynamic_point_pool + FullySparseBboxHead) and box decode / NMS are SURVEY.md §8f "next"
+rows and are not part of this round.  One sample per call (samples_per_gpu = 1 in both stock configs).
+All arithmetic goes through the C-ABI ops; torch is used for allocation, views and concatenation only.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import modules as M
+from . import ops
+
+# ---- the stock nuScenes configuration (projects/configs/nuScenes/FSF_nuScenes_config.py) ----------------
+NUSC = dict(
+    class_names=["car", "truck", "trailer", "bus", "construction_vehicle", "bicycle", "motorcycle", "pedestrian",
+                 "traffic_cone", "barrier"],
+    group_names=[["car"], ["truck", "construction_vehicle"], ["bus", "trailer"], ["barrier"], ["motorcycle", "bicycle"],
+                 ["pedestrian", "traffic_cone"]],
+    seg_voxel_size=(0.2, 0.2, 0.2), point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], sparse_shape=[40, 512, 512],
+    score_thresh=[0.1] * 6, pre_voxelization_size=(0.1, 0.1, 0.1),
+    cluster_voxel_size=[(0.3, 0.3, 8), (0.3, 0.3, 8), (0.3, 0.3, 8), (0.1, 0.1, 8), (0.2, 0.2, 8), (0.05, 0.05, 8)],
+    connected_dist=[0.6, 0.6, 0.6, 0.2, 0.4, 0.1], min_points=2, num_cams=6,
+)
+BN = dict(type="naiveSyncBN1d", eps=1e-3, momentum=0.01)
+LN3 = dict(type="LN", eps=1e-3)
+LN5 = dict(type="LN")
+
+
+class FSDSeparateHead(nn.Module):
+    """models/dense_heads/sparse_cluster_head_v2.py:17-41."""
+
+    def __init__(self, in_channels, attrs, norm_cfg=LN5, act="relu"):
+        super().__init__()
+        self.attrs = attrs
+        for name, (out_dim, num_layer, hidden) in attrs.items():
+            setattr(self, name, M.build_mlp(in_channels, [hidden] * num_layer + [out_dim], norm_cfg, is_head=True, act=act))
+
+    def forward(self, x):
+        return {name: getattr(self, name)(x) for name in self.attrs}
+
+
+class SparseClusterHeadV2(nn.Module):
+    """SparseClusterHead.__init__ shared MLP (sparse_cluster_head.py:75-77) + SparseClusterHeadV2.forward
+    (sparse_cluster_head_v2.py:134-168); FrustumClusterHead inherits this forward."""
+
+    def __init__(self, num_classes, in_channel, shared_mlp_dims, tasks, common_attrs, num_cls_layer, cls_hidden_dim,
+                 separate_head, norm_cfg=LN5, act="relu"):
+        super().__init__()
+        self.shared_mlp = M.build_mlp(in_channel, list(shared_mlp_dims), norm_cfg, act=act) if len(shared_mlp_dims) else None
+        sep_in = shared_mlp_dims[-1] if len(shared_mlp_dims) else in_channel
+        self.task_heads = nn.ModuleList()
+        for t in tasks:
+            attrs = dict(common_attrs)
+            attrs["score"] = (len(t["class_names"]), num_cls_layer, cls_hidden_dim)
+            self.task_heads.append(FSDSeparateHead(sep_in, attrs, norm_cfg=separate_head.get("norm_cfg", LN5),
+                                                   act=separate_head.get("act", "relu")))
+
+    def forward(self, feats, pts_xyz=None, pts_inds=None):
+        if self.shared_mlp is not None:
+            feats = self.shared_mlp(feats)
+        cls_list, reg_list = [], []
+        for h in self.task_heads:
+            r = h(feats)
+            cls_list.append(r["score"])
+            parts = [r["center"], r["dim"], r["rot"]] + ([r["vel"]] if "vel" in r else [])
+            reg_list.append(torch.cat(parts, dim=-1))
+        return dict(cls_logits=cls_list, reg_preds=reg_list)
+
+
+def _head(in_channel, class_names):
+    return SparseClusterHeadV2(
+        num_classes=len(class_names), in_channel=in_channel, shared_mlp_dims=[1024, 1024],
+        tasks=[dict(num_class=len(class_names), class_names=class_names)],
+        common_attrs=dict(center=(3, 2, 128), dim=(3, 2, 128), rot=(2, 2, 128), vel=(2, 2, 128)), num_cls_layer=2,
+        cls_hidden_dim=128, separate_head=dict(norm_cfg=LN5, act="gelu"), norm_cfg=LN5, act="relu")
+
+
+class FSF(nn.Module):
+    """The FSF detector's inference forward on synthetic or real frames (random init unless weights are loaded)."""
+
+    def __init__(self, cfg: dict = NUSC):
+        super().__init__()
+        self.cfg = cfg
+        nc = len(cfg["class_names"])
+        self.num_classes = nc
+        self.groups = [[cfg["class_names"].index(n) for n in g] for g in cfg["group_names"]]
+        # segmentor (FSF_nuScenes_config.py:33-102)
+        self.voxel_encoder = M.DynamicScatterVFE(in_channels=5, feat_channels=[64, 64], voxel_size=cfg["seg_voxel_size"],
+                                                 with_cluster_center=True, with_voxel_center=True,
+                                                 point_cloud_range=cfg["point_cloud_range"], norm_cfg=BN, unique_once=True)
+        self.backbone_unet = M.SimpleSparseUNet(
+            in_channels=64, sparse_shape=cfg["sparse_shape"], norm_cfg=BN, base_channels=64, output_channels=128,
+            encoder_channels=((128,), (128, 128, 128), (128, 128, 128), (256, 256, 256), (512, 512, 512)),
+            encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1), (1, 1, 1)),
+            decoder_channels=((512, 512, 256), (256, 256, 128), (128, 128, 128), (128, 128, 128), (128, 128, 128)),
+            decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1)))
+        self.decode_neck = M.Voxel2PointScatterNeck(voxel_size=cfg["seg_voxel_size"], point_cloud_range=cfg["point_cloud_range"])
+        self.segmentation_head = M.VoteSegHead(in_channel=67 + 64, hidden_dims=[128, 128], num_classes=nc,
+                                               norm_cfg=dict(type="naiveSyncBN1d"), act_cfg=dict(type="ReLU"))
+        # FSF.__init__ (FSF.py:100-164)
+        self.segmentor_updated_mlp = M.build_mlp(10, [128, 131], LN3, is_head=True, act="gelu")
+        nn.init.constant_(self.segmentor_updated_mlp[-1].weight, 0.0)   # FSF.py:142-143
+        nn.init.constant_(self.segmentor_updated_mlp[-1].bias, 0.0)
+        self.encode_2d_mlp = M.build_mlp(16, [128, 128], LN3, is_head=False, act="gelu")
+        sir_kw = dict(num_blocks=3, feat_channels=[[128, 128]] * 3, rel_mlp_hidden_dims=[[16, 32]] * 3, norm_cfg=LN3, mode="max",
+                      xyz_normalizer=[20, 20, 4], act="gelu", unique_once=True)
+        self.backbone = M.SIR(in_channels=[116 + 64, 133, 133], **sir_kw)          # LiDAR queries (:113-124)
+        self.frustum_sir = M.SIR(in_channels=[67 + 64 + 5, 133, 133], **sir_kw)    # camera queries (:201-212)
+        self.bbox_head = _head(128 * 3 * 2, cfg["class_names"])
+        self.frustum_obj_head = _head(128 * 3 * 2 + 128, cfg["class_names"])
+        self.combine_frustum_feat_mlp = M.build_mlp(128 * 3 * 2 + 128, [1024], LN3, act="gelu")
+        self.combine_fsd_feat_mlp = M.build_mlp(128 * 3 * 2, [1024], LN3, act="gelu")
+        self.fsd_begin_idx = 1000
+        self.eval()
+
+    def refresh(self):
+        for m in self.modules():
+            if m is not self and hasattr(m, "refresh"):
+                m.refresh()
+
+    # ------------------------------------------------------------------------------------------------
+    def stages(self, points: torch.Tensor, mask_data: torch.Tensor, mask_anno: torch.Tensor, lidar2img: torch.Tensor
+               ) -> Tuple[List[Tuple[str, Callable[[], None]]], Dict[str, torch.Tensor]]:
+        """points [N,8] f32 (x,y,z,intensity,dt + un-augmented xyz), mask_data u8 [cams,classes,H,W],
+        mask_anno f32 [250,9], lidar2img f32 [cams,4,4].  Returns ([(stage name, fn)], state)."""
+        st: Dict[str, torch.Tensor] = {}
+        cfg = self.cfg
+        dev = points.device
+        rng, vs = cfg["point_cloud_range"], cfg["seg_voxel_size"]
+        grid_zyx = cfg["sparse_shape"]
+
+        def segment():
+            pts5 = points[:, :5]
+            coors3 = ops.voxelize(points, vs, rng, floor_mode=0)                       # single_stage_fsd.py:217-219
+            coors4 = F.pad(coors3, (1, 0), value=0)                                    # batch pad (:222-225)
+            plan = M.ScatterPlan(coors4, lo=[0, 0, 0, 0], ext=[1] + list(grid_zyx), want_index=True)
+            voxel_feats, voxel_coors, _ = self.voxel_encoder(pts5, coors4, return_inv=True, plan=plan)
+            rb, _ = self.backbone_unet.build_rulebooks(voxel_coors, plan.index, 1)
+            x = self.backbone_unet(dict(voxel_feats=voxel_feats, voxel_coors=voxel_coors), rulebooks=rb)[0]["voxel_feats"]
+            neck_out, mask = self.decode_neck(pts5, coors4, x, plan.inv32, -1)
+            st.update(coors4=coors4, voxel_coors=voxel_coors, vfe_feats=voxel_feats, voxel_feats=x, pts_lidar_feats=neck_out,
+                      valid_pts_mask=mask, voxel2point_inds=plan.inv32)
+
+        def enhance():
+            # img_cross_attn (FSF.py:694-728): the whole gather/select/lookup chain is one kernel
+            _, cam, fg, ov, scores = ops.project_sample_select(points[:, 5:8], lidar2img, mask_data, want_overlap=True,
+                                                               anno=mask_anno, anno_col=4, want_ids=False)
+            img_feat = self.segmentor_updated_mlp(scores)
+            st["img_scores"] = scores
+            pts_feats = ops.add_(img_feat, st["pts_lidar_feats"])                      # :790
+            logits, vote_preds = self.segmentation_head(pts_feats)
+            offsets = self.segmentation_head.decode_vote_targets(vote_preds)
+            st.update(fg=fg, overlap=ov, cam_sel=cam, seg_feats=pts_feats, seg_logits=logits, seg_vote_preds=vote_preds,
+                      offsets=offsets)
+
+        def frustum():
+            pts5 = points[:, :5]
+            fgw, _, _ = ops.group_sample(st["seg_logits"], want_fg_weight=True)         # get_point_fg_weights (:345-355)
+            rows, sir_coors, n_fg = ops.frustum_rows(points[:, 5:8], lidar2img, mask_data, st["fg"], st["overlap"])
+            if rows.numel() == 0:   # fake one object (FSF.py:407-414)
+                r_pts = torch.zeros((1, 5), device=dev)
+                r_feat = torch.zeros((1, st["seg_feats"].size(1)), device=dev)
+                sir_coors = torch.zeros((1, 3), dtype=torch.int32, device=dev)
+                f_cluster = torch.zeros((1, 3), device=dev)
+                center = torch.zeros((1, 3), device=dev)
+                plan = M.ScatterPlan(sir_coors)
+            else:
+                r_pts = ops.gather_rows(pts5, rows)
+                r_feat = ops.gather_rows(st["seg_feats"], rows)
+                plan = M.ScatterPlan(sir_coors)
+                w4 = ops.weighted_xyz(pts5, fgw, rows)                                  # :313-318
+                mean4 = plan.reduce(w4, "mean")
+                f_cluster, center = ops.cluster_delta(pts5, mean4, plan.inv32, rows)    # :324-329
+            _, cluster_feats, out_coors = self.frustum_sir(r_pts, r_feat, sir_coors, f_cluster, plan=plan)
+            preds_2d, enc = ops.encode_preds_2d(mask_anno, out_coors, mask_data.shape[-1], mask_data.shape[-2], self.num_classes)
+            img_feat = self.encode_2d_mlp(enc)
+            obj_feat = torch.cat([cluster_feats, img_feat], dim=-1)
+            res = self.frustum_obj_head(obj_feat)
+            st.update(frustum_sir_coors=sir_coors, frustum_f_cluster=f_cluster, frustum_pts=r_pts, frustum_pts_feats=r_feat,
+                      frustum_enc_2d=enc)
+            st.update(frustum_rows=rows, frustum_obj_feats=obj_feat, frustum_obj_centers=center, frustum_obj_coors=out_coors,
+                      frustum_cls=res["cls_logits"][0], frustum_reg=res["reg_preds"][0], frustum_preds_2d=preds_2d,
+                      point_fg_weights=fgw)
+
+        def fsd():
+            pts5 = points[:, :5].contiguous()
+            # pre_voxelize (single_stage_fsd.py:585-605)
+            c3 = ops.voxelize(pts5, cfg["pre_voxelization_size"], rng, floor_mode=1)
+            c4 = F.pad(c3, (1, 0), value=0)
+            plan = M.ScatterPlan(c4, lo=[0, 0, 0, 0], ext=[1] + [g * 2 for g in grid_zyx])
+            v_pts = plan.reduce(pts5, "mean")
+            v_logits = plan.reduce(st["seg_logits"], "mean")
+            v_votes = plan.reduce(st["seg_vote_preds"], "mean")
+            v_feats = plan.reduce(st["seg_feats"], "mean")
+            v_off = plan.reduce(st["offsets"], "mean")
+            # group_sample (:802-865)
+            _, score, centers = ops.group_sample(v_logits, self.groups, xyz=v_pts, offsets=v_off)
+            sel_rows, cls_ids, clu_ids, ctr_list = [], [], [], []
+            for g in range(len(self.groups)):
+                idx = ops.compact_indices(ops.threshold_mask(score, g, cfg["score_thresh"][g]))
+                if idx.numel() == 0:                                                     # at least one point per sample (:833-835)
+                    idx = torch.zeros(1, dtype=torch.int32, device=dev)
+                ctr = ops.gather_rows(centers.view(-1, 3 * len(self.groups))[:, 3 * g:3 * g + 3].contiguous(), idx)
+                # ClusterAssigner.forward_single_class (:936-982)
+                cv = ops.voxelize(ctr, cfg["cluster_voxel_size"][g], rng, floor_mode=1, order_xyz=True, check_range=False)
+                cc4 = F.pad(cv, (1, 0), value=0)
+                _, inv, cnt = ops.unique_rows(cc4, return_counts=True, return_unique=False, inv_dtype=torch.int32)
+                keep = ops.compact_indices(ops.count_mask(cnt, inv, cfg["min_points"]))
+                if keep.numel() == 0:                                                    # `valid_mask = ~valid_mask` (:953-955)
+                    keep = torch.arange(idx.numel(), dtype=torch.int32, device=dev)
+                ctr_k = ops.gather_rows(ctr, keep)
+                plan_c = M.ScatterPlan(ops.gather_int_rows(cc4, keep))
+                sampled_centers = plan_c.reduce(ctr_k, "mean")
+                labels = ops.connected_components(sampled_centers, None, cfg["connected_dist"][g])   # single-batch variant (:977)
+                clu = ops.gather_int_rows(labels.view(-1, 1), plan_c.inv32)
+                sel_rows.append(ops.gather_int_rows(idx.view(-1, 1), keep).view(-1))
+                cls_ids.append(torch.full((keep.numel(), 1), g, dtype=torch.int32, device=dev))
+                clu_ids.append(clu)
+                ctr_list.append(ctr_k)
+            rows = torch.cat(sel_rows)
+            n = rows.numel()
+            pts_cluster_inds = torch.cat([torch.cat(cls_ids), torch.zeros((n, 1), dtype=torch.int32, device=dev),
+                                          torch.cat(clu_ids)], dim=1)                    # (cls, batch, cluster) (:145-152)
+            center_preds = torch.cat(ctr_list)
+            s_pts = ops.gather_rows(v_pts, rows)
+            pts_feats = torch.empty((n, 11 + 33 + 131), dtype=torch.float32, device=dev)
+            ops.gather_rows(v_logits, rows, out=pts_feats[:, :11])
+            ops.gather_rows(v_votes, rows, out=pts_feats[:, 11:44])
+            ops.gather_rows(v_feats, rows, out=pts_feats[:, 44:])
+            # extract_feat (:458-474)
+            plan_q = M.ScatterPlan(pts_cluster_inds)
+            cluster_xyz_mean = plan_q.reduce(center_preds, "mean")
+            f_cluster, cluster_xyz = ops.cluster_delta(s_pts, cluster_xyz_mean, plan_q.inv32)
+            _, cluster_feats, cluster_inds = self.backbone(s_pts, pts_feats, pts_cluster_inds, f_cluster, plan=plan_q)
+            res = self.bbox_head(cluster_feats)
+            st.update(pre_points=v_pts, pre_logits=v_logits, pre_votes=v_votes, pre_feats=v_feats, pre_offsets=v_off,
+                      group_score=score, group_centers=centers, fsd_pts=s_pts, fsd_pts_feats=pts_feats,
+                      fsd_center_preds=center_preds, fsd_f_cluster=f_cluster)
+            st.update(pre_coors=plan.new_coors, fsd_rows=rows, pts_cluster_inds=pts_cluster_inds, fsd_obj_feats=cluster_feats,
+                      fsd_obj_centers=cluster_xyz, fsd_obj_coors=cluster_inds, fsd_cls=res["cls_logits"][0],
+                      fsd_reg=res["reg_preds"][0])
+
+        def combine():
+            fr = self.combine_frustum_feat_mlp(st["frustum_obj_feats"])                  # FSF.py:683-684
+            fs = self.combine_fsd_feat_mlp(st["fsd_obj_feats"])
+            fc = st["fsd_obj_coors"]
+            fsd_re = torch.stack([fc[:, 1], fc[:, 0], fc[:, 2] + self.fsd_begin_idx], dim=1)
+            st.update(obj_feats=torch.cat([fr, fs], dim=0),
+                      obj_centers=torch.cat([st["frustum_obj_centers"], st["fsd_obj_centers"]], dim=0),
+                      obj_coors=torch.cat([st["frustum_obj_coors"], fsd_re], dim=0),
+                      obj_cls=torch.cat([st["frustum_cls"], st["fsd_cls"]], dim=0),
+                      obj_reg=torch.cat([st["frustum_reg"], st["fsd_reg"]], dim=0))
+
+        return [("segment", segment), ("enhance", enhance), ("frustum", frustum), ("fsd", fsd), ("combine", combine)], st
+
+    @torch.no_grad()
+    def forward(self, points, mask_data, mask_anno, lidar2img):
+        stages, st = self.stages(points, mask_data, mask_anno, lidar2img)
+        for _, fn in stages:
+            fn()
+        return st

@@ -283,7 +283,7 @@ class SIRLayer(nn.Module):
             plan = ScatterPlan(coors)
         n = features.size(0)
         dev = features.device
-        gate = self.rel_mlp(ops.scale_cols(f_cluster, [1.0 / self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
+        gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
         x = ops.sir_input(features, self.xyz_normalizer, gate)   # cat(xyz/norm, feats) * gate, one pass
         ori = x
         cluster_list = []

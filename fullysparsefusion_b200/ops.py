@@ -66,7 +66,8 @@ def grid_shape(point_cloud_range: Sequence[float], voxel_size: Sequence[float]) 
 
 
 def voxelize(points: torch.Tensor, voxel_size: Sequence[float], point_cloud_range: Sequence[float],
-             floor_mode: int = 0, grid: Optional[Sequence[int]] = None) -> torch.Tensor:
+             floor_mode: int = 0, grid: Optional[Sequence[int]] = None, order_xyz: bool = False,
+             check_range: bool = True) -> torch.Tensor:
     """Dynamic voxelization → coors [N,3] int32 (z,y,x); out-of-range → -1.
 
     Mirrors mmdet3d.ops.Voxelization(max_num_points=-1)(points)
@@ -81,7 +82,8 @@ def voxelize(points: torch.Tensor, voxel_size: Sequence[float], point_cloud_rang
     g = tuple(grid) if grid is not None else grid_shape(point_cloud_range, voxel_size)
     coors = torch.empty((n, 3), dtype=torch.int32, device=dev)
     rc = load().fsfb_voxelize(_ptr(points), n, points.stride(0) if n else 3, _host_f32(point_cloud_range[:3]),
-                              _host_f32(voxel_size), _host_i32(g), int(floor_mode), _ptr(coors), _stream(dev))
+                              _host_f32(voxel_size), _host_i32(g), int(floor_mode), int(order_xyz), int(check_range),
+                              _ptr(coors), _stream(dev))
     check(rc, "fsfb_voxelize")
     return coors
 
@@ -156,7 +158,9 @@ def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Opt
     if status & 1:
         raise _capi.FsfbError("unique_rows: a row lies outside the given lo/ext bounds")
     inv = inv64 if inv64 is not None else inv32
-    res = (uniq[:m] if uniq is not None else None, inv, counts[:m].long() if counts is not None else None)
+    if counts is not None:
+        counts = counts[:m] if inv_dtype == torch.int32 else counts[:m].long()
+    res = (uniq[:m] if uniq is not None else None, inv, counts)
     if return_index:
         return res + (VoxelIndex(ws, tuple(int(v) for v in lo), tuple(int(v) for v in ext), m),)
     return res
@@ -286,9 +290,11 @@ def project_sample(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torch.Tenso
     return out
 
 
-def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torch.Tensor, want_overlap: bool = False):
-    """Fused contract: (ids_sel [N,classes] i32, cam_sel [N] u8, fg [N] u8[, overlap [N] u8])."""
-    dev = _need_cuda(xyz, lidar2img, mask)
+def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torch.Tensor, want_overlap: bool = False,
+                          anno: Optional[torch.Tensor] = None, anno_col: int = 4, want_ids: bool = True):
+    """Fused contract: (ids_sel [N,classes] i32, cam_sel [N] u8, fg [N] u8[, overlap [N] u8][, scores [N,classes] f32]).
+    scores = mask_anno[id-1][anno_col] of the camera-selected ids (FSF.img_cross_attn's MLP input on nuScenes)."""
+    dev = _need_cuda(xyz, lidar2img, mask, anno)
     assert xyz.dim() == 2 and xyz.size(1) >= 3 and xyz.dtype == torch.float32
     if xyz.stride(1) != 1:
         xyz = xyz.contiguous()
@@ -296,15 +302,27 @@ def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torc
     cams, classes, H, W = mask.shape
     l2i = lidar2img.to(torch.float32).contiguous()
     n = xyz.size(0)
-    ids = torch.empty((n, classes), dtype=torch.int32, device=dev)
+    ids = torch.empty((n, classes), dtype=torch.int32, device=dev) if want_ids else None
     cam = torch.empty(n, dtype=torch.uint8, device=dev)
     fg = torch.empty(n, dtype=torch.uint8, device=dev)
     ov = torch.empty(n, dtype=torch.uint8, device=dev) if want_overlap else None
+    scores = None
+    a_rows = a_cols = 0
+    if anno is not None:
+        assert anno.dim() == 2 and anno.dtype == torch.float32
+        anno = anno.contiguous()
+        a_rows, a_cols = anno.shape
+        scores = torch.empty((n, classes), dtype=torch.float32, device=dev)
     rc = load().fsfb_project_sample_select(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask),
                                            is_i32, classes, H, W, _ptr(ids), _ptr(cam), _ptr(fg), _ptr(ov),
-                                           _stream(dev))
+                                           _ptr(anno), a_rows, a_cols, int(anno_col), _ptr(scores), _stream(dev))
     check(rc, "fsfb_project_sample_select")
-    return (ids, cam, fg, ov) if want_overlap else (ids, cam, fg)
+    out = (ids, cam, fg)
+    if want_overlap:
+        out += (ov,)
+    if anno is not None:
+        out += (scores,)
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -521,12 +539,12 @@ def sir_input(features, xyz_normalizer, gate=None, out=None):
 _DIVISORS: dict = {}
 
 
-def scale_cols(x, inv_scales):
-    """x[:, c] / (1 / inv_scales[c]) — i.e. division by the scaler (f_cluster / rel_dist_scaler)."""
+def div_cols(x, divisors):
+    """x[:, c] / divisors[c]  (f_cluster / rel_dist_scaler)."""
     dev = _need_cuda(x)
     x = _rowmajor(x)
     n, c = x.shape
-    key = (dev, tuple(float(1.0 / s) for s in inv_scales))
+    key = (dev, tuple(float(d) for d in divisors))
     if key not in _DIVISORS:
         _DIVISORS[key] = torch.tensor(key[1], dtype=torch.float32, device=dev)
     out = torch.empty((n, c), dtype=torch.float32, device=dev)
@@ -599,3 +617,128 @@ def vote_decode(preds: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(preds)
     check(load().fsfb_vote_decode(_ptr(preds), preds.numel(), _ptr(out), _stream(dev)), "fsfb_vote_decode")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# query-generation helpers
+# ------------------------------------------------------------------------------------------
+def group_sample(logits: torch.Tensor, groups: Optional[Sequence[Sequence[int]]] = None, xyz=None, offsets=None,
+                 want_fg_weight: bool = False):
+    """softmax-derived quantities of one [n, C+1] logit tensor (include/fsf_b200.h: fsfb_group_sample).
+    Returns (fg_weight [n] | None, group_score [n,G] | None, group_center [n,G,3] | None)."""
+    dev = _need_cuda(logits, xyz, offsets)
+    logits = logits.contiguous()
+    n, c1 = logits.shape
+    groups = [list(g) for g in (groups or [])]
+    G = len(groups)
+    fgw = torch.empty(n, dtype=torch.float32, device=dev) if want_fg_weight else None
+    score = torch.empty((n, G), dtype=torch.float32, device=dev) if G else None
+    center = None
+    if G and xyz is not None:
+        xyz = _rowmajor(xyz)
+        offsets = offsets.contiguous()
+        assert offsets.numel() == n * c1 * 3
+        center = torch.empty((n, G, 3), dtype=torch.float32, device=dev)
+    flat = [c for g in groups for c in g]
+    rc = load().fsfb_group_sample(_ptr(logits), n, c1, _ptr(xyz), xyz.stride(0) if xyz is not None and n else 3,
+                                  _ptr(offsets), _host_i32([len(g) for g in groups]) if G else None,
+                                  _host_i32(flat) if G else None, G, _ptr(fgw), _ptr(score), _ptr(center), _stream(dev))
+    check(rc, "fsfb_group_sample")
+    return fgw, score, center
+
+
+def frustum_rows(xyz_noaug, lidar2img, mask, fg: torch.Tensor, overlap: torch.Tensor, batch_idx=None):
+    """extract_fg_pts + double_overlap_pts + get_sir_coors (FSF.py:260-308, 357-365).
+    Returns (rows_point int32 [R] — source point of every output row, sir_coors int32 [R,3] = (batch, 0, obj id),
+    n_fg).  R = 0 when no point hits a mask (the caller fakes one object, FSF.py:407-414)."""
+    dev = _need_cuda(xyz_noaug, lidar2img, mask, fg, overlap)
+    idx_fg = compact_indices(fg if fg.dtype == torch.uint8 else fg.to(torch.uint8))
+    n_fg = idx_fg.numel()
+    if n_fg == 0:
+        return torch.empty(0, dtype=torch.int32, device=dev), torch.empty((0, 3), dtype=torch.int32, device=dev), 0
+    lib = load()
+    ov32 = torch.empty(n_fg, dtype=torch.int32, device=dev)
+    check(lib.fsfb_gather_overlap(_ptr(overlap), _ptr(idx_fg), n_fg, _ptr(ov32), _stream(dev)), "fsfb_gather_overlap")
+    csr = build_csr(ov32, 17)
+    off = csr.offsets.tolist()  # 18 ints: the one sync that sizes the output (the reference syncs per overlap count)
+    extra = sum((off[k + 1] - off[k]) * (k - 1) for k in range(2, 17))
+    rows = n_fg + extra
+    xyz_noaug = _rowmajor(xyz_noaug)
+    mask, is_i32 = _mask_args(mask)
+    cams, classes, H, W = mask.shape
+    l2i = lidar2img.to(torch.float32).contiguous()
+    rows_point = torch.empty(rows, dtype=torch.int32, device=dev)
+    sir_coors = torch.empty((rows, 3), dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    if batch_idx is not None:
+        batch_idx = batch_idx.to(torch.int32).contiguous()
+    rc = lib.fsfb_frustum_expand(_ptr(xyz_noaug), xyz_noaug.stride(0), _ptr(l2i), cams, _ptr(mask), is_i32, classes, H, W,
+                                 _ptr(idx_fg), n_fg, _ptr(csr.perm), _ptr(csr.seg), _ptr(csr.offsets), _ptr(batch_idx),
+                                 _ptr(rows_point), _ptr(sir_coors), _ptr(status), _stream(dev))
+    check(rc, "fsfb_frustum_expand")
+    return rows_point, sir_coors, n_fg
+
+
+def weighted_xyz(xyz, weight, rows: Optional[torch.Tensor] = None):
+    dev = _need_cuda(xyz, weight)
+    xyz = _rowmajor(xyz)
+    n_rows = rows.numel() if rows is not None else xyz.size(0)
+    out = torch.empty((n_rows, 4), dtype=torch.float32, device=dev)
+    check(load().fsfb_weighted_xyz(_ptr(xyz), xyz.stride(0) if xyz.size(0) else 3, _ptr(weight.contiguous()), _ptr(rows),
+                                   n_rows, _ptr(out), _stream(dev)), "fsfb_weighted_xyz")
+    return out
+
+
+def cluster_delta(xyz, mean, inv32, rows: Optional[torch.Tensor] = None):
+    """(f_cluster [R,3], center [K,3]) from per-cluster means ([K,3] plain or [K,4] weighted sums)."""
+    dev = _need_cuda(xyz, mean, inv32)
+    xyz = _rowmajor(xyz)
+    mean = mean.contiguous()
+    k, mc = mean.shape
+    n_rows = inv32.numel()
+    center = torch.empty((k, 3), dtype=torch.float32, device=dev)
+    f = torch.empty((n_rows, 3), dtype=torch.float32, device=dev)
+    check(load().fsfb_cluster_delta(_ptr(xyz), xyz.stride(0) if xyz.size(0) else 3, _ptr(rows), n_rows, _ptr(mean), k, mc,
+                                    _ptr(inv32), _ptr(center), _ptr(f), _stream(dev)), "fsfb_cluster_delta")
+    return f, center
+
+
+def encode_preds_2d(anno, obj_coors32, img_w, img_h, num_classes, coor_col: int = 2):
+    """(preds_2d [K, 9], feat [K, 5+num_classes+1]) — get_single_cls_preds_2d + encode_preds_2d (FSF.py:449-504)."""
+    dev = _need_cuda(anno, obj_coors32)
+    anno = anno.contiguous()
+    obj_coors32 = obj_coors32.contiguous()
+    assert obj_coors32.dtype == torch.int32
+    k = obj_coors32.size(0)
+    preds = torch.empty((k, anno.size(1)), dtype=torch.float32, device=dev)
+    feat = torch.empty((k, 5 + num_classes + 1), dtype=torch.float32, device=dev)
+    check(load().fsfb_encode_preds_2d(_ptr(anno), anno.size(0), anno.size(1), _ptr(obj_coors32), obj_coors32.size(1), coor_col,
+                                      k, float(img_w), float(img_h), num_classes, _ptr(preds), _ptr(feat), _stream(dev)),
+          "fsfb_encode_preds_2d")
+    return preds, feat
+
+
+def gather_int_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """Row gather of an int32 [m, c] tensor (a pure copy: routed through the fp32 row-gather kernel bit-for-bit)."""
+    assert src.dtype == torch.int32 and src.dim() == 2
+    return gather_rows(src.contiguous().view(torch.float32), idx).view(torch.int32)
+
+
+def threshold_mask(x: torch.Tensor, col: int, thr: float) -> torch.Tensor:
+    dev = _need_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
+    n = x.size(0)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(load().fsfb_threshold_mask(_ptr(x), n, x.stride(0) if n else x.size(1), col, float(thr), _ptr(mask), _stream(dev)),
+          "fsfb_threshold_mask")
+    return mask
+
+
+def count_mask(counts32: torch.Tensor, inv32: torch.Tensor, min_count: int) -> torch.Tensor:
+    dev = _need_cuda(counts32, inv32)
+    assert counts32.dtype == torch.int32 and inv32.dtype == torch.int32
+    n = inv32.numel()
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    check(load().fsfb_count_mask(_ptr(counts32.contiguous()), _ptr(inv32.contiguous()), n, int(min_count), _ptr(mask),
+                                 _stream(dev)), "fsfb_count_mask")
+    return mask

@@ -42,7 +42,7 @@ extern "C" {
 #define FSFB_NORM_AFFINE 2    /* per-channel scale/shift (eval-mode BN folded)  */
 
 /* ABI version (bumped on any signature change). */
-int fsfb_version(void);
+int fsfb_version(void);  /* currently 2 */
 /* Thread-local text of the last error on this thread ("" if none). */
 const char* fsfb_last_error(void);
 /* Number of kernel launches issued through this library since process start
@@ -61,11 +61,14 @@ int64_t fsfb_launch_count(void);
  * a point with any coordinate outside [0, grid) (or NaN) gets (-1,-1,-1).
  *   pts      dev  [n, row_stride] f32, xyz in columns 0..2
  *   range_min, voxel  host [3] f32 (x,y,z);  grid host [3] i32 (x,y,z)
- *   coors_zyx dev [n,3] i32 (z,y,x) — written
+ *   coors_zyx dev [n,3] i32 (z,y,x) — written.  order_xyz = 1 writes (x,y,z) instead and
+ *   check_range = 0 keeps raw (possibly negative / beyond-grid) coordinates: the ClusterAssigner's
+ *   BEV voxels of voted centres (single_stage_fsd.py:946-950), which are not range-filtered.
  * ------------------------------------------------------------------------- */
 int fsfb_voxelize(const float* pts, int64_t n, int64_t row_stride,
                   const float* range_min, const float* voxel, const int32_t* grid,
-                  int floor_mode, int32_t* coors_zyx, void* stream);
+                  int floor_mode, int order_xyz, int check_range, int32_t* coors_zyx,
+                  void* stream);
 
 /* ---------------------------------------------------------------------------
  * a2  Row ranking = torch.unique(rows, dim=0, return_inverse, return_counts)
@@ -164,12 +167,16 @@ int fsfb_project_sample(const float* xyz, int64_t n, int64_t xyz_stride,
  * the camera with the largest id sum is kept (first maximal camera on ties):
  *   ids_sel dev [n, classes] i32 (i32 so AV2 ids fit), cam_sel dev [n] u8,
  *   fg dev [n] u8 = any id > 0 over all cams/classes (FSF.extract_fg_pts, :299-308);
- *   overlap dev [n] u8 (nullable) = number of (cam,class) slots with id > 0. */
+ *   overlap dev [n] u8 (nullable) = number of (cam,class) slots with id > 0;
+ *   scores dev [n, classes] f32 (nullable) = anno[id-1][anno_col] of the selected ids, 0 for id 0 —
+ *   get_all_cls_preds_2d + encode_preds_2d's score column (FSF.py:506-535, 449-474) with
+ *   anno dev [anno_rows, anno_cols] f32 = mask_anno of the sample.  Every output is nullable. */
 int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
                                const float* lidar2img, int cams,
                                const void* mask, int mask_i32, int classes, int H, int W,
                                int32_t* ids_sel, uint8_t* cam_sel, uint8_t* fg,
-                               uint8_t* overlap, void* stream);
+                               uint8_t* overlap, const float* anno, int anno_rows, int anno_cols,
+                               int anno_col, float* scores, void* stream);
 
 /* ---------------------------------------------------------------------------
  * a5 / a9 / a10 / a16 / a17  Gather-GEMM with fused epilogue — the one dense
@@ -319,8 +326,52 @@ int fsfb_vote_decode(const float* preds, int64_t total, float* out, void* stream
 /* Stable boolean-mask compaction: idx[k] = position of the k-th non-zero mask byte; *count = how many.
  * (points[mask] of FSF.extract_fg_pts, FSF.py:299-308; group_sample, single_stage_fsd.py:828-850) */
 int fsfb_compact_workspace_bytes(int64_t n, size_t* bytes);
+/* mask[i] = x[i*stride + col] > thr  (SingleStageFSD.get_fg_mask, single_stage_fsd.py:753-757) */
+int fsfb_threshold_mask(const float* x, int64_t n, int64_t stride, int col, float thr, uint8_t* mask, void* stream);
+/* mask[i] = counts[inv[i]] >= min_count  (filter_almost_empty, single_stage_fsd.py:31-35) */
+int fsfb_count_mask(const int32_t* counts, const int32_t* inv, int64_t n, int min_count, uint8_t* mask, void* stream);
 int fsfb_compact_indices(const uint8_t* mask, int64_t n, int32_t* idx, int32_t* count, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a11 / a13 / a15  Query-generation helpers.
+ * ------------------------------------------------------------------------- */
+
+/* FSF.get_point_fg_weights (projects/mmdet3d_plugin/models/detectors/FSF.py:345-355) and
+ * SingleStageFSD.group_sample (models/detectors/single_stage_fsd.py:802-865) in one pass:
+ *   p = softmax(logits[i, 0:C+1]);  fg_weight[i] = 1 - p[C]
+ *   group_score[i,g] = sum_{c in group g} p[c];   w = offset weights ('max' mode, :868-874)
+ *   group_center[i,g,:] = xyz[i] + sum_{c in g} w_c * offsets[i, c, :]
+ * group_lens host [n_groups], group_classes host [sum lens] (class indices).  Outputs nullable. */
+int fsfb_group_sample(const float* logits, int64_t n, int num_classes_with_bg, const float* xyz, int64_t xyz_stride,
+                      const float* offsets, const int32_t* group_lens, const int32_t* group_classes, int n_groups,
+                      float* fg_weight, float* group_score, float* group_center, void* stream);
+
+/* FSF.extract_fg_pts + double_overlap_pts + get_sir_coors (FSF.py:260-308, 357-365).
+ * gather_overlap: ov32[j] = overlap[idx_fg[j]] (input of fsfb_csr_build with m = 17 groups).
+ * frustum_expand: given that CSR (perm/seg/offsets over overlap counts), writes for every output row
+ * the source point (rows_point, index into the full point array) and sir_coors (batch, 0, object id)
+ * in the reference's row order; total rows = n_fg + sum_k cnt_k*(k-1).  status bit 2 = a point's
+ * re-sampled id count disagrees with its overlap count (or exceeds 16). */
+int fsfb_gather_overlap(const uint8_t* overlap, const int32_t* idx_fg, int64_t n_fg, int32_t* ov32, void* stream);
+int fsfb_frustum_expand(const float* xyz, int64_t xyz_stride, const float* lidar2img, int cams, const void* mask,
+                        int mask_i32, int classes, int H, int W, const int32_t* idx_fg, int64_t n_fg,
+                        const int32_t* perm, const int32_t* seg, const int32_t* offsets, const int32_t* batch_idx,
+                        int32_t* rows_point, int32_t* sir_coors, int32_t* status, void* stream);
+
+/* get_cluster_delta_weighted (FSF.py:313-329): out4[r] = (xyz*w, w), w = clamp(weight[src], 1e-5). */
+int fsfb_weighted_xyz(const float* xyz, int64_t xyz_stride, const float* weight, const int32_t* rows, int64_t n_rows,
+                      float* out4, void* stream);
+/* center[k] = mean[k,:3] / mean[k,3] (mean_cols == 4) or mean[k,:3] (== 3);
+ * f_cluster[r] = xyz[src] - center[inv[r]]   (FSF.py:324-329; single_stage_fsd.py:460-462) */
+int fsfb_cluster_delta(const float* xyz, int64_t xyz_stride, const int32_t* rows, int64_t n_rows, const float* mean,
+                       int64_t k, int mean_cols, const int32_t* inv, float* center, float* f_cluster, void* stream);
+
+/* get_single_cls_preds_2d + encode_preds_2d (FSF.py:449-504): preds_2d dev [k, anno_cols],
+ * feat dev [k, 5 + num_classes + 1] = (bbox / (w,h,w,h), score, one-hot category). */
+int fsfb_encode_preds_2d(const float* anno, int anno_rows, int anno_cols, const int32_t* obj_coors, int coor_stride,
+                         int coor_col, int64_t k, float img_w, float img_h, int num_classes, float* preds_2d,
+                         float* feat, void* stream);
 
 #ifdef __cplusplus
 }

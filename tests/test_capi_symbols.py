@@ -40,7 +40,7 @@ def test_bad_arguments_fail_without_gpu():
     need = ctypes.c_size_t(0)
     assert lib.fsfb_rank_workspace_bytes(10, 1 << 40, ctypes.byref(need)) == _capi.ERR_BADARG
     assert b"2^32" in lib.fsfb_last_error()
-    assert lib.fsfb_voxelize(None, -1, 3, None, None, None, 0, None, None) == _capi.ERR_BADARG
+    assert lib.fsfb_voxelize(None, -1, 3, None, None, None, 0, 0, 1, None, None) == _capi.ERR_BADARG
     assert lib.fsfb_csr_workspace_bytes(100, 10, ctypes.byref(need)) == 0 and need.value > 0
 
 

@@ -1,0 +1,168 @@
+"""End-to-end parity of one FSF frame (fullysparsefusion_b200.fsf.FSF) against the CPU oracle, stage by stage.
+
+Each stage's oracle is fed the GPU path's inputs to that stage ("teacher forcing"), so a threshold flip in
+one stage cannot cascade: discrete outputs (voxel/cluster indices, foreground rows, object ids, CCL
+labels) are compared bit-exact, features within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from fullysparsefusion_b200 import fsf as FSFM
+from fullysparsefusion_b200 import synth
+from oracle import fsf_oracle as O
+from oracle import fsf_oracle_frame as OF
+from oracle import fsf_oracle_models as OM
+from tests.test_gpu_modules import randomize, sd_np
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 5e-5
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(N(a) if torch.is_tensor(a) else a, b, rtol=rtol, atol=atol)
+
+
+def head_oracle(x, sd, prefix):
+    """SparseClusterHeadV2.forward: shared MLP (LN, eps 1e-5, relu) + 5 task MLPs (LN, gelu, head)."""
+    h = O.mlp_from_state_dict(x, sub(sd, prefix + "shared_mlp."), "ln", "relu", 1e-5)
+    out = {k: O.mlp_from_state_dict(h, sub(sd, f"{prefix}task_heads.0.{k}."), "ln", "gelu", 1e-5)
+           for k in ("center", "dim", "rot", "vel", "score")}
+    return out["score"], np.concatenate([out["center"], out["dim"], out["rot"], out["vel"]], 1)
+
+
+@pytest.fixture(scope="module")
+def frame(cuda):
+    n, H, W = 2500, 90, 160
+    pts = synth.ring_points(n, sweeps=2, seed=21)
+    mask = synth.mask_planes(6, 10, H, W, seed=21, overlap=True)
+    anno = synth.mask_anno(mask, seed=21)
+    l2i = synth.lidar2img(6, H, W)
+    torch.manual_seed(0)
+    model = randomize(FSFM.FSF(), seed=1)
+    with torch.no_grad():  # un-zero the zero-initialised enhancement head so the stage is exercised
+        model.segmentor_updated_mlp[-1].weight.normal_(0, 0.05)
+        model.segmentor_updated_mlp[-1].bias.normal_(0, 0.05)
+        model.segmentation_head.conv_seg.bias.copy_(torch.linspace(-1.0, 1.0, 11))
+    model = model.to(cuda)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    st = model(T(pts), T(mask), T(anno), T(l2i))
+    torch.cuda.synchronize()
+    return dict(pts=pts, mask=mask, anno=anno, l2i=l2i, st=st, sd=sd_np(model), model=model)
+
+
+def test_segment_stage(frame):
+    st, sd, pts = frame["st"], frame["sd"], frame["pts"]
+    cfg = FSFM.NUSC
+    coors = np.concatenate([np.zeros((len(pts), 1), np.int64),
+                            O.voxelize(pts, cfg["seg_voxel_size"], cfg["point_cloud_range"], 0).astype(np.int64)], 1)
+    assert np.array_equal(N(st["coors4"]), coors)
+    vf, vc, inv = OM.dynamic_scatter_vfe(pts[:, :5], coors, sub(sd, "voxel_encoder."), cfg["seg_voxel_size"], cfg["point_cloud_range"])
+    assert np.array_equal(N(st["voxel_coors"]), vc) and np.array_equal(N(st["voxel2point_inds"]), inv)
+    close(st["vfe_feats"], vf)
+    m = frame["model"].backbone_unet
+    want, _, _ = OM.simple_sparse_unet(N(st["vfe_feats"]), vc, sub(sd, "backbone_unet."), cfg["sparse_shape"], m.encoder_channels,
+                                       m.encoder_paddings, ((512, 512, 256), (256, 256, 128), (128, 128, 128), (128, 128, 128), (128, 128, 128)))
+    close(st["voxel_feats"], want, rtol=3e-4, atol=2e-4)          # 34 chained tensor-core layers
+    neck, mask = O.voxel2point_neck(pts[:, :5], coors, N(st["voxel_feats"]), inv, cfg["seg_voxel_size"], cfg["point_cloud_range"])
+    assert mask.all() and np.array_equal(N(st["pts_lidar_feats"]), neck)
+
+
+def test_enhance_stage(frame):
+    st, sd = frame["st"], frame["sd"]
+    scores, ids, cam, fg, ov = OF.img_scores(frame["pts"][:, 5:8], frame["mask"], frame["l2i"], frame["anno"])
+    assert np.array_equal(N(st["fg"]).astype(bool), fg) and np.array_equal(N(st["overlap"]), ov) and np.array_equal(N(st["cam_sel"]), cam)
+    assert np.array_equal(N(st["img_scores"]), scores)
+    assert fg.mean() > 0.05
+    img = O.mlp_from_state_dict(scores, sub(sd, "segmentor_updated_mlp."), "ln", "gelu", 1e-3)
+    close(st["seg_feats"], (img + N(st["pts_lidar_feats"])).astype(np.float32))
+    logits, votes = OM.vote_seg_head(N(st["seg_feats"]), sub(sd, "segmentation_head."))
+    close(st["seg_logits"], logits)
+    close(st["seg_vote_preds"], votes)
+    assert np.array_equal(N(st["offsets"]), O.decode_vote_targets(N(st["seg_vote_preds"])))
+
+
+def test_frustum_stage(frame):
+    st, sd, pts = frame["st"], frame["sd"], frame["pts"]
+    ids = O.points_in_mask(pts[:, 5:8], frame["mask"], frame["l2i"])
+    rows, obj = OF.frustum_rows(ids)
+    assert np.array_equal(N(st["frustum_rows"]), rows)
+    sir_coors = np.stack([np.zeros_like(obj), np.zeros_like(obj), obj], 1)
+    assert np.array_equal(N(st["frustum_sir_coors"]), sir_coors)
+    assert len(rows) > int(N(st["fg"]).sum()) > 0                    # overlap duplication happened
+    fgw = OF.point_fg_weights(N(st["seg_logits"]))
+    close(st["point_fg_weights"], fgw, atol=1e-6)
+    f_cluster, center, ccoors, _ = OF.cluster_delta_weighted(pts[rows, :3], sir_coors, N(st["point_fg_weights"])[rows])
+    close(st["frustum_f_cluster"], f_cluster)
+    close(st["frustum_obj_centers"], center)
+    assert np.array_equal(N(st["frustum_obj_coors"]), ccoors)
+    assert np.array_equal(N(st["frustum_pts"]), pts[rows, :5]) and np.array_equal(N(st["frustum_pts_feats"]), N(st["seg_feats"])[rows])
+    _, cl, oc = OM.sir(pts[rows, :5], N(st["seg_feats"])[rows], sir_coors, N(st["frustum_f_cluster"]), sub(sd, "frustum_sir."), 3, [20, 20, 4])
+    assert np.array_equal(oc, ccoors)
+    close(st["frustum_obj_feats"][:, :768], cl)
+    preds, enc = OF.encode_preds_2d(frame["anno"], ccoors[:, 2], frame["mask"].shape[-1], frame["mask"].shape[-2], 10)
+    assert np.array_equal(N(st["frustum_preds_2d"]), preds) and np.array_equal(N(st["frustum_enc_2d"]), enc)
+    img = O.mlp_from_state_dict(enc, sub(sd, "encode_2d_mlp."), "ln", "gelu", 1e-3)
+    close(st["frustum_obj_feats"][:, 768:], img)
+    cls, reg = head_oracle(N(st["frustum_obj_feats"]), sd, "frustum_obj_head.")
+    close(st["frustum_cls"], cls, rtol=2e-4, atol=1e-4)
+    close(st["frustum_reg"], reg, rtol=2e-4, atol=1e-4)
+
+
+def test_fsd_stage(frame):
+    st, sd, pts = frame["st"], frame["sd"], frame["pts"]
+    cfg = FSFM.NUSC
+    data = dict(p=pts[:, :5], l=N(st["seg_logits"]), v=N(st["seg_vote_preds"]), f=N(st["seg_feats"]), o=N(st["offsets"]))
+    pre, uniq, _ = OF.pre_voxelize(data, pts[:, :5], cfg["pre_voxelization_size"], cfg["point_cloud_range"])
+    assert np.array_equal(N(st["pre_coors"]), uniq)
+    for k, name in (("p", "pre_points"), ("l", "pre_logits"), ("v", "pre_votes"), ("f", "pre_feats"), ("o", "pre_offsets")):
+        close(st[name], pre[k])
+    groups = frame["model"].groups
+    score, centers = OF.group_sample(N(st["pre_logits"]), N(st["pre_points"]), N(st["pre_offsets"]), groups, cfg["score_thresh"])
+    close(st["group_score"], score, atol=1e-6)
+    close(st["group_centers"], centers, atol=1e-5)
+    g_score, g_centers = N(st["group_score"]), N(st["group_centers"])
+    rows_all, inds_all = [], []
+    for g in range(len(groups)):
+        idx = np.flatnonzero(g_score[:, g] > np.float32(cfg["score_thresh"][g]))
+        if len(idx) == 0:
+            idx = np.zeros(1, np.int64)
+        labels, keep = OF.cluster_assign_single(g_centers[idx, g], cfg["cluster_voxel_size"][g], cfg["point_cloud_range"],
+                                                cfg["connected_dist"][g], cfg["min_points"])
+        rows_all.append(idx[keep])
+        inds_all.append(np.stack([np.full(len(keep), g), np.zeros(len(keep), np.int64), labels], 1))
+    rows_all, inds_all = np.concatenate(rows_all), np.concatenate(inds_all)
+    assert np.array_equal(N(st["fsd_rows"]), rows_all)
+    assert np.array_equal(N(st["pts_cluster_inds"]), inds_all)          # CCL labels bit-exact through the whole assigner
+    assert len(rows_all) > 50
+    # extract_feat
+    center_preds = N(st["fsd_center_preds"])
+    cxyz, ccoors, cinv = O.scatter_v2(center_preds, inds_all, "avg")
+    close(st["fsd_obj_centers"], cxyz)
+    close(st["fsd_f_cluster"], (N(st["fsd_pts"])[:, :3] - cxyz[cinv]).astype(np.float32))
+    want_feats = np.concatenate([N(st["pre_logits"])[rows_all], N(st["pre_votes"])[rows_all], N(st["pre_feats"])[rows_all]], 1)
+    assert np.array_equal(N(st["fsd_pts_feats"]), want_feats)
+    _, cl, oc = OM.sir(N(st["fsd_pts"]), want_feats, inds_all, N(st["fsd_f_cluster"]), sub(sd, "backbone."), 3, [20, 20, 4])
+    assert np.array_equal(N(st["fsd_obj_coors"]), oc)
+    close(st["fsd_obj_feats"], cl)
+    cls, reg = head_oracle(N(st["fsd_obj_feats"]), sd, "bbox_head.")
+    close(st["fsd_cls"], cls, rtol=2e-4, atol=1e-4)
+    close(st["fsd_reg"], reg, rtol=2e-4, atol=1e-4)
+
+
+def test_combine_stage(frame):
+    st, sd = frame["st"], frame["sd"]
+    fr = O.mlp_from_state_dict(N(st["frustum_obj_feats"]), sub(sd, "combine_frustum_feat_mlp."), "ln", "gelu", 1e-3)
+    fs = O.mlp_from_state_dict(N(st["fsd_obj_feats"]), sub(sd, "combine_fsd_feat_mlp."), "ln", "gelu", 1e-3)
+    close(st["obj_feats"], np.concatenate([fr, fs], 0), rtol=2e-4, atol=1e-4)
+    kf = len(fr)
+    fc = N(st["fsd_obj_coors"])
+    assert np.array_equal(N(st["obj_coors"])[kf:], np.stack([fc[:, 1], fc[:, 0], fc[:, 2] + 1000], 1))
+    assert st["obj_cls"].shape == (kf + len(fs), 10) and st["obj_reg"].shape == (kf + len(fs), 10)
