@@ -4,13 +4,14 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--points P] [--sweeps S]
 
 One "step" = one frame (P points x 6 cameras, default the 10-sweep 300k-point configuration the
-BASELINE.json metric is quoted on) through every stage of fullysparsefusion_b200.frame.  Frames are
+BASELINE.json metric is quoted on) through every stage of fullysparsefusion_b200.fsf.FSF (segment, enhance, frustum, fsd, combine).  Frames are
 sharded one per GPU per step (weak scaling, no data-path collective — SURVEY.md §8e).
 
 `value`  frames/s with the frame's inputs already resident in HBM (device-timed, max over ranks).
 `e2e`    frames/s through the same public API starting from pinned HOST buffers: the H2D copy of
          points / id planes / lidar2img and a D2H read of the result are inside the timed region.
-`roofline`  the dominant HBM-bound stage: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json.
+`roofline`  the dominant scatter/projection op: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json;
+            `kernels` lists every timed op family (GB/s, and TFLOP/s for the tensor-core GEMMs).
 `cpu_baseline`  the torch-CPU port of the reference path (oracle/fsf_torch_cpu.py) on this box's cores.
 `--impl reference` times that CPU port alone (the reference cannot be installed: DESIGN.md).
 """
@@ -36,8 +37,8 @@ FALLBACK_HBM_GBS = 6650.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=300000)
     ap.add_argument("--sweeps", type=int, default=10)
@@ -86,39 +87,94 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def run_cpu_port(args, steps: int, warmup: int):
+def make_model(seed: int = 0):
+    """Random-init FSF (stock nuScenes architecture).  The segmentation logits are calibrated so that the
+    synthetic scene behaves like a busy real one: ~5 % of voxels per class pass the 0.1 group-score
+    threshold (a constant-logit random head would pass none or all of them)."""
+    import torch
+
+    from fullysparsefusion_b200 import fsf as FSFM
+
+    torch.manual_seed(seed)
+    model = FSFM.FSF()
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in model.modules():  # non-trivial eval-mode BN statistics
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
+    return model
+
+
+def calibrate_seg_head(model, logits) -> None:
+    """Rescale conv_seg so foreground logits have sigma 1.5 around 0 and background sits at +4.7."""
+    import torch
+
+    with torch.no_grad():
+        head = model.segmentation_head.conv_seg
+        fgl = logits[:, :-1]
+        std, mean = fgl.std(0).clamp(min=1e-3).cpu(), fgl.mean(0).cpu()
+        scale = torch.cat([1.5 / std, torch.ones(1)])
+        head.weight.mul_(scale[:, None].to(head.weight.device))
+        bias = head.bias.cpu() * scale
+        bias[:-1] -= mean * scale[:-1]
+        bias[-1] = 4.7 - float(logits[:, -1].mean())
+        head.bias.copy_(bias.to(head.bias.device))
+    model.segmentation_head.refresh()
+
+
+def synth_frame(points: int, sweeps: int, seed: int):
+    import torch
+
+    from fullysparsefusion_b200 import synth
+
+    mask = synth.mask_planes(seed=seed)
+    return dict(points=torch.from_numpy(synth.ring_points(points, sweeps=sweeps, seed=seed)), mask=torch.from_numpy(mask),
+                anno=torch.from_numpy(synth.mask_anno(mask, seed=seed)), lidar2img=torch.from_numpy(synth.lidar2img()))
+
+
+def run_cpu_port(args, steps: int, warmup: int, model=None, frame=None):
     """Time the torch-CPU port of the reference path; one step = one full frame on all host cores."""
     import torch
 
-    from fullysparsefusion_b200 import frame
     from oracle import fsf_torch_cpu as P
 
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
-    host = frame.synth_frame_host(args.points, args.sweeps, seed=0, pin=False)
-    stages, _ = P.build_stages(host)
-    per_stage = {name: 0.0 for name, _ in stages}
-    for _ in range(warmup):
-        for _, fn in stages:
-            fn()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for name, fn in stages:
-            t = time.perf_counter()
-            fn()
-            per_stage[name] += time.perf_counter() - t
-    dt = (time.perf_counter() - t0) / steps
+    if model is None:
+        model = make_model()
+    model = model.cpu()
+    frame = frame or synth_frame(args.points, args.sweeps, seed=0)
+    cpu = P.CpuFSF(model)
+    per_stage = {}
+    n_run = 0
+    t_total = 0.0
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            stages, st = cpu.stages(frame["points"], frame["mask"], frame["anno"], frame["lidar2img"])
+            t0 = time.perf_counter()
+            for name, fn in stages:
+                t = time.perf_counter()
+                fn()
+                if it >= warmup:
+                    per_stage[name] = per_stage.get(name, 0.0) + time.perf_counter() - t
+            if it == 0 and not getattr(model, "_calibrated", False):
+                calibrate_seg_head(model, st["seg_logits"])
+                model._calibrated = True
+            if it >= warmup:
+                t_total += time.perf_counter() - t0
+                n_run += 1
+    dt = t_total / n_run
     return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} full frame(s) of the same workload after {warmup} warm-up, torch {torch.__version__} CPU ops, "
-                      f"{cores} threads", "ms_per_frame": dt * 1e3,
-            "stage_ms": {k: v / steps * 1e3 for k, v in per_stage.items()}}
+            "sample": f"{n_run} full frame(s) of the same workload after {warmup} warm-up, torch {torch.__version__} CPU ops "
+                      f"+ scipy CCL, {cores} threads", "ms_per_frame": dt * 1e3,
+            "stage_ms": {k: v / n_run * 1e3 for k, v in per_stage.items()}}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 2)), 1
     base = run_cpu_port(args, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_frame"], "higher_is_better": True,
@@ -131,6 +187,13 @@ def main_reference(args):
     return 0
 
 
+def resolve(v):
+    """Profiler byte/flop entries: int, or (device scalar, multiplier, constant)."""
+    if isinstance(v, tuple):
+        return int(v[0].item()) * v[1] + v[2]
+    return v
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -139,7 +202,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from fullysparsefusion_b200 import _capi, frame
+    from fullysparsefusion_b200 import _capi, ops
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU port)")
@@ -152,12 +215,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _capi.load()
 
-    # three distinct frames rotate through the steps: 3 x 96 MB of inputs (+ ~1 GB of intermediates per
-    # frame) exceed the 126 MB L2, so no step starts on a warm cache
+    # three distinct frames rotate through the steps: 3 x 96 MB of inputs plus > 1 GB of per-frame
+    # intermediates exceed the 126 MB L2, so no step starts on a warm cache
     n_frames = 3
-    hosts = [frame.synth_frame_host(args.points, args.sweeps, seed=rank * 16 + i) for i in range(n_frames)]
-    frames = [frame.frame_to_device(h, dev, seed=i) for i, h in enumerate(hosts)]
-    pipes = [frame.build_stages(f) for f in frames]
+    hosts = [{k: v.pin_memory() for k, v in synth_frame(args.points, args.sweeps, seed=rank * 16 + i).items()}
+             for i in range(n_frames)]
+    frames = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
+    model = make_model().to(dev)
+    with torch.no_grad():
+        st0 = model(frames[0]["points"], frames[0]["mask"], frames[0]["anno"], frames[0]["lidar2img"])
+        calibrate_seg_head(model, st0["seg_logits"])
+        del st0
     torch.cuda.synchronize()
 
     def barrier():
@@ -165,8 +233,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step(i, events=None):
-        stages, _ = pipes[i % n_frames]
+        f = frames[i % n_frames]
+        stages, st = model.stages(f["points"], f["mask"], f["anno"], f["lidar2img"])
         for name, fn in stages:
             if events is not None:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -176,49 +247,51 @@ def main():
                 events.append((name, a, b))
             else:
                 fn()
+        last["st"] = st
+        return st
 
     # ---- device-resident throughput ------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()  # nvidia-smi needs ~0.2 s to start: begin before the warm-up so samples cover the timed region
     t_w = time.perf_counter()
-    for i in range(args.warmup):
-        step(i)
-    while time.perf_counter() - t_w < 0.5:  # keep the GPU under load until the sampler is running
-        step(0)
-    barrier()
-    events = []
-    launches0 = _capi.launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_start.record()
-    for i in range(args.steps):
-        step(i, events)
-    t_end.record()
-    barrier()
-    launches = _capi.launch_count() - launches0
-    ms_total = t_start.elapsed_time(t_end)
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i)
+        while time.perf_counter() - t_w < 0.5:
+            step(0)
+        barrier()
+        events = []
+        ops.PROFILER = []
+        launches0 = _capi.launch_count()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_start.record()
+        for i in range(args.steps):
+            step(i, events)
+        t_end.record()
+        barrier()
+        prof, ops.PROFILER = ops.PROFILER, None
+        launches = _capi.launch_count() - launches0
+        ms_total = t_start.elapsed_time(t_end)
 
-    # ---- end to end from pinned host buffers ------------------------------------------------------
-    def e2e_step(i):
-        h = hosts[i % n_frames]
-        f = frames[i % n_frames]
-        f.points.copy_(h["points"], non_blocking=True)
-        f.mask.copy_(h["mask"], non_blocking=True)
-        f.lidar2img.copy_(h["lidar2img"], non_blocking=True)
-        step(i)
-        _, st = pipes[i % n_frames]
-        return st["fg"].cpu(), st["pre_coors"].size(0)
+        # ---- end to end from pinned host buffers --------------------------------------------------
+        def e2e_step(i):
+            h, f = hosts[i % n_frames], frames[i % n_frames]
+            for k in ("points", "mask", "anno", "lidar2img"):
+                f[k].copy_(h[k], non_blocking=True)
+            st = step(i)
+            return st["obj_cls"].cpu(), st["obj_reg"].cpu(), st["obj_centers"].cpu()   # the frame's result (D2H)
 
-    for i in range(max(3, args.warmup // 2)):
-        e2e_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        fg_host, _ = e2e_step(i)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            res = e2e_step(i)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -231,34 +304,58 @@ def main():
         for name, a, b in events:
             per_stage.setdefault(name, []).append(a.elapsed_time(b))
         stage_ms = {k: sum(v) / len(v) for k, v in per_stage.items()}
-        _, st = pipes[0]
-        alg = frame.algorithmic_bytes(frames[0], st)
+        kern = {}
+        for name, a, b, nb, fl in prof:
+            k = kern.setdefault(name, dict(ms=0.0, bytes=0, flops=0, calls=0))
+            k["ms"] += a.elapsed_time(b)
+            k["bytes"] += resolve(nb)
+            k["flops"] += resolve(fl)
+            k["calls"] += 1
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (FALLBACK_HBM_GBS, "fallback")
-        stage_gbs = {k: alg[k] / (stage_ms[k] * 1e-3) / 1e9 for k in stage_ms if k in alg}
-        # dominant = the HBM-bound stage with the most time (scatter + projection are the named targets)
-        dom = max(("vfe_scatter", "pre_voxelize", "project", "neck"), key=lambda k: stage_ms.get(k, 0.0))
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": stage_gbs[dom], "peak": peak, "peak_source": peak_src,
-                    "unit": "GB/s", "frac": stage_gbs[dom] / peak, "traffic": None,
-                    "stage_gbs": {k: round(v, 1) for k, v in stage_gbs.items()},
-                    "stage_frac": {k: round(v / peak, 4) for k, v in stage_gbs.items()}}
-        h2d = frames[0].nbytes()
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        table = {}
+        for name, k in kern.items():
+            sec = k["ms"] * 1e-3
+            table[name] = {"ms_per_frame": round(k["ms"] / args.steps, 4), "calls_per_frame": k["calls"] // args.steps,
+                           "GB/s": round(k["bytes"] / sec / 1e9, 1), "hbm_frac": round(k["bytes"] / sec / 1e9 / peak, 4)}
+            if k["flops"]:
+                table[name]["TFLOP/s"] = round(k["flops"] / sec / 1e12, 2)
+                table[name]["tensor_frac_of_bf16_sustained"] = round(k["flops"] / sec / 1e12 / tpeak, 4)
+        # the metric names the scatter + projection kernels: the dominant one (most time) carries `roofline`
+        dom = max(("segment_reduce", "project_sample_select", "gather_rows"), key=lambda n: kern.get(n, {"ms": 0})["ms"])
+        d = kern[dom]
+        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "launches_timed": d["calls"],
+                    "note": "algorithmic bytes / CUDA-event time of every launch of this op in the timed region"}
+        st = last["st"]
+        h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
+        d2h = sum(r.numel() * r.element_size() for r in res)
         line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core GEMMs: 3xTF32)",
+                "data": "synthetic",
                 "config": {**workload(args), "l2": "3 distinct frames rotate (288 MB of inputs > 126 MB L2)",
-                           "stages": [n for n, _ in pipes[0][0]], "voxels": int(st["voxel_coors"].size(0)),
-                           "pre_voxels": int(st["pre_coors"].size(0))},
+                           "stages": list(stage_ms), "voxels": int(st["voxel_coors"].size(0)),
+                           "pre_voxels": int(st["pre_coors"].size(0)), "frustum_rows": int(st["frustum_rows"].numel()),
+                           "frustum_queries": int(st["frustum_obj_coors"].size(0)), "fsd_rows": int(st["fsd_rows"].numel()),
+                           "fsd_queries": int(st["fsd_obj_coors"].size(0)),
+                           "scope": "FSF.simple_test through combine_frustum_and_fsd (refine stage + NMS not included)"},
                 "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": int(fg_host.numel())},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": table,
                 "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}}
         if world == 1 and not args.no_cpu_baseline:
-            base = run_cpu_port(args, steps=3, warmup=1)
+            import copy
+
+            cpu_model = copy.deepcopy(model).cpu()
+            cpu_model._calibrated = True  # same calibrated weights as the GPU arm
+            base = run_cpu_port(args, steps=1, warmup=0, model=cpu_model, frame={k: v.clone() for k, v in hosts[0].items()})
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:

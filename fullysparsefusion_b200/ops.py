@@ -18,6 +18,32 @@ from ._capi import REDUCE_MAX, REDUCE_MEAN, REDUCE_SUM, check, load
 _MODES = {"sum": REDUCE_SUM, "add": REDUCE_SUM, "mean": REDUCE_MEAN, "avg": REDUCE_MEAN, "max": REDUCE_MAX}
 
 
+# Optional per-op CUDA-event timing (bench.py): set PROFILER to a list to collect
+# (op family, start event, end event, algorithmic bytes, algorithmic flops) for the HBM-/tensor-bound ops.
+PROFILER = None
+
+
+class _Prof:
+    __slots__ = ("name", "nbytes", "flops", "a")
+
+    def __init__(self, name: str, nbytes=0, flops=0):
+        # nbytes / flops: ints, or (device scalar tensor, multiplier, constant) resolved by the reader after the run
+        self.name, self.nbytes, self.flops, self.a = name, nbytes, flops, None
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.a is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            PROFILER.append((self.name, self.a, b, self.nbytes, self.flops))
+        return False
+
+
 def _need_cuda(*ts: torch.Tensor) -> torch.device:
     dev = None
     for t in ts:
@@ -150,9 +176,10 @@ def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Opt
     uniq = torch.empty((n, d), dtype=rows.dtype, device=dev) if return_unique else None
     counts = torch.empty(n, dtype=torch.int32, device=dev) if return_counts else None
     meta = torch.empty(2, dtype=torch.int32, device=dev)  # [num_unique, status]
-    rc = lib.fsfb_rank_rows(_ptr(rows), int(rows.dtype == torch.int64), n, d, _host_i64(lo), _host_i64(ext),
-                            _ptr(ws), ws.numel(), _ptr(inv32), _ptr(inv64), _ptr(uniq), n, _ptr(counts),
-                            C.c_void_p(meta.data_ptr()), C.c_void_p(meta.data_ptr() + 4), _stream(dev))
+    with _Prof("rank_rows", n * d * rows.element_size() + n * (8 if inv64 is not None else 4)):
+        rc = lib.fsfb_rank_rows(_ptr(rows), int(rows.dtype == torch.int64), n, d, _host_i64(lo), _host_i64(ext),
+                                _ptr(ws), ws.numel(), _ptr(inv32), _ptr(inv64), _ptr(uniq), n, _ptr(counts),
+                                C.c_void_p(meta.data_ptr()), C.c_void_p(meta.data_ptr() + 4), _stream(dev))
     check(rc, "fsfb_rank_rows")
     m, status = meta.tolist()  # the one sync torch.unique also pays (output size)
     if status & 1:
@@ -191,8 +218,9 @@ def build_csr(index: torch.Tensor, m: int) -> SegmentCSR:
     offsets = torch.empty(m + 1, dtype=torch.int32, device=dev)
     perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     seg = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    rc = lib.fsfb_csr_build(_ptr(index), int(index.dtype == torch.int64), n, m, _ptr(offsets), _ptr(perm),
-                            _ptr(seg), _ptr(ws), ws.numel(), _stream(dev))
+    with _Prof("csr_build", index.element_size() * n + 8 * n + 4 * (m + 1)):
+        rc = lib.fsfb_csr_build(_ptr(index), int(index.dtype == torch.int64), n, m, _ptr(offsets), _ptr(perm),
+                                _ptr(seg), _ptr(ws), ws.numel(), _stream(dev))
     check(rc, "fsfb_csr_build")
     return SegmentCSR(offsets, perm[:n], seg[:n], n, m)
 
@@ -219,9 +247,10 @@ def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax
     check(lib.fsfb_segment_reduce_workspace_bytes(n, c, int(want_arg), C.byref(need)),
           "fsfb_segment_reduce_workspace_bytes")
     ws = _ws(need.value, dev)
-    rc = lib.fsfb_segment_reduce(_ptr(feat), n, c, feat.stride(0) if n else c, _ptr(csr.perm), _ptr(csr.seg),
-                                 _ptr(csr.offsets), csr.m, mode_id, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
-                                 _stream(dev))
+    with _Prof("segment_reduce", 4 * n * c + 8 * n + 4 * csr.m * c + (8 * csr.m * c if want_arg else 0)):
+        rc = lib.fsfb_segment_reduce(_ptr(feat), n, c, feat.stride(0) if n else c, _ptr(csr.perm), _ptr(csr.seg),
+                                     _ptr(csr.offsets), csr.m, mode_id, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
+                                     _stream(dev))
     check(rc, "fsfb_segment_reduce")
     return (out, arg) if return_argmax else out
 
@@ -239,8 +268,9 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0, out: Op
     assert out.size(0) == n and out.size(1) >= c and out.stride(1) == 1
     if n == 0 or c == 0:
         return out
-    rc = load().fsfb_gather_rows(_ptr(src), src.size(0), c, _ptr(idx), int(idx.dtype == torch.int64), n,
-                                 float(fill), _ptr(out), out.stride(0), _stream(dev))
+    with _Prof("gather_rows", 2 * 4 * n * c + idx.element_size() * n):
+        rc = load().fsfb_gather_rows(_ptr(src), src.size(0), c, _ptr(idx), int(idx.dtype == torch.int64), n,
+                                     float(fill), _ptr(out), out.stride(0), _stream(dev))
     check(rc, "fsfb_gather_rows")
     return out
 
@@ -313,9 +343,11 @@ def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torc
         anno = anno.contiguous()
         a_rows, a_cols = anno.shape
         scores = torch.empty((n, classes), dtype=torch.float32, device=dev)
-    rc = load().fsfb_project_sample_select(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask),
-                                           is_i32, classes, H, W, _ptr(ids), _ptr(cam), _ptr(fg), _ptr(ov),
-                                           _ptr(anno), a_rows, a_cols, int(anno_col), _ptr(scores), _stream(dev))
+    out_b = (4 * classes if want_ids else 0) + 2 + (1 if want_overlap else 0) + (4 * classes if anno is not None else 0)
+    with _Prof("project_sample_select", n * (12 + cams * classes * mask.element_size() + out_b)):
+        rc = load().fsfb_project_sample_select(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask),
+                                               is_i32, classes, H, W, _ptr(ids), _ptr(cam), _ptr(fg), _ptr(ov),
+                                               _ptr(anno), a_rows, a_cols, int(anno_col), _ptr(scores), _stream(dev))
     check(rc, "fsfb_project_sample_select")
     out = (ids, cam, fg)
     if want_overlap:
@@ -395,7 +427,17 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
     if simt:
         assert w.raw is not None, "gemm_prepack(..., keep_raw=True) needed for the SIMT cross-check"
         check(lib.fsfb_gather_gemm_simt(*args, _ptr(w.raw), *tail), "fsfb_gather_gemm_simt")
+        return out
+    if nbr is None:
+        prof = _Prof("gather_gemm_linear", 4 * rows * (w.cin + w.cout) + 4 * w.cin * w.cout, 2 * rows * w.cin * w.cout)
     else:
+        pairs = getattr(nbr, "_fsfb_pairs", None)
+        if PROFILER is not None and pairs is None:   # profiling only: exact pair count of this rulebook, kept on device
+            pairs = (nbr >= 0).sum()
+            nbr._fsfb_pairs = pairs
+        prof = _Prof("gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
+                     (pairs, 2 * w.cin * w.cout, 0))
+    with prof:
         check(lib.fsfb_gather_gemm(*args, _ptr(w.data), *tail), "fsfb_gather_gemm")
     return out
 
@@ -432,8 +474,9 @@ def conv_rulebook(out_coors: torch.Tensor, index: VoxelIndex, ksize=3, stride=1,
     koff = k[0] * k[1] * k[2]
     m_out = out_coors.size(0)
     nbr = torch.empty((koff, m_out), dtype=torch.int32, device=dev)
-    rc = load().fsfb_conv_rulebook(_ptr(out_coors), m_out, _ptr(index.ws), _host_i64(index.lo), _host_i64(index.ext),
-                                   _host_i32(k), _host_i32(s_), _host_i32(p), int(transposed), _ptr(nbr), _stream(dev))
+    with _Prof("conv_rulebook", 16 * m_out + 4 * koff * m_out):
+        rc = load().fsfb_conv_rulebook(_ptr(out_coors), m_out, _ptr(index.ws), _host_i64(index.lo), _host_i64(index.ext),
+                                       _host_i32(k), _host_i32(s_), _host_i32(p), int(transposed), _ptr(nbr), _stream(dev))
     check(rc, "fsfb_conv_rulebook")
     return nbr
 
@@ -486,8 +529,9 @@ def connected_components(points: torch.Tensor, batch_idx: Optional[torch.Tensor]
     need = C.c_size_t(0)
     check(lib.fsfb_ccl_workspace_bytes(m, C.byref(need)), "fsfb_ccl_workspace_bytes")
     ws = _ws(need.value, dev)
-    rc = lib.fsfb_connected_components(_ptr(points), m, points.stride(0) if m else 3, _ptr(batch_idx), float(dist),
-                                       _ptr(labels), _ptr(count), _ptr(ws), ws.numel(), _stream(dev))
+    with _Prof("connected_components", 16 * m):
+        rc = lib.fsfb_connected_components(_ptr(points), m, points.stride(0) if m else 3, _ptr(batch_idx), float(dist),
+                                           _ptr(labels), _ptr(count), _ptr(ws), ws.numel(), _stream(dev))
     check(rc, "fsfb_connected_components")
     return (labels, count) if return_count else labels
 

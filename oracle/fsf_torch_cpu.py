@@ -1,48 +1,56 @@
-"""CPU port of the reference's forward sequence in stock torch ops — TEST/BENCH INFRASTRUCTURE ONLY.
+"""CPU port of the reference's forward path in stock torch ops — TEST/BENCH INFRASTRUCTURE ONLY.
 
-This is the "reference's CPU torch_scatter / SIR path" of BASELINE.json's north_star, restated with
-the ATen CPU operators the reference's Python calls (or, for torch_scatter 2.0.2 — absent here —
-their nearest ATen equivalents scatter_reduce_/index_add_).  It is multi-threaded through
-torch.set_num_threads and is what bench.py times as `cpu_baseline` / `--impl reference`
-(kind "port": the reference itself cannot be installed — no mmcv/mmdet3d/spconv/torch_scatter).
-Only tests/ and bench.py may import this module.  Parity pinning: see oracle/fsf_oracle.py.
-
-Stage names match fullysparsefusion_b200/frame.py.
+This is "the reference's CPU torch_scatter / SIR path" of BASELINE.json's north_star: the same frame as
+fullysparsefusion_b200.fsf.FSF, executed with the ATen CPU operators the reference's Python calls
+(torch.unique, index_add_/scatter_reduce_ in place of the absent torch_scatter 2.0.2, F.grid_sample on
+the float-cast id planes, nn.Linear/LayerNorm/BatchNorm1d, scipy connected_components on a dense
+distance matrix) and, for the un-vendored spconv, the classic gather → matmul → scatter-add per kernel
+offset.  Multi-threaded through torch.set_num_threads.  bench.py times it as `cpu_baseline` and as
+`--impl reference` (kind "port": the reference itself cannot be installed here — no mmcv / mmdet3d fork /
+spconv / torch_scatter).  It reads its weights from an FSF module instance (parameter containers only).
+Stage names match fullysparsefusion_b200/fsf.py.  Only tests/ and bench.py may import this module.
 """
 from __future__ import annotations
 
 from typing import Callable, Dict, List, Tuple
 
+import numpy as np
 import torch
 import torch.nn.functional as F
+from scipy.sparse.csgraph import connected_components
+from torch import nn
 
-NUSC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)
+
+def seq(mlp, x):
+    """Run a build_mlp stack through the stock nn.Sequential path."""
+    return nn.Sequential.forward(mlp, x)
 
 
-def _voxel_coors(points, voxel, rng):
-    """torch.div(p - min, vs, rounding_mode='floor') in zyx order, batch-padded
-    (single_stage_fsd.py:222-225, :591-593)."""
+def scatter_v2(feat, coors, mode, unq=None):
+    """sst_ops.scatter_v2 (:150-177) with torch_scatter replaced by ATen CPU ops."""
+    if unq is None:
+        new_coors, inv = torch.unique(coors, return_inverse=True, dim=0)
+    else:
+        new_coors, inv = unq
+    m = new_coors.size(0)
+    if mode == "max":
+        out = torch.full((m, feat.size(1)), float("-inf"), dtype=feat.dtype)
+        out.scatter_reduce_(0, inv[:, None].expand_as(feat), feat, reduce="amax", include_self=True)
+    else:
+        out = torch.zeros((m, feat.size(1)), dtype=feat.dtype).index_add_(0, inv, feat)
+        if mode == "avg":
+            out = out / torch.bincount(inv, minlength=m).clamp(min=1).to(feat.dtype)[:, None]
+    return out, new_coors, inv
+
+
+def floor_coors(points, voxel, rng):
     lo = torch.tensor(rng[:3], dtype=torch.float32)
     vs = torch.tensor(voxel, dtype=torch.float32)
-    c = torch.div(points[:, :3] - lo[None], vs[None], rounding_mode="floor").long()[:, [2, 1, 0]]
-    return F.pad(c, (1, 0), value=0)
+    return torch.div(points[:, :3] - lo[None], vs[None], rounding_mode="floor").long()
 
 
-def scatter_mean(feat, inv, m):
-    """torch_scatter.scatter(reduce='mean') (sst_ops.py:170)."""
-    s = torch.zeros((m, feat.size(1)), dtype=feat.dtype).index_add_(0, inv, feat)
-    cnt = torch.bincount(inv, minlength=m).clamp(min=1).to(feat.dtype)
-    return s / cnt[:, None]
-
-
-def scatter_max(feat, inv, m):
-    """torch_scatter.scatter_max values (sst_ops.py:168; argmax is discarded by scatter_v2)."""
-    out = torch.full((m, feat.size(1)), float("-inf"), dtype=feat.dtype)
-    return out.scatter_reduce_(0, inv[:, None].expand_as(feat), feat, reduce="amax", include_self=True)
-
-
+# ---- projection + sampling, literal FSF.py:169-226 ---------------------------------------------------
 def prj_points_2d(points, lidar2img, img_h, img_w):
-    """FSF.prj_points_2d, op for op (FSF.py:169-200)."""
     pts_4d = torch.cat([points[:, :3], points.new_ones((points.size(0), 1))], dim=-1)
     pts_2d = pts_4d @ lidar2img.permute(0, 2, 1)
     depth_valid = pts_2d[..., 2] > 1e-3
@@ -51,18 +59,16 @@ def prj_points_2d(points, lidar2img, img_h, img_w):
     pts_2d[..., 1] /= pts_2d[..., 2]
     pts_2d[..., 0] /= img_w
     pts_2d[..., 1] /= img_h
-    pts_2d = pts_2d[..., :2]
-    pts_2d = (pts_2d - 0.5) * 2
+    pts_2d = (pts_2d[..., :2] - 0.5) * 2
     valid = depth_valid & (pts_2d[..., 0] > -1) & (pts_2d[..., 0] < 1) & (pts_2d[..., 1] > -1) & (pts_2d[..., 1] < 1)
     pts_2d[~valid] = -2.0
     return pts_2d
 
 
 def points_in_mask(points, mask_data, lidar2img):
-    """FSF.points_in_mask (FSF.py:202-226): float cast of the planes, one grid_sample per camera."""
     cams, classes, H, W = mask_data.shape
     pts_2d = prj_points_2d(points, lidar2img, H, W)
-    mask_f = mask_data.float()
+    mask_f = mask_data.float()                                                     # FSF.py:209
     out = []
     for cam in range(cams):
         s = F.grid_sample(mask_f[cam][None], pts_2d[cam][None, None], mode="nearest", align_corners=False)
@@ -70,49 +76,231 @@ def points_in_mask(points, mask_data, lidar2img):
     return torch.stack(out, 1).long()
 
 
-def build_stages(host: Dict[str, torch.Tensor], seed: int = 0) -> Tuple[List[Tuple[str, Callable[[], None]]], dict]:
-    points, mask, l2i = host["points"], host["mask"], host["lidar2img"]
-    n = points.size(0)
-    g = torch.Generator().manual_seed(seed)
-    pt_feats = torch.randn(n, 64, generator=g)
-    seg_logits, vote_preds, seg_feats = torch.randn(n, 11, generator=g), torch.randn(n, 33, generator=g), torch.randn(n, 131, generator=g)
-    st: dict = {}
+# ---- sparse convolution: gather → matmul → scatter-add per offset (spconv's CPU algorithm) -----------
+def _keys(coors, shape):
+    k = coors[:, 0].long()
+    for a in range(3):
+        k = k * shape[1 + a] + coors[:, 1 + a].long()
+    return k
 
-    def voxelize():
-        st["coors"] = _voxel_coors(points, (0.2, 0.2, 0.2), NUSC_RANGE)
 
-    def rank():
-        st["voxel_coors"], st["inv"] = torch.unique(st["coors"], return_inverse=True, dim=0)
+def rulebook(out_coors, in_coors, in_shape, stride, pad, transposed=False):
+    in_keys = _keys(in_coors, in_shape)            # ascending (rows are in lexicographic order)
+    pairs = []
+    for kz in range(3):
+        for ky in range(3):
+            for kx in range(3):
+                k = torch.tensor([kz, ky, kx])
+                if not transposed:
+                    c = out_coors[:, 1:].long() * torch.tensor(stride) - torch.tensor(pad) + k
+                    ok = torch.ones(len(c), dtype=torch.bool)
+                else:
+                    t = out_coors[:, 1:].long() + torch.tensor(pad) - k
+                    ok = ((t >= 0) & (t % torch.tensor(stride) == 0)).all(1)
+                    c = torch.div(t, torch.tensor(stride), rounding_mode="floor")
+                ok &= ((c >= 0) & (c < torch.tensor(in_shape[1:]))).all(1)
+                q = _keys(torch.cat([out_coors[:, :1].long(), c.clamp(min=0)], 1), in_shape)
+                pos = torch.searchsorted(in_keys, q).clamp(max=max(len(in_keys) - 1, 0))
+                hit = ok & (in_keys[pos] == q)
+                o = torch.nonzero(hit)[:, 0]
+                pairs.append((pos[o], o))
+    return pairs
 
-    def csr():
-        pass  # the reference has no rulebook for scatters: every call re-walks the index
 
-    def vfe_scatter():
-        m = st["voxel_coors"].size(0)
-        st["voxel_mean"] = scatter_mean(points[:, :5], st["inv"], m)
-        st["vfe0"] = scatter_max(pt_feats, st["inv"], m)
-        st["vfe1"] = scatter_max(pt_feats, st["inv"], m)
+def sparse_conv(x, pairs, n_out, module, residual=None):
+    out = torch.zeros((n_out, module.weight.size(1)), dtype=x.dtype)
+    for k, (i, o) in enumerate(pairs):
+        if len(i):
+            out.index_add_(0, o, x[i] @ module.weight[k].t())
+    bn = module.bn
+    out = F.batch_norm(out, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out) if module.act else out
 
-    def neck():
-        st["pt_voxel_feats"] = torch.cat([st["vfe0"][st["inv"]], st["vfe1"][st["inv"]]], 1)
 
-    def project():
-        ids = points_in_mask(points[:, 5:8], mask, l2i)
-        cam = ids.sum(-1).max(-1)[1]
-        st["cam_sel"] = cam
-        st["ids_sel"] = ids[torch.arange(n), cam]
-        st["fg"] = ids.sum((-2, -1)) > 0
+class CpuFSF:
+    def __init__(self, model):
+        self.m = model
+        self.cfg = model.cfg
 
-    def pre_voxelize():
-        coors = _voxel_coors(points, (0.1, 0.1, 0.1), NUSC_RANGE)
-        uniq, inv = torch.unique(coors, return_inverse=True, dim=0)
-        m = uniq.size(0)
-        st["pre_coors"] = uniq
-        st["pre_points"] = scatter_mean(points[:, :5], inv, m)
-        st["pre_logits"] = scatter_mean(seg_logits, inv, m)
-        st["pre_votes"] = scatter_mean(vote_preds, inv, m)
-        st["pre_feats"] = scatter_mean(seg_feats, inv, m)
-        st["pre_centers"] = scatter_mean(vote_preds, inv, m)
+    def stages(self, points, mask_data, mask_anno, lidar2img) -> Tuple[List[Tuple[str, Callable[[], None]]], Dict]:
+        m, cfg, st = self.m, self.cfg, {}
+        rng = cfg["point_cloud_range"]
 
-    return [("voxelize", voxelize), ("rank", rank), ("csr", csr), ("vfe_scatter", vfe_scatter), ("neck", neck),
-            ("project", project), ("pre_voxelize", pre_voxelize)], st
+        def sir_layer(layer, feats, inv, unq, f_cluster, return_pts=True):
+            x = torch.cat([feats[:, :3] / torch.tensor(layer.xyz_normalizer), feats[:, 3:]], 1)
+            x = x * seq(layer.rel_mlp, f_cluster / layer.rel_dist_scaler)
+            ori, cl = x, []
+            for i, vfe in enumerate(layer.vfe_layers):
+                pf = F.gelu(vfe.norm(vfe.linear(x))) if vfe.act == "gelu" else F.relu(vfe.norm(vfe.linear(x)))
+                c, _, _ = scatter_v2(pf, None, "max", unq=(unq, inv))
+                cl.append(c)
+                if i != len(layer.vfe_layers) - 1:
+                    x = torch.cat([pf, c[inv]], 1)
+            if pf.shape == ori.shape:
+                pf = pf + ori
+            return pf, torch.cat(cl, 1)
+
+        def sir(net, pts, feats, coors, f_cluster):
+            unq, inv = torch.unique(coors, return_inverse=True, dim=0)
+            out, cl = feats, []
+            for block in net.block_list:
+                out, c = sir_layer(block, torch.cat([pts, out], 1), inv, unq, f_cluster)
+                cl.append(c)
+            return out, torch.cat(cl, 1), unq
+
+        def head(h, x):
+            x = seq(h.shared_mlp, x)
+            r = {k: seq(getattr(h.task_heads[0], k), x) for k in h.task_heads[0].attrs}
+            return r["score"], torch.cat([r["center"], r["dim"], r["rot"], r["vel"]], 1)
+
+        def segment():
+            pts5 = points[:, :5]
+            c = floor_coors(points, cfg["seg_voxel_size"], rng)[:, [2, 1, 0]]
+            coors = F.pad(c, (1, 0), value=0)
+            unq, inv = torch.unique(coors, return_inverse=True, dim=0)
+            vfe = m.voxel_encoder
+            mean, _, _ = scatter_v2(pts5, None, "avg", unq=(unq, inv))
+            f_cluster = pts5[:, :3] - mean[inv][:, :3]
+            vs = torch.tensor(cfg["seg_voxel_size"])
+            off = torch.tensor([cfg["seg_voxel_size"][a] / 2 + rng[a] for a in range(3)])
+            f_center = pts5[:, :3] - (coors[:, [3, 2, 1]].float() * vs + off)
+            x = torch.cat([pts5, f_cluster, f_center], 1)
+            for i, layer in enumerate(vfe.vfe_layers):
+                pf = nn.Sequential.forward(layer, x)
+                vf, _, _ = scatter_v2(pf, None, "max", unq=(unq, inv))
+                if i != len(vfe.vfe_layers) - 1:
+                    x = torch.cat([pf, vf[inv]], 1)
+            # SimpleSparseUNet
+            net = m.backbone_unet
+            shape = [1] + list(cfg["sparse_shape"])
+            levels = [(unq, shape)]
+            rb = {"subm1": rulebook(unq, unq, shape, [1, 1, 1], [1, 1, 1])}
+            for i in range(1, net.stage_num):
+                pad = net._triple(tuple(net.encoder_paddings[i])[0])
+                pc, ps = levels[-1]
+                oshape = [1] + [(ps[1 + a] + 2 * pad[a] - 3) // 2 + 1 for a in range(3)]
+                cand = []
+                for kz in range(3):
+                    for ky in range(3):
+                        for kx in range(3):
+                            t = pc[:, 1:] + torch.tensor(pad) - torch.tensor([kz, ky, kx])
+                            ok = ((t >= 0) & (t % 2 == 0)).all(1)
+                            o = torch.div(t, 2, rounding_mode="floor")
+                            ok &= (o < torch.tensor(oshape[1:])).all(1)
+                            cand.append(torch.cat([pc[ok, :1], o[ok]], 1))
+                oc = torch.unique(torch.cat(cand), dim=0)
+                rb[f"spconv{i + 1}"] = rulebook(oc, pc, ps, [2, 2, 2], pad)
+                rb[f"spconv{i + 1}_inv"] = rulebook(pc, oc, oshape, [2, 2, 2], pad, transposed=True)
+                rb[f"subm{i + 1}"] = rulebook(oc, oc, oshape, [1, 1, 1], [1, 1, 1])
+                levels.append((oc, oshape))
+            x = sparse_conv(vf, rb["subm1"], len(unq), net.conv_input)
+            enc = []
+            for i, stage in enumerate(net.encoder_layers):
+                for layer in stage:
+                    x = sparse_conv(x, rb[layer.indice_key], len(levels[i][0]), layer)
+                enc.append(x)
+            x = enc[-1]
+            for lvl in range(net.stage_num, 0, -1):
+                lat_in, n_l = enc[lvl - 1], len(levels[lvl - 1][0])
+                lat = getattr(net, f"lateral_layer{lvl}")
+                h = sparse_conv(lat_in, rb[f"subm{lvl}"], n_l, lat.conv1)
+                h = sparse_conv(h, rb[f"subm{lvl}"], n_l, lat.conv2, residual=lat_in)
+                cat = torch.cat([x, h], 1)
+                merged = sparse_conv(cat, rb[f"subm{lvl}"], n_l, getattr(net, f"merge_layer{lvl}"))
+                x = merged + cat.view(n_l, merged.size(1), -1).sum(2)
+                up = getattr(net, f"upsample_layer{lvl}")
+                x = sparse_conv(x, rb[f"spconv{lvl}_inv"] if lvl != 1 else rb["subm1"], len(levels[max(lvl - 2, 0)][0]), up)
+            # Voxel2PointScatterNeck
+            pts_feats = x[inv]
+            centre = (coors[:, [3, 2, 1]].float() + 0.5) * vs + torch.tensor(rng[:3])
+            st.update(voxel_feats=x, pts_lidar_feats=torch.cat([pts_feats, pts5[:, :3] - centre], 1))
+
+        def enhance():
+            ids = points_in_mask(points[:, 5:8], mask_data, lidar2img)               # frustum_gather (FSF.py:228-258)
+            cam = ids.sum(-1).max(-1)[1]
+            sel = F.one_hot(cam, ids.size(1)).bool().unsqueeze(-1)
+            ids_sel = ids.masked_select(sel).reshape(-1, ids.size(2))
+            preds = torch.zeros((len(ids_sel), ids.size(2), mask_anno.size(1)))
+            valid = ids_sel >= 1
+            preds[valid] = mask_anno[ids_sel[valid] - 1]                             # get_all_cls_preds_2d
+            img_feat = seq(m.segmentor_updated_mlp, preds[..., 4])
+            feats = st["pts_lidar_feats"] + img_feat
+            h = seq(m.segmentation_head.pre_seg_conv, feats)
+            logits, votes = m.segmentation_head.conv_seg(h), m.segmentation_head.voting(h)
+            st.update(ids=ids, seg_feats=feats, seg_logits=logits, seg_vote_preds=votes, offsets=votes * votes.abs())
+
+        def frustum():
+            pts5, ids = points[:, :5], st["ids"]
+            fgw = 1 - st["seg_logits"].softmax(1)[:, -1]
+            fg = ids.sum((-2, -1)) > 0                                              # extract_fg_pts
+            feat, p, o, w = st["seg_feats"][fg], pts5[fg], ids[fg].reshape(int(fg.sum()), -1), fgw[fg]
+            ov = (o > 0).sum(-1)
+            raw = o.max(-1)[0]
+            feat_c, p_c, w_c = feat.clone(), p.clone(), w.clone()
+            for k in range(2, int(ov.max()) + 1 if len(ov) else 0):                  # double_overlap_pts
+                mk = ov == k
+                if mk.sum() == 0:
+                    continue
+                feat = torch.cat([feat, feat_c[mk].repeat(k - 1, 1)])
+                p = torch.cat([p, p_c[mk].repeat(k - 1, 1)])
+                w = torch.cat([w, w_c[mk].repeat(k - 1)])
+                sv = o[mk].topk(k, dim=-1)[0]
+                for pad in range(1, k):
+                    raw = torch.cat([raw, sv[:, pad]])
+            sir_coors = torch.stack([torch.zeros_like(raw), torch.zeros_like(raw), raw], 1)
+            wc = w.clamp(min=1e-5)[:, None]
+            mean, _, inv = scatter_v2(torch.cat([p[:, :3] * wc, wc], 1), sir_coors, "avg")
+            center = mean[:, :3] / mean[:, 3:4]
+            _, cl, oc = sir(m.frustum_sir, p, feat, sir_coors, p[:, :3] - center[inv])
+            pr = torch.zeros((len(oc), mask_anno.size(1)))
+            ok = oc[:, 2] >= 1
+            pr[ok] = mask_anno[oc[ok, 2] - 1]
+            pr[~ok, 5] = m.num_classes
+            box = pr[:, :4].clone()
+            box[:, 0::2] /= mask_data.shape[-1]
+            box[:, 1::2] /= mask_data.shape[-2]
+            enc = torch.cat([box, pr[:, 4:5], F.one_hot(pr[:, 5].long(), m.num_classes + 1).float()], 1)
+            obj = torch.cat([cl, seq(m.encode_2d_mlp, enc)], 1)
+            st.update(frustum_obj_feats=obj, frustum_out=head(m.frustum_obj_head, obj))
+
+        def fsd():
+            pts5 = points[:, :5]
+            c = F.pad(floor_coors(pts5, cfg["pre_voxelization_size"], rng)[:, [2, 1, 0]], (1, 0), value=0)
+            unq = torch.unique(c, return_inverse=True, dim=0)
+            v = {k: scatter_v2(t, None, "avg", unq=unq)[0] for k, t in dict(p=pts5, l=st["seg_logits"], v=st["seg_vote_preds"],
+                                                                            f=st["seg_feats"], o=st["offsets"]).items()}
+            scores = v["l"].softmax(1)
+            off = v["o"].reshape(-1, m.num_classes + 1, 3)
+            rows, inds, ctrs = [], [], []
+            for g, idx in enumerate(m.groups):
+                fgm = scores[:, idx].sum(1) > cfg["score_thresh"][g]
+                if not fgm.any():
+                    fgm[0] = True
+                lg = v["l"][:, idx][fgm]
+                wt = ((lg - lg.max(1)[0][:, None]).abs() < 1e-6).float()
+                wt = wt / wt.sum(1)[:, None]
+                ctr = v["p"][fgm, :3] + (off[:, idx, :][fgm] * wt[:, :, None]).sum(1)
+                cc = F.pad(floor_coors(ctr, cfg["cluster_voxel_size"][g], rng), (1, 0), value=0)   # forward_single_class
+                _, inv, cnt = torch.unique(cc, return_inverse=True, return_counts=True, dim=0)
+                valid = cnt[inv] >= cfg["min_points"]
+                if not valid.any():
+                    valid = ~valid
+                sc, _, inv2 = scatter_v2(ctr[valid], cc[valid], "avg")
+                d = ((sc[:, None, :2] - sc[None, :, :2]) ** 2).sum(2) ** 0.5          # find_connected_componets_single_batch
+                lab = torch.from_numpy(connected_components((d < cfg["connected_dist"][g]).numpy(), directed=False)[1]).long()
+                rows.append(torch.nonzero(fgm)[:, 0][valid])
+                inds.append(torch.stack([torch.full_like(lab[inv2], g), torch.zeros_like(lab[inv2]), lab[inv2]], 1))
+                ctrs.append(ctr[valid])
+            rows, inds, ctrs = torch.cat(rows), torch.cat(inds), torch.cat(ctrs)
+            feats = torch.cat([v["l"][rows], v["v"][rows], v["f"][rows]], 1)
+            cxyz, _, inv = scatter_v2(ctrs, inds, "avg")
+            _, cl, _ = sir(m.backbone, v["p"][rows], feats, inds, v["p"][rows, :3] - cxyz[inv])
+            st.update(fsd_obj_feats=cl, fsd_out=head(m.bbox_head, cl), fsd_rows=rows)
+
+        def combine():
+            st["obj_feats"] = torch.cat([seq(m.combine_frustum_feat_mlp, st["frustum_obj_feats"]),
+                                         seq(m.combine_fsd_feat_mlp, st["fsd_obj_feats"])], 0)
+
+        return [("segment", segment), ("enhance", enhance), ("frustum", frustum), ("fsd", fsd), ("combine", combine)], st
