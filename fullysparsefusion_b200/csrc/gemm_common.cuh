@@ -43,9 +43,9 @@ __host__ __device__ inline uint32_t sw128_offset(int n, int j) {
 // Round-to-nearest tf32 (low 13 mantissa bits zero afterwards), so the tensor core's own
 // operand truncation is a no-op and the split is unbiased: x = hi + lo + O(2^-23 |x|).
 __device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // round-half-away on the magnitude bits (what cvt.rna.tf32.f32 does for finite inputs) in two integer
+  // ops; Inf/NaN inputs are outside the contract of this path
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
 __device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }

@@ -227,24 +227,40 @@ __global__ void __launch_bounds__(kSrWarps * 32)
 }
 
 // ---- row gather ------------------------------------------------------------------------
+// Flat mapping: one thread per 16-byte (VEC = 4) or 4-byte chunk of the output, so every lane is busy
+// whatever the row width (C = 3 ... 768 on this path); 4 chunks in flight per thread.
 template <typename IdxT, int VEC>
 __global__ void __launch_bounds__(256)
     k_gather_rows(const float* __restrict__ src, int64_t m, int C, const IdxT* __restrict__ idx,
                   int64_t n, float fill, float* __restrict__ out, int64_t out_stride) {
-  // one warp per output row, lanes over channels; several rows in flight per warp
-  const int lane = lane_id();
-  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
-    const long long s = (long long)idx[i];
-    const bool ok = s >= 0 && s < m;
-    const float* p = src + (ok ? s : 0) * C;
-    float* o = out + i * out_stride;
-    for (int c = lane * VEC; c < C; c += 32 * VEC) {
-      if (VEC == 4) {
-        float4 v = ok ? __ldg(reinterpret_cast<const float4*>(p + c)) : make_float4(fill, fill, fill, fill);
-        stg_stream_f4(reinterpret_cast<float4*>(o + c), v);
-      } else {
-        o[c] = ok ? __ldg(p + c) : fill;
+  const int cv = C / VEC;
+  const int64_t total = n * cv;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += 4 * step) {
+    float4 v[4];
+    int64_t dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t t = t0 + u * step;
+      dst[u] = -1;
+      if (t < total) {
+        const int64_t i = t / cv;
+        const int j = (int)(t - i * cv) * VEC;
+        const long long s = (long long)__ldg(idx + i);
+        const bool ok = s >= 0 && s < m;
+        dst[u] = i * out_stride + j;
+        if (VEC == 4) {
+          v[u] = ok ? __ldg(reinterpret_cast<const float4*>(src + s * C + j)) : make_float4(fill, fill, fill, fill);
+        } else {
+          v[u].x = ok ? __ldg(src + s * C + j) : fill;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] >= 0) {
+        if (VEC == 4) stg_stream_f4(reinterpret_cast<float4*>(out + dst[u]), v[u]);
+        else out[dst[u]] = v[u].x;
       }
     }
   }
@@ -345,7 +361,8 @@ int fsfb_gather_rows(const float* src, int64_t m, int c, const void* idx, int id
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec4 = (c % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
                     ((uintptr_t)out % 16 == 0);
-  const int grid = (int)std::min<int64_t>(ceil_div(n, 8), (int64_t)kNumSMs * 32);
+  const int64_t chunks = n * (vec4 ? c / 4 : c);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(chunks, 256 * 4), (int64_t)kNumSMs * 16));
   if (idx_i64) {
     auto kern = vec4 ? k_gather_rows<long long, 4> : k_gather_rows<long long, 1>;
     FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, (const long long*)idx, n, fill, out, out_stride);
