@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(256)
       bad = true;
     } else {
       uint32_t blk = key / kCellsPerBlock, bit = key - blk * kCellsPerBlock;
-      atomicOr(bitmap + (size_t)blk * 4 + (bit >> 5), 1u << (bit & 31));
+      uint32_t* w = bitmap + (size_t)blk * 4 + (bit >> 5);
+      const uint32_t b = 1u << (bit & 31);
+      // few distinct keys (instance ids): after the first hit every later row only reads
+      if (!(*reinterpret_cast<volatile uint32_t*>(w) & b)) atomicOr(w, b);
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane_id() == 0) atomicOr(status, 1);
@@ -241,35 +244,37 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- 4. unique rows --------------------------------------------------------------------
+// one thread per 32-bit bitmap word (3 per block): decodes its set bits into rows
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_rank_unique_rows(const uint4* __restrict__ blocks, int64_t nblocks, RowSpec S,
                        T* __restrict__ uniq, int64_t cap_unique) {
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks;
-       b += (int64_t)gridDim.x * blockDim.x) {
-    uint4 blk = __ldg(blocks + b);
-    uint32_t words[3] = {blk.x, blk.y, blk.z};
-    uint32_t r = blk.w;
+  const int64_t nwords = nblocks * 3;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nwords;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = t / 3;
+    const int w = (int)(t - b * 3);
+    const uint4 blk = __ldg(blocks + b);
+    uint32_t bits = w == 0 ? blk.x : (w == 1 ? blk.y : blk.z);
+    if (!bits) continue;
+    uint32_t r = blk.w + (w > 0 ? __popc(blk.x) : 0) + (w > 1 ? __popc(blk.y) : 0);
+    while (bits) {
+      const int tb = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if ((int64_t)r < cap_unique) {
+        uint32_t key = (uint32_t)b * kCellsPerBlock + w * 32 + tb;
+        T* o = uniq + (int64_t)r * S.d;
 #pragma unroll
-    for (int w = 0; w < 3; ++w) {
-      uint32_t bits = words[w];
-      while (bits) {
-        int t = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if ((int64_t)r < cap_unique) {
-          uint32_t key = (uint32_t)b * kCellsPerBlock + w * 32 + t;
-          T* o = uniq + (int64_t)r * S.d;
-#pragma unroll
-          for (int j = kMaxCols - 1; j >= 0; --j) {
-            if (j < S.d) {
-              uint32_t q = key / S.ext[j];
-              o[j] = (T)((long long)(key - q * S.ext[j]) + S.lo[j]);
-              key = q;
-            }
+        for (int j = kMaxCols - 1; j >= 0; --j) {
+          if (j < S.d) {
+            const uint32_t e = S.ext[j];
+            const uint32_t q = e == 1 ? key : key / e;
+            o[j] = (T)((long long)(e == 1 ? 0u : key - q * e) + S.lo[j]);
+            key = q;
           }
         }
-        ++r;
       }
+      ++r;
     }
   }
 }
@@ -466,7 +471,7 @@ int fsfb_rank_rows(const void* rows, int rows_i64, int64_t n, int d, const int64
                 (long long*)inv64, counts, cap_unique);
   }
   if (uniq && n > 0) {
-    int grid = grid_for(nblocks, 256, 8);
+    int grid = grid_for(nblocks * 3, 256, 8);
     if (rows_i64) {
       FSFB_LAUNCH(k_rank_unique_rows<long long>, grid, 256, 0, st, blocks, nblocks, S,
                   (long long*)uniq, cap_unique);
@@ -559,7 +564,7 @@ int fsfb_conv_out_index(const int32_t* in_coors, int64_t m_in, const int64_t* ou
               status);
   FSFB_LAUNCH(k_rank_apply, (int)ntiles, kScanThreads, 0, st, blocks, nblocks, tile_sums);
   if (out_coors && cap_out > 0) {
-    FSFB_LAUNCH(k_rank_unique_rows<int>, grid_for(nblocks, 256, 8), 256, 0, st, blocks, nblocks, S, (int*)out_coors,
+    FSFB_LAUNCH(k_rank_unique_rows<int>, grid_for(nblocks * 3, 256, 8), 256, 0, st, blocks, nblocks, S, (int*)out_coors,
                 cap_out);
   }
   return FSFB_OK;

@@ -97,11 +97,12 @@ __global__ void __launch_bounds__(kSrWarps * 32)
     Acc<VEC, K, IS_MAX, HAS_ARG> acc;
     acc.reset();
     int cur = __shfl_sync(0xffffffffu, my_seg, 0);
+    int run = 0;  // rows accumulated into `cur` inside this chunk (== segment size when it is not partial)
 
     auto flush = [&](int s) {
       const bool partial = (s == seg_prev) | (s == seg_next);
       if (!partial) {
-        const float denom = mean ? (float)max(1, offsets[s + 1] - offsets[s]) : 1.f;
+        const float denom = mean ? (float)max(1, run) : 1.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const int c = chan<VEC>(c0, lane, k, 0);
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kSrWarps * 32)
         }
       }
       acc.reset();
+      run = 0;
     };
 
     for (int r0 = 0; r0 < cnt; r0 += kSrUnroll) {
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(kSrWarps * 32)
           }
 #pragma unroll
           for (int k = 0; k < K; ++k) acc.add(k, v[u][k], rows[u]);
+          ++run;
         }
       }
     }
@@ -177,50 +180,66 @@ __global__ void __launch_bounds__(kSrWarps * 32)
 }
 
 // Fold partial rows of segments that cross chunk boundaries; zero-fill empty segments.
+// One warp per (chunk, block of 32 channels); the walk over the chunks a long segment spans is unrolled
+// four-wide so its loads are independent (instance-level segments can span hundreds of chunks).
 template <bool IS_MAX, bool HAS_ARG>
 __global__ void __launch_bounds__(kSrWarps * 32)
-    k_segreduce_fixup(int C, const int32_t* __restrict__ offsets, int m, int mean, int64_t n,
+    k_segreduce_fixup(int C, const int32_t* __restrict__ offsets, int m, int mean, int dense, int64_t n,
                       float* __restrict__ out, long long* __restrict__ argout,
                       const int32_t* __restrict__ part_seg, const float* __restrict__ part_val,
                       const int32_t* __restrict__ part_arg, int64_t n_chunks) {
   const int lane = lane_id();
-  const int64_t gw = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  const int cblocks = (C + 31) / 32;
+  const int64_t gwarp = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  const int64_t gw = gwarp / cblocks;
+  const int c = (int)(gwarp - gw * cblocks) * 32 + lane;
   // part 1: owner = chunk whose tail slot holds a segment that started inside it
   if (gw < n_chunks) {
     const int s = part_seg[2 * gw + 1];
-    if (s >= 0) {
+    if (s >= 0 && c < C) {
       const int64_t last_chunk = ((int64_t)offsets[s + 1] - 1) / kSrChunk;
       const int count = offsets[s + 1] - offsets[s];
-      for (int c = lane; c < C; c += 32) {
-        float best = part_val[(2 * gw + 1) * C + c];
-        int arg = HAS_ARG ? part_arg[(2 * gw + 1) * C + c] : 0;
-        for (int64_t w = gw + 1; w <= last_chunk; ++w) {
-          const float v = part_val[(2 * w) * C + c];
-          if (IS_MAX) {
-            if (HAS_ARG) {
-              const int a = part_arg[(2 * w) * C + c];
-              const bool take = (v > best) | ((v == best) & (a < arg));
-              arg = take ? a : arg;
-              best = take ? v : best;
-            } else {
-              best = fmaxf(best, v);
-            }
+      float best = part_val[(2 * gw + 1) * C + c];
+      int arg = HAS_ARG ? part_arg[(2 * gw + 1) * C + c] : 0;
+      auto fold = [&](float v, int a) {
+        if (IS_MAX) {
+          if (HAS_ARG) {
+            const bool take = (v > best) | ((v == best) & (a < arg));
+            arg = take ? a : arg;
+            best = take ? v : best;
           } else {
-            best += v;
+            best = fmaxf(best, v);
           }
+        } else {
+          best += v;
         }
-        if (mean) best = best / (float)max(1, count);
-        out[(int64_t)s * C + c] = best;
-        if (HAS_ARG) argout[(int64_t)s * C + c] = (long long)arg;
+      };
+      int64_t w = gw + 1;
+      for (; w + 3 <= last_chunk; w += 4) {
+        float v[4];
+        int a[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = part_val[(2 * (w + u)) * C + c];
+          if (HAS_ARG) a[u] = part_arg[(2 * (w + u)) * C + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fold(v[u], a[u]);  // ascending chunk order: deterministic sums
       }
+      for (; w <= last_chunk; ++w) fold(part_val[(2 * w) * C + c], HAS_ARG ? part_arg[(2 * w) * C + c] : 0);
+      if (mean) best = best / (float)max(1, count);
+      out[(int64_t)s * C + c] = best;
+      if (HAS_ARG) argout[(int64_t)s * C + c] = (long long)arg;
     }
   }
-  // part 2: empty segments (only possible when the index does not come from a ranking)
-  for (int64_t s = gw; s < m; s += (int64_t)gridDim.x * kSrWarps) {
+  // part 2: empty segments (only possible when the index does not come from a ranking: `dense` skips it)
+  if (dense) return;
+  const int64_t n_warps = (int64_t)gridDim.x * kSrWarps;
+  for (int64_t s = gwarp; s < m; s += n_warps) {
     if (offsets[s + 1] == offsets[s]) {
-      for (int c = lane; c < C; c += 32) {
-        out[s * C + c] = 0.f;
-        if (HAS_ARG) argout[s * C + c] = (long long)n;
+      for (int cc = lane; cc < C; cc += 32) {
+        out[s * C + cc] = 0.f;
+        if (HAS_ARG) argout[s * C + cc] = (long long)n;
       }
     }
   }
@@ -305,6 +324,8 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
   FSFB_CHECK_ARG(n >= 0 && n < (1ll << 31) && m >= 0 && m < (1ll << 31) && c >= 1 && feat_stride >= c,
                  "segment_reduce: bad n=%lld m=%lld c=%d stride=%lld", (long long)n, (long long)m, c,
                  (long long)feat_stride);
+  const int dense = (mode & FSFB_REDUCE_DENSE) ? 1 : 0;
+  mode &= ~FSFB_REDUCE_DENSE;
   FSFB_CHECK_ARG(mode == FSFB_REDUCE_SUM || mode == FSFB_REDUCE_MEAN || mode == FSFB_REDUCE_MAX,
                  "segment_reduce: bad mode %d", mode);
   FSFB_CHECK_ARG(argmax == nullptr || mode == FSFB_REDUCE_MAX, "segment_reduce: argmax needs MAX");
@@ -336,18 +357,23 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
     const int lanes_groups = (int)ceil_div(c, 32);
     if (lanes_groups <= 1) SR_DISPATCH(1, 1);
     else if (lanes_groups <= 2) SR_DISPATCH(1, 2);
+    else if (lanes_groups <= 3) SR_DISPATCH(1, 3);
     else if (lanes_groups <= 4) SR_DISPATCH(1, 4);
+    else if (lanes_groups <= 5) SR_DISPATCH(1, 5);
+    else if (lanes_groups <= 6) SR_DISPATCH(1, 6);
     else SR_DISPATCH(1, 8);
   }
 #undef SR_DISPATCH
   if (rc != FSFB_OK) return rc;
-  const int64_t items = std::max<int64_t>(n_chunks, std::min<int64_t>(m, (int64_t)kNumSMs * 64));
+  const int64_t cblocks = ceil_div(c, 32);
+  const int64_t items = dense ? n_chunks * cblocks
+                              : std::max<int64_t>(n_chunks * cblocks, std::min<int64_t>(m, (int64_t)kNumSMs * 64));
   const int grid = (int)ceil_div(items, kSrWarps);
   const int mean = mode == FSFB_REDUCE_MEAN;
   auto fix = (mode == FSFB_REDUCE_MAX)
                  ? (argmax ? k_segreduce_fixup<true, true> : k_segreduce_fixup<true, false>)
                  : k_segreduce_fixup<false, false>;
-  FSFB_LAUNCH(fix, grid, kSrWarps * 32, 0, st, c, offsets, (int)m, mean, n, out, argout, part_seg,
+  FSFB_LAUNCH(fix, grid, kSrWarps * 32, 0, st, c, offsets, (int)m, mean, dense, n, out, argout, part_seg,
               part_val, part_arg, n_chunks);
   return FSFB_OK;
 }

@@ -51,53 +51,80 @@ __global__ void __launch_bounds__(kRsThreads)
   for (int b = threadIdx.x; b < nbins; b += kRsThreads) hist[(size_t)b * ntiles + blockIdx.x] = s_cnt[b];
 }
 
-// ---- pass kernel 2: flat exclusive scan of hist (single CTA) ---------------------------
-__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ hist, int64_t total) {
-  __shared__ uint32_t s_warp[32];
+// ---- pass kernel 2: exclusive scan of hist in [bin][tile] order, two levels ---------------------
+// (a) one CTA per bin scans that bin's per-tile counts in place and records the bin total;
+// (b) one CTA scans the <= 2048 bin totals.  Global offset of (bin, tile) = bin_base[bin] + hist[bin][tile].
+__global__ void __launch_bounds__(256) k_rs_scan_bins(uint32_t* __restrict__ hist, int ntiles,
+                                                      uint32_t* __restrict__ bin_total) {
+  __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_carry;
+  uint32_t* h = hist + (size_t)blockIdx.x * ntiles;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  // each thread owns a contiguous run per round → sequential in registers, scan of run sums
-  constexpr int kRun = 8;
-  for (int64_t base = 0; base < total; base += 1024 * kRun) {
-    int64_t i0 = base + (int64_t)threadIdx.x * kRun;
-    uint32_t v[kRun];
-    uint32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kRun; ++k) {
-      v[k] = (i0 + k < total) ? hist[i0 + k] : 0;
-      s += v[k];
-    }
-    // CTA exclusive scan of s
-    uint32_t x = s;
+  for (int base = 0; base < ntiles; base += 256) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? h[i] : 0;
+    uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
       if ((int)lane_id() >= o) x += y;
     }
-    int w = threadIdx.x >> 5;
-    const uint32_t carry = s_carry;  // written before the previous round's trailing barrier
+    const int w = threadIdx.x >> 5;
+    const uint32_t carry = s_carry;
     if (lane_id() == 31) s_warp[w] = x;
     __syncthreads();
-    if (w == 0) {
-      uint32_t t = s_warp[lane_id()];
-      uint32_t u = t;
+    uint32_t woff = 0, total = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, u, o);
-        if ((int)lane_id() >= o) u += y;
-      }
-      s_warp[lane_id()] = u - t;
-      if (lane_id() == 31) s_carry = carry + u;
+    for (int ww = 0; ww < 8; ++ww) {
+      const uint32_t t = s_warp[ww];
+      if (ww < w) woff += t;
+      total += t;
     }
+    if (i < ntiles) h[i] = carry + woff + x - v;
     __syncthreads();
-    uint32_t ex = carry + s_warp[w] + x - s;
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bin_total[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan_totals(uint32_t* __restrict__ bin_total, int nbins) {
+  __shared__ uint32_t s_warp[32];
+  uint32_t v[2];
+  uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < kRun; ++k) {
-      if (i0 + k < total) hist[i0 + k] = ex;
-      ex += v[k];
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x * 2 + k;
+    v[k] = i < nbins ? bin_total[i] : 0;
+    s += v[k];
+  }
+  uint32_t x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((int)lane_id() >= o) x += y;
+  }
+  const int w = threadIdx.x >> 5;
+  if (lane_id() == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    const uint32_t t = s_warp[lane_id()];
+    uint32_t u = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, u, o);
+      if ((int)lane_id() >= o) u += y;
     }
-    __syncthreads();
+    s_warp[lane_id()] = u - t;
+  }
+  __syncthreads();
+  uint32_t ex = s_warp[w] + x - s;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x * 2 + k;
+    if (i < nbins) bin_total[i] = ex;
+    ex += v[k];
   }
 }
 
@@ -107,7 +134,7 @@ __global__ void __launch_bounds__(kRsThreads)
     k_rs_scatter(const IdxT* __restrict__ index, const uint32_t* __restrict__ keys_in,
                  const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
                  uint32_t* __restrict__ vals_out, int64_t n, uint32_t m, int shift, int rbits,
-                 const uint32_t* __restrict__ hist, int ntiles) {
+                 const uint32_t* __restrict__ hist, const uint32_t* __restrict__ bin_base, int ntiles) {
   extern __shared__ uint32_t s_wcnt[];  // [kRsWarps][nbins]
   const int nbins = 1 << rbits;
   for (int b = threadIdx.x; b < nbins * kRsWarps; b += kRsThreads) s_wcnt[b] = 0;
@@ -142,7 +169,7 @@ __global__ void __launch_bounds__(kRsThreads)
   __syncthreads();
   // cross-warp exclusive offsets per digit, plus the tile's global offset for that digit
   for (int b = threadIdx.x; b < nbins; b += kRsThreads) {
-    uint32_t run = hist[(size_t)b * ntiles + blockIdx.x];
+    uint32_t run = hist[(size_t)b * ntiles + blockIdx.x] + bin_base[b];
 #pragma unroll
     for (int ww = 0; ww < kRsWarps; ++ww) {
       uint32_t c = s_wcnt[ww * nbins + b];
@@ -227,9 +254,11 @@ static int radix_sort_index(const IdxT* index, int64_t n, uint32_t m, uint32_t* 
     auto scatter_kernel = (p == 0) ? k_rs_scatter<IdxT, true> : k_rs_scatter<IdxT, false>;
     FSFB_LAUNCH(hist_kernel, ntiles, kRsThreads, smem_hist, st, index, kin, n, m, shift, rbits,
                 hist, ntiles);
-    FSFB_LAUNCH(k_rs_scan, 1, 1024, 0, st, hist, (int64_t)nbins * ntiles);
+    uint32_t* bin_base = hist + (size_t)nbins * ntiles;
+    FSFB_LAUNCH(k_rs_scan_bins, nbins, 256, 0, st, hist, ntiles, bin_base);
+    FSFB_LAUNCH(k_rs_scan_totals, 1, 1024, 0, st, bin_base, nbins);
     FSFB_LAUNCH(scatter_kernel, ntiles, kRsThreads, smem_scatter, st, index, kin, vin, kout, vout,
-                n, m, shift, rbits, hist, ntiles);
+                n, m, shift, rbits, hist, bin_base, ntiles);
     kin = kout;
     vin = vout;
   }
@@ -244,7 +273,7 @@ static size_t csr_ws_layout(int64_t n, int64_t m, Workspace& ws, uint32_t** tk, 
   const int64_t ntiles = std::max<int64_t>(1, ceil_div(n, kRsTile));
   uint32_t* a = ws.take<uint32_t>(std::max<int64_t>(n, 1));
   uint32_t* b = ws.take<uint32_t>(std::max<int64_t>(n, 1));
-  uint32_t* h = ws.take<uint32_t>((size_t)(1 << rbits) * ntiles);
+  uint32_t* h = ws.take<uint32_t>((size_t)(1 << rbits) * (ntiles + 1));
   if (tk) *tk = a;
   if (tv) *tv = b;
   if (hist) *hist = h;

@@ -36,6 +36,7 @@ class ScatterPlan:
         self.index = res[3] if want_index else None
         self.m = self.new_coors.size(0)
         self.csr = ops.build_csr(self.inv32, self.m)
+        self.csr.dense = True  # ranks of existing rows: no empty segment
         self._inv64 = None
 
     @property

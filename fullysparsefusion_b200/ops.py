@@ -204,6 +204,7 @@ class SegmentCSR:
     seg: torch.Tensor      # [n] int32 segment of each sorted position
     n: int
     m: int
+    dense: bool = False  # every segment has at least one row (ids come from a ranking): skips the empty-segment pass
 
 
 def build_csr(index: torch.Tensor, m: int) -> SegmentCSR:
@@ -238,6 +239,7 @@ def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax
     n, c = feat.shape
     mode_id = _MODES[mode]
     want_arg = return_argmax and mode_id == REDUCE_MAX
+    mode_flags = mode_id | (0x100 if csr.dense else 0)
     out = torch.empty((csr.m, c), dtype=torch.float32, device=dev)
     arg = torch.empty((csr.m, c), dtype=torch.int64, device=dev) if want_arg else None
     if c == 0 or csr.m == 0:
@@ -249,7 +251,7 @@ def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax
     ws = _ws(need.value, dev)
     with _Prof("segment_reduce", 4 * n * c + 8 * n + 4 * csr.m * c + (8 * csr.m * c if want_arg else 0)):
         rc = lib.fsfb_segment_reduce(_ptr(feat), n, c, feat.stride(0) if n else c, _ptr(csr.perm), _ptr(csr.seg),
-                                     _ptr(csr.offsets), csr.m, mode_id, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
+                                     _ptr(csr.offsets), csr.m, mode_flags, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
                                      _stream(dev))
     check(rc, "fsfb_segment_reduce")
     return (out, arg) if return_argmax else out

@@ -32,6 +32,7 @@ extern "C" {
 #define FSFB_REDUCE_SUM 0
 #define FSFB_REDUCE_MEAN 1
 #define FSFB_REDUCE_MAX 2
+#define FSFB_REDUCE_DENSE 0x100 /* OR-able hint: every segment in [0,m) has at least one row (index from a ranking) */
 
 #define FSFB_ACT_NONE 0
 #define FSFB_ACT_RELU 1
@@ -123,7 +124,7 @@ int fsfb_csr_build(const void* index, int index_i64, int64_t n, int64_t m,
 int fsfb_segment_reduce_workspace_bytes(int64_t n, int c, int with_arg, size_t* bytes);
 
 /* out[s, :] = reduce over rows r with index[r]==s of feat[r, :].
- * mode FSFB_REDUCE_{SUM,MEAN,MAX}.  MAX: ties → lowest source row (torch_scatter's
+ * mode FSFB_REDUCE_{SUM,MEAN,MAX} (| FSFB_REDUCE_DENSE to skip the empty-segment pass).  MAX: ties → lowest source row (torch_scatter's
  * sequential CPU rule); argmax (nullable) dev [m,c] i64.  Empty segment → 0 and
  * argmax = n.  perm == NULL means rows are already grouped (perm = identity).
  *   feat dev [n, feat_stride] f32 (c <= feat_stride), out dev [m, c] f32 */
