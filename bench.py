@@ -203,6 +203,7 @@ def main():
     import torch.distributed as dist
 
     from fullysparsefusion_b200 import _capi, ops
+    from fullysparsefusion_b200 import dist as fdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU port)")
@@ -218,7 +219,7 @@ def main():
     # three distinct frames rotate through the steps: 3 x 96 MB of inputs plus > 1 GB of per-frame
     # intermediates exceed the 126 MB L2, so no step starts on a warm cache
     n_frames = 3
-    hosts = [{k: v.pin_memory() for k, v in synth_frame(args.points, args.sweeps, seed=rank * 16 + i).items()}
+    hosts = [{k: v.pin_memory() for k, v in synth_frame(args.points, args.sweeps, seed=fdist.frame_seed(rank, i)).items()}
              for i in range(n_frames)]
     frames = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
     model = make_model().to(dev)
@@ -294,10 +295,7 @@ def main():
         ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
+    ms_total, ms_e2e = fdist.max_over_ranks(torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)).tolist()
 
     if rank == 0:
         per_stage = {}
@@ -336,7 +334,7 @@ def main():
         st = last["st"]
         h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
         d2h = sum(r.numel() * r.element_size() for r in res)
-        line = {"metric": METRIC, "value": world * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": fdist.throughput(args.steps, world, ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tensor-core GEMMs: 3xTF32)",
                 "data": "synthetic",
@@ -346,7 +344,7 @@ def main():
                            "frustum_queries": int(st["frustum_obj_coors"].size(0)), "fsd_rows": int(st["fsd_rows"].numel()),
                            "fsd_queries": int(st["fsd_obj_coors"].size(0)),
                            "scope": "FSF.simple_test through combine_frustum_and_fsd (refine stage + NMS not included)"},
-                "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "e2e": {"value": fdist.throughput(args.steps, world, ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": table,
                 "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}}

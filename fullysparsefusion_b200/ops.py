@@ -21,6 +21,7 @@ _MODES = {"sum": REDUCE_SUM, "add": REDUCE_SUM, "mean": REDUCE_MEAN, "avg": REDU
 # Optional per-op CUDA-event timing (bench.py): set PROFILER to a list to collect
 # (op family, start event, end event, algorithmic bytes, algorithmic flops) for the HBM-/tensor-bound ops.
 PROFILER = None
+DETAIL = False  # per-shape op names in the profile (tools only)
 
 
 class _Prof:
@@ -437,7 +438,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         if PROFILER is not None and pairs is None:   # profiling only: exact pair count of this rulebook, kept on device
             pairs = (nbr >= 0).sum()
             nbr._fsfb_pairs = pairs
-        prof = _Prof("gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
+        prof = _Prof(f"gather_gemm_conv_{w.cin}x{w.cout}" if DETAIL else "gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
                      (pairs, 2 * w.cin * w.cout, 0))
     with prof:
         check(lib.fsfb_gather_gemm(*args, _ptr(w.data), *tail), "fsfb_gather_gemm")
