@@ -22,7 +22,7 @@
 namespace fsfb {
 
 constexpr int kTsProducers = 512;  // 16 warps: warp w owns TMEM lane quarter w%4 and K quarter w/4
-constexpr int kTsThreads = 576;    // + MMA warp (16) + W loader warp (17)
+constexpr int kTsThreads = 608;    // + two MMA warps (16, 17) + W loader warp (18)
 constexpr int kTsAStages = 4;
 constexpr int kTsMaxWStages = 6;
 
@@ -81,14 +81,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
   if (tid == 0) {
     if (base & 1023u) __trap();
     for (int s = 0; s < kTsAStages; ++s) {
-      mbar_init(smem_u32(&sh->a_full[s]), kTsProducers / 32);
-      mbar_init(smem_u32(&sh->a_empty[s]), 1);
+      mbar_init(smem_u32(&sh->a_full[s]), kTsProducers / 32 + 1);  // producer warps + the W loader (with its tx bytes)
+      mbar_init(smem_u32(&sh->a_empty[s]), 2);                     // both MMA issuers commit
     }
     for (int s = 0; s < w_stages; ++s) {
       mbar_init(smem_u32(&sh->w_full[s]), 1);
       mbar_init(smem_u32(&sh->w_empty[s]), 1);
     }
-    mbar_init(smem_u32(&sh->accum), 1);
+    mbar_init(smem_u32(&sh->accum), 2);
     sh->off_mask = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -207,58 +207,65 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
         ph ^= 1u;
       }
     }
-  } else if (warp == kTsProducers / 32 && lane == 0) {
-    // ================= MMA issuer =================
+  } else if ((warp == kTsProducers / 32 || warp == kTsProducers / 32 + 1) && lane == 0) {
+    // ================= two MMA issuers =================
+    // warp 16: main accumulator (a_hi * w_hi); warp 17: correction accumulator (a_lo * w_hi + a_hi * w_lo).
+    // The two instruction streams touch different TMEM accumulators, so they need no mutual ordering; splitting
+    // them doubles the issue rate of the single-thread MMA front end (the limiter at 12 MMAs per 32-wide K chunk).
+    const bool is_main = warp == kTsProducers / 32;
     const uint32_t idesc = make_idesc_tf32(n_w);
+    const uint32_t d_acc = is_main ? tmem_d : tmem_d + acc_cols;
     StageCursor c;
     c.init(off_mask);
-    int sa = 0, sw = 0;
-    uint32_t pha = 0, phw = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < n_active; ++it) {
-      mbar_wait(smem_u32(&sh->w_full[sw]), phw);
-      mbar_wait(smem_u32(&sh->a_full[sa]), pha);
+      mbar_wait(smem_u32(&sh->a_full[s]), ph);
       tc_fence_after();
-      const uint32_t w_hi = base + (uint32_t)sw * w_bytes, w_lo = w_hi + (uint32_t)n_w * 128u;
-      const uint32_t a_hi = tmem_a + (uint32_t)(64 * sa), a_lo = a_hi + 32;
+      const uint32_t w_hi = base + (uint32_t)s * w_bytes;
+      const uint32_t w_lo = w_hi + (uint32_t)n_w * 128u;
+      const uint32_t a_hi = tmem_a + (uint32_t)(64 * s), a_lo = a_hi + 32;
       const int k_valid = min(kGemmKChunk, P.cin - c.kc * kGemmKChunk);
       const int ksteps = (k_valid + 7) >> 3;
-      for (int kk = 0; kk < ksteps && !(P.debug & 4); ++kk) {
-        const uint64_t db_hi = make_sw128_desc(w_hi + (uint32_t)kk * 32u), db_lo = make_sw128_desc(w_lo + (uint32_t)kk * 32u);
-        const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
-        tc_mma_tf32_ts(tmem_d, a_hi + 8 * kk, db_hi, idesc, first);
-        tc_mma_tf32_ts(tmem_d + acc_cols, a_lo + 8 * kk, db_hi, idesc, first);
-        tc_mma_tf32_ts(tmem_d + acc_cols, a_hi + 8 * kk, db_lo, idesc, 1u);
+      if (!(P.debug & 4)) {
+        if (is_main) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (kk < ksteps) tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            if (kk < ksteps) {
+              tc_mma_tf32_ts(d_acc, a_lo + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+              tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_lo + 32u * kk), idesc, 1u);
+            }
+        }
       }
-      tc_commit(smem_u32(&sh->a_empty[sa]));
-      tc_commit(smem_u32(&sh->w_empty[sw]));
+      tc_commit(smem_u32(&sh->a_empty[s]));
       c.next(kc_n);
-      if (++sa == kTsAStages) {
-        sa = 0;
-        pha ^= 1u;
-      }
-      if (++sw == w_stages) {
-        sw = 0;
-        phw ^= 1u;
+      if (++s == kTsAStages) {
+        s = 0;
+        ph ^= 1u;
       }
     }
     if (n_active > 0) tc_commit(smem_u32(&sh->accum));
-  } else if (warp == kTsProducers / 32 + 1 && lane == 0) {
-    // ================= W loader: bulk-async copies into the shared-memory ring =================
+  } else if (warp == kTsProducers / 32 + 2 && lane == 0) {
+    // ================= W loader: bulk-async copies into the stage ring =================
     StageCursor c;
     c.init(off_mask);
-    int sw = 0;
-    uint32_t phw = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < n_active; ++it) {
-      mbar_wait(smem_u32(&sh->w_empty[sw]), phw ^ 1u);
+      mbar_wait(smem_u32(&sh->a_empty[s]), ph ^ 1u);
       if (!(P.debug & 2)) {
-        mbar_expect_tx(smem_u32(&sh->w_full[sw]), w_bytes);
-        bulk_g2s(base + (uint32_t)sw * w_bytes, P.w_packed + P.S.block_offset(nt, c.k, c.kc), w_bytes, smem_u32(&sh->w_full[sw]));
+        mbar_expect_tx(smem_u32(&sh->a_full[s]), w_bytes);
+        bulk_g2s(base + (uint32_t)s * w_bytes, P.w_packed + P.S.block_offset(nt, c.k, c.kc), w_bytes, smem_u32(&sh->a_full[s]));
       }
-      mbar_arrive(smem_u32(&sh->w_full[sw]));
+      mbar_arrive(smem_u32(&sh->a_full[s]));
       c.next(kc_n);
-      if (++sw == w_stages) {
-        sw = 0;
-        phw ^= 1u;
+      if (++s == kTsAStages) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   }
@@ -289,9 +296,7 @@ int launch_gather_gemm_ts(TcParams P, bool a_vec, cudaStream_t st) {
   const size_t staging = (size_t)kTcRows * (((n_w_max + 31) & ~31) + 4) * 4;
   const size_t fixed = (size_t)P.koff * kTcRows * 4 + sizeof(TsShared) + 1024;
   const size_t budget = 227 * 1024;
-  int stages = (int)std::min<size_t>(kTsMaxWStages, (budget - fixed) / w_bytes);
-  const int64_t total_iters = (int64_t)P.koff * P.S.kc();
-  if (total_iters < stages) stages = (int)std::max<int64_t>(1, total_iters);
+  const int stages = kTsAStages;  // one ring: stage s = TMEM columns of A + shared-memory block of W
   P.stages = stages;
   P.data_bytes = (uint32_t)align_up(std::max((size_t)stages * w_bytes, staging), 1024);
   const size_t smem = (size_t)P.data_bytes + fixed;
