@@ -63,6 +63,7 @@ SIGNATURES = {
     "fsfb_encode_preds_2d": (_i, [_p, _i, _i, _p, _i, _i, _i64, _f, _f, _i, _p, _p, _p]),
     "fsfb_threshold_mask": (_i, [_p, _i64, _i64, _i, _f, _p, _p]),
     "fsfb_count_mask": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "fsfb_sir_gate_input": (_i, [_p, _i64, _i, _i64, _p, _i64, _f, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _i64, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

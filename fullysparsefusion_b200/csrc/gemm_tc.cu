@@ -216,38 +216,54 @@ __global__ void __launch_bounds__(kTcThreads, DEEP ? 1 : 2) k_gather_gemm_tc(con
     // phase 2 (all 8 producer warps, lanes along channels): residual + activation + coalesced stores
     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");
     epilogue_phase2(P, base, n_w, nt, row0, warp, lane, kTcProducers / 32);
-  } else if (warp == kTcProducers / 32 && lane == 0 && !(P.debug & 128)) {
-    // ================= MMA issuer =================
+  } else if (warp == kTcProducers / 32 && !(P.debug & 128)) {
+    // ================= MMA issuer warp =================
+    // warp-uniform loop, one elected lane issues: keeps descriptors in uniform registers (a UTCHMMA fed from
+    // vector registers pays ~100 clk of R2UR moves, more than the math of a 128x128x8 tf32 MMA)
+    const uint32_t u_tmem_d = __shfl_sync(0xffffffffu, tmem_d, 0);
+    const uint32_t u_base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t u_mask = __shfl_sync(0xffffffffu, off_mask, 0);
+    const uint32_t bar_full0 = __shfl_sync(0xffffffffu, smem_u32(&sh->full[0]), 0);
+    const uint32_t bar_empty0 = __shfl_sync(0xffffffffu, smem_u32(&sh->empty[0]), 0);
     const uint32_t idesc = make_idesc_tf32(n_w);
     StageCursor c;
-    c.init(off_mask);
+    c.init(u_mask);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < n_active; ++it) {
-      mbar_wait(smem_u32(&sh->full[s]), ph);
+      if (lane == 0) mbar_wait(bar_full0 + 8u * s, ph);
+      __syncwarp();
       tc_fence_after();
-      const uint32_t st = base + (uint32_t)s * stage_bytes;
+      const uint32_t st = u_base + (uint32_t)s * stage_bytes;
       const uint32_t a_hi = st, a_lo = st + kStageABytes;
       const uint32_t w_hi = st + 2 * kStageABytes, w_lo = w_hi + (uint32_t)n_w * 128u;
       const int k_valid = min(kGemmKChunk, P.cin - c.kc * kGemmKChunk);
       const int ksteps = (k_valid + 7) >> 3;
-      for (int kk = 0; kk < ksteps && !(P.debug & 4); ++kk) {
-        const uint32_t ko = (uint32_t)kk * 32u;  // 8 tf32 = 32 bytes along K inside the swizzle row
-        const uint64_t da_hi = make_sw128_desc(a_hi + ko), da_lo = make_sw128_desc(a_lo + ko);
-        const uint64_t db_hi = make_sw128_desc(w_hi + ko), db_lo = make_sw128_desc(w_lo + ko);
-        const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
-        tc_mma_tf32(tmem_d, da_hi, db_hi, idesc, first);
-        tc_mma_tf32(tmem_d + acc_cols, da_lo, db_hi, idesc, first);
-        tc_mma_tf32(tmem_d + acc_cols, da_hi, db_lo, idesc, 1u);
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+      if (elected) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < ksteps && !(P.debug & 4)) {
+            const uint32_t ko = (uint32_t)kk * 32u;  // 8 tf32 = 32 bytes along K inside the swizzle row
+            const uint64_t da_hi = make_sw128_desc(a_hi + ko), da_lo = make_sw128_desc(a_lo + ko);
+            const uint64_t db_hi = make_sw128_desc(w_hi + ko), db_lo = make_sw128_desc(w_lo + ko);
+            const uint32_t first = (it > 0 || kk > 0) ? 1u : 0u;
+            tc_mma_tf32(u_tmem_d, da_hi, db_hi, idesc, first);
+            tc_mma_tf32(u_tmem_d + acc_cols, da_lo, db_hi, idesc, first);
+            tc_mma_tf32(u_tmem_d + acc_cols, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        tc_commit(bar_empty0 + 8u * s);
+        if (it == n_active - 1) tc_commit(smem_u32(&sh->accum));
       }
-      tc_commit(smem_u32(&sh->empty[s]));
+      __syncwarp();
       c.next(kc_n);
       if (++s == P.stages) {
         s = 0;
         ph ^= 1u;
       }
     }
-    if (n_active > 0) tc_commit(smem_u32(&sh->accum));
   }
   __syncthreads();
   if (warp == kTcProducers / 32) {

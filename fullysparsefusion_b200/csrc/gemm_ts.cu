@@ -55,6 +55,18 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const float (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const float (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -81,7 +93,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
   if (tid == 0) {
     if (base & 1023u) __trap();
     for (int s = 0; s < kTsAStages; ++s) {
-      mbar_init(smem_u32(&sh->a_full[s]), kTsProducers / 32 + 1);  // producer warps + the W loader (with its tx bytes)
+      mbar_init(smem_u32(&sh->a_full[s]), 4 + 1);  // the 4 warps of the stage's producer group + the W loader (with its tx bytes)
       mbar_init(smem_u32(&sh->a_empty[s]), 2);                     // both MMA issuers commit
     }
     for (int s = 0; s < w_stages; ++s) {
@@ -138,19 +150,24 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
   const int n_active = __popc(off_mask) * kc_n;
 
   if (tid < kTsProducers) {
-    // ================= A producers: thread = (row, K half) → TMEM =================
-    constexpr int kF4 = 32 * kTcRows / kTsProducers / 4;  // float4 loads per thread per stage (2)
-    const int q = warp & 3, h = warp >> 2;
+    // ================= A producers: stage-striped warp groups =================
+    // group g = warps 4g..4g+3 (one per TMEM lane quarter) produces stages it = g, g+4, g+8, ... into ring slot g:
+    // a thread owns one ROW of the tile and gathers its whole 128-byte K chunk (8 predicated 128-bit loads), so the
+    // per-stage bookkeeping (barrier wait/arrive, cursor, index lookup, addressing) is paid by 4 warps instead of
+    // 16 and every group has four stage-times to hide its gather latency.
+    const int grp = warp >> 2, q = warp & 3;
     const int row = 32 * q + lane;
-    const uint32_t t_lane = (uint32_t)(32 * q) << 16;
-    auto load_stage = [&](const StageCursor& c, float4(&v)[kF4]) {
+    const uint32_t ta = tmem_a + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * grp);
+    const uint32_t full_bar = smem_u32(&sh->a_full[grp]), empty_bar = smem_u32(&sh->a_empty[grp]);
+    auto load_stage = [&](const StageCursor& c, float4(&v)[8]) {
       const int32_t src = lds_i32(s_nbr + (uint32_t)(c.k * kTcRows + row) * 4u);
-      const int col0 = c.kc * kGemmKChunk + 4 * kF4 * h;
+      const int col0 = c.kc * kGemmKChunk;
+      const float* g0 = P.a + (int64_t)(src >= 0 ? src : 0) * P.a_stride + col0;
 #pragma unroll
-      for (int j = 0; j < kF4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const int col = col0 + 4 * j;
         const bool ok = src >= 0 && col < P.cin && !(P.debug & 1);
-        const float* g = P.a + (int64_t)(ok ? src : 0) * P.a_stride + (ok ? col : 0);
+        const float* g = ok ? g0 + 4 * j : P.a;
         if (AVEC && col + 4 <= P.cin) {
           v[j] = ldg_pred_f4(g, ok);
         } else {
@@ -161,94 +178,103 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
         }
       }
     };
-    float4 cur[kF4], n1[kF4], n2[kF4];
+    float4 cur[8];
     StageCursor c_ld;
     c_ld.init(off_mask);
-    if (n_active > 0) load_stage(c_ld, cur);
-    c_ld.next(kc_n);
-    if (n_active > 1) load_stage(c_ld, n1);
-    c_ld.next(kc_n);
-    int s = 0;
+    for (int j = 0; j < grp; ++j) c_ld.next(kc_n);
+    if (grp < n_active) load_stage(c_ld, cur);
     uint32_t ph = 0;
-    for (int it = 0; it < n_active; ++it) {
-      if (it + 2 < n_active) load_stage(c_ld, n2);
-      c_ld.next(kc_n);
-      // hi = x with the 13 low mantissa bits cleared (what the tensor core keeps of a tf32 operand),
-      // lo = x - hi exactly (the MMA truncates it to tf32 itself): 2 ALU ops per element
-      float hi[4 * kF4], lo[4 * kF4];
-#pragma unroll
-      for (int j = 0; j < kF4; ++j) {
-        const float x[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hi[4 * j + e] = __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
-          lo[4 * j + e] = x[e] - hi[4 * j + e];
-        }
-      }
-      if (lane == 0) mbar_wait(smem_u32(&sh->a_empty[s]), ph ^ 1u);
+    for (int it = grp; it < n_active; it += kTsAStages) {
+      if (lane == 0) mbar_wait(empty_bar, ph ^ 1u);
       __syncwarp();
       tc_fence_after();
-      const uint32_t ta = tmem_a + t_lane + (uint32_t)(64 * s + 4 * kF4 * h);
+      // hi = x with the 13 low mantissa bits cleared (what the tensor core keeps of a tf32 operand),
+      // lo = x - hi exactly (the MMA truncates it to tf32 itself): 2 ALU ops per element
+      uint32_t t32[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        t32[4 * j + 0] = __float_as_uint(cur[j].x) & 0xFFFFE000u;
+        t32[4 * j + 1] = __float_as_uint(cur[j].y) & 0xFFFFE000u;
+        t32[4 * j + 2] = __float_as_uint(cur[j].z) & 0xFFFFE000u;
+        t32[4 * j + 3] = __float_as_uint(cur[j].w) & 0xFFFFE000u;
+      }
+      if (!(P.debug & 8)) tc_st32(ta, t32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        t32[4 * j + 0] = __float_as_uint(cur[j].x - __uint_as_float(t32[4 * j + 0]));
+        t32[4 * j + 1] = __float_as_uint(cur[j].y - __uint_as_float(t32[4 * j + 1]));
+        t32[4 * j + 2] = __float_as_uint(cur[j].z - __uint_as_float(t32[4 * j + 2]));
+        t32[4 * j + 3] = __float_as_uint(cur[j].w - __uint_as_float(t32[4 * j + 3]));
+      }
       if (!(P.debug & 8)) {
-        tc_st8(ta, hi);
-        tc_st8(ta + 32, lo);
+        tc_st32(ta + 32, t32);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&sh->a_full[s]));
+      if (lane == 0) mbar_arrive(full_bar);
+      // this group's next stage is four stage-times away: its gathers fly while the other groups work
 #pragma unroll
-      for (int j = 0; j < kF4; ++j) {
-        cur[j] = n1[j];
-        n1[j] = n2[j];
-      }
-      if (++s == kTsAStages) {
-        s = 0;
-        ph ^= 1u;
-      }
+      for (int j = 0; j < kTsAStages; ++j) c_ld.next(kc_n);
+      if (it + kTsAStages < n_active) load_stage(c_ld, cur);
+      ph ^= 1u;
     }
-  } else if ((warp == kTsProducers / 32 || warp == kTsProducers / 32 + 1) && lane == 0) {
-    // ================= two MMA issuers =================
+  } else if (warp == kTsProducers / 32 || warp == kTsProducers / 32 + 1) {
+    // ================= two MMA issuer warps =================
     // warp 16: main accumulator (a_hi * w_hi); warp 17: correction accumulator (a_lo * w_hi + a_hi * w_lo).
-    // The two instruction streams touch different TMEM accumulators, so they need no mutual ordering; splitting
-    // them doubles the issue rate of the single-thread MMA front end (the limiter at 12 MMAs per 32-wide K chunk).
+    // The whole warp runs the loop with warp-uniform operands (values laundered through __shfl_sync so ptxas keeps
+    // descriptors / TMEM addresses in uniform registers) and one elected lane issues: a UTCHMMA whose operands
+    // come from vector registers costs ~100 clk of R2UR moves per instruction, more than the 69 clk of math of a
+    // 128x128x8 tf32 MMA (measured: run time was independent of N).
     const bool is_main = warp == kTsProducers / 32;
-    const uint32_t idesc = make_idesc_tf32(n_w);
-    const uint32_t d_acc = is_main ? tmem_d : tmem_d + acc_cols;
+    const uint32_t u_tmem_d = __shfl_sync(0xffffffffu, tmem_d, 0);
+    const uint32_t u_tmem_a = __shfl_sync(0xffffffffu, tmem_a, 0);
+    const uint32_t u_base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t u_mask = __shfl_sync(0xffffffffu, off_mask, 0);
+    const uint32_t idesc = make_idesc_tf32((P.debug & 1024) ? 16 : n_w);
+    const uint32_t d_acc = is_main ? u_tmem_d : u_tmem_d + acc_cols;
+    const uint32_t bar_full0 = __shfl_sync(0xffffffffu, smem_u32(&sh->a_full[0]), 0);
+    const uint32_t bar_empty0 = __shfl_sync(0xffffffffu, smem_u32(&sh->a_empty[0]), 0);
     StageCursor c;
-    c.init(off_mask);
+    c.init(u_mask);
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < n_active; ++it) {
-      mbar_wait(smem_u32(&sh->a_full[s]), ph);
+      if (lane == 0) mbar_wait(bar_full0 + 8u * s, ph);
+      __syncwarp();
       tc_fence_after();
-      const uint32_t w_hi = base + (uint32_t)s * w_bytes;
+      const uint32_t w_hi = u_base + (uint32_t)s * w_bytes;
       const uint32_t w_lo = w_hi + (uint32_t)n_w * 128u;
-      const uint32_t a_hi = tmem_a + (uint32_t)(64 * s), a_lo = a_hi + 32;
+      const uint32_t a_hi = u_tmem_a + (uint32_t)(64 * s), a_lo = a_hi + 32;
       const int k_valid = min(kGemmKChunk, P.cin - c.kc * kGemmKChunk);
       const int ksteps = (k_valid + 7) >> 3;
-      if (!(P.debug & 4)) {
-        if (is_main) {
+      uint32_t elected;
+      asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+      if (elected) {
+        if (!(P.debug & 4)) {
+          if (is_main) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            if (kk < ksteps) tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-        } else {
+            for (int kk = 0; kk < 4; ++kk)
+              if (kk < ksteps) tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          } else {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            if (kk < ksteps) {
-              tc_mma_tf32_ts(d_acc, a_lo + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-              tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_lo + 32u * kk), idesc, 1u);
-            }
+            for (int kk = 0; kk < 4; ++kk)
+              if (kk < ksteps) {
+                tc_mma_tf32_ts(d_acc, a_lo + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                tc_mma_tf32_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_lo + 32u * kk), idesc, 1u);
+              }
+          }
         }
+        tc_commit(bar_empty0 + 8u * s);
+        if (it == n_active - 1) tc_commit(smem_u32(&sh->accum));
       }
-      tc_commit(smem_u32(&sh->a_empty[s]));
+      __syncwarp();
       c.next(kc_n);
       if (++s == kTsAStages) {
         s = 0;
         ph ^= 1u;
       }
     }
-    if (n_active > 0) tc_commit(smem_u32(&sh->accum));
   } else if (warp == kTsProducers / 32 + 2 && lane == 0) {
     // ================= W loader: bulk-async copies into the stage ring =================
     StageCursor c;

@@ -278,14 +278,41 @@ class SIRLayer(nn.Module):
             [DynamicVFELayer(chans[i] * (2 if i > 0 else 1), chans[i + 1], norm_cfg, act=act) for i in range(len(chans) - 1)])
         self.num_vfe = len(self.vfe_layers)
 
+    def refresh(self):
+        self._gate_pack = None
+
+    def _fused_gate(self):
+        """(layers, eps, act) for ops.sir_gate_input when rel_mlp is the stock 3-block LN stack that kernel covers."""
+        if not self.with_rel_mlp:
+            return None
+        pack = getattr(self, "_gate_pack", None)
+        if pack is None:
+            blocks = list(self.rel_mlp)
+            ok = (len(blocks) == 3 and all(isinstance(b, nn.Sequential) and isinstance(b[1], nn.LayerNorm) and b[0].bias is None
+                                           for b in blocks)
+                  and blocks[0][0].in_features == 3 and blocks[0][0].out_features <= 32 and blocks[1][0].out_features <= 32
+                  and self.in_channels <= 256 and len({b[1].eps for b in blocks}) == 1)
+            if ok:
+                layers = [(b[0].weight.detach().float().contiguous(), b[1].weight.detach().float().contiguous(),
+                           b[1].bias.detach().float().contiguous()) for b in blocks]
+                pack = (layers, blocks[0][1].eps, self.rel_mlp._act)
+            else:
+                pack = False
+            self._gate_pack = pack
+        return pack or None
+
     def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_both=False,
                 unq_inv_once=None, new_coors_once=None, plan: Optional[ScatterPlan] = None):
         if plan is None:
             plan = ScatterPlan(coors)
         n = features.size(0)
         dev = features.device
-        gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
-        x = ops.sir_input(features, self.xyz_normalizer, gate)   # cat(xyz/norm, feats) * gate, one pass
+        fused = self._fused_gate()
+        if fused is not None:   # 3 → h1 → h2 → Cin gate MLP + normalisation + multiply in one kernel
+            x = ops.sir_gate_input(features, f_cluster, self.rel_dist_scaler, self.xyz_normalizer, fused[0], fused[1], fused[2])
+        else:
+            gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
+            x = ops.sir_input(features, self.xyz_normalizer, gate)   # cat(xyz/norm, feats) * gate, one pass
         ori = x
         cluster_list = []
         point_feats = None

@@ -432,7 +432,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         check(lib.fsfb_gather_gemm_simt(*args, _ptr(w.raw), *tail), "fsfb_gather_gemm_simt")
         return out
     if nbr is None:
-        prof = _Prof("gather_gemm_linear", 4 * rows * (w.cin + w.cout) + 4 * w.cin * w.cout, 2 * rows * w.cin * w.cout)
+        prof = _Prof(f"gather_gemm_linear_{rows >> 10}k_{w.cin}x{w.cout}" if DETAIL else "gather_gemm_linear", 4 * rows * (w.cin + w.cout) + 4 * w.cin * w.cout, 2 * rows * w.cin * w.cout)
     else:
         pairs = getattr(nbr, "_fsfb_pairs", None)
         if PROFILER is not None and pairs is None:   # profiling only: exact pair count of this rulebook, kept on device
@@ -789,3 +789,24 @@ def count_mask(counts32: torch.Tensor, inv32: torch.Tensor, min_count: int) -> t
     check(load().fsfb_count_mask(_ptr(counts32.contiguous()), _ptr(inv32.contiguous()), n, int(min_count), _ptr(mask),
                                  _stream(dev)), "fsfb_count_mask")
     return mask
+
+
+def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers, eps: float, act: str, out=None):
+    """Fused SIRLayer input: cat(xyz/normalizer, feats) * rel_mlp(f_cluster / scaler)  (include/fsf_b200.h).
+    layers: [(W1, ln_w1, ln_b1), (W2, ln_w2, ln_b2), (W3, ln_w3, ln_b3)] contiguous fp32 CUDA tensors."""
+    dev = _need_cuda(features, f_cluster)
+    features = _rowmajor(features)
+    f_cluster = _rowmajor(f_cluster)
+    n, c = features.shape
+    (w1, g1, b1), (w2, g2, b2), (w3, g3, b3) = layers
+    h1, h2 = w1.size(0), w2.size(0)
+    assert w1.shape == (h1, 3) and w2.shape == (h2, h1) and w3.shape == (c, h2)
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=dev)
+    with _Prof("sir_gate_input", 4 * n * (2 * c + 3)):
+        rc = load().fsfb_sir_gate_input(_ptr(features), n, c, features.stride(0) if n else c, _ptr(f_cluster),
+                                        f_cluster.stride(0) if n else 3, float(rel_dist_scaler), _host_f32(xyz_normalizer),
+                                        h1, h2, _ptr(w1), _ptr(g1), _ptr(b1), _ptr(w2), _ptr(g2), _ptr(b2), _ptr(w3), _ptr(g3),
+                                        _ptr(b3), float(eps), _ACTS[act], _ptr(out), out.stride(0) if n else c, _stream(dev))
+    check(rc, "fsfb_sir_gate_input")
+    return out

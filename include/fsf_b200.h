@@ -374,6 +374,17 @@ int fsfb_encode_preds_2d(const float* anno, int anno_rows, int anno_cols, const 
                          int coor_col, int64_t k, float img_w, float img_h, int num_classes, float* preds_2d,
                          float* feat, void* stream);
 
+/* a12  SIRLayer relative-position gate, fused: out = cat(xyz/xyz_normalizer, feats[:,3:]) * rel_mlp(f_cluster/scaler)
+ * with rel_mlp = build_mlp(3, [h1, h2, c], LN(eps), act) (three Linear(bias=False) → LayerNorm → act blocks;
+ * built by SIR at projects/mmdet3d_plugin/models/backbones/sir.py:41-62, rel_dist_scaler = 10 at :57).
+ * w1 dev [h1,3], w2 dev [h2,h1], w3 dev [c,h2] (nn.Linear layouts), ln*_w/ln*_b the LayerNorm affines.
+ * h1, h2 <= 32, 3 <= c <= 256. */
+int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* f_cluster,
+                        int64_t fc_stride, float rel_dist_scaler, const float* xyz_normalizer, int h1, int h2,
+                        const float* w1, const float* ln1_w, const float* ln1_b, const float* w2,
+                        const float* ln2_w, const float* ln2_b, const float* w3, const float* ln3_w,
+                        const float* ln3_b, float eps, int act, float* out, int64_t out_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
