@@ -302,13 +302,15 @@ def main():
         for name, a, b in events:
             per_stage.setdefault(name, []).append(a.elapsed_time(b))
         stage_ms = {k: sum(v) / len(v) for k, v in per_stage.items()}
-        kern = {}
+        kern, shapes = {}, {}
         for name, a, b, nb, fl in prof:
-            k = kern.setdefault(name, dict(ms=0.0, bytes=0, flops=0, calls=0))
-            k["ms"] += a.elapsed_time(b)
-            k["bytes"] += resolve(nb)
-            k["flops"] += resolve(fl)
-            k["calls"] += 1
+            ms, nb, fl = a.elapsed_time(b), resolve(nb), resolve(fl)
+            for table, key in ((kern, name.split("[")[0]), (shapes, name)):
+                k = table.setdefault(key, dict(ms=0.0, bytes=0, flops=0, calls=0))
+                k["ms"] += ms
+                k["bytes"] += nb
+                k["flops"] += fl
+                k["calls"] += 1
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -324,13 +326,19 @@ def main():
             if k["flops"]:
                 table[name]["TFLOP/s"] = round(k["flops"] / sec / 1e12, 2)
                 table[name]["tensor_frac_of_bf16_sustained"] = round(k["flops"] / sec / 1e12 / tpeak, 4)
-        # the metric names the scatter + projection kernels: the dominant one (most time) carries `roofline`
-        dom = max(("segment_reduce", "project_sample_select", "gather_rows"), key=lambda n: kern.get(n, {"ms": 0})["ms"])
-        d = kern[dom]
+        # the metric names the scatter + projection kernels: the launch class (op + shape) with the most time among
+        # them carries `roofline`; achieved = its algorithmic bytes per launch / its average launch duration
+        cand = {n: v for n, v in shapes.items() if n.split("[")[0] in ("segment_reduce", "project_sample_select", "gather_rows")}
+        dom = max(cand, key=lambda n: cand[n]["ms"])
+        d = cand[dom]
         ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "launches_timed": d["calls"],
-                    "note": "algorithmic bytes / CUDA-event time of every launch of this op in the timed region"}
+                    "bytes_per_launch": d["bytes"] // d["calls"], "us_per_launch": round(d["ms"] / d["calls"] * 1e3, 2),
+                    "family_frac": {f: round(kern[f]["bytes"] / (kern[f]["ms"] * 1e-3) / 1e9 / peak, 4)
+                                    for f in ("segment_reduce", "gather_rows", "project_sample_select") if f in kern},
+                    "note": "algorithmic bytes / CUDA-event time, averaged over every launch of this op+shape in the timed "
+                            "region (each op = main kernel + boundary fix-up kernel); family_frac aggregates all shapes"}
         st = last["st"]
         h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
         d2h = sum(r.numel() * r.element_size() for r in res)

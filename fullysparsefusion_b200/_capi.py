@@ -33,7 +33,7 @@ SIGNATURES = {
     "fsfb_csr_build": (_i, [_p, _i, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "fsfb_segment_reduce_workspace_bytes": (_i, [_i64, _i, _i, _psz]),
     "fsfb_segment_reduce": (_i, [_p, _i64, _i, _i64, _p, _p, _p, _i64, _i, _p, _p, _p, _sz, _p]),
-    "fsfb_gather_rows": (_i, [_p, _i64, _i, _p, _i, _i64, _f, _p, _i64, _p]),
+    "fsfb_gather_rows": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _f, _p, _i64, _p]),
     "fsfb_ingroup_workspace_bytes": (_i, [_i64, _i64, _psz]),
     "fsfb_ingroup_indices": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),
     "fsfb_project_sample": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p]),
@@ -51,7 +51,7 @@ SIGNATURES = {
     "fsfb_div_cols": (_i, [_p, _i64, _i, _i64, _p, _p, _i64, _p]),
     "fsfb_add_inplace": (_i, [_p, _i64, _i, _i64, _p, _i64, _p]),
     "fsfb_reduce_channel": (_i, [_p, _i64, _i, _i64, _i, _p, _p]),
-    "fsfb_neck_points": (_i, [_p, _i64, _i64, _p, _i, _p, _i64, _i, _p, _i, _p, _p, _f, _p, _p, _p, _p]),
+    "fsfb_neck_points": (_i, [_p, _i64, _i64, _p, _i, _p, _i64, _i, _p, _i, _p, _p, _f, _p, _i64, _p, _p, _p]),
     "fsfb_vote_decode": (_i, [_p, _i64, _p, _p]),
     "fsfb_compact_workspace_bytes": (_i, [_i64, _psz]),
     "fsfb_compact_indices": (_i, [_p, _i64, _p, _p, _p, _sz, _p]),
@@ -63,7 +63,7 @@ SIGNATURES = {
     "fsfb_encode_preds_2d": (_i, [_p, _i, _i, _p, _i, _i, _i64, _f, _f, _i, _p, _p, _p]),
     "fsfb_threshold_mask": (_i, [_p, _i64, _i64, _i, _f, _p, _p]),
     "fsfb_count_mask": (_i, [_p, _p, _i64, _i, _p, _p]),
-    "fsfb_sir_gate_input": (_i, [_p, _i64, _i, _i64, _p, _i64, _f, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _i64, _p]),
+    "fsfb_sir_gate_input": (_i, [_p, _i64, _i, _i64, _p, _i64, _i, _p, _i64, _f, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _i64, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

@@ -59,7 +59,7 @@ struct Epilogue {
   float eps;
   const float* residual;  // [rows, residual_stride] or null
   int64_t residual_stride;
-  int act;                // FSFB_ACT_*
+  int act;                // FSFB_ACT_* (| FSFB_RESIDUAL_POST: add the residual after the activation)
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -98,8 +98,10 @@ __device__ __forceinline__ void warp_row_epilogue(const float* x, int c, const E
     } else if (E.norm == FSFB_NORM_AFFINE) {
       v = fmaf(v, __ldg(E.norm_w + j), __ldg(E.norm_b + j));
     }
-    if (E.residual) v += __ldg(E.residual + row * E.residual_stride + j);
-    out[j] = apply_act(v, E.act);
+    const int act = E.act & 0xff;
+    const bool post = (E.act & FSFB_RESIDUAL_POST) != 0;
+    const float rsd = E.residual ? __ldg(E.residual + row * E.residual_stride + j) : 0.f;
+    out[j] = post ? apply_act(v, act) + rsd : apply_act(v + rsd, act);
   }
 }
 
@@ -109,8 +111,9 @@ inline int check_epilogue(int cout, const float* bias, int norm, const float* no
   FSFB_CHECK_ARG(norm == FSFB_NORM_NONE || norm == FSFB_NORM_LAYERNORM || norm == FSFB_NORM_AFFINE,
                  "%s: bad norm %d", who, norm);
   FSFB_CHECK_ARG(norm == FSFB_NORM_NONE || (norm_w && norm_b), "%s: norm needs norm_w and norm_b", who);
-  FSFB_CHECK_ARG(act == FSFB_ACT_NONE || act == FSFB_ACT_RELU || act == FSFB_ACT_GELU, "%s: bad act %d",
-                 who, act);
+  FSFB_CHECK_ARG((act & ~FSFB_RESIDUAL_POST) == FSFB_ACT_NONE || (act & ~FSFB_RESIDUAL_POST) == FSFB_ACT_RELU ||
+                     (act & ~FSFB_RESIDUAL_POST) == FSFB_ACT_GELU,
+                 "%s: bad act %d", who, act);
   FSFB_CHECK_ARG(cout >= 1, "%s: cout must be >= 1", who);
   return FSFB_OK;
 }

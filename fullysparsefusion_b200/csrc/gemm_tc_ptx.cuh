@@ -234,6 +234,8 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
   const Epilogue& E = P.E;
   const int c0 = nt * kGemmNTile;
   const int c_n = min(n_w, P.S.cout - c0);
+  const int act = E.act & 0xff;
+  const bool post = (E.act & FSFB_RESIDUAL_POST) != 0;
   const bool res_vec = E.residual && ((uintptr_t)E.residual % 16 == 0) && (E.residual_stride % 4 == 0);
   for (int rl = warp; rl < kTcRows; rl += n_warps) {
     const int64_t r = row0 + rl;
@@ -245,19 +247,21 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
       for (int c = lane * 4; c < c_n; c += 128) {
         float4 x;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(srow + c * 4));
-        if (res) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(res + c));
-          x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) q = __ldg(reinterpret_cast<const float4*>(res + c));
+        if (post) {
+          x.x = apply_act(x.x, act) + q.x; x.y = apply_act(x.y, act) + q.y; x.z = apply_act(x.z, act) + q.z; x.w = apply_act(x.w, act) + q.w;
+        } else {
+          x.x = apply_act(x.x + q.x, act); x.y = apply_act(x.y + q.y, act); x.z = apply_act(x.z + q.z, act); x.w = apply_act(x.w + q.w, act);
         }
-        x.x = apply_act(x.x, E.act); x.y = apply_act(x.y, E.act); x.z = apply_act(x.z, E.act); x.w = apply_act(x.w, E.act);
         *reinterpret_cast<float4*>(o + c) = x;
       }
     } else {
       for (int c = lane; c < c_n; c += 32) {
         float x;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(srow + c * 4));
-        if (res) x += __ldg(res + c);
-        o[c] = apply_act(x, E.act);
+        const float q = res ? __ldg(res + c) : 0.f;
+        o[c] = post ? apply_act(x, act) + q : apply_act(x + q, act);
       }
     }
   }

@@ -107,14 +107,14 @@ template <typename CoorT, typename IdxT>
 __global__ void __launch_bounds__(256)
     k_neck_points(const float* __restrict__ pts, int64_t n, int64_t pts_stride, const CoorT* __restrict__ coors,
                   const float* __restrict__ vf, int64_t m, int c, const IdxT* __restrict__ inv, Vec3 vs, Vec3 lo,
-                  float padding, float* __restrict__ out, uint8_t* __restrict__ mask, int* __restrict__ dropped) {
+                  float padding, float* __restrict__ out, int64_t out_stride, uint8_t* __restrict__ mask,
+                  int* __restrict__ dropped) {
   const int lane = lane_id();
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int oc = c + 3;
   for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
     const int64_t s = (int64_t)inv[i];
     const float* src = vf + s * c;
-    float* o = out + i * oc;
+    float* o = out + i * out_stride;
     bool all_pad = true;
     for (int j = lane; j < c; j += 32) {
       const float v = __ldg(src + j);
@@ -310,10 +310,11 @@ int fsfb_reduce_channel(const float* x, int64_t n, int cin, int64_t x_stride, in
 
 int fsfb_neck_points(const float* points, int64_t n, int64_t pts_stride, const void* coors, int coors_i64,
                      const float* voxel_feats, int64_t m, int c, const void* inv, int inv_i64,
-                     const float* voxel_size, const float* range_min, float padding, float* out, uint8_t* mask,
-                     int32_t* dropped, void* stream) {
+                     const float* voxel_size, const float* range_min, float padding, float* out, int64_t out_stride,
+                     uint8_t* mask, int32_t* dropped, void* stream) {
   using namespace fsfb;
-  FSFB_CHECK_ARG(n >= 0 && m >= 0 && c >= 1 && pts_stride >= 3 && voxel_size && range_min, "neck_points: bad argument");
+  FSFB_CHECK_ARG(n >= 0 && m >= 0 && c >= 1 && pts_stride >= 3 && out_stride >= c + 3 && voxel_size && range_min,
+                 "neck_points: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (dropped) FSFB_CUDA(cudaMemsetAsync(dropped, 0, 4, st));
   if (n == 0) return FSFB_OK;
@@ -322,7 +323,7 @@ int fsfb_neck_points(const float* points, int64_t n, int64_t pts_stride, const v
   const int grid = (int)std::min<int64_t>(ceil_div(n, 8), (int64_t)kNumSMs * 32);
 #define NECK(CT, IT)                                                                                          \
   FSFB_LAUNCH((k_neck_points<CT, IT>), grid, 256, 0, st, points, n, pts_stride, (const CT*)coors, voxel_feats, m, c, \
-              (const IT*)inv, vs, lo, padding, out, mask, dropped)
+              (const IT*)inv, vs, lo, padding, out, out_stride, mask, dropped)
   if (coors_i64 && inv_i64) NECK(long long, long long);
   else if (coors_i64) NECK(long long, int);
   else if (inv_i64) NECK(int, long long);

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kSrWarps * 32)
 // whatever the row width (C = 3 ... 768 on this path); 4 chunks in flight per thread.
 template <typename IdxT, int VEC>
 __global__ void __launch_bounds__(256)
-    k_gather_rows(const float* __restrict__ src, int64_t m, int C, const IdxT* __restrict__ idx,
+    k_gather_rows(const float* __restrict__ src, int64_t m, int C, int64_t src_stride, const IdxT* __restrict__ idx,
                   int64_t n, float fill, float* __restrict__ out, int64_t out_stride) {
   const int cv = C / VEC;
   const int64_t total = n * cv;
@@ -269,9 +269,9 @@ __global__ void __launch_bounds__(256)
         const bool ok = s >= 0 && s < m;
         dst[u] = i * out_stride + j;
         if (VEC == 4) {
-          v[u] = ok ? __ldg(reinterpret_cast<const float4*>(src + s * C + j)) : make_float4(fill, fill, fill, fill);
+          v[u] = ok ? __ldg(reinterpret_cast<const float4*>(src + s * src_stride + j)) : make_float4(fill, fill, fill, fill);
         } else {
-          v[u].x = ok ? __ldg(src + s * C + j) : fill;
+          v[u].x = ok ? __ldg(src + s * src_stride + j) : fill;
         }
       }
     }
@@ -378,23 +378,23 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
   return FSFB_OK;
 }
 
-int fsfb_gather_rows(const float* src, int64_t m, int c, const void* idx, int idx_i64, int64_t n,
+int fsfb_gather_rows(const float* src, int64_t m, int c, int64_t src_stride, const void* idx, int idx_i64, int64_t n,
                      float fill, float* out, int64_t out_stride, void* stream) {
   using namespace fsfb;
-  FSFB_CHECK_ARG(n >= 0 && m >= 0 && c >= 1 && out_stride >= c, "gather_rows: bad argument");
+  FSFB_CHECK_ARG(n >= 0 && m >= 0 && c >= 1 && out_stride >= c && src_stride >= c, "gather_rows: bad argument");
   if (n == 0) return FSFB_OK;
   FSFB_CHECK_ARG(idx && out && (m == 0 || src), "gather_rows: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec4 = (c % 4 == 0) && (out_stride % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
+  const bool vec4 = (c % 4 == 0) && (out_stride % 4 == 0) && (src_stride % 4 == 0) && ((uintptr_t)src % 16 == 0) &&
                     ((uintptr_t)out % 16 == 0);
   const int64_t chunks = n * (vec4 ? c / 4 : c);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(chunks, 256 * 4), (int64_t)kNumSMs * 16));
   if (idx_i64) {
     auto kern = vec4 ? k_gather_rows<long long, 4> : k_gather_rows<long long, 1>;
-    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, (const long long*)idx, n, fill, out, out_stride);
+    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, src_stride, (const long long*)idx, n, fill, out, out_stride);
   } else {
     auto kern = vec4 ? k_gather_rows<int, 4> : k_gather_rows<int, 1>;
-    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, (const int*)idx, n, fill, out, out_stride);
+    FSFB_LAUNCH(kern, grid, 256, 0, st, src, m, c, src_stride, (const int*)idx, n, fill, out, out_stride);
   }
   return FSFB_OK;
 }

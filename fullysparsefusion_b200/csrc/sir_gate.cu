@@ -23,6 +23,9 @@ struct GateParams {
   int64_t n;
   int c;
   int64_t feat_stride;
+  const float* feats_b;   // optional second source: channels [c_a, c) come from feats_b[:, 0:c-c_a]
+  int64_t feats_b_stride;
+  int c_a;
   const float* f_cluster;
   int64_t fc_stride;
   float inv_dummy;
@@ -206,13 +209,14 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
       if (i >= P.n) break;
       const float rstd = 1.f / sqrtf(q[p] / (float)P.c + P.eps);
       const float* fr = P.feats + i * P.feat_stride;
+      const float* fb = P.feats_b ? P.feats_b + i * P.feats_b_stride - P.c_a : fr;
       float* o = P.out + i * P.out_stride;
 #pragma unroll
       for (int t = 0; t < kGateMaxC / 32; ++t) {
         const int c = lane + 32 * t;
         if (t < nt && c < P.c) {
           const float gate = apply_act((g[p][t] - mu[p]) * rstd * g3[c] + b3[c], P.act);
-          float x = __ldg(fr + c);
+          float x = __ldg((c < P.c_a ? fr : fb) + c);
           if (c < 3) x = __fdiv_rn(x, P.nrm[c]);
           o[c] = __fmul_rn(x, gate);
         }
@@ -223,13 +227,16 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
 
 }  // namespace fsfb
 
-extern "C" int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* f_cluster,
+extern "C" int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* feats_b,
+                                   int64_t feats_b_stride, int c_a, const float* f_cluster,
                                    int64_t fc_stride, float rel_dist_scaler, const float* xyz_normalizer, int h1, int h2,
                                    const float* w1, const float* ln1_w, const float* ln1_b, const float* w2,
                                    const float* ln2_w, const float* ln2_b, const float* w3, const float* ln3_w,
                                    const float* ln3_b, float eps, int act, float* out, int64_t out_stride, void* stream) {
   using namespace fsfb;
-  FSFB_CHECK_ARG(n >= 0 && c >= 3 && c <= kGateMaxC && feat_stride >= c && out_stride >= c && fc_stride >= 3,
+  if (!feats_b) c_a = c;
+  FSFB_CHECK_ARG(n >= 0 && c >= 3 && c <= kGateMaxC && c_a >= 3 && c_a <= c && feat_stride >= c_a && out_stride >= c &&
+                     fc_stride >= 3 && (!feats_b || feats_b_stride >= c - c_a),
                  "sir_gate_input: bad shape (c must be 3..%d)", kGateMaxC);
   FSFB_CHECK_ARG(h1 >= 1 && h1 <= kGateMaxH && h2 >= 1 && h2 <= kGateMaxH, "sir_gate_input: hidden widths must be 1..%d", kGateMaxH);
   FSFB_CHECK_ARG(act == FSFB_ACT_NONE || act == FSFB_ACT_RELU || act == FSFB_ACT_GELU, "sir_gate_input: bad act");
@@ -238,7 +245,7 @@ extern "C" int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t
   FSFB_CHECK_ARG(feats && f_cluster && out && w1 && ln1_w && ln1_b && w2 && ln2_w && ln2_b && w3 && ln3_w && ln3_b,
                  "sir_gate_input: null pointer");
   GateParams P;
-  P.feats = feats; P.n = n; P.c = c; P.feat_stride = feat_stride; P.f_cluster = f_cluster; P.fc_stride = fc_stride;
+  P.feats = feats; P.n = n; P.c = c; P.feat_stride = feat_stride; P.feats_b = feats_b; P.feats_b_stride = feats_b_stride; P.c_a = c_a; P.f_cluster = f_cluster; P.fc_stride = fc_stride;
   P.inv_dummy = 0.f; P.scaler = rel_dist_scaler;
   P.nrm[0] = xyz_normalizer[0]; P.nrm[1] = xyz_normalizer[1]; P.nrm[2] = xyz_normalizer[2];
   P.h1 = h1; P.h2 = h2;

@@ -302,15 +302,19 @@ class SIRLayer(nn.Module):
         return pack or None
 
     def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_both=False,
-                unq_inv_once=None, new_coors_once=None, plan: Optional[ScatterPlan] = None):
+                unq_inv_once=None, new_coors_once=None, plan: Optional[ScatterPlan] = None, features_b=None):
+        """features_b (extension): the input rows are cat(features, features_b) — lets SIR skip its torch.cat."""
         if plan is None:
             plan = ScatterPlan(coors)
         n = features.size(0)
         dev = features.device
         fused = self._fused_gate()
         if fused is not None:   # 3 → h1 → h2 → Cin gate MLP + normalisation + multiply in one kernel
-            x = ops.sir_gate_input(features, f_cluster, self.rel_dist_scaler, self.xyz_normalizer, fused[0], fused[1], fused[2])
+            x = ops.sir_gate_input(features, f_cluster, self.rel_dist_scaler, self.xyz_normalizer, fused[0], fused[1], fused[2],
+                                   features_b=features_b)
         else:
+            if features_b is not None:
+                features = torch.cat([features, features_b], 1)
             gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
             x = ops.sir_input(features, self.xyz_normalizer, gate)   # cat(xyz/norm, feats) * gate, one pass
         ori = x
@@ -358,11 +362,11 @@ class SIR(nn.Module):
         cluster_feat_list = []
         out_coors = None
         for i, block in enumerate(self.block_list):
-            in_feats = torch.cat([points, out_feats], 1)
+            # in_feats = torch.cat([points, out_feats], 1) (sir.py:76), read from its two sources by the gate kernel
             if i < self.num_blocks - 1:
-                out_feats, c = block(in_feats, coors, f_cluster, plan=plan)
+                out_feats, c = block(points, coors, f_cluster, plan=plan, features_b=out_feats)
             else:
-                out_feats, c, out_coors = block(in_feats, coors, f_cluster, return_both=True, plan=plan)
+                out_feats, c, out_coors = block(points, coors, f_cluster, return_both=True, plan=plan, features_b=out_feats)
             cluster_feat_list.append(c)
         return out_feats, torch.cat(cluster_feat_list, dim=1), out_coors
 
@@ -388,7 +392,7 @@ class SparseConvModule(nn.Module):
     def refresh(self):
         self._pack = None
 
-    def forward(self, feats, nbr, out=None, residual=None):
+    def forward(self, feats, nbr, out=None, residual=None, residual_post=False):
         if self._pack is None:
             n = self.bn
             scale = n.weight.detach().float() / torch.sqrt(n.running_var.float() + n.eps)
@@ -396,7 +400,7 @@ class SparseConvModule(nn.Module):
             self._pack = (ops.gemm_prepack(self.weight.detach().float()), scale.contiguous(), shift.contiguous())
         w, scale, shift = self._pack
         return ops.gather_gemm(feats, w, nbr=nbr, norm="affine", norm_w=scale, norm_b=shift, residual=residual,
-                               act=self.act, out=out)
+                               act=self.act, out=out, residual_post=residual_post)
 
 
 class SparseBasicBlock(nn.Module):
@@ -492,19 +496,27 @@ class SimpleSparseUNet(nn.Module):
             for layer in stage:
                 x = layer(x, rb[layer.indice_key])
             enc.append(x)
-        x = enc[-1]
+        # decoder: every level's [x_bottom | lateral] concatenation is written in place (the upsample conv of the
+        # level above stores straight into the left half), and x_merge + reduce_channel(x) is the merge conv's epilogue
+        cat = None
         for lvl in range(self.stage_num, 0, -1):
             lat_in = enc[lvl - 1]
             n, c = lat_in.shape
-            cat = torch.empty((n, 2 * c), dtype=torch.float32, device=x.device)
-            cat[:, :c].copy_(x)                                   # torch.cat((x_bottom.features, x.features), 1)
+            if cat is None:   # top level: x_bottom is the last encoder output itself
+                cat = torch.empty((n, 2 * c), dtype=torch.float32, device=lat_in.device)
+                cat[:, :c].copy_(enc[-1])
             getattr(self, f"lateral_layer{lvl}")(lat_in, rb[f"subm{lvl}"], out=cat[:, c:])
             merge = getattr(self, f"merge_layer{lvl}")
             reduced = ops.reduce_channel(cat, merge.weight.size(1))   # reduce_channel(x, C): sum of channel groups
-            x = merge(cat, rb[f"subm{lvl}"])
-            x = ops.add_(x, reduced)
+            x = merge(cat, rb[f"subm{lvl}"], residual=reduced, residual_post=True)   # x_merge.features + x.features
             up = getattr(self, f"upsample_layer{lvl}")
-            x = up(x, rb[f"spconv{lvl}_inv"] if lvl != 1 else rb["subm1"])
+            if lvl != 1:
+                n_next, c_next = enc[lvl - 2].shape
+                assert up.weight.size(1) == c_next
+                cat = torch.empty((n_next, 2 * c_next), dtype=torch.float32, device=x.device)
+                up(x, rb[f"spconv{lvl}_inv"], out=cat[:, :c_next])
+            else:
+                x = up(x, rb["subm1"])
         return [{"voxel_feats": x}]
 
 

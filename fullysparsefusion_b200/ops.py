@@ -71,6 +71,24 @@ def _ws(nbytes: int, dev: torch.device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
 
 
+def empty_rows(n: int, c: int, dev: torch.device) -> torch.Tensor:
+    """[n, c] fp32 whose rows start 16-byte aligned: wide odd widths (131, 133, 175 ...) are carved out of a
+    [n, round_up(c, 4)] allocation so every consumer can use 128-bit accesses."""
+    if c % 4 == 0 or c < 64:
+        return torch.empty((n, c), dtype=torch.float32, device=dev)
+    return torch.empty((n, (c + 3) // 4 * 4), dtype=torch.float32, device=dev)[:, :c]
+
+
+def _padded_base(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """The [n, round_up(c,4)] allocation `t` is a [:, :c] view of (see empty_rows), or None."""
+    b = t._base
+    if (b is not None and t.dim() == 2 and t.size(1) >= 64 and b.dim() == 2 and b.is_contiguous() and b.data_ptr() == t.data_ptr()
+            and b.size(0) == t.size(0) and b.size(1) == (t.size(1) + 3) // 4 * 4 and b.size(1) != t.size(1)
+            and t.stride(0) == b.size(1) and t.stride(1) == 1):
+        return b
+    return None
+
+
 def _host_f32(vals: Sequence[float]):
     return (C.c_float * len(vals))(*[float(v) for v in vals])
 
@@ -235,6 +253,9 @@ def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax
     """
     dev = _need_cuda(feat, csr.offsets)
     assert feat.dim() == 2 and feat.dtype == torch.float32 and feat.size(0) == csr.n
+    base = _padded_base(feat)
+    if base is not None and not return_argmax:   # reduce the padded rows with 128-bit accesses, drop the pad column
+        return segment_reduce(base, csr, mode)[:, :feat.size(1)]
     if feat.stride(1) != 1 and feat.numel():
         feat = feat.contiguous()
     n, c = feat.shape
@@ -250,7 +271,7 @@ def segment_reduce(feat: torch.Tensor, csr: SegmentCSR, mode: str, return_argmax
     check(lib.fsfb_segment_reduce_workspace_bytes(n, c, int(want_arg), C.byref(need)),
           "fsfb_segment_reduce_workspace_bytes")
     ws = _ws(need.value, dev)
-    with _Prof("segment_reduce", 4 * n * c + 8 * n + 4 * csr.m * c + (8 * csr.m * c if want_arg else 0)):
+    with _Prof(f"segment_reduce[{mode},n={n},c={c}]", 4 * n * c + 8 * n + 4 * csr.m * c + (8 * csr.m * c if want_arg else 0)):
         rc = lib.fsfb_segment_reduce(_ptr(feat), n, c, feat.stride(0) if n else c, _ptr(csr.perm), _ptr(csr.seg),
                                      _ptr(csr.offsets), csr.m, mode_flags, _ptr(out), _ptr(arg), _ptr(ws), ws.numel(),
                                      _stream(dev))
@@ -263,7 +284,10 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0, out: Op
     dev = _need_cuda(src, idx)
     assert src.dim() == 2 and src.dtype == torch.float32
     assert idx.dim() == 1 and idx.dtype in (torch.int64, torch.int32)
-    src = src.contiguous()
+    base = _padded_base(src)
+    if base is not None and out is None:   # gather whole padded rows (128-bit), hand back the same padded view
+        return gather_rows(base, idx, fill)[:, :src.size(1)]
+    src = _rowmajor(src)
     idx = idx.contiguous()
     n, c = idx.numel(), src.size(1)
     if out is None:
@@ -271,9 +295,9 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, fill: float = 0.0, out: Op
     assert out.size(0) == n and out.size(1) >= c and out.stride(1) == 1
     if n == 0 or c == 0:
         return out
-    with _Prof("gather_rows", 2 * 4 * n * c + idx.element_size() * n):
-        rc = load().fsfb_gather_rows(_ptr(src), src.size(0), c, _ptr(idx), int(idx.dtype == torch.int64), n,
-                                     float(fill), _ptr(out), out.stride(0), _stream(dev))
+    with _Prof(f"gather_rows[n={n},c={c}]", 2 * 4 * n * c + idx.element_size() * n):
+        rc = load().fsfb_gather_rows(_ptr(src), src.size(0), c, src.stride(0) if src.size(0) else c, _ptr(idx),
+                                     int(idx.dtype == torch.int64), n, float(fill), _ptr(out), out.stride(0), _stream(dev))
     check(rc, "fsfb_gather_rows")
     return out
 
@@ -401,7 +425,7 @@ def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
 
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
-                out: Optional[torch.Tensor] = None, simt: bool = False) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False) -> torch.Tensor:
     """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual)  (include/fsf_b200.h).
 
     nbr: int32 [koff, rows] neighbour table (< 0 = none) or None for a plain Linear over rows of `a`.
@@ -418,7 +442,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         assert w.koff == 1
         rows = a.size(0) if rows is None else rows
     if out is None:
-        out = torch.empty((rows, w.cout), dtype=torch.float32, device=dev)
+        out = empty_rows(rows, w.cout, dev)
     assert out.size(0) == rows and out.size(1) == w.cout and out.stride(1) == 1
     if rows == 0:
         return out
@@ -426,7 +450,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
     lib = load()
     args = (_ptr(a), a.size(0), w.cin, a.stride(0), _ptr(nbr), w.koff, rows)
     tail = (w.cout, b, nid, nw, nb, float(eps), _ptr(residual), residual.stride(0) if residual is not None else 0,
-            _ACTS[act], _ptr(out), out.stride(0), _stream(dev))
+            _ACTS[act] | (0x100 if residual_post else 0), _ptr(out), out.stride(0), _stream(dev))
     if simt:
         assert w.raw is not None, "gemm_prepack(..., keep_raw=True) needed for the SIMT cross-check"
         check(lib.fsfb_gather_gemm_simt(*args, _ptr(w.raw), *tail), "fsfb_gather_gemm_simt")
@@ -644,13 +668,13 @@ def voxel2point_neck(points, pts_coors, voxel_feats, voxel2point_inds, voxel_siz
     voxel_feats = voxel_feats.contiguous()
     inv = voxel2point_inds.contiguous()
     n, (m, c) = points.size(0), voxel_feats.shape
-    out = torch.empty((n, c + 3), dtype=torch.float32, device=dev)
+    out = empty_rows(n, c + 3, dev)
     mask = torch.empty(n, dtype=torch.uint8, device=dev)
     dropped = torch.empty(1, dtype=torch.int32, device=dev)
     rc = load().fsfb_neck_points(_ptr(points), n, points.stride(0) if n else 3, _ptr(pts_coors),
                                  int(pts_coors.dtype == torch.int64), _ptr(voxel_feats), m, c, _ptr(inv),
                                  int(inv.dtype == torch.int64), _host_f32(voxel_size), _host_f32(point_cloud_range[:3]),
-                                 float(voxel_padding), _ptr(out), _ptr(mask), _ptr(dropped), _stream(dev))
+                                 float(voxel_padding), _ptr(out), out.stride(0), _ptr(mask), _ptr(dropped), _stream(dev))
     check(rc, "fsfb_neck_points")
     if int(dropped.item()):  # padded voxels present: compact exactly as the boolean indexing at :50-52 does
         keep = compact_indices(mask)
@@ -791,20 +815,27 @@ def count_mask(counts32: torch.Tensor, inv32: torch.Tensor, min_count: int) -> t
     return mask
 
 
-def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers, eps: float, act: str, out=None):
+def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers, eps: float, act: str, out=None,
+                   features_b=None):
     """Fused SIRLayer input: cat(xyz/normalizer, feats) * rel_mlp(f_cluster / scaler)  (include/fsf_b200.h).
     layers: [(W1, ln_w1, ln_b1), (W2, ln_w2, ln_b2), (W3, ln_w3, ln_b3)] contiguous fp32 CUDA tensors."""
     dev = _need_cuda(features, f_cluster)
     features = _rowmajor(features)
     f_cluster = _rowmajor(f_cluster)
-    n, c = features.shape
+    n, c_a = features.shape
+    c = c_a
+    if features_b is not None:   # input row = cat(features, features_b) without materialising it
+        features_b = _rowmajor(features_b)
+        assert features_b.size(0) == n
+        c = c_a + features_b.size(1)
     (w1, g1, b1), (w2, g2, b2), (w3, g3, b3) = layers
     h1, h2 = w1.size(0), w2.size(0)
     assert w1.shape == (h1, 3) and w2.shape == (h2, h1) and w3.shape == (c, h2)
     if out is None:
         out = torch.empty((n, c), dtype=torch.float32, device=dev)
     with _Prof("sir_gate_input", 4 * n * (2 * c + 3)):
-        rc = load().fsfb_sir_gate_input(_ptr(features), n, c, features.stride(0) if n else c, _ptr(f_cluster),
+        rc = load().fsfb_sir_gate_input(_ptr(features), n, c, features.stride(0) if n else c, _ptr(features_b),
+                                        features_b.stride(0) if features_b is not None and n else 0, c_a, _ptr(f_cluster),
                                         f_cluster.stride(0) if n else 3, float(rel_dist_scaler), _host_f32(xyz_normalizer),
                                         h1, h2, _ptr(w1), _ptr(g1), _ptr(b1), _ptr(w2), _ptr(g2), _ptr(b2), _ptr(w3), _ptr(g3),
                                         _ptr(b3), float(eps), _ACTS[act], _ptr(out), out.stride(0) if n else c, _stream(dev))

@@ -37,6 +37,7 @@ extern "C" {
 #define FSFB_ACT_NONE 0
 #define FSFB_ACT_RELU 1
 #define FSFB_ACT_GELU 2
+#define FSFB_RESIDUAL_POST 0x100 /* OR into `act`: y = act(norm(x + bias)) + residual (default adds before act) */
 
 #define FSFB_NORM_NONE 0
 #define FSFB_NORM_LAYERNORM 1 /* per-row LN over channels (mmcv 'LN')            */
@@ -136,7 +137,7 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
 /* out[i, :] = idx[i] >= 0 ? src[idx[i], :] : fill.  Voxel→point gather of
  * models/necks/voxel2point_neck.py:42-50 and voxel_center[unq_inv]
  * (models/detectors/FSF.py:310-311).  idx_i64 selects the index dtype. */
-int fsfb_gather_rows(const float* src, int64_t m, int c, const void* idx, int idx_i64,
+int fsfb_gather_rows(const float* src, int64_t m, int c, int64_t src_stride, const void* idx, int idx_i64,
                      int64_t n, float fill, float* out, int64_t out_stride, void* stream);
 
 /* In-group index: out[i] = number of j < i with group[j] == group[i]  (stable
@@ -314,12 +315,12 @@ int fsfb_reduce_channel(const float* x, int64_t n, int cin, int64_t x_stride, in
 
 /* a6  Voxel2PointScatterNeck.forward (projects/mmdet3d_plugin/models/necks/voxel2point_neck.py:42-67):
  *   out[i] = [ voxel_feats[inv[i], :] | xyz - ((coor + 0.5)*vs + min) ],  mask[i] = !(gathered row == padding everywhere)
- * out dev [n, c+3]; mask dev [n] u8; dropped dev [1] i32 = number of masked-out points (the caller compacts
+ * out dev [n, out_stride >= c+3]; mask dev [n] u8; dropped dev [1] i32 = number of masked-out points (the caller compacts
  * only when it is non-zero, as the reference's boolean indexing would). */
 int fsfb_neck_points(const float* points, int64_t n, int64_t pts_stride, const void* coors, int coors_i64,
                      const float* voxel_feats, int64_t m, int c, const void* inv, int inv_i64,
-                     const float* voxel_size, const float* range_min, float padding, float* out, uint8_t* mask,
-                     int32_t* dropped, void* stream);
+                     const float* voxel_size, const float* range_min, float padding, float* out, int64_t out_stride,
+                     uint8_t* mask, int32_t* dropped, void* stream);
 
 /* a10  VoteSegHead.decode_vote_targets (models/decode_heads/segmentation_head.py:265-266): v * |v| */
 int fsfb_vote_decode(const float* preds, int64_t total, float* out, void* stream);
@@ -378,8 +379,10 @@ int fsfb_encode_preds_2d(const float* anno, int anno_rows, int anno_cols, const 
  * with rel_mlp = build_mlp(3, [h1, h2, c], LN(eps), act) (three Linear(bias=False) → LayerNorm → act blocks;
  * built by SIR at projects/mmdet3d_plugin/models/backbones/sir.py:41-62, rel_dist_scaler = 10 at :57).
  * w1 dev [h1,3], w2 dev [h2,h1], w3 dev [c,h2] (nn.Linear layouts), ln*_w/ln*_b the LayerNorm affines.
- * h1, h2 <= 32, 3 <= c <= 256. */
-int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* f_cluster,
+ * h1, h2 <= 32, 3 <= c <= 256.  feats_b (nullable): the input row is cat(feats[:, :c_a], feats_b[:, :c-c_a]) —
+ * SIR.forward's torch.cat([points, out_feats], 1) (sir.py:76) without materialising it. */
+int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_stride, const float* feats_b,
+                        int64_t feats_b_stride, int c_a, const float* f_cluster,
                         int64_t fc_stride, float rel_dist_scaler, const float* xyz_normalizer, int h1, int h2,
                         const float* w1, const float* ln1_w, const float* ln1_b, const float* w2,
                         const float* ln2_w, const float* ln2_b, const float* w3, const float* ln3_w,
