@@ -213,6 +213,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _capi.load()
 
@@ -335,6 +337,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "launches_timed": d["calls"],
                     "bytes_per_launch": d["bytes"] // d["calls"], "us_per_launch": round(d["ms"] / d["calls"] * 1e3, 2),
+                    "shapes": {n: {"us_per_launch": round(v["ms"] / v["calls"] * 1e3, 1), "launches_per_frame": v["calls"] // args.steps,
+                                   "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)}
+                               for n, v in sorted(cand.items(), key=lambda kv: -kv[1]["ms"])[:8]},
                     "family_frac": {f: round(kern[f]["bytes"] / (kern[f]["ms"] * 1e-3) / 1e9 / peak, 4)
                                     for f in ("segment_reduce", "gather_rows", "project_sample_select") if f in kern},
                     "note": "algorithmic bytes / CUDA-event time, averaged over every launch of this op+shape in the timed "

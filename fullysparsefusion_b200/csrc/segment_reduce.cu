@@ -179,6 +179,66 @@ __global__ void __launch_bounds__(kSrWarps * 32)
   }
 }
 
+// ---- short segments: one warp per OUTPUT segment ---------------------------------------------------
+// Voxel-level reductions (0.1-0.2 m voxels hold 1-2 points on average) are dominated by the chunk kernel's
+// boundary bookkeeping; here a warp owns a segment, walks its rows two at a time and writes the result once —
+// no partial slots, no fix-up pass, no workspace.  Used when n / m <= kSrSmallAvg.
+constexpr int kSrSmallAvg = 8;
+
+template <int VEC, int K, bool IS_MAX, bool HAS_ARG>
+__global__ void __launch_bounds__(kSrWarps * 32)
+    k_segreduce_small(const float* __restrict__ feat, int64_t stride, int C, const int32_t* __restrict__ perm,
+                      const int32_t* __restrict__ offsets, int m, int mean, int64_t n, float* __restrict__ out,
+                      long long* __restrict__ argout) {
+  const int lane = lane_id();
+  const int c0 = blockIdx.y * (32 * VEC * K);
+  const int64_t n_warps = (int64_t)gridDim.x * kSrWarps;
+  for (int64_t s = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5); s < m; s += n_warps) {
+    const int beg = offsets[s], end = offsets[s + 1];
+    Acc<VEC, K, IS_MAX, HAS_ARG> acc;
+    acc.reset();
+    for (int p = beg; p < end; p += 2) {
+      const bool two = p + 1 < end;
+      const int r0 = perm ? perm[p] : p;
+      const int r1 = two ? (perm ? perm[p + 1] : p + 1) : r0;
+      float v0[K][VEC], v1[K][VEC];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int c = chan<VEC>(c0, lane, k, 0);
+        load_row<VEC>(feat + (int64_t)r0 * stride + c, c < C, v0[k]);
+        load_row<VEC>(feat + (int64_t)r1 * stride + c, two && c < C, v1[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc.add(k, v0[k], r0);
+      if (two) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc.add(k, v1[k], r1);
+      }
+    }
+    const bool empty = end == beg;
+    const float denom = mean ? (float)max(1, end - beg) : 1.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int c = chan<VEC>(c0, lane, k, 0);
+      if (c < C) {
+        float r[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) r[e] = empty ? 0.f : (mean ? acc.val[k][e] / denom : acc.val[k][e]);
+        float* o = out + s * C + c;
+        if (VEC == 4) {
+          stg_stream_f4(reinterpret_cast<float4*>(o), make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]));
+        } else {
+          o[0] = r[0];
+        }
+        if (HAS_ARG) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) argout[s * C + c + e] = empty ? (long long)n : (long long)acc.arg[k][e];
+        }
+      }
+    }
+  }
+}
+
 // Fold partial rows of segments that cross chunk boundaries; zero-fill empty segments.
 // One warp per (chunk, block of 32 channels); the walk over the chunks a long segment spans is unrolled
 // four-wide so its loads are independent (instance-level segments can span hundreds of chunks).
@@ -286,6 +346,18 @@ __global__ void __launch_bounds__(256)
 }
 
 template <int VEC, int K>
+static int launch_segreduce_small(const float* feat, int64_t stride, int C, const int32_t* perm, const int32_t* offsets,
+                                  int m, int mode, int64_t n, float* out, long long* argout, cudaStream_t st) {
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, kSrWarps), (int64_t)kNumSMs * 32), (unsigned)ceil_div(C, 32 * VEC * K));
+  const int mean = mode == FSFB_REDUCE_MEAN;
+  auto kern = (mode == FSFB_REDUCE_MAX)
+                  ? (argout ? k_segreduce_small<VEC, K, true, true> : k_segreduce_small<VEC, K, true, false>)
+                  : k_segreduce_small<VEC, K, false, false>;
+  FSFB_LAUNCH(kern, grid, kSrWarps * 32, 0, st, feat, stride, C, perm, offsets, m, mean, n, out, argout);
+  return FSFB_OK;
+}
+
+template <int VEC, int K>
 static int launch_segreduce(const float* feat, int64_t stride, int C, const int32_t* perm,
                             const int32_t* seg, const int32_t* offsets, int m, int mode, float* out,
                             long long* argout, int32_t* part_seg, float* part_val,
@@ -345,6 +417,26 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
                     ((uintptr_t)out % 16 == 0);
   long long* argout = (long long*)argmax;
   int rc;
+  if (n <= (int64_t)kSrSmallAvg * m) {  // short segments on average: warp-per-segment kernel, single pass
+#define SRS_DISPATCH(VEC, K) rc = launch_segreduce_small<VEC, K>(feat, feat_stride, c, perm, offsets, (int)m, mode, n, out, argout, st)
+    if (vec4) {
+      const int g = (int)ceil_div(c, 128);
+      if (g <= 1) SRS_DISPATCH(4, 1);
+      else if (g <= 2) SRS_DISPATCH(4, 2);
+      else SRS_DISPATCH(4, 4);
+    } else {
+      const int g = (int)ceil_div(c, 32);
+      if (g <= 1) SRS_DISPATCH(1, 1);
+      else if (g <= 2) SRS_DISPATCH(1, 2);
+      else if (g <= 3) SRS_DISPATCH(1, 3);
+      else if (g <= 4) SRS_DISPATCH(1, 4);
+      else if (g <= 5) SRS_DISPATCH(1, 5);
+      else if (g <= 6) SRS_DISPATCH(1, 6);
+      else SRS_DISPATCH(1, 8);
+    }
+#undef SRS_DISPATCH
+    return rc;
+  }
 #define SR_DISPATCH(VEC, K)                                                                     \
   rc = launch_segreduce<VEC, K>(feat, feat_stride, c, perm, seg, offsets, (int)m, mode, out,     \
                                 argout, part_seg, part_val, part_arg, n_chunks, st)
