@@ -40,7 +40,7 @@ SIGNATURES = {
     "fsfb_project_sample_select": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "fsfb_gemm_prepack_bytes": (_i, [_i, _i, _i, _psz]),
     "fsfb_gemm_prepack": (_i, [_p, _i, _i, _i, _p, _p]),
-    "fsfb_gather_gemm": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
+    "fsfb_gather_gemm": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_gather_gemm_simt": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_conv_rulebook": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),
@@ -64,6 +64,8 @@ SIGNATURES = {
     "fsfb_threshold_mask": (_i, [_p, _i64, _i64, _i, _f, _p, _p]),
     "fsfb_count_mask": (_i, [_p, _p, _i64, _i, _p, _p]),
     "fsfb_sir_gate_input": (_i, [_p, _i64, _i, _i64, _p, _i64, _i, _p, _i64, _f, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _p, _i64, _p]),
+    "fsfb_rulebook_order_workspace_bytes": (_i, [_i64, _i, _psz]),
+    "fsfb_rulebook_row_order": (_i, [_p, _i, _i64, _p, _p, _sz, _p]),
     "fsfb_rownorm_act": (_i, [_p, _i64, _i, _i64, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
 }
 

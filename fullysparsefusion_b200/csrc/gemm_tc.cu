@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kTcThreads, DEEP ? 1 : 2) k_gather_gemm_tc(con
   // thread t: row t & 127, offsets (t >> 7), (t >> 7) + 2, ...  (loads of a batch are independent)
   if (tid < kTcProducers) {
     const int r_l = tid & (kTcRows - 1);
-    const int64_t r = row0 + r_l;
+    const int64_t r = row0 + r_l < P.rows ? (P.row_order ? (int64_t)__ldg(P.row_order + row0 + r_l) : row0 + r_l) : P.rows;
     uint32_t my_mask = 0;
     constexpr int kPar = kTcProducers / kTcRows;
     for (int k0 = tid / kTcRows; k0 < P.koff; k0 += 4 * kPar) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTcThreads, DEEP ? 1 : 2) k_gather_gemm_tc(con
 }  // namespace fsfb
 
 extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
-                                int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
+                                const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
                                 int norm, const float* norm_w, const float* norm_b, float eps,
                                 const float* residual, int64_t residual_stride, int act, float* out,
                                 int64_t out_stride, void* stream) {
@@ -300,6 +300,7 @@ extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t
   P.cin = cin;
   P.a_stride = a_stride;
   P.nbr = nbr;
+  P.row_order = row_order;
   P.koff = koff;
   P.rows = rows;
   P.w_packed = (const unsigned char*)w_packed;

@@ -146,6 +146,7 @@ struct TcParams {
   int cin;
   int64_t a_stride;
   const int32_t* nbr;
+  const int32_t* row_order;  // optional: tile row i of the grid handles output row row_order[i] (mask-sorted rows)
   int koff;
   int64_t rows;
   const unsigned char* w_packed;
@@ -238,8 +239,8 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
   const bool post = (E.act & FSFB_RESIDUAL_POST) != 0;
   const bool res_vec = E.residual && ((uintptr_t)E.residual % 16 == 0) && (E.residual_stride % 4 == 0);
   for (int rl = warp; rl < kTcRows; rl += n_warps) {
-    const int64_t r = row0 + rl;
-    if (r >= P.rows || (P.debug & 16)) break;
+    if (row0 + rl >= P.rows || (P.debug & 16)) break;
+    const int64_t r = P.row_order ? (int64_t)__ldg(P.row_order + row0 + rl) : row0 + rl;
     const uint32_t srow = base + (uint32_t)rl * (uint32_t)(((n_w + 31) & ~31) + 4) * 4u;
     float* o = P.out + r * P.out_stride + c0;
     const float* res = E.residual ? E.residual + r * E.residual_stride + c0 : nullptr;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
   __syncthreads();
   if (tid < kTsProducers) {  // neighbour tile + active-offset mask (as in gemm_tc.cu)
     const int r_l = tid & (kTcRows - 1);
-    const int64_t r = row0 + r_l;
+    const int64_t r = row0 + r_l < P.rows ? (P.row_order ? (int64_t)__ldg(P.row_order + row0 + r_l) : row0 + r_l) : P.rows;
     uint32_t my_mask = 0;
     constexpr int kPar = kTsProducers / kTcRows;
     for (int k0 = tid / kTcRows; k0 < P.koff; k0 += 4 * kPar) {

@@ -216,6 +216,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// mask[r] = bit k set iff nbr[k][r] >= 0
+__global__ void __launch_bounds__(256)
+    k_rulebook_masks(const int32_t* __restrict__ nbr, int koff, int64_t rows, int32_t* __restrict__ mask) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t m = 0;
+    for (int k = 0; k < koff; ++k) m |= (__ldg(nbr + (int64_t)k * rows + r) >= 0 ? 1u : 0u) << k;
+    mask[r] = (int32_t)m;
+  }
+}
+
 static int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b) != 0) ++b;
@@ -326,6 +336,39 @@ int fsfb_csr_build(const void* index, int index_i64, int64_t n, int64_t m, int32
   FSFB_CHECK_ARG(offsets && (n == 0 || (index && perm && seg)), "csr_build: null pointer");
   return csr_build_impl(index, index_i64, n, m, offsets, (uint32_t*)perm, (uint32_t*)seg, workspace,
                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int fsfb_rulebook_order_workspace_bytes(int64_t rows, int koff, size_t* bytes) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(bytes && rows >= 0 && rows < (1ll << 31) && koff >= 1 && koff <= 30, "rulebook_order_workspace_bytes: bad argument");
+  Workspace ws(nullptr, 0);
+  ws.take<int32_t>(std::max<int64_t>(rows, 1));   // masks
+  ws.take<uint32_t>(std::max<int64_t>(rows, 1));  // sorted keys
+  csr_ws_layout(rows, (1ll << koff) - 1, ws, nullptr, nullptr, nullptr);
+  *bytes = ws.used;
+  return FSFB_OK;
+}
+
+int fsfb_rulebook_row_order(const int32_t* nbr, int koff, int64_t rows, int32_t* order, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(rows >= 0 && rows < (1ll << 31) && koff >= 1 && koff <= 30, "rulebook_row_order: bad argument");
+  if (rows == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(nbr && order, "rulebook_row_order: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* mask = ws.take<int32_t>(rows);
+  uint32_t* keys = ws.take<uint32_t>(rows);
+  uint32_t *tk, *tv, *hist;
+  csr_ws_layout(rows, (1ll << koff) - 1, ws, &tk, &tv, &hist);
+  if (!ws.ok()) {
+    set_error("rulebook_row_order: workspace too small (%zu given, %zu needed)", workspace_bytes, ws.used);
+    return FSFB_ERR_CAPACITY;
+  }
+  const int grid = (int)std::min<int64_t>(ceil_div(rows, 256), (int64_t)kNumSMs * 8);
+  FSFB_LAUNCH(k_rulebook_masks, grid, 256, 0, st, nbr, koff, rows, mask);
+  // stable LSD sort of the masks: rows with the same set of neighbour offsets become adjacent
+  return radix_sort_index<int>(mask, rows, (uint32_t)((1u << koff) - 1u), keys, (uint32_t*)order, tk, tv, hist, st);
 }
 
 int fsfb_ingroup_workspace_bytes(int64_t n, int64_t m, size_t* bytes) {

@@ -425,7 +425,8 @@ def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
 
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
-                out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False,
+                row_order: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual)  (include/fsf_b200.h).
 
     nbr: int32 [koff, rows] neighbour table (< 0 = none) or None for a plain Linear over rows of `a`.
@@ -448,6 +449,8 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         return out
     b, nid, nw, nb = _epilogue_args(w.cout, bias, norm, norm_w, norm_b, residual, act, dev)
     lib = load()
+    if row_order is not None:
+        assert row_order.dtype == torch.int32 and row_order.numel() == rows and row_order.is_contiguous()
     args = (_ptr(a), a.size(0), w.cin, a.stride(0), _ptr(nbr), w.koff, rows)
     tail = (w.cout, b, nid, nw, nb, float(eps), _ptr(residual), residual.stride(0) if residual is not None else 0,
             _ACTS[act] | (0x100 if residual_post else 0), _ptr(out), out.stride(0), _stream(dev))
@@ -465,7 +468,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         prof = _Prof(f"gather_gemm_conv_{w.cin}x{w.cout}" if DETAIL else "gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
                      (pairs, 2 * w.cin * w.cout, 0))
     with prof:
-        check(lib.fsfb_gather_gemm(*args, _ptr(w.data), *tail), "fsfb_gather_gemm")
+        check(lib.fsfb_gather_gemm(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail), "fsfb_gather_gemm")
     return out
 
 
@@ -841,3 +844,19 @@ def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers,
                                         _ptr(b3), float(eps), _ACTS[act], _ptr(out), out.stride(0) if n else c, _stream(dev))
     check(rc, "fsfb_sir_gate_input")
     return out
+
+
+def rulebook_row_order(nbr: torch.Tensor) -> torch.Tensor:
+    """Permutation of a rulebook's output rows sorted by their mask of present offsets (int32 [rows])."""
+    dev = _need_cuda(nbr)
+    assert nbr.dtype == torch.int32 and nbr.dim() == 2 and nbr.is_contiguous()
+    koff, rows = nbr.shape
+    order = torch.empty(rows, dtype=torch.int32, device=dev)
+    lib = load()
+    need = C.c_size_t(0)
+    check(lib.fsfb_rulebook_order_workspace_bytes(rows, koff, C.byref(need)), "fsfb_rulebook_order_workspace_bytes")
+    ws = _ws(need.value, dev)
+    with _Prof("rulebook_row_order", 4 * koff * rows + 4 * rows):
+        check(lib.fsfb_rulebook_row_order(_ptr(nbr), koff, rows, _ptr(order), _ptr(ws), ws.numel(), _stream(dev)),
+              "fsfb_rulebook_row_order")
+    return order

@@ -128,3 +128,8 @@ def test_gather_gemm_large_vs_simt(cuda):
     got = ops.gather_gemm(a, pw, nbr=nbr, act="relu")
     want = ops.gather_gemm(a, pw, nbr=nbr, act="relu", simt=True)
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    # mask-sorted row order: same rows, same values (tiles only change which rows they hold)
+    order = ops.rulebook_row_order(nbr)
+    assert torch.equal(torch.sort(order.long())[0], torch.arange(m, device=cuda))
+    got2 = ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order)
+    torch.testing.assert_close(got2, want, rtol=1e-4, atol=1e-4)

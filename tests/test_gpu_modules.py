@@ -94,7 +94,12 @@ def test_simple_sparse_unet(cuda):
                                              ops.unique_rows(T(uniq.astype(np.int32), cuda), lo=[0] * 4, ext=[1, 40, 512, 512],
                                                              return_index=True)[3], 1)
     for key in rb:                                         # rulebooks bit-exact at every level
-        assert np.array_equal(got_rb[key].cpu().numpy(), rb[key]), key
+        assert np.array_equal(got_rb[key].nbr.cpu().numpy(), rb[key]), key
+        if got_rb[key].order is not None:                  # a permutation, sorted by offset mask
+            order = got_rb[key].order.cpu().numpy()
+            assert np.array_equal(np.sort(order), np.arange(rb[key].shape[1]))
+            mask = ((rb[key] >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+            assert np.array_equal(order, np.argsort(mask, kind="stable"))
     for a, b in zip(got_levels, levels):
         assert np.array_equal(a["coors"].cpu().numpy(), b["coors"])
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-4, atol=1e-4)   # 34 chained layers

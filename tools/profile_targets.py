@@ -36,8 +36,9 @@ if which in ("conv", "all"):
     nbr = ops.conv_rulebook(plan.new_coors, plan.index, 3, 1, 1)
     a = torch.randn(plan.m, 128, device=dev, generator=g)
     w = ops.gemm_prepack(torch.randn(27, 128, 128, device=dev, generator=g) * 0.03)
+    order = ops.rulebook_row_order(nbr) if os.environ.get("FSFB_NO_ROW_ORDER") != "1" else None
     for _ in range(3):
-        y = ops.gather_gemm(a, w, nbr=nbr, act="relu")
+        y = ops.gather_gemm(a, w, nbr=nbr, act="relu", row_order=order)
     torch.cuda.synchronize()
     pairs = int((nbr >= 0).sum())
     print("conv voxels", plan.m, "pairs", pairs, "useful flops", 2 * pairs * 128 * 128)
