@@ -41,6 +41,9 @@ SIGNATURES = {
     "fsfb_gemm_prepack_bytes": (_i, [_i, _i, _i, _psz]),
     "fsfb_gemm_prepack": (_i, [_p, _i, _i, _i, _p, _p]),
     "fsfb_gather_gemm": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
+    "fsfb_gather_gemm_splitk_bytes": (_i, [_i64, _i, _i, _p]),
+    "fsfb_gather_gemm_splitk": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _i, _p, _sz, _p]),
+    "fsfb_debug_gemm_timers": (_i, [_p]),
     "fsfb_gather_gemm_simt": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_conv_rulebook": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),

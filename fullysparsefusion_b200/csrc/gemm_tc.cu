@@ -274,12 +274,12 @@ __global__ void __launch_bounds__(kTcThreads, DEEP ? 1 : 2) k_gather_gemm_tc(con
 
 }  // namespace fsfb
 
-extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
-                                const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
-                                int norm, const float* norm_w, const float* norm_b, float eps,
-                                const float* residual, int64_t residual_stride, int act, float* out,
-                                int64_t out_stride, void* stream) {
-  using namespace fsfb;
+namespace fsfb {
+static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
+                            const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
+                            int norm, const float* norm_w, const float* norm_b, float eps,
+                            const float* residual, int64_t residual_stride, int act, float* out,
+                            int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_epilogue(cout, bias, norm, norm_w, norm_b, act, "gather_gemm");
   if (rc != FSFB_OK) return rc;
   FSFB_CHECK_ARG(rows >= 0 && a_rows >= 0 && a_rows < (1ll << 31) && cin >= 1 && a_stride >= cin &&
@@ -316,12 +316,15 @@ extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t
   }
   const int n_w_max = P.S.n_w(0);
   {
-    // A-through-TMEM kernel (gemm_ts.cu) for column tiles <= 128: FSFB_GEMM_TS=0 disables, =2 forces it for
-    // short K loops too (default: long K loops only — the 27-offset convolutions and wide-input Linears)
+    // persistent A-through-TMEM kernel (gemm_ts.cu) whenever the output splits into column tiles of <= 128
+    // channels; the kernel below remains for widths like 131 / 144 (one 256-wide tile) and fused LayerNorms wider
+    // than 128.  FSFB_GEMM_TS=0 forces the kernel below (A/B experiments).
     static const int ts_mode = [] { const char* e = getenv("FSFB_GEMM_TS"); return e ? atoi(e) : 1; }();
-    const int64_t iters = (int64_t)koff * P.S.kc();
-    if (ts_mode && P.S.n_pad() <= 128 && (iters > 8 || ts_mode == 2))
-      return launch_gather_gemm_ts(P, a_vec, (cudaStream_t)stream);
+    const int n_pad = P.S.n_pad();
+    const bool ts_ok = n_pad <= 128 || (n_pad % 128 == 0 && norm != FSFB_NORM_LAYERNORM);
+    if (ts_mode && ts_ok)
+      return launch_gather_gemm_ts(P, a_vec, (float*)workspace, workspace_bytes, splits, (cudaStream_t)stream);
+    FSFB_CHECK_ARG(splits <= 1, "gather_gemm: offset splits need cout <= 128 or a multiple of 128 (cout=%d)", cout);
   }
   const size_t stage_bytes = 2 * (size_t)kStageABytes + (size_t)2 * n_w_max * 128;
   const size_t fixed = (size_t)koff * kTcRows * 4 + sizeof(TcShared) + 1024 /* alignment slack */;
@@ -358,4 +361,34 @@ extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t
     else FSFB_LAUNCH((k_gather_gemm_tc<false, false>), grid, kTcThreads, smem, st, P);
   }
   return FSFB_OK;
+}
+}  // namespace fsfb
+
+extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
+                                const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
+                                int norm, const float* norm_w, const float* norm_b, float eps,
+                                const float* residual, int64_t residual_stride, int act, float* out,
+                                int64_t out_stride, void* stream) {
+  return fsfb::gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b,
+                                eps, residual, residual_stride, act, out, out_stride, 1, nullptr, 0, stream);
+}
+
+extern "C" int fsfb_gather_gemm_splitk_bytes(int64_t rows, int cout, int splits, size_t* bytes) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(bytes && rows >= 0 && cout >= 1 && splits >= 1, "gather_gemm_splitk_bytes: bad argument");
+  const size_t cpad = (size_t)((cout + 127) / 128 * 128);
+  *bytes = splits > 1 ? (size_t)splits * (size_t)rows * cpad * sizeof(float) : 0;
+  return FSFB_OK;
+}
+
+extern "C" int fsfb_gather_gemm_splitk(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
+                                       const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout,
+                                       const float* bias, int norm, const float* norm_w, const float* norm_b, float eps,
+                                       const float* residual, int64_t residual_stride, int act, float* out,
+                                       int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(splits >= 1 && splits <= koff, "gather_gemm_splitk: splits=%d must be in 1..koff", splits);
+  FSFB_CHECK_ARG(splits == 1 || ((uintptr_t)workspace & 15) == 0, "gather_gemm_splitk: workspace must be 16-byte aligned");
+  return gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b, eps,
+                          residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, stream);
 }

@@ -157,6 +157,11 @@ struct TcParams {
   int stages;
   int out_vec;  // 1: rows of `out` are 16-byte aligned → 128-bit stores
   uint32_t data_bytes;  // stage ring (or epilogue staging, whichever is larger); nbr tile + barriers follow
+  // persistent TS kernel (gemm_ts.cu): 128-wide column tiles, offset splits, unit count, split slabs [splits][rows][cpad]
+  int n_ct, splits, cpad, n_row_tiles, sched_slot;
+  int64_t n_units;
+  float* partial;
+  uint32_t* timers;  // diagnostics (FSFB_GEMM_TIMERS=1), else null
   int debug;    // FSFB_GEMM_DEBUG bits (profiling experiments only): 1 no A loads, 2 no W copy, 4 no MMA, 8 no A stores
 };
 
@@ -269,6 +274,6 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
 }
 
 // gemm_ts.cu
-int launch_gather_gemm_ts(TcParams P, bool a_vec, cudaStream_t st);
+int launch_gather_gemm_ts(TcParams P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, cudaStream_t st);
 
 }  // namespace fsfb

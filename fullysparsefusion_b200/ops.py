@@ -426,8 +426,11 @@ def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
                 out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False,
-                row_order: Optional[torch.Tensor] = None) -> torch.Tensor:
+                row_order: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
     """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual)  (include/fsf_b200.h).
+
+    splits: offset ranges run as independent work units (fsfb_gather_gemm_splitk); None picks it from the shape
+    (only when rows/128 x cout/128 tiles would leave most SMs idle).
 
     nbr: int32 [koff, rows] neighbour table (< 0 = none) or None for a plain Linear over rows of `a`.
     simt=True runs the CUDA-core cross-check (tests only; needs w.raw).
@@ -465,10 +468,22 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         if PROFILER is not None and pairs is None:   # profiling only: exact pair count of this rulebook, kept on device
             pairs = (nbr >= 0).sum()
             nbr._fsfb_pairs = pairs
-        prof = _Prof(f"gather_gemm_conv_{w.cin}x{w.cout}" if DETAIL else "gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
+        prof = _Prof(f"gather_gemm_conv_{rows >> 10}k_k{w.koff}_{w.cin}x{w.cout}" if DETAIL else "gather_gemm_conv", (pairs, 4 * w.cin, 4 * rows * w.cout + 4 * w.koff * w.cin * w.cout),
                      (pairs, 2 * w.cin * w.cout, 0))
+    cpad = (w.cout + 127) // 128 * 128
+    tileable = w.cout <= 128 or (((w.cout + 15) // 16 * 16) % 128 == 0 and norm != "layernorm" and norm != "ln")
+    if splits is None:
+        splits = 1
+        units = ((rows + 127) // 128) * (cpad // 128)
+        if tileable and w.koff >= 6 and cpad <= 1024 and units * 2 <= 148 and w.koff * ((w.cin + 31) // 32) >= 32:
+            splits = max(1, min(w.koff // 3, 148 // units))
     with prof:
-        check(lib.fsfb_gather_gemm(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail), "fsfb_gather_gemm")
+        if splits > 1:
+            ws = torch.empty(splits * rows * cpad, dtype=torch.float32, device=dev)
+            check(lib.fsfb_gather_gemm_splitk(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail[:-1], splits, _ptr(ws),
+                                              ws.numel() * 4, tail[-1]), "fsfb_gather_gemm_splitk")
+        else:
+            check(lib.fsfb_gather_gemm(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail), "fsfb_gather_gemm")
     return out
 
 

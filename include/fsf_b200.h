@@ -220,6 +220,24 @@ int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t a_stride,
                      float eps, const float* residual, int64_t residual_stride, int act,
                      float* out, int64_t out_stride, void* stream);
 
+/* Same contract with the offsets cut into `splits` contiguous ranges that run as independent work units
+ * (split-K over the 27 offsets): each unit writes raw partial sums to workspace[split][rows][round_up(cout,128)]
+ * and a second kernel sums the slabs in a fixed order and applies the epilogue (deterministic).  For levels with
+ * few rows and wide channels (the 1 k / 11 k-row U-Net levels, models cited above), where rows/128 tiles leave most
+ * SMs idle.  splits == 1 is fsfb_gather_gemm.  Needs cout <= 128 or a multiple of 128, cout <= 1024. */
+int fsfb_gather_gemm_splitk_bytes(int64_t rows, int cout, int splits, size_t* bytes);
+int fsfb_gather_gemm_splitk(const float* a, int64_t a_rows, int cin, int64_t a_stride,
+                            const int32_t* nbr, const int32_t* row_order, int koff, int64_t rows,
+                            const void* w_packed, int cout,
+                            const float* bias, int norm, const float* norm_w, const float* norm_b,
+                            float eps, const float* residual, int64_t residual_stride, int act,
+                            float* out, int64_t out_stride, int splits, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Diagnostics only: per-CTA role cycle counters [148][32] u32 of the last fsfb_gather_gemm launch made with
+ * FSFB_GEMM_TIMERS=1 in the environment (layout in csrc/gemm_ts.cu). */
+int fsfb_debug_gemm_timers(unsigned int* out);
+
 /* Same contract evaluated with plain fp32 FMAs on CUDA cores from the UNPACKED weights
  * (w dev [koff,cout,cin]).  Independent cross-check of the tensor-core path at sizes the
  * CPU oracle cannot reach; tests only — nothing in the product path calls it. */

@@ -133,3 +133,30 @@ def test_gather_gemm_large_vs_simt(cuda):
     assert torch.equal(torch.sort(order.long())[0], torch.arange(m, device=cuda))
     got2 = ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order)
     torch.testing.assert_close(got2, want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("rows,a_rows,koff,cin,cout,splits,density", [(300, 300, 27, 64, 256, 3, 0.4), (1100, 900, 27, 256, 512, 4, 0.3),
+                                                                       (1100, 900, 27, 96, 128, 9, 0.1), (129, 200, 8, 40, 384, 2, 0.6),
+                                                                       (700, 700, 27, 512, 512, None, 0.3)])
+def test_gather_gemm_splitk(cuda, rows, a_rows, koff, cin, cout, splits, density):
+    """Offset-split work units (fsfb_gather_gemm_splitk): partial slabs + reduce/epilogue kernel vs the oracle; includes
+    tiles whose split has no active offset at all (sparse masks) and the shape-driven choice of `splits`."""
+    rng = np.random.default_rng(rows + koff + cout)
+    a = rng.standard_normal((a_rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((koff, cout, cin)) / np.sqrt(cin * koff * density)).astype(np.float32)
+    nbr = rng.integers(0, a_rows, (koff, rows)).astype(np.int32)
+    nbr[rng.random((koff, rows)) > density] = -1
+    nbr[: koff // 3, :128] = -1   # first tile: the first split(s) see no offset
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((rows, cout)).astype(np.float32)
+    want = O.gather_gemm(a, w, nbr, norm="affine", norm_w=scale, norm_b=shift, residual=res, act="relu")
+    pw = ops.gemm_prepack(T(w, cuda))
+    kw = dict(nbr=T(nbr, cuda), norm="affine", norm_w=T(scale, cuda), norm_b=T(shift, cuda), residual=T(res, cuda), act="relu")
+    # outputs are O(1..5); a 27 x 512-long 3xTF32 accumulation leaves up to ~3e-5 of the output scale, which shows as a
+    # larger relative error only near the ReLU zero crossings: the 1e-4 budget is taken relative to the feature scale
+    atol = 4e-5 * float(np.abs(want).max())
+    got = ops.gather_gemm(T(a, cuda), pw, splits=splits, **kw).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=atol)
+    one = ops.gather_gemm(T(a, cuda), pw, splits=1, **kw).cpu().numpy()
+    np.testing.assert_allclose(one, want, rtol=RTOL, atol=atol)

@@ -33,7 +33,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         res[name] = round(e0.elapsed_time(e1) / 10, 4)
     print(json.dumps(res))
 else:
-    for dbg in (0,):
+    for dbg in [int(x) for x in os.environ.get('FSFB_DBG_LIST', '0').split(',')]:
         env = dict(os.environ, FSFB_GEMM_DEBUG=str(dbg))
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print("debug", dbg, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)
