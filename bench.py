@@ -10,8 +10,12 @@ sharded one per GPU per step (weak scaling, no data-path collective — SURVEY.m
 `value`  frames/s with the frame's inputs already resident in HBM (device-timed, max over ranks).
 `e2e`    frames/s through the same public API starting from pinned HOST buffers: the H2D copy of
          points / id planes / lidar2img and a D2H read of the result are inside the timed region.
-`roofline`  the dominant scatter/projection op: algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json;
-            `kernels` lists every timed op family (GB/s, and TFLOP/s for the tensor-core GEMMs).
+`roofline`  the dominant kernel of the frame (the tcgen05 gather-GEMM of the sparse convolutions): useful flops per
+            launch / its CUDA-event time inside the timed region vs the measured bf16 tensor peak (MEASURED_PEAKS.json).
+`roofline_hbm`  the scatter + projection family BASELINE.json's metric names: algorithmic bytes / event time vs the
+            measured HBM peak, per shape in the frame (profile pass) and at op level for 300 k and 1 M points.
+`kernels`   every timed op family from a separate profile pass (per-op events cost ~3 ms per frame, so they stay
+            out of the timed region except around the dominant kernel).
 `cpu_baseline`  the torch-CPU port of the reference path (oracle/fsf_torch_cpu.py) on this box's cores.
 `--impl reference` times that CPU port alone (the reference cannot be installed: DESIGN.md).
 """
@@ -263,19 +267,27 @@ def main():
         while time.perf_counter() - t_w < 0.5:
             step(0)
         barrier()
-        events = []
-        ops.PROFILER = []
+        ops.PROFILER, ops.PROFILE_ONLY = [], {"gather_gemm_conv"}   # events only around the dominant kernel
         launches0 = _capi.launch_count()
         t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t_start.record()
         for i in range(args.steps):
-            step(i, events)
+            step(i)
         t_end.record()
         barrier()
-        prof, ops.PROFILER = ops.PROFILER, None
+        prof_dom, ops.PROFILER, ops.PROFILE_ONLY = ops.PROFILER, None, None
         launches = _capi.launch_count() - launches0
         ms_total = t_start.elapsed_time(t_end)
+
+        # ---- profile pass (not part of `value`): per-stage and per-op events ---------------------------
+        events = []
+        ops.PROFILER = []
+        n_prof = min(args.steps, 10)
+        for i in range(n_prof):
+            step(i, events)
+        torch.cuda.synchronize()
+        prof, ops.PROFILER = ops.PROFILER, None
 
         # ---- end to end from pinned host buffers --------------------------------------------------
         def e2e_step(i):
@@ -304,46 +316,66 @@ def main():
         for name, a, b in events:
             per_stage.setdefault(name, []).append(a.elapsed_time(b))
         stage_ms = {k: sum(v) / len(v) for k, v in per_stage.items()}
-        kern, shapes = {}, {}
-        for name, a, b, nb, fl in prof:
-            ms, nb, fl = a.elapsed_time(b), resolve(nb), resolve(fl)
-            for table, key in ((kern, name.split("[")[0]), (shapes, name)):
-                k = table.setdefault(key, dict(ms=0.0, bytes=0, flops=0, calls=0))
-                k["ms"] += ms
-                k["bytes"] += nb
-                k["flops"] += fl
-                k["calls"] += 1
+        def fold(records, n_steps):
+            kern, shapes = {}, {}
+            for name, a, b, nb, fl in records:
+                ms, nb, fl = a.elapsed_time(b), resolve(nb), resolve(fl)
+                for table, key in ((kern, name.split("[")[0]), (shapes, name)):
+                    k = table.setdefault(key, dict(ms=0.0, bytes=0, flops=0, calls=0))
+                    k["ms"] += ms
+                    k["bytes"] += nb
+                    k["flops"] += fl
+                    k["calls"] += 1
+            return kern, shapes
+
+        kern, shapes = fold(prof, n_prof)
+        dom_kern, _ = fold(prof_dom, args.steps)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (FALLBACK_HBM_GBS, "fallback")
-        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tpeak, tpeak_src = (peaks["bf16_tflops_sustained"], "measured (bf16 dense, sustained)") if "bf16_tflops_sustained" in peaks \
+            else (1400.0, "fallback")
         table = {}
         for name, k in kern.items():
             sec = k["ms"] * 1e-3
-            table[name] = {"ms_per_frame": round(k["ms"] / args.steps, 4), "calls_per_frame": k["calls"] // args.steps,
+            table[name] = {"ms_per_frame": round(k["ms"] / n_prof, 4), "calls_per_frame": k["calls"] // n_prof,
                            "GB/s": round(k["bytes"] / sec / 1e9, 1), "hbm_frac": round(k["bytes"] / sec / 1e9 / peak, 4)}
             if k["flops"]:
                 table[name]["TFLOP/s"] = round(k["flops"] / sec / 1e12, 2)
                 table[name]["tensor_frac_of_bf16_sustained"] = round(k["flops"] / sec / 1e12 / tpeak, 4)
-        # the metric names the scatter + projection kernels: the launch class (op + shape) with the most time among
-        # them carries `roofline`; achieved = its algorithmic bytes per launch / its average launch duration
+        # dominant kernel: the gather-GEMM launches of the sparse convolutions, timed inside the timed region
+        d = dom_kern["gather_gemm_conv"]
+        ach_t = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "k_gather_gemm_ts (sparse-convolution gather-GEMM, 3xTF32 on tcgen05)",
+                    "achieved": ach_t, "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s", "frac": ach_t / tpeak,
+                    "traffic": None, "launches_timed": d["calls"], "launches_per_frame": d["calls"] // args.steps,
+                    "flops_per_launch": d["flops"] // d["calls"], "us_per_launch": round(d["ms"] / d["calls"] * 1e3, 2),
+                    "share_of_step": round(d["ms"] / ms_total, 3),
+                    "note": "achieved = USEFUL flops (2*Cin*Cout per rulebook pair) / CUDA-event time of every launch in the timed "
+                            "region; the kernel executes 3 tf32 MMAs per useful product (3xTF32 keeps fp32 parity) plus zero rows "
+                            "of partially filled tiles, so executed tensor work is >= 3x this figure (DESIGN.md section 4)"}
+        # the scatter + projection family (BASELINE metric): per shape in the frame + op level at 300 k / 1 M points
         cand = {n: v for n, v in shapes.items() if n.split("[")[0] in ("segment_reduce", "project_sample_select", "gather_rows")}
         dom = max(cand, key=lambda n: cand[n]["ms"])
-        d = cand[dom]
-        ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "launches_timed": d["calls"],
-                    "bytes_per_launch": d["bytes"] // d["calls"], "us_per_launch": round(d["ms"] / d["calls"] * 1e3, 2),
-                    "shapes": {n: {"us_per_launch": round(v["ms"] / v["calls"] * 1e3, 1), "launches_per_frame": v["calls"] // args.steps,
-                                   "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)}
-                               for n, v in sorted(cand.items(), key=lambda kv: -kv[1]["ms"])[:8]},
-                    "family_frac": {f: round(kern[f]["bytes"] / (kern[f]["ms"] * 1e-3) / 1e9 / peak, 4)
-                                    for f in ("segment_reduce", "gather_rows", "project_sample_select") if f in kern},
-                    "note": "algorithmic bytes / CUDA-event time, averaged over every launch of this op+shape in the timed "
-                            "region (each op = main kernel + boundary fix-up kernel); family_frac aggregates all shapes"}
+        dd = cand[dom]
+        ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
+        roofline_hbm = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                        "frac": ach / peak, "bytes_per_launch": dd["bytes"] // dd["calls"],
+                        "us_per_launch": round(dd["ms"] / dd["calls"] * 1e3, 2),
+                        "shapes": {n: {"us_per_launch": round(v["ms"] / v["calls"] * 1e3, 1), "launches_per_frame": v["calls"] // n_prof,
+                                       "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)}
+                                   for n, v in sorted(cand.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+                        "family_frac": {f: round(kern[f]["bytes"] / (kern[f]["ms"] * 1e-3) / 1e9 / peak, 4)
+                                        for f in ("segment_reduce", "gather_rows", "project_sample_select") if f in kern},
+                        "note": "algorithmic bytes (SURVEY.md 8d) / CUDA-event time from the profile pass; inside the frame the "
+                                "events also see launch gaps of small shapes, `ops` below times each op back to back"}
+        if world == 1:
+            sys.path.insert(0, os.path.join(REPO, "tools"))
+            import op_bench
+            roofline_hbm["ops"] = [op_bench.run(p, peak, dev) for p in (300000, 1000000)]
         st = last["st"]
         h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
         d2h = sum(r.numel() * r.element_size() for r in res)
@@ -359,7 +391,7 @@ def main():
                            "scope": "FSF.simple_test through combine_frustum_and_fsd (refine stage + NMS not included)"},
                 "e2e": {"value": fdist.throughput(args.steps, world, ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": table,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "kernels": table,
                 "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}}
         if world == 1 and not args.no_cpu_baseline:
             import copy

@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(kSrWarps * 32)
 // no partial slots, no fix-up pass, no workspace.  Used when n / m <= kSrSmallAvg.
 constexpr int kSrSmallAvg = 8;
 
+// A warp handles PAIRS of adjacent segments and runs a three-level software pipeline over its pairs, because the walk
+// offsets[s] → perm[p] → feat[row] is three dependent global loads: while the rows of pair i are in flight, the row ids
+// of pair i+1 and the offsets of pair i+2 are already requested (each is one value per lane).  Measured before: one
+// segment at a time left the kernel latency-bound at 42 % of HBM peak on the 300 k x 132 pre-voxel mean.
 template <int VEC, int K, bool IS_MAX, bool HAS_ARG>
 __global__ void __launch_bounds__(kSrWarps * 32)
     k_segreduce_small(const float* __restrict__ feat, int64_t stride, int C, const int32_t* __restrict__ perm,
@@ -193,49 +197,106 @@ __global__ void __launch_bounds__(kSrWarps * 32)
   const int lane = lane_id();
   const int c0 = blockIdx.y * (32 * VEC * K);
   const int64_t n_warps = (int64_t)gridDim.x * kSrWarps;
-  for (int64_t s = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5); s < m; s += n_warps) {
-    const int beg = offsets[s], end = offsets[s + 1];
-    Acc<VEC, K, IS_MAX, HAS_ARG> acc;
-    acc.reset();
-    for (int p = beg; p < end; p += 2) {
-      const bool two = p + 1 < end;
-      const int r0 = perm ? perm[p] : p;
-      const int r1 = two ? (perm ? perm[p + 1] : p + 1) : r0;
-      float v0[K][VEC], v1[K][VEC];
+  const int64_t w = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  auto pair_base = [&](int64_t it) { return 2 * (w + it * n_warps); };
+  // level 1: lanes 0..2 hold offsets[s], offsets[s+1], offsets[s+2] of the pair starting at segment s
+  auto load_off = [&](int64_t s) -> int {
+    int v = 0;
+    if (lane < 3 && s + lane <= m) v = __ldg(offsets + s + lane);
+    return v;
+  };
+  // level 2: lanes 0..3 hold the first two row ids of both segments (-1: the segment has no such row)
+  auto load_perm = [&](int off, int64_t s) -> int {
+    const int b0 = __shfl_sync(0xffffffffu, off, 0), b1 = __shfl_sync(0xffffffffu, off, 1);
+    const int e1 = s + 1 < m ? __shfl_sync(0xffffffffu, off, 2) : b1;
+    int r = -1;
+    if (lane < 4 && s < m) {
+      const int p = (lane < 2 ? b0 : b1) + (lane & 1);
+      if (p < (lane < 2 ? b1 : e1)) r = perm ? __ldg(perm + p) : p;
+    }
+    return r;
+  };
+  int off_a = load_off(pair_base(0));
+  int off_b = load_off(pair_base(1));
+  int prm_a = load_perm(off_a, pair_base(0));
+  for (int64_t it = 0;; ++it) {
+    const int64_t s = pair_base(it);
+    if (s >= m) break;
+    const int off_c = load_off(pair_base(it + 2));
+    const int prm_b = load_perm(off_b, pair_base(it + 1));
+    int beg[2], end[2], row[2][2];
+    beg[0] = __shfl_sync(0xffffffffu, off_a, 0);
+    end[0] = beg[1] = __shfl_sync(0xffffffffu, off_a, 1);
+    end[1] = s + 1 < m ? __shfl_sync(0xffffffffu, off_a, 2) : end[0];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) row[j][i] = __shfl_sync(0xffffffffu, prm_a, 2 * j + i);
+    // level 3: up to four rows in flight
+    float v[2][2][K][VEC];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = chan<VEC>(c0, lane, k, 0);
+          load_row<VEC>(feat + (int64_t)max(row[j][i], 0) * stride + c, row[j][i] >= 0 && c < C, v[j][i][k]);
+        }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (s + j >= m) break;  // warp-uniform
+      Acc<VEC, K, IS_MAX, HAS_ARG> acc;
+      acc.reset();
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (row[j][i] >= 0) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc.add(k, v[j][i][k], row[j][i]);
+        }
+      for (int p = beg[j] + 2; p < end[j]; p += 2) {  // longer segments: the rest, two rows at a time
+        const bool two = p + 1 < end[j];
+        const int r0 = perm ? __ldg(perm + p) : p;
+        const int r1 = two ? (perm ? __ldg(perm + p + 1) : p + 1) : r0;
+        float v0[K][VEC], v1[K][VEC];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int c = chan<VEC>(c0, lane, k, 0);
+          load_row<VEC>(feat + (int64_t)r0 * stride + c, c < C, v0[k]);
+          load_row<VEC>(feat + (int64_t)r1 * stride + c, two && c < C, v1[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc.add(k, v0[k], r0);
+        if (two) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) acc.add(k, v1[k], r1);
+        }
+      }
+      const bool empty = end[j] == beg[j];
+      const float denom = mean ? (float)max(1, end[j] - beg[j]) : 1.f;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int c = chan<VEC>(c0, lane, k, 0);
-        load_row<VEC>(feat + (int64_t)r0 * stride + c, c < C, v0[k]);
-        load_row<VEC>(feat + (int64_t)r1 * stride + c, two && c < C, v1[k]);
-      }
+        if (c < C) {
+          float r[VEC];
 #pragma unroll
-      for (int k = 0; k < K; ++k) acc.add(k, v0[k], r0);
-      if (two) {
+          for (int e = 0; e < VEC; ++e) r[e] = empty ? 0.f : (mean ? acc.val[k][e] / denom : acc.val[k][e]);
+          float* o = out + (s + j) * C + c;
+          if (VEC == 4) {
+            stg_stream_f4(reinterpret_cast<float4*>(o), make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]));
+          } else {
+            o[0] = r[0];
+          }
+          if (HAS_ARG) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc.add(k, v1[k], r1);
-      }
-    }
-    const bool empty = end == beg;
-    const float denom = mean ? (float)max(1, end - beg) : 1.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int c = chan<VEC>(c0, lane, k, 0);
-      if (c < C) {
-        float r[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) r[e] = empty ? 0.f : (mean ? acc.val[k][e] / denom : acc.val[k][e]);
-        float* o = out + s * C + c;
-        if (VEC == 4) {
-          stg_stream_f4(reinterpret_cast<float4*>(o), make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]));
-        } else {
-          o[0] = r[0];
-        }
-        if (HAS_ARG) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) argout[s * C + c + e] = empty ? (long long)n : (long long)acc.arg[k][e];
+            for (int e = 0; e < VEC; ++e) argout[(s + j) * C + c + e] = empty ? (long long)n : (long long)acc.arg[k][e];
+          }
         }
       }
     }
+    off_a = off_b;
+    off_b = off_c;
+    prm_a = prm_b;
   }
 }
 
@@ -348,11 +409,17 @@ __global__ void __launch_bounds__(256)
 template <int VEC, int K>
 static int launch_segreduce_small(const float* feat, int64_t stride, int C, const int32_t* perm, const int32_t* offsets,
                                   int m, int mode, int64_t n, float* out, long long* argout, cudaStream_t st) {
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(m, kSrWarps), (int64_t)kNumSMs * 32), (unsigned)ceil_div(C, 32 * VEC * K));
-  const int mean = mode == FSFB_REDUCE_MEAN;
+  const int mean = mode == FSFB_REDUCE_MAX ? 0 : (mode == FSFB_REDUCE_MEAN);
   auto kern = (mode == FSFB_REDUCE_MAX)
                   ? (argout ? k_segreduce_small<VEC, K, true, true> : k_segreduce_small<VEC, K, true, false>)
                   : k_segreduce_small<VEC, K, false, false>;
+  // persistent grid-stride warps: one wave of resident CTAs (the software pipeline wants long runs per warp)
+  static int resident_of[3] = {0, 0, 0};  // per instantiation of this template: max / max+arg / sum-mean kernels
+  int& resident = resident_of[mode == FSFB_REDUCE_MAX ? (argout ? 1 : 0) : 2];
+  if (resident == 0) FSFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kSrWarps * 32, 0));
+  const int cblocks = (int)ceil_div(C, 32 * VEC * K);
+  const int64_t wave = (int64_t)kNumSMs * std::max(1, resident / cblocks);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(ceil_div(m, 2), kSrWarps), wave), (unsigned)cblocks);
   FSFB_LAUNCH(kern, grid, kSrWarps * 32, 0, st, feat, stride, C, perm, offsets, m, mean, n, out, argout);
   return FSFB_OK;
 }

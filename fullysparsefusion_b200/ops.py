@@ -21,6 +21,7 @@ _MODES = {"sum": REDUCE_SUM, "add": REDUCE_SUM, "mean": REDUCE_MEAN, "avg": REDU
 # Optional per-op CUDA-event timing (bench.py): set PROFILER to a list to collect
 # (op family, start event, end event, algorithmic bytes, algorithmic flops) for the HBM-/tensor-bound ops.
 PROFILER = None
+PROFILE_ONLY = None  # optional set of op-family names: only these are timed (keeps event overhead out of a timed region)
 DETAIL = False  # per-shape op names in the profile (tools only)
 
 
@@ -32,7 +33,7 @@ class _Prof:
         self.name, self.nbytes, self.flops, self.a = name, nbytes, flops, None
 
     def __enter__(self):
-        if PROFILER is not None:
+        if PROFILER is not None and (PROFILE_ONLY is None or self.name.split("[")[0] in PROFILE_ONLY):
             self.a = torch.cuda.Event(enable_timing=True)
             self.a.record()
         return self
@@ -59,8 +60,18 @@ def _need_cuda(*ts: torch.Tensor) -> torch.device:
     return dev
 
 
+_STREAM_CACHE = {}
+
+
 def _stream(dev: torch.device) -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    """Raw handle of torch's current stream on `dev`.  torch.cuda.current_stream builds a Stream object per call
+    (~8 us, 300 calls per frame), so the handle is cached per (device, stream id) through the cheap C getter."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    raw = torch._C._cuda_getCurrentRawStream(idx)
+    h = _STREAM_CACHE.get(raw)
+    if h is None:
+        h = _STREAM_CACHE[raw] = C.c_void_p(raw)
+    return h
 
 
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
