@@ -44,6 +44,14 @@ SIGNATURES = {
     "fsfb_gather_gemm_splitk_bytes": (_i, [_i64, _i, _i, _p]),
     "fsfb_gather_gemm_splitk": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _i, _p, _sz, _p]),
     "fsfb_debug_gemm_timers": (_i, [_p]),
+    "fsfb_group_flags": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p]),
+    "fsfb_group_split": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p]),
+    "fsfb_group_voxelize": (_i, [_p, _i64, _p, _p, _p, _i, _p, _p]),
+    "fsfb_group_keep": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p]),
+    "fsfb_group_relabel": (_i, [_p, _p, _i64, _i64, _i, _p, _i64, _p, _p, _p]),
+    "fsfb_connected_components_groups": (_i, [_p, _i64, _i64, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "fsfb_dynamic_point_pool_workspace_bytes": (_i, [_i64, _i, _p]),
+    "fsfb_dynamic_point_pool": (_i, [_p, _i64, _p, _i64, _i64, _p, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "fsfb_gather_gemm_simt": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_conv_rulebook": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),

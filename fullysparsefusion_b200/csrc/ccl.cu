@@ -52,8 +52,13 @@ __global__ void __launch_bounds__(256) k_ccl_init(int* __restrict__ parent, int 
 }
 
 // One CTA per tile pair (I <= J).  pts: [m, stride] f32 (x, y first).
+struct CclDist {  // one distance, or one per batch id (class groups clustered in one launch)
+  float d[8];
+  int per_batch;
+};
+
 __global__ void __launch_bounds__(kCclTile)
-    k_ccl_pairs(const float* __restrict__ pts, int64_t stride, const int* __restrict__ batch, int m, float dist,
+    k_ccl_pairs(const float* __restrict__ pts, int64_t stride, const int* __restrict__ batch, int m, CclDist D,
                 int n_tiles, int* __restrict__ parent) {
   // linear block id → (I, J) with I <= J, row-major over the upper triangle
   int b = blockIdx.x, I = 0;
@@ -77,6 +82,7 @@ __global__ void __launch_bounds__(kCclTile)
   if (i >= m) return;
   const float xi = __ldg(pts + (int64_t)i * stride), yi = __ldg(pts + (int64_t)i * stride + 1);
   const int bi = batch ? __ldg(batch + i) : 0;
+  const float dist = D.per_batch ? D.d[bi & 7] : D.d[0];
   const int jn = min(kCclTile, m - j0);
   for (int jj = 0; jj < jn; ++jj) {
     const int j = j0 + jj;
@@ -199,10 +205,37 @@ int fsfb_ccl_workspace_bytes(int64_t m, size_t* bytes) {
   return FSFB_OK;
 }
 
+namespace fsfb {
+static int ccl_impl(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx, CclDist D, int32_t* labels,
+                    int32_t* num_components, void* workspace, size_t workspace_bytes, void* stream);
+}
+
 int fsfb_connected_components(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx,
                               float dist, int32_t* labels, int32_t* num_components, void* workspace,
                               size_t workspace_bytes, void* stream) {
+  fsfb::CclDist D;
+  D.per_batch = 0;
+  for (int i = 0; i < 8; ++i) D.d[i] = dist;
+  return fsfb::ccl_impl(points, m, stride, batch_idx, D, labels, num_components, workspace, workspace_bytes, stream);
+}
+
+int fsfb_connected_components_groups(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx,
+                                     const float* dist_per_batch, int n_batches, int32_t* labels, int32_t* num_components,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
   using namespace fsfb;
+  FSFB_CHECK_ARG(batch_idx && dist_per_batch && n_batches >= 1 && n_batches <= 8,
+                 "connected_components_groups: needs batch ids and 1..8 distances");
+  CclDist D;
+  D.per_batch = 1;
+  for (int i = 0; i < 8; ++i) D.d[i] = dist_per_batch[i < n_batches ? i : n_batches - 1];
+  return ccl_impl(points, m, stride, batch_idx, D, labels, num_components, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace fsfb {
+static int ccl_impl(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx, CclDist dist, int32_t* labels,
+                    int32_t* num_components, void* workspace, size_t workspace_bytes, void* stream) {
   FSFB_CHECK_ARG(m >= 0 && m < (1ll << 31) && stride >= 2, "connected_components: bad m/stride");
   cudaStream_t st = (cudaStream_t)stream;
   if (m == 0) {
@@ -236,4 +269,4 @@ int fsfb_connected_components(const float* points, int64_t m, int64_t stride, co
   return FSFB_OK;
 }
 
-}  // extern "C"
+}  // namespace fsfb

@@ -126,12 +126,44 @@ class FSF(nn.Module):
         self.combine_frustum_feat_mlp = M.build_mlp(128 * 3 * 2 + 128, [1024], LN3, act="gelu")
         self.combine_fsd_feat_mlp = M.build_mlp(128 * 3 * 2, [1024], LN3, act="gelu")
         self.fsd_begin_idx = 1000
+        self.group_loop = False   # True: the reference's per-group Python loop (kept for the equivalence test)
         self.eval()
 
     def refresh(self):
         for m in self.modules():
             if m is not self and hasattr(m, "refresh"):
                 m.refresh()
+
+    def _cluster_groups_loop(self, score, centers, dev):
+        """group_sample's selection + ClusterAssigner.forward_single_class group by group, as the reference loops
+        (single_stage_fsd.py:822-842, 936-982)."""
+        cfg = self.cfg
+        rng = cfg["point_cloud_range"]
+        sel_rows, cls_ids, clu_ids, ctr_list = [], [], [], []
+        for g in range(len(self.groups)):
+            idx = ops.compact_indices(ops.threshold_mask(score, g, cfg["score_thresh"][g]))
+            if idx.numel() == 0:                                                     # at least one point per sample (:833-835)
+                idx = torch.zeros(1, dtype=torch.int32, device=dev)
+            ctr = ops.gather_rows(centers.view(-1, 3 * len(self.groups))[:, 3 * g:3 * g + 3].contiguous(), idx)
+            cv = ops.voxelize(ctr, cfg["cluster_voxel_size"][g], rng, floor_mode=1, order_xyz=True, check_range=False)
+            cc4 = F.pad(cv, (1, 0), value=0)
+            _, inv, cnt = ops.unique_rows(cc4, return_counts=True, return_unique=False, inv_dtype=torch.int32)
+            keep = ops.compact_indices(ops.count_mask(cnt, inv, cfg["min_points"]))
+            if keep.numel() == 0:                                                    # `valid_mask = ~valid_mask` (:953-955)
+                keep = torch.arange(idx.numel(), dtype=torch.int32, device=dev)
+            ctr_k = ops.gather_rows(ctr, keep)
+            plan_c = M.ScatterPlan(ops.gather_int_rows(cc4, keep))
+            sampled_centers = plan_c.reduce(ctr_k, "mean")
+            labels = ops.connected_components(sampled_centers, None, cfg["connected_dist"][g])   # single-batch variant (:977)
+            clu = ops.gather_int_rows(labels.view(-1, 1), plan_c.inv32)
+            sel_rows.append(ops.gather_int_rows(idx.view(-1, 1), keep).view(-1))
+            cls_ids.append(torch.full((keep.numel(), 1), g, dtype=torch.int32, device=dev))
+            clu_ids.append(clu)
+            ctr_list.append(ctr_k)
+        rows = torch.cat(sel_rows)
+        pts_cluster_inds = torch.cat([torch.cat(cls_ids), torch.zeros((rows.numel(), 1), dtype=torch.int32, device=dev),
+                                      torch.cat(clu_ids)], dim=1)                    # (cls, batch, cluster) (:145-152)
+        return rows, pts_cluster_inds, torch.cat(ctr_list)
 
     # ------------------------------------------------------------------------------------------------
     def stages(self, points: torch.Tensor, mask_data: torch.Tensor, mask_anno: torch.Tensor, lidar2img: torch.Tensor
@@ -210,33 +242,14 @@ class FSF(nn.Module):
             v_off = plan.reduce(st["offsets"], "mean")
             # group_sample (:802-865)
             _, score, centers = ops.group_sample(v_logits, self.groups, xyz=v_pts, offsets=v_off)
-            sel_rows, cls_ids, clu_ids, ctr_list = [], [], [], []
-            for g in range(len(self.groups)):
-                idx = ops.compact_indices(ops.threshold_mask(score, g, cfg["score_thresh"][g]))
-                if idx.numel() == 0:                                                     # at least one point per sample (:833-835)
-                    idx = torch.zeros(1, dtype=torch.int32, device=dev)
-                ctr = ops.gather_rows(centers.view(-1, 3 * len(self.groups))[:, 3 * g:3 * g + 3].contiguous(), idx)
-                # ClusterAssigner.forward_single_class (:936-982)
-                cv = ops.voxelize(ctr, cfg["cluster_voxel_size"][g], rng, floor_mode=1, order_xyz=True, check_range=False)
-                cc4 = F.pad(cv, (1, 0), value=0)
-                _, inv, cnt = ops.unique_rows(cc4, return_counts=True, return_unique=False, inv_dtype=torch.int32)
-                keep = ops.compact_indices(ops.count_mask(cnt, inv, cfg["min_points"]))
-                if keep.numel() == 0:                                                    # `valid_mask = ~valid_mask` (:953-955)
-                    keep = torch.arange(idx.numel(), dtype=torch.int32, device=dev)
-                ctr_k = ops.gather_rows(ctr, keep)
-                plan_c = M.ScatterPlan(ops.gather_int_rows(cc4, keep))
-                sampled_centers = plan_c.reduce(ctr_k, "mean")
-                labels = ops.connected_components(sampled_centers, None, cfg["connected_dist"][g])   # single-batch variant (:977)
-                clu = ops.gather_int_rows(labels.view(-1, 1), plan_c.inv32)
-                sel_rows.append(ops.gather_int_rows(idx.view(-1, 1), keep).view(-1))
-                cls_ids.append(torch.full((keep.numel(), 1), g, dtype=torch.int32, device=dev))
-                clu_ids.append(clu)
-                ctr_list.append(ctr_k)
-            rows = torch.cat(sel_rows)
+            if self.group_loop:
+                rows, pts_cluster_inds, center_preds = self._cluster_groups_loop(score, centers, dev)
+            else:
+                # every class group in one pass (csrc/group_cluster.cu): same candidates, order and cluster ids as the loop
+                rows, cls, clu, center_preds = ops.group_cluster(
+                    score, centers, cfg["score_thresh"], cfg["cluster_voxel_size"], rng, cfg["connected_dist"], cfg["min_points"])
+                pts_cluster_inds = torch.stack([cls, torch.zeros_like(cls), clu], dim=1)   # (cls, batch, cluster) (:145-152)
             n = rows.numel()
-            pts_cluster_inds = torch.cat([torch.cat(cls_ids), torch.zeros((n, 1), dtype=torch.int32, device=dev),
-                                          torch.cat(clu_ids)], dim=1)                    # (cls, batch, cluster) (:145-152)
-            center_preds = torch.cat(ctr_list)
             s_pts = ops.gather_rows(v_pts, rows)
             pts_feats = torch.empty((n, 11 + 33 + 131), dtype=torch.float32, device=dev)
             ops.gather_rows(v_logits, rows, out=pts_feats[:, :11])

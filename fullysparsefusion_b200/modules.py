@@ -579,3 +579,32 @@ class VoteSegHead(nn.Module):
     @staticmethod
     def decode_vote_targets(preds):
         return ops.vote_decode(preds)
+
+
+# ------------------------------------------------------------------------------------------------
+# DynamicPointROIExtractor (query refinement)
+# ------------------------------------------------------------------------------------------------
+class DynamicPointROIExtractor(nn.Module):
+    """models/roi_heads/roi_extractors/dynamic_point_roi_extractor.py:11-100 (config FSF_nuScenes_config.py:290-294).
+    forward(pts_xyz [N,3+], batch_inds [N], rois [K,8] = (batch, x,y,z,w,l,h,rz)) ->
+        (point ids [P] i64, roi ids [P] i64, dict(local_xyz [P,3], boundary_offset [P,6], is_in_margin [P]))
+    One sample per call here (samples_per_gpu = 1); an empty result keeps one fake row of -1 ids as upstream
+    (dynamic_point_pool_op.py:36-40)."""
+
+    def __init__(self, init_cfg=None, debug=True, extra_wlh=(0, 0, 0), max_inbox_point=512, max_all_pts=50000):
+        super().__init__()
+        self.debug, self.extra_wlh, self.max_inbox_point, self.max_all_pts = debug, list(extra_wlh), max_inbox_point, max_all_pts
+
+    @torch.no_grad()
+    def forward(self, pts_xyz: torch.Tensor, batch_inds: torch.Tensor, rois: torch.Tensor):
+        assert len(pts_xyz) > 0 and len(batch_inds) > 0 and len(rois) > 0
+        dev = pts_xyz.device
+        cap = self.max_all_pts
+        out_pts_idx = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        out_roi_idx = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+        out_feats = torch.zeros((cap, 13), dtype=torch.float32, device=dev)
+        num = ops.dynamic_point_pool(rois[:, 1:8], pts_xyz, self.extra_wlh, self.max_inbox_point, out_pts_idx, out_roi_idx,
+                                     out_feats)
+        p = max(int(num.item()), 1)   # the output-size read the reference performs as a boolean mask (:34-44)
+        inds, roi_inds, info = out_pts_idx[:p], out_roi_idx[:p], out_feats[:p]
+        return inds, roi_inds, dict(local_xyz=info[:, 3:6], boundary_offset=info[:, 6:12], is_in_margin=info[:, 12])

@@ -886,3 +886,88 @@ def rulebook_row_order(nbr: torch.Tensor) -> torch.Tensor:
         check(lib.fsfb_rulebook_row_order(_ptr(nbr), koff, rows, _ptr(order), _ptr(ws), ws.numel(), _stream(dev)),
               "fsfb_rulebook_row_order")
     return order
+
+
+# ------------------------------------------------------------------------------------------
+# f1 dynamic point pooling (query refinement)
+# ------------------------------------------------------------------------------------------
+def dynamic_point_pool(rois: torch.Tensor, pts: torch.Tensor, extra_wlh: Sequence[float], max_inbox_point: int,
+                       out_pts_idx: torch.Tensor, out_roi_idx: torch.Tensor, out_pts_feats: torch.Tensor) -> torch.Tensor:
+    """dynamic_point_pool_ext.forward (projects/mmdet3d_plugin/ops/dynamic_point_pool_op.py:27-32): fills the caller's
+    prefilled buffers in canonical (roi, point) order and returns the device count [1] i32 of rows written."""
+    dev = _need_cuda(rois, pts, out_pts_idx, out_roi_idx, out_pts_feats)
+    assert rois.dim() == 2 and rois.size(1) == 7 and rois.dtype == torch.float32
+    assert pts.dim() == 2 and pts.size(1) >= 3 and pts.dtype == torch.float32
+    assert out_pts_idx.dtype == torch.int64 and out_roi_idx.dtype == torch.int64 and out_pts_feats.dtype == torch.float32
+    assert out_pts_idx.is_contiguous() and out_roi_idx.is_contiguous() and out_pts_feats.is_contiguous()
+    cap = out_pts_idx.numel()
+    assert out_roi_idx.numel() == cap and tuple(out_pts_feats.shape) == (cap, 13)
+    rois = rois.contiguous()
+    if pts.stride(1) != 1:
+        pts = pts.contiguous()
+    lib = load()
+    need = C.c_size_t()
+    check(lib.fsfb_dynamic_point_pool_workspace_bytes(rois.size(0), int(max_inbox_point), C.byref(need)),
+          "fsfb_dynamic_point_pool_workspace_bytes")
+    ws = _ws(need.value, dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)
+    with _Prof("dynamic_point_pool", 12 * pts.size(0) + 28 * rois.size(0) + 68 * cap):
+        check(lib.fsfb_dynamic_point_pool(_ptr(rois), rois.size(0), _ptr(pts), pts.size(0), pts.stride(0) if pts.size(0) else 3,
+                                          _host_f32(extra_wlh), int(max_inbox_point), cap, _ptr(out_pts_idx), _ptr(out_roi_idx),
+                                          _ptr(out_pts_feats), _ptr(num), _ptr(ws), ws.numel(), _stream(dev)),
+              "fsfb_dynamic_point_pool")
+    return num
+
+
+# ------------------------------------------------------------------------------------------
+# a13/a14 all class groups at once (csrc/group_cluster.cu)
+# ------------------------------------------------------------------------------------------
+def group_cluster(score: torch.Tensor, centers: torch.Tensor, thresholds: Sequence[float], voxel_sizes: Sequence[Sequence[float]],
+                  range_min: Sequence[float], dists: Sequence[float], min_points: int):
+    """group_sample's per-group selection + ClusterAssigner.forward_single_class for every class group in one pass
+    (single_stage_fsd.py:822-842, 936-982).  score [n,G], centers [n,G,3] →
+        rows [P] i32 (row of the per-voxel tensors), grp [P] i32 (class group), clu [P] i32 (cluster id inside the group),
+        center_preds [P,3] f32 — ordered (group, row), exactly the concatenation the reference's loop builds."""
+    dev = _need_cuda(score, centers)
+    n, G = score.shape
+    assert score.dtype == torch.float32 and score.stride(1) == 1 and centers.is_contiguous() and centers.numel() == n * G * 3
+    lib, st = load(), _stream(dev)
+    flags = torch.empty(G * n, dtype=torch.uint8, device=dev)
+    small = torch.empty(3 * 8, dtype=torch.int32, device=dev)   # counts | kept | base
+    check(lib.fsfb_group_flags(_ptr(score), n, score.stride(0) if n else G, G, _host_f32(thresholds), _ptr(flags), _ptr(small), st),
+          "fsfb_group_flags")
+    flat = compact_indices(flags)                                                        # list length 1
+    t = flat.numel()
+    grp, vox, cidx = (torch.empty(t, dtype=torch.int32, device=dev) for _ in range(3))
+    check(lib.fsfb_group_split(_ptr(flat), t, n, G, _ptr(grp), _ptr(vox), _ptr(cidx), st), "fsfb_group_split")
+    ctr = gather_rows(centers.view(n * G, 3), cidx)
+    rows4 = torch.empty((t, 4), dtype=torch.int32, device=dev)
+    check(lib.fsfb_group_voxelize(_ptr(ctr), t, _ptr(grp), _host_f32(range_min[:3]), _host_f32([v for vs in voxel_sizes for v in vs]),
+                                  G, _ptr(rows4), st), "fsfb_group_voxelize")
+    _, inv, cnt = unique_rows(rows4, return_counts=True, return_unique=False, inv_dtype=torch.int32)   # list length 2
+    keep_flag = torch.empty(t, dtype=torch.uint8, device=dev)
+    check(lib.fsfb_group_keep(_ptr(cnt), _ptr(inv), _ptr(grp), t, G, int(min_points), _ptr(keep_flag), _ptr(small[8:]), st),
+          "fsfb_group_keep")
+    keep = compact_indices(keep_flag)                                                    # list length 3
+    p = keep.numel()
+    ctr_k = gather_rows(ctr, keep)
+    rows4_k = gather_int_rows(rows4, keep)
+    sel = gather_int_rows(torch.stack([vox, grp], dim=1), keep)
+    new_coors, inv_c, _ = unique_rows(rows4_k, inv_dtype=torch.int32)[:3]                # list length 4
+    m = new_coors.size(0)
+    csr = build_csr(inv_c, m)
+    csr.dense = True
+    sampled_centers = segment_reduce(ctr_k, csr, "mean")
+    batch_c = new_coors[:, 0].contiguous()
+    labels = torch.empty(m, dtype=torch.int32, device=dev)
+    need = C.c_size_t(0)
+    check(lib.fsfb_ccl_workspace_bytes(m, C.byref(need)), "fsfb_ccl_workspace_bytes")
+    ws = _ws(need.value, dev)
+    with _Prof("connected_components", 16 * m):
+        check(lib.fsfb_connected_components_groups(_ptr(sampled_centers), m, sampled_centers.stride(0) if m else 3, _ptr(batch_c),
+                                                   _host_f32(dists), G, _ptr(labels), None, _ptr(ws), ws.numel(), st),
+              "fsfb_connected_components_groups")
+    clu = torch.empty(p, dtype=torch.int32, device=dev)
+    check(lib.fsfb_group_relabel(_ptr(labels), _ptr(batch_c), 1, m, G, _ptr(inv_c), p, _ptr(small[16:]), _ptr(clu), st),
+          "fsfb_group_relabel")
+    return sel[:, 0].contiguous(), sel[:, 1].contiguous(), clu, ctr_k

@@ -1,7 +1,7 @@
 """Drop-in modules under the names the reference plugin imports.
 
     import fullysparsefusion_b200.shims as shims
-    shims.install()          # registers torch_scatter, ingroup_indices, torchex in sys.modules
+    shims.install()          # registers torch_scatter, ingroup_indices, torchex, dynamic_point_pool_ext in sys.modules
     import projects.mmdet3d_plugin   # the plugin's `import torch_scatter` etc. now bind to the B200 path
 
 Every function is a thin wrapper over the C-ABI ops (no torch arithmetic on the hot path, no CPU
@@ -12,13 +12,14 @@ from __future__ import annotations
 
 import sys
 
-from . import ingroup_indices, mmdet3d_ops, torch_scatter, torchex  # noqa: F401
+from . import dynamic_point_pool_ext, ingroup_indices, mmdet3d_ops, torch_scatter, torchex  # noqa: F401
 
 
 def install(force: bool = False) -> None:
     """Register the shims under the import names used by projects/mmdet3d_plugin
-    (ops/sst_ops.py:5-6,239; models/detectors/single_stage_fsd.py:13,20-23)."""
-    for name, mod in (("torch_scatter", torch_scatter), ("ingroup_indices", ingroup_indices), ("torchex", torchex)):
+    (ops/sst_ops.py:5-6,239; ops/dynamic_point_pool_op.py:5; models/detectors/single_stage_fsd.py:13,20-23)."""
+    for name, mod in (("torch_scatter", torch_scatter), ("ingroup_indices", ingroup_indices), ("torchex", torchex),
+                      ("dynamic_point_pool_ext", dynamic_point_pool_ext)):
         if force or name not in sys.modules:
             sys.modules[name] = mod
 

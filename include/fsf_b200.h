@@ -417,6 +417,55 @@ int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t feat_strid
                         const float* ln2_w, const float* ln2_b, const float* w3, const float* ln3_w,
                         const float* ln3_b, float eps, int act, float* out, int64_t out_stride, void* stream);
 
+/* a13/a14 for ALL class groups in one pass (csrc/group_cluster.cu): the per-group selection of
+ * SingleStageFSD.group_sample (projects/mmdet3d_plugin/models/detectors/single_stage_fsd.py:822-842) and
+ * ClusterAssigner.forward_single_class (:936-982), which the reference runs as a Python loop over the class groups.
+ * The candidate list is ordered (group, row); the group id is the batch column of the ranking and of the CCL.
+ *   fsfb_group_flags     flags dev [G, n] u8 = score[:, g] > thresholds[g] (host [G]); a group with no candidate keeps
+ *                        row 0 (:833-835); counts dev [G] i32 = candidates per group before that fallback
+ *   fsfb_group_split     flat (ascending indices into flags, from fsfb_compact_indices) → grp, vox, cidx = vox*G + grp
+ *   fsfb_group_voxelize  rows4 dev [t,4] i32 = (grp, floor_div(centre - range_min, voxel_sizes[grp]))  (:946-950);
+ *                        voxel_sizes host [G,3]
+ *   fsfb_group_keep      keep = counts[inv] >= min_points, and everything of a group where nothing survives (:953-955)
+ *   fsfb_group_relabel   out[i] = labels[inv[i]] - (smallest label of that row's group): cluster ids from 0 per group;
+ *                        batch = group id of each labelled row (stride in i32 elements), base dev [G] scratch
+ *   fsfb_connected_components_groups   fsfb_connected_components with one distance per batch id (host [n_batches] <= 8)
+ */
+int fsfb_group_flags(const float* score, int64_t n, int64_t stride, int n_groups, const float* thresholds, uint8_t* flags,
+                     int32_t* counts, void* stream);
+int fsfb_group_split(const int32_t* flat, int64_t t, int64_t n, int n_groups, int32_t* grp, int32_t* vox, int32_t* cidx,
+                     void* stream);
+int fsfb_group_voxelize(const float* centers, int64_t t, const int32_t* grp, const float* range_min, const float* voxel_sizes,
+                        int n_groups, int32_t* rows4, void* stream);
+int fsfb_group_keep(const int32_t* counts, const int32_t* inv, const int32_t* grp, int64_t t, int n_groups, int min_points,
+                    uint8_t* keep, int32_t* kept_per_group, void* stream);
+int fsfb_group_relabel(const int32_t* labels, const int32_t* batch, int64_t batch_stride, int64_t m, int n_groups,
+                       const int32_t* inv, int64_t t, int32_t* base, int32_t* out, void* stream);
+int fsfb_connected_components_groups(const float* points, int64_t m, int64_t stride, const int32_t* batch_idx,
+                                     const float* dist_per_batch, int n_batches, int32_t* labels, int32_t* num_components,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * f1  Dynamic point pooling of the query-refinement stage.
+ * Replaces dynamic_point_pool_ext.forward(rois, pts, extra_wlh, max_inbox_point, out_pts_idx, out_roi_idx,
+ * out_pts_feats) (projects/mmdet3d_plugin/ops/dynamic_point_pool_op.py:27-32; caller
+ * models/roi_heads/roi_extractors/dynamic_point_roi_extractor.py:52-57).  Source un-vendored: semantics restated
+ * from the published FSD kernel and the invariants asserted in-tree (dynamic_point_roi_extractor.py:84-92).
+ *   rois dev [k,7] f32 (cx,cy,cz,w,l,h,rz), gravity centre; pts dev rows of >= 3 floats (x,y,z first).
+ *   A point belongs to a roi when it lies inside the box enlarged by extra_wlh (host [3]: added to l, w, h).
+ *   Outputs (caller-allocated, `capacity` rows, upstream 50000; rows past *num_out are left untouched so the caller's
+ *   -1 / 0 prefill keeps its meaning): out_pts_idx / out_roi_idx dev i64, out_pts_feats dev [capacity,13] f32 =
+ *   (x,y,z, local x,y,z, local + half dims (3), half dims - local (3), in-margin flag).
+ *   Order: roi-major, point index ascending; at most max_inbox_point lowest-index points per roi; the first
+ *   `capacity` entries of that order (upstream's atomics make both choices run-dependent).
+ *   num_out dev [1] i32: rows written.
+ * ------------------------------------------------------------------------- */
+int fsfb_dynamic_point_pool_workspace_bytes(int64_t k, int max_inbox_point, size_t* bytes);
+int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float* pts, int64_t n, int64_t pts_stride,
+                            const float* extra_wlh, int max_inbox_point, int64_t capacity,
+                            long long* out_pts_idx, long long* out_roi_idx, float* out_pts_feats,
+                            int32_t* num_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

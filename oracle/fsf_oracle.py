@@ -530,3 +530,48 @@ def conv_rulebook(out_coors, in_coors, in_shape_bzyx, ksize, stride, pad, transp
                 nbr[k, hit] = order[pos[hit]].astype(np.int32)
                 k += 1
     return nbr
+
+
+# ------------------------------------------------------------------------------------------
+# f1 dynamic point pooling (query refinement) — PARITY UNPINNED: the extension's source is not vendored; restated
+# from the published FSD kernel under the invariants asserted at
+# projects/mmdet3d_plugin/models/roi_heads/roi_extractors/dynamic_point_roi_extractor.py:84-92, with the canonical
+# (roi, point) order documented in include/fsf_b200.h.
+# ------------------------------------------------------------------------------------------
+def dynamic_point_pool(rois, pts, extra_wlh, max_inbox_point, capacity, margin=None):
+    """rois [K,7] (cx,cy,cz,w,l,h,rz) f32, pts [N,3] f32 -> (pts_idx [P], roi_idx [P], feats [P,13]).
+    margin: if given, also returns a bool [P'] mask over ALL (roi, point) candidates is not needed; instead the
+    function returns `ambiguous` = set of (roi, point) pairs whose membership lies within `margin` of a face."""
+    rois = np.asarray(rois, F32)
+    pts = np.asarray(pts, F32)[:, :3]
+    e = np.asarray(extra_wlh, F32)
+    out_p, out_r, out_f, ambiguous = [], [], [], set()
+    total = 0
+    for r in range(rois.shape[0]):
+        cx, cy, cz, w, l, h, rz = rois[r]
+        hl, hw, hh = F32(l * F32(0.5)), F32(w * F32(0.5)), F32(h * F32(0.5))
+        el, ew, eh = F32((l + e[0]) * F32(0.5)), F32((w + e[1]) * F32(0.5)), F32((h + e[2]) * F32(0.5))
+        cosa, sina = F32(np.cos(F32(-rz))), F32(np.sin(F32(-rz)))
+        sx, sy = (pts[:, 0] - cx).astype(F32), (pts[:, 1] - cy).astype(F32)
+        lz = (pts[:, 2] - cz).astype(F32)
+        lx = ((sx * cosa).astype(F32) + (sy * (-sina)).astype(F32)).astype(F32)
+        ly = ((sx * sina).astype(F32) + (sy * cosa).astype(F32)).astype(F32)
+        hit = (np.abs(lz) <= eh) & (lx > -el) & (lx < el) & (ly > -ew) & (ly < ew)
+        if margin is not None:
+            near = (np.abs(np.abs(lz) - eh) < margin) | (np.abs(np.abs(lx) - el) < margin) | (np.abs(np.abs(ly) - ew) < margin)
+            box = (np.abs(lz) <= eh + margin) & (np.abs(lx) < el + margin) & (np.abs(ly) < ew + margin)
+            for p in np.nonzero(near & box)[0]:
+                ambiguous.add((r, int(p)))
+        idx = np.nonzero(hit)[0][:max_inbox_point]
+        idx = idx[: max(0, capacity - total)]
+        total += idx.size
+        inner = (np.abs(lx[idx]) < hl) & (np.abs(ly[idx]) < hw) & (np.abs(lz[idx]) <= hh)
+        f = np.stack([pts[idx, 0], pts[idx, 1], pts[idx, 2], lx[idx], ly[idx], lz[idx],
+                      lx[idx] + hl, ly[idx] + hw, lz[idx] + hh, hl - lx[idx], hw - ly[idx], hh - lz[idx],
+                      (~inner).astype(F32)], axis=1).astype(F32) if idx.size else np.zeros((0, 13), F32)
+        out_p.append(idx.astype(np.int64))
+        out_r.append(np.full(idx.size, r, np.int64))
+        out_f.append(f)
+    res = (np.concatenate(out_p) if out_p else np.zeros(0, np.int64), np.concatenate(out_r) if out_r else np.zeros(0, np.int64),
+           np.concatenate(out_f) if out_f else np.zeros((0, 13), F32))
+    return res + (ambiguous,) if margin is not None else res

@@ -166,3 +166,26 @@ def test_combine_stage(frame):
     fc = N(st["fsd_obj_coors"])
     assert np.array_equal(N(st["obj_coors"])[kf:], np.stack([fc[:, 1], fc[:, 0], fc[:, 2] + 1000], 1))
     assert st["obj_cls"].shape == (kf + len(fs), 10) and st["obj_reg"].shape == (kf + len(fs), 10)
+
+
+@pytest.mark.parametrize("thr", [0.1, 0.02, 0.9])
+def test_group_cluster_equals_loop(cuda, frame, thr):
+    """All class groups in one pass (csrc/group_cluster.cu) == the reference's per-group loop (single_stage_fsd.py:822-842,
+    936-982), bit for bit: candidate rows, (cls, batch, cluster) ids, centres and everything computed from them.
+    thr 0.9 empties groups (the `at least one point` and `keep everything` fallbacks), 0.02 floods them."""
+    model = frame["model"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    args = (T(frame["pts"]), T(frame["mask"]), T(frame["anno"]), T(frame["l2i"]))
+    old = model.cfg
+    model.cfg = dict(old, score_thresh=[thr] * 6)
+    try:
+        with torch.no_grad():
+            model.group_loop = True
+            a = model(*args)
+            model.group_loop = False
+            b = model(*args)
+    finally:
+        model.group_loop, model.cfg = False, old
+    assert a["fsd_rows"].numel() > 0
+    for k in ("fsd_rows", "pts_cluster_inds", "fsd_center_preds", "fsd_obj_coors", "fsd_obj_centers", "fsd_obj_feats", "fsd_cls"):
+        assert torch.equal(a[k], b[k]), k

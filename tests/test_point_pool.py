@@ -1,0 +1,95 @@
+"""Dynamic point pooling: oracle invariants (the ones the reference's extractor asserts in-tree)
+and GPU parity of fsfb_dynamic_point_pool / the dynamic_point_pool_ext shim / DynamicPointROIExtractor."""
+import numpy as np
+import pytest
+
+from oracle import fsf_oracle as O
+
+
+def _scene(n, k, seed, extra=(1.0, 1.0, 1.0)):
+    rng = np.random.default_rng(seed)
+    pts = np.concatenate([rng.uniform(-50, 50, (n, 2)), rng.uniform(-4, 2, (n, 1))], axis=1).astype(np.float32)
+    centers = pts[rng.integers(0, n, k)] + rng.normal(0, 0.3, (k, 3)).astype(np.float32)
+    dims = rng.uniform([1.5, 3.0, 1.2], [2.5, 6.0, 2.5], (k, 3))
+    rois = np.concatenate([centers, dims, rng.uniform(-np.pi, np.pi, (k, 1))], axis=1).astype(np.float32)
+    # dense clusters around some boxes so the per-roi cap matters
+    extra_pts = (centers[: max(1, k // 8), None, :] + rng.normal(0, 0.4, (max(1, k // 8), 40, 3))).reshape(-1, 3).astype(np.float32)
+    pts = np.concatenate([pts, extra_pts])[rng.permutation(n + extra_pts.shape[0])]
+    return pts, rois, list(extra)
+
+
+def test_oracle_invariants():
+    """dynamic_point_roi_extractor.py:84-92 restated on the oracle's output."""
+    pts, rois, extra = _scene(5000, 40, 0)
+    pi, ri, f = O.dynamic_point_pool(rois, pts, extra, 512, 50000)
+    assert pi.size > 0 and (np.diff(ri) >= 0).all()
+    roi = rois[ri]
+    np.testing.assert_allclose(pts[pi], f[:, :3])
+    np.testing.assert_allclose(f[:, 6] + f[:, 9], roi[:, 4], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(f[:, 7] + f[:, 10], roi[:, 3], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(f[:, 8] + f[:, 11], roi[:, 5], rtol=1e-5, atol=1e-5)
+    assert (np.abs(f[:, 3]) < roi[:, 4] + extra[0] + 1e-5).all()
+    assert (np.abs(f[:, 4]) < roi[:, 3] + extra[1] + 1e-5).all()
+    assert (np.abs(f[:, 5]) < roi[:, 5] + extra[2] + 1e-5).all()
+    # local coordinates really are the roi frame: rotating back recovers the offset to the centre
+    c, s = np.cos(roi[:, 6]), np.sin(roi[:, 6])
+    back = np.stack([f[:, 3] * c - f[:, 4] * s, f[:, 3] * s + f[:, 4] * c], 1)
+    np.testing.assert_allclose(back, pts[pi][:, :2] - roi[:, :2], atol=2e-4)
+    assert set(np.unique(f[:, 12])) <= {0.0, 1.0} and 0 < f[:, 12].mean() < 1
+    # caps
+    pi2, ri2, _ = O.dynamic_point_pool(rois, pts, extra, 8, 100)
+    assert pi2.size <= 100 and np.bincount(ri2).max() <= 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,k,max_inbox,cap,seed", [(5000, 40, 512, 50000, 1), (60000, 300, 512, 50000, 2), (3000, 9, 16, 50, 3),
+                                                    (200, 1, 512, 50000, 4), (20000, 1030, 64, 50000, 5)])
+def test_dynamic_point_pool_parity(cuda, n, k, max_inbox, cap, seed):
+    import torch
+    from fullysparsefusion_b200 import ops
+    pts, rois, extra = _scene(n, k, seed)
+    want_p, want_r, want_f, amb = O.dynamic_point_pool(rois, pts, extra, max_inbox, cap, margin=1e-4)
+    out_p = torch.full((cap,), -1, dtype=torch.int64, device=cuda)
+    out_r = torch.full((cap,), -1, dtype=torch.int64, device=cuda)
+    out_f = torch.zeros((cap, 13), device=cuda)
+    num = ops.dynamic_point_pool(torch.from_numpy(rois).to(cuda), torch.from_numpy(pts).to(cuda), extra, max_inbox, out_p, out_r, out_f)
+    m = int(num.item())
+    got_p, got_r, got_f = out_p[:m].cpu().numpy(), out_r[:m].cpu().numpy(), out_f[:m].cpu().numpy()
+    assert (out_p[m:] == -1).all() and (out_r[m:] == -1).all() and (out_f[m:] == 0).all()   # prefill untouched
+    if not amb:   # no point within 1e-4 of a face: ids must match exactly (integer outputs are bit-exact)
+        np.testing.assert_array_equal(got_p, want_p)
+        np.testing.assert_array_equal(got_r, want_r)
+        np.testing.assert_allclose(got_f, want_f, rtol=1e-5, atol=1e-5)
+    else:         # cosf/sinf differ from numpy by an ulp: pairs that sit on a face may flip, everything else must agree
+        got = set(zip(got_r.tolist(), got_p.tolist()))
+        want = set(zip(want_r.tolist(), want_p.tolist()))
+        assert (got ^ want) <= amb or max_inbox < 512 or m == cap, sorted(got ^ want)[:5]
+    assert (np.diff(got_r) >= 0).all()
+    for r in np.unique(got_r)[:20]:
+        assert (np.diff(got_p[got_r == r]) > 0).all()
+
+
+@pytest.mark.gpu
+def test_roi_extractor_and_shim(cuda):
+    import torch
+    from fullysparsefusion_b200 import modules as M
+    from fullysparsefusion_b200.shims import dynamic_point_pool_ext
+    pts, rois, extra = _scene(8000, 25, 7)
+    tp, tr = torch.from_numpy(pts).to(cuda), torch.from_numpy(rois).to(cuda)
+    ext = M.DynamicPointROIExtractor(extra_wlh=extra, max_inbox_point=512)
+    rois8 = torch.cat([torch.zeros(len(rois), 1, device=cuda), tr], 1)
+    inds, roi_inds, info = ext(tp, torch.zeros(len(pts), dtype=torch.int64, device=cuda), rois8)
+    want_p, want_r, want_f = O.dynamic_point_pool(rois, pts, extra, 512, 50000)
+    assert abs(inds.numel() - want_p.size) <= 2
+    assert info["local_xyz"].shape == (inds.numel(), 3) and info["boundary_offset"].shape == (inds.numel(), 6)
+    # the shim: same buffers protocol as dynamic_point_pool_op.py:27-32
+    op, orr, of = (torch.full((50000,), -1, dtype=torch.int64, device=cuda), torch.full((50000,), -1, dtype=torch.int64, device=cuda),
+                   torch.zeros(50000, 13, device=cuda))
+    dynamic_point_pool_ext.forward(tr, tp, extra, 512, op, orr, of)
+    valid = op >= 0
+    assert int(valid.sum()) == inds.numel() and torch.equal(op[valid], inds) and torch.equal(orr[valid], roi_inds)
+    # a far-away roi: empty result keeps one fake row (dynamic_point_pool_op.py:36-40)
+    far = rois8[:1].clone()
+    far[:, 1:4] = 1e4
+    i2, r2, _ = ext(tp, torch.zeros(len(pts), dtype=torch.int64, device=cuda), far)
+    assert i2.numel() == 1 and int(i2[0]) == -1 and int(r2[0]) == -1
