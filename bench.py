@@ -315,7 +315,7 @@ def main():
         per_stage = {}
         for name, a, b in events:
             per_stage.setdefault(name, []).append(a.elapsed_time(b))
-        stage_ms = {k: sum(v) / len(v) for k, v in per_stage.items()}
+        stage_ms = {k: statistics.median(v) for k, v in per_stage.items()}   # median: one slow frame must not skew a stage
         def fold(records, n_steps):
             kern, shapes = {}, {}
             for name, a, b, nb, fl in records:

@@ -52,6 +52,8 @@ SIGNATURES = {
     "fsfb_connected_components_groups": (_i, [_p, _i64, _i64, _p, _p, _i, _p, _p, _p, _sz, _p]),
     "fsfb_dynamic_point_pool_workspace_bytes": (_i, [_i64, _i, _p]),
     "fsfb_dynamic_point_pool": (_i, [_p, _i64, _p, _i64, _i64, _p, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "fsfb_gather_gemm_hv": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _i, _p, _sz,
+                                _p, _p, _p, _p]),
     "fsfb_gather_gemm_simt": (_i, [_p, _i64, _i, _i64, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),
     "fsfb_conv_rulebook": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "fsfb_conv_out_index": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),

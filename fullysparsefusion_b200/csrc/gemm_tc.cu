@@ -279,7 +279,8 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
                             const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout, const float* bias,
                             int norm, const float* norm_w, const float* norm_b, float eps,
                             const float* residual, int64_t residual_stride, int act, float* out,
-                            int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, void* stream) {
+                            int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, const float* host_bias,
+                            const float* host_norm_w, const float* host_norm_b, void* stream) {
   int rc = check_epilogue(cout, bias, norm, norm_w, norm_b, act, "gather_gemm");
   if (rc != FSFB_OK) return rc;
   FSFB_CHECK_ARG(rows >= 0 && a_rows >= 0 && a_rows < (1ll << 31) && cin >= 1 && a_stride >= cin &&
@@ -323,7 +324,8 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
     const int n_pad = P.S.n_pad();
     const bool ts_ok = n_pad <= 128 || (n_pad % 128 == 0 && norm != FSFB_NORM_LAYERNORM);
     if (ts_mode && ts_ok)
-      return launch_gather_gemm_ts(P, a_vec, (float*)workspace, workspace_bytes, splits, (cudaStream_t)stream);
+      return launch_gather_gemm_ts(P, a_vec, (float*)workspace, workspace_bytes, splits, host_bias, host_norm_w, host_norm_b,
+                                   (cudaStream_t)stream);
     FSFB_CHECK_ARG(splits <= 1, "gather_gemm: offset splits need cout <= 128 or a multiple of 128 (cout=%d)", cout);
   }
   const size_t stage_bytes = 2 * (size_t)kStageABytes + (size_t)2 * n_w_max * 128;
@@ -370,7 +372,7 @@ extern "C" int fsfb_gather_gemm(const float* a, int64_t a_rows, int cin, int64_t
                                 const float* residual, int64_t residual_stride, int act, float* out,
                                 int64_t out_stride, void* stream) {
   return fsfb::gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b,
-                                eps, residual, residual_stride, act, out, out_stride, 1, nullptr, 0, stream);
+                                eps, residual, residual_stride, act, out, out_stride, 1, nullptr, 0, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int fsfb_gather_gemm_splitk_bytes(int64_t rows, int cout, int splits, size_t* bytes) {
@@ -390,5 +392,19 @@ extern "C" int fsfb_gather_gemm_splitk(const float* a, int64_t a_rows, int cin, 
   FSFB_CHECK_ARG(splits >= 1 && splits <= koff, "gather_gemm_splitk: splits=%d must be in 1..koff", splits);
   FSFB_CHECK_ARG(splits == 1 || ((uintptr_t)workspace & 15) == 0, "gather_gemm_splitk: workspace must be 16-byte aligned");
   return gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b, eps,
-                          residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, stream);
+                          residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fsfb_gather_gemm_hv(const float* a, int64_t a_rows, int cin, int64_t a_stride, const int32_t* nbr,
+                                   const int32_t* row_order, int koff, int64_t rows, const void* w_packed, int cout,
+                                   const float* bias, int norm, const float* norm_w, const float* norm_b, float eps,
+                                   const float* residual, int64_t residual_stride, int act, float* out, int64_t out_stride,
+                                   int splits, void* workspace, size_t workspace_bytes, const float* host_bias,
+                                   const float* host_norm_w, const float* host_norm_b, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(splits >= 1 && splits <= koff, "gather_gemm_hv: splits=%d must be in 1..koff", splits);
+  FSFB_CHECK_ARG(splits == 1 || ((uintptr_t)workspace & 15) == 0, "gather_gemm_hv: workspace must be 16-byte aligned");
+  return gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b, eps,
+                          residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, host_bias,
+                          host_norm_w, host_norm_b, stream);
 }

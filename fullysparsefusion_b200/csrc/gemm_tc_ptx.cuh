@@ -162,6 +162,8 @@ struct TcParams {
   int64_t n_units;
   float* partial;
   uint32_t* timers;  // diagnostics (FSFB_GEMM_TIMERS=1), else null
+  // host copies of the per-channel epilogue vectors (cout <= 128): read as constant-bank operands by the epilogue warps
+  float hv_bias[128], hv_w[128], hv_h[128];
   int debug;    // FSFB_GEMM_DEBUG bits (profiling experiments only): 1 no A loads, 2 no W copy, 4 no MMA, 8 no A stores
 };
 
@@ -274,6 +276,7 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
 }
 
 // gemm_ts.cu
-int launch_gather_gemm_ts(TcParams P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, cudaStream_t st);
+int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, const float* host_bias,
+                          const float* host_norm_w, const float* host_norm_b, cudaStream_t st);
 
 }  // namespace fsfb

@@ -158,13 +158,95 @@ __device__ __forceinline__ bool ts_unit(const TcParams& P, uint32_t u, TsUnit& U
   return true;
 }
 
+// Epilogue of one unit in the HV form (per-channel vectors in the kernel parameters), thread = TMEM lane = row, 32 columns
+// per tcgen05.ld pair.  NORM / ACT / POST are compile-time so that a fully unrolled instance (UNROLL) is a few hundred
+// instructions whose vector operands are constant-bank immediates — no load instruction of any kind (measured: the same
+// body rolled, with ld.const indexing, was no faster than shared-memory vectors; GELU layers therefore keep that path).  Leaves the finished row in the staging row `my_row`; arrives on `acc_empty_bar` after the last TMEM read.
+template <int NORM, int ACT, bool POST, bool UNROLL>
+__device__ __forceinline__ void ts_epi32(const TcParams& P, uint32_t t_row, uint32_t acc_cols, uint32_t my_row, int c_n, int n_sub,
+                                         bool have_acc, bool use_res, bool valid, uint32_t acc_empty_bar, int lane) {
+  float v[32];
+  auto ld32 = [&](int cb) {  // warp-collective: executed by all lanes, valid row or not
+    if (have_acc) {
+      float c2[32];
+      tc_ld32(t_row + cb, v);
+      tc_ld32(t_row + acc_cols + cb, c2);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) v[jj] += c2[jj];
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+    }
+  };
+  float mean = 0.f, rstd = 1.f;
+  if (NORM == FSFB_NORM_LAYERNORM) {  // two-pass row statistics (the whole row is in this tile)
+    float sum = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < c_n; cb += 32) {
+      ld32(cb);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        if (cb + jj < c_n) sum += v[jj] + P.hv_bias[cb + jj];
+    }
+    mean = sum / (float)c_n;
+    float qq = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < c_n; cb += 32) {
+      ld32(cb);
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj)
+        if (cb + jj < c_n) {
+          const float d = v[jj] + P.hv_bias[cb + jj] - mean;
+          qq += d * d;
+        }
+    }
+    rstd = 1.f / sqrtf(qq / (float)c_n + P.E.eps);
+  }
+  auto block = [&](int cb) {
+    ld32(cb);
+    if (cb + 32 >= n_sub) {  // last TMEM read of this unit: the MMA warps may start the next unit
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty_bar);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 32; jj += 4) {
+      float y[4] = {v[jj], v[jj + 1], v[jj + 2], v[jj + 3]};
+      if (cb + jj < c_n) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use_res && valid) g = lds_f4(my_row + (uint32_t)(cb + jj) * 4u);
+        const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = y[e] + P.hv_bias[cb + jj + e];
+          if (NORM == FSFB_NORM_LAYERNORM) x = (x - mean) * rstd * P.hv_w[cb + jj + e] + P.hv_h[cb + jj + e];
+          else if (NORM == FSFB_NORM_AFFINE) x = fmaf(x, P.hv_w[cb + jj + e], P.hv_h[cb + jj + e]);
+          const float a = apply_act(POST ? x : x + gg[e], ACT);
+          y[e] = POST ? a + gg[e] : a;
+        }
+      }
+      sts_f4(my_row + (uint32_t)(cb + jj) * 4u, make_float4(y[0], y[1], y[2], y[3]));
+    }
+  };
+  if (UNROLL) {
+#pragma unroll
+    for (int cbi = 0; cbi < 4; ++cbi)
+      if (32 * cbi < n_sub) block(32 * cbi);
+  } else {
+#pragma unroll 1
+    for (int cb = 0; cb < n_sub; cb += 32) block(cb);
+  }
+}
+
 // AVEC: rows of `a` are 16-byte aligned; KFULL: additionally cin % 32 == 0 (every K chunk complete) → the gather is 8 plain
 // 128-bit loads per thread and stage
 // TIMED (FSFB_GEMM_TIMERS=1, tools/gemm_timers.py): per-role wait/work cycle counters, one row of 16 per CTA
 #define TS_T0() uint32_t t0_ = TIMED ? (uint32_t)clock() : 0u
 #define TS_ACC(var) do { if (TIMED) { const uint32_t t1_ = (uint32_t)clock(); var += t1_ - t0_; t0_ = t1_; } } while (0)
-template <bool AVEC, bool KFULL, bool TIMED = false>
-__global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams P) {
+// HV: the per-channel epilogue vectors travel in the kernel parameters (cout <= 128, host copies given): the epilogue reads
+// them as constant-bank operands of its FMAs, i.e. with no load instruction at all
+template <bool AVEC, bool KFULL, bool TIMED = false, bool HV = false>
+__global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t base = smem_u32(smem_raw);
@@ -558,7 +640,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
         if (valid) bulk_g2s(my_row, E.residual + r_cur * E.residual_stride + c0, (uint32_t)c_n * 4u, res_bar);
         if (lane == 0) mbar_arrive(res_bar);
       }
-      if (fused && vec_ct != U.ct) {  // per-channel vectors of this column tile (missing ones default to no-ops)
+      if (!HV && fused && vec_ct != U.ct) {  // per-channel vectors of this column tile (missing ones default to no-ops)
         asm volatile("bar.sync 1, 128;" ::: "memory");  // every epilogue warp is done with the previous tile's vectors
         const int c = c0 + r_l;
         const bool in = r_l < c_n;
@@ -572,6 +654,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
       mbar_wait(smem_u32(&sh->acc_full), (uint32_t)iter & 1u);
       tc_fence_after();
       TS_ACC(tm_accf);
+      const bool blk32 = split || (HV && fused);
+      if (blk32) {
+        if (use_res) {
+          mbar_wait(res_bar, res_ph);
+          res_ph ^= 1u;
+        }
+        const uint32_t ae = smem_u32(&sh->acc_empty);
+        const int nrm = (HV && fused) ? E.norm : FSFB_NORM_NONE;
+        const int ac = (HV && fused) ? act : FSFB_ACT_NONE;
+        const int cn = (HV && fused) ? c_n : 0;  // raw sums (offset splits): no column is finished here
+#define TS_EPI(N, A, PO, UN) ts_epi32<N, A, PO, UN>(P, t_row, acc_cols, my_row, cn, U.n_sub, have_acc, use_res, valid, ae, lane)
+        if (ac == FSFB_ACT_RELU) {
+          if (nrm == FSFB_NORM_LAYERNORM) { if (post) TS_EPI(FSFB_NORM_LAYERNORM, FSFB_ACT_RELU, true, true); else TS_EPI(FSFB_NORM_LAYERNORM, FSFB_ACT_RELU, false, true); }
+          else if (nrm == FSFB_NORM_AFFINE) { if (post) TS_EPI(FSFB_NORM_AFFINE, FSFB_ACT_RELU, true, true); else TS_EPI(FSFB_NORM_AFFINE, FSFB_ACT_RELU, false, true); }
+          else { if (post) TS_EPI(FSFB_NORM_NONE, FSFB_ACT_RELU, true, true); else TS_EPI(FSFB_NORM_NONE, FSFB_ACT_RELU, false, true); }
+        } else {
+          if (nrm == FSFB_NORM_LAYERNORM) TS_EPI(FSFB_NORM_LAYERNORM, FSFB_ACT_NONE, false, true);
+          else if (nrm == FSFB_NORM_AFFINE) TS_EPI(FSFB_NORM_AFFINE, FSFB_ACT_NONE, false, true);
+          else TS_EPI(FSFB_NORM_NONE, FSFB_ACT_NONE, false, true);
+        }
+#undef TS_EPI
+      } else {
       float v[8];
       auto ld_issue = [&](int cb, uint32_t (&a)[8], uint32_t (&b)[8]) {  // warp-collective; pair with ld_wait
         if (have_acc) {
@@ -677,6 +781,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const TcParams
           sts_f4(srow + 16 * t, y);
         }
       }
+      }
       TS_ACC(tm_p1);
       // ---- rows leave shared memory ----
       if (fast) {
@@ -750,7 +855,8 @@ __global__ void __launch_bounds__(256) k_splitk_epilogue(const float* __restrict
 uint32_t* g_ts_timers = nullptr;  // FSFB_GEMM_TIMERS=1: counters of the last timed launch (fsfb_debug_gemm_timers)
 
 // Launch helper called from fsfb_gather_gemm (gemm_tc.cu).
-int launch_gather_gemm_ts(TcParams P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, cudaStream_t st) {
+int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, const float* host_bias,
+                          const float* host_norm_w, const float* host_norm_b, cudaStream_t st) {
   const int n_pad = P.S.n_pad();
   const int cpad = (n_pad + 127) & ~127;
   P.n_ct = (n_pad + 127) / 128;
@@ -780,8 +886,25 @@ int launch_gather_gemm_ts(TcParams P, bool a_vec, float* workspace, size_t works
     set_error("gather_gemm: tile does not fit shared memory");
     return FSFB_ERR_BADARG;
   }
+  // host copies of every per-channel vector that is present, one column tile, no offset split: vectors ride in the parameters
+  static const bool hv_on = [] { const char* e = getenv("FSFB_GEMM_HV"); return !e || atoi(e) != 0; }();
+  // (GELU layers keep the shared-memory vector path: erff dominates their epilogue and the unrolled form would not fit
+  // the instruction cache)
+  const bool hv = hv_on && P.n_ct == 1 && P.splits == 1 && (!P.E.bias || host_bias) && (!P.E.norm_w || host_norm_w) &&
+                  (!P.E.norm_b || host_norm_b) && (P.E.act & 0xff) != FSFB_ACT_GELU;
+  if (hv) {
+    for (int c = 0; c < 128; ++c) {
+      const bool in = c < P.S.cout;
+      P.hv_bias[c] = (in && P.E.bias) ? host_bias[c] : 0.f;
+      P.hv_w[c] = (in && P.E.norm_w) ? host_norm_w[c] : 1.f;
+      P.hv_h[c] = (in && P.E.norm_b) ? host_norm_b[c] : 0.f;
+    }
+  }
   static bool attr = false;
   if (!attr) {
+    FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<false, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     FSFB_CUDA(cudaFuncSetAttribute(k_gather_gemm_ts<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     FSFB_CUDA(cudaFuncSetAttribute(k_gather_gemm_ts<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     FSFB_CUDA(cudaFuncSetAttribute(k_gather_gemm_ts<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
@@ -796,18 +919,35 @@ int launch_gather_gemm_ts(TcParams P, bool a_vec, float* workspace, size_t works
     static uint32_t* dev_timers = nullptr;
     if (!dev_timers) {
       FSFB_CUDA(cudaMalloc(&dev_timers, (size_t)kNumSMs * 32 * 4));
-      FSFB_CUDA(cudaFuncSetAttribute(k_gather_gemm_ts<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, true, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, true, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     }
     FSFB_CUDA(cudaMemsetAsync(dev_timers, 0, (size_t)kNumSMs * 32 * 4, st));
     P.timers = dev_timers;
     g_ts_timers = dev_timers;
-    FSFB_LAUNCH((k_gather_gemm_ts<true, true, true>), grid, kTsThreads, smem, st, P);
+    if (hv) {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true, true, true>), grid, kTsThreads, smem, st, P);
+    } else {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true, true, false>), grid, kTsThreads, smem, st, P);
+    }
   } else if (kfull) {
-    FSFB_LAUNCH((k_gather_gemm_ts<true, true>), grid, kTsThreads, smem, st, P);
+    if (hv) {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true, false, true>), grid, kTsThreads, smem, st, P);
+    } else {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true>), grid, kTsThreads, smem, st, P);
+    }
   } else if (a_vec) {
-    FSFB_LAUNCH((k_gather_gemm_ts<true, false>), grid, kTsThreads, smem, st, P);
+    if (hv) {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, false, false, true>), grid, kTsThreads, smem, st, P);
+    } else {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, false>), grid, kTsThreads, smem, st, P);
+    }
   } else {
-    FSFB_LAUNCH((k_gather_gemm_ts<false, false>), grid, kTsThreads, smem, st, P);
+    if (hv) {
+      FSFB_LAUNCH((k_gather_gemm_ts<false, false, false, true>), grid, kTsThreads, smem, st, P);
+    } else {
+      FSFB_LAUNCH((k_gather_gemm_ts<false, false>), grid, kTsThreads, smem, st, P);
+    }
   }
   if (P.splits > 1) {
     const int g2 = (int)std::min<int64_t>(ceil_div(P.rows, 8), (int64_t)kNumSMs * 8);

@@ -426,6 +426,23 @@ def gemm_prepack(w: torch.Tensor, keep_raw: bool = False) -> PackedWeight:
     return PackedWeight(data, koff, cin, cout, w3 if keep_raw else None)
 
 
+_HOSTVEC = {}
+
+
+def _host_vec(t: Optional[torch.Tensor]):
+    """Host copy (ctypes float array) of a per-channel vector, cached per (storage, version): layer parameters are
+    read back once, at the first call that uses them."""
+    if t is None:
+        return None
+    key = (t.data_ptr(), t._version, t.numel())
+    h = _HOSTVEC.get(key)
+    if h is None:
+        if len(_HOSTVEC) > 4096:
+            _HOSTVEC.clear()
+        h = _HOSTVEC[key] = (C.c_float * t.numel())(*t.detach().float().cpu().tolist())
+    return h
+
+
 def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
     for t in (bias, norm_w, norm_b):
         assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.numel() == cout and t.is_contiguous())
@@ -493,6 +510,10 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
             ws = torch.empty(splits * rows * cpad, dtype=torch.float32, device=dev)
             check(lib.fsfb_gather_gemm_splitk(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail[:-1], splits, _ptr(ws),
                                               ws.numel() * 4, tail[-1]), "fsfb_gather_gemm_splitk")
+        elif w.cout <= 128 and (bias is not None or norm_w is not None or norm_b is not None):
+            # per-channel vectors also as host copies: they ride in the kernel parameters (include/fsf_b200.h)
+            check(lib.fsfb_gather_gemm_hv(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail[:-1], 1, None, 0,
+                                          _host_vec(bias), _host_vec(norm_w), _host_vec(norm_b), tail[-1]), "fsfb_gather_gemm_hv")
         else:
             check(lib.fsfb_gather_gemm(*args[:5], _ptr(row_order), *args[5:], _ptr(w.data), *tail), "fsfb_gather_gemm")
     return out

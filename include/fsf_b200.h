@@ -234,6 +234,19 @@ int fsfb_gather_gemm_splitk(const float* a, int64_t a_rows, int cin, int64_t a_s
                             float* out, int64_t out_stride, int splits, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* fsfb_gather_gemm_splitk plus HOST copies (nullable, [cout] f32) of the per-channel vectors bias / norm_w / norm_b.
+ * When every device vector that is present has its host copy, cout <= 128 and splits == 1, the vectors travel in the
+ * kernel parameters and the epilogue reads them as constant-bank operands (no shared-memory or global loads in the
+ * epilogue warps, whose memory instructions otherwise queue behind the gathers).  Results are identical. */
+int fsfb_gather_gemm_hv(const float* a, int64_t a_rows, int cin, int64_t a_stride,
+                        const int32_t* nbr, const int32_t* row_order, int koff, int64_t rows,
+                        const void* w_packed, int cout,
+                        const float* bias, int norm, const float* norm_w, const float* norm_b,
+                        float eps, const float* residual, int64_t residual_stride, int act,
+                        float* out, int64_t out_stride, int splits, void* workspace,
+                        size_t workspace_bytes, const float* host_bias, const float* host_norm_w,
+                        const float* host_norm_b, void* stream);
+
 /* Diagnostics only: per-CTA role cycle counters [148][32] u32 of the last fsfb_gather_gemm launch made with
  * FSFB_GEMM_TIMERS=1 in the environment (layout in csrc/gemm_ts.cu). */
 int fsfb_debug_gemm_timers(unsigned int* out);
