@@ -216,9 +216,12 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # rank 0 prints exactly ONE JSON line on stdout: native libraries (NCCL's version banner at NCCL_DEBUG=VERSION/WARN, ...)
+    # write to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the line goes to the saved fd
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     _capi.load()
 
@@ -400,7 +403,8 @@ def main():
             cpu_model._calibrated = True  # same calibrated weights as the GPU arm
             base = run_cpu_port(args, steps=1, warmup=0, model=cpu_model, frame={k: v.clone() for k, v in hosts[0].items()})
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0

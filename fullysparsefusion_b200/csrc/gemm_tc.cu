@@ -322,7 +322,8 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
     // than 128.  FSFB_GEMM_TS=0 forces the kernel below (A/B experiments).
     static const int ts_mode = [] { const char* e = getenv("FSFB_GEMM_TS"); return e ? atoi(e) : 1; }();
     const int n_pad = P.S.n_pad();
-    const bool ts_ok = n_pad <= 128 || (n_pad % 128 == 0 && norm != FSFB_NORM_LAYERNORM);
+    // (31 or 32 offsets: two neighbour tables no longer fit next to the rings in shared memory)
+    const bool ts_ok = koff <= 30 && (n_pad <= 128 || (n_pad % 128 == 0 && norm != FSFB_NORM_LAYERNORM));
     if (ts_mode && ts_ok)
       return launch_gather_gemm_ts(P, a_vec, (float*)workspace, workspace_bytes, splits, host_bias, host_norm_w, host_norm_b,
                                    (cudaStream_t)stream);

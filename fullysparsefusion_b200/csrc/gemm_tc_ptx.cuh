@@ -159,6 +159,7 @@ struct TcParams {
   uint32_t data_bytes;  // stage ring (or epilogue staging, whichever is larger); nbr tile + barriers follow
   // persistent TS kernel (gemm_ts.cu): 128-wide column tiles, offset splits, unit count, split slabs [splits][rows][cpad]
   int n_ct, splits, cpad, n_row_tiles, sched_slot;
+  uint32_t sched_base;
   int64_t n_units;
   float* partial;
   uint32_t* timers;  // diagnostics (FSFB_GEMM_TIMERS=1), else null

@@ -60,10 +60,11 @@ struct TsShared {
   int32_t rows[2][kTcRows]; // output row of each tile row (-1: past the end)
 };
 
-// Work counters of the persistent launches: slot = launch sequence number mod kTsSchedSlots; the last CTA of a launch
-// to finish zeroes its slot again, so no memset precedes a launch.
+// Work counters of the persistent launches: slot = launch sequence number mod kTsSchedSlots.  A counter is never reset:
+// a launch draws exactly n_units + gridDim.x tickets (every CTA ends on one ticket past the end), so the host knows
+// the value the next user of the slot starts from (P.sched_base) and no memset or clean-up kernel is needed.
 constexpr int kTsSchedSlots = 256;
-__device__ unsigned int g_ts_sched[kTsSchedSlots][2];
+__device__ unsigned int g_ts_sched[kTsSchedSlots];
 
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
         const uint32_t nb = s_nbr + (uint32_t)b * nbr_bytes;
         if (iter >= 2) mbar_wait(smem_u32(&sh->nbr_empty[b]), (uint32_t)((iter >> 1) + 1) & 1u);  // readers of unit iter-2 are done
         uint32_t u = 0;
-        if (lane == 0) u = atomicAdd(&g_ts_sched[P.sched_slot][0], 1u);
+        if (lane == 0) u = atomicAdd(&g_ts_sched[P.sched_slot], 1u) - P.sched_base;
         u = __shfl_sync(0xffffffffu, u, 0);
         TsUnit U;
         const bool have = ts_unit(P, u, U);
@@ -822,14 +823,6 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
   }
-  if (tid == 0) {  // the last CTA out re-arms the launch's scheduler slot
-    __threadfence();
-    if (atomicAdd(&g_ts_sched[P.sched_slot][1], 1u) == gridDim.x - 1) {
-      g_ts_sched[P.sched_slot][0] = 0;
-      g_ts_sched[P.sched_slot][1] = 0;
-      __threadfence();
-    }
-  }
 }
 
 // Sum of the split slabs + the fused epilogue (one warp per output row, fixed summation order).
@@ -874,7 +867,9 @@ int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t work
   P.cpad = cpad;
   P.n_row_tiles = (int)ceil_div(P.rows, kTcRows);
   static unsigned launch_seq = 0;
+  static unsigned sched_next[kTsSchedSlots] = {0};  // tickets drawn so far from each slot (wraps with the device counter)
   P.sched_slot = (int)(launch_seq++ % kTsSchedSlots);
+  P.sched_base = sched_next[P.sched_slot];
   P.n_units = ceil_div(P.rows, kTcRows) * P.n_ct * P.splits;
   if (P.n_units >= (1ll << 31)) {
     set_error("gather_gemm: too many work units");
@@ -911,6 +906,7 @@ int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t work
     attr = true;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(P.n_units, kNumSMs);
+  sched_next[P.sched_slot] += (unsigned)P.n_units + grid;
   static const bool timed = [] { const char* e = getenv("FSFB_GEMM_TIMERS"); return e && atoi(e) != 0; }();
   // complete K chunks from 32-byte aligned rows: the 256-bit gather path
   const bool kfull = a_vec && P.cin % kGemmKChunk == 0 && P.cin <= kTsZeroRow && (uintptr_t)P.a % 32 == 0 && P.a_stride % 8 == 0;
