@@ -354,7 +354,12 @@ def main():
         ach_t = d["flops"] / (d["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "k_gather_gemm_ts (sparse-convolution gather-GEMM, 3xTF32 on tcgen05)",
                     "achieved": ach_t, "peak": tpeak, "peak_source": tpeak_src, "unit": "TFLOP/s", "frac": ach_t / tpeak,
-                    "traffic": None, "launches_timed": d["calls"], "launches_per_frame": d["calls"] // args.steps,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` capture
+                    # (profiles/r1_ncu_summary.md section 7: SubM 27x128->128 on the frame's 159,897 voxels, whose algorithmic
+                    # bytes are 172.6 MB); `achieved` above averages all 34 convolution shapes of the frame
+                    "traffic": 156.6e6, "traffic_of": "k_gather_gemm_ts, SubM 27x128->128 @159,897 voxels (111.5 MB read + 45.1 MB "
+                                                      "written; algorithmic 172.6 MB)",
+                    "launches_timed": d["calls"], "launches_per_frame": d["calls"] // args.steps,
                     "flops_per_launch": d["flops"] // d["calls"], "us_per_launch": round(d["ms"] / d["calls"] * 1e3, 2),
                     "share_of_step": round(d["ms"] / ms_total, 3),
                     "note": "achieved = USEFUL flops (2*Cin*Cout per rulebook pair) / CUDA-event time of every launch in the timed "
@@ -367,6 +372,8 @@ def main():
         ach = dd["bytes"] / (dd["ms"] * 1e-3) / 1e9
         roofline_hbm = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                         "frac": ach / peak, "bytes_per_launch": dd["bytes"] // dd["calls"],
+                        # profiles/r1_ncu_summary.md section 8: k_segreduce_small, 300,000 x 132 mean (algorithmic 271.2 MB)
+                        "traffic": 233.9e6,
                         "us_per_launch": round(dd["ms"] / dd["calls"] * 1e3, 2),
                         "shapes": {n: {"us_per_launch": round(v["ms"] / v["calls"] * 1e3, 1), "launches_per_frame": v["calls"] // n_prof,
                                        "frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / peak, 3)}

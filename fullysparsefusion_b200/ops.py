@@ -7,6 +7,7 @@ tensor is not on a CUDA device — there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -430,17 +431,18 @@ _HOSTVEC = {}
 
 
 def _host_vec(t: Optional[torch.Tensor]):
-    """Host copy (ctypes float array) of a per-channel vector, cached per (storage, version): layer parameters are
-    read back once, at the first call that uses them."""
+    """Host copy (ctypes float array) of a per-channel vector for fsfb_gather_gemm_hv.  Cached per tensor OBJECT (weak
+    reference + in-place version counter), never per address: layer parameters are read back once, at the first call that
+    uses them; a vector built on the fly is read back at every call (correct, just slower — keep such vectors on the module)."""
     if t is None:
         return None
-    key = (t.data_ptr(), t._version, t.numel())
-    h = _HOSTVEC.get(key)
-    if h is None:
-        if len(_HOSTVEC) > 4096:
-            _HOSTVEC.clear()
-        h = _HOSTVEC[key] = (C.c_float * t.numel())(*t.detach().float().cpu().tolist())
-    return h
+    key = id(t)
+    hit = _HOSTVEC.get(key)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    arr = (C.c_float * t.numel())(*t.detach().float().cpu().tolist())
+    _HOSTVEC[key] = (weakref.ref(t, lambda _r, k=key: _HOSTVEC.pop(k, None)), t._version, arr)
+    return arr
 
 
 def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):

@@ -160,3 +160,24 @@ def test_gather_gemm_splitk(cuda, rows, a_rows, koff, cin, cout, splits, density
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=atol)
     one = ops.gather_gemm(T(a, cuda), pw, splits=1, **kw).cpu().numpy()
     np.testing.assert_allclose(one, want, rtol=RTOL, atol=atol)
+
+
+def test_epilogue_vectors_not_cached_by_address(cuda):
+    """fsfb_gather_gemm_hv takes host copies of bias / norm vectors; ops caches them per tensor object.  New tensors that
+    land on the addresses of freed ones (the caching allocator reuses blocks) must not pick up the old values."""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((500, 64)).astype(np.float32)
+    w = (rng.standard_normal((128, 64)) / 8).astype(np.float32)
+    pw = ops.gemm_prepack(T(w, cuda))
+    ta = T(a, cuda)
+    for trial in range(4):
+        b = rng.standard_normal(128).astype(np.float32)
+        nw = rng.uniform(0.5, 1.5, 128).astype(np.float32)
+        nb = rng.standard_normal(128).astype(np.float32)
+        tb, tw, th = T(b, cuda), T(nw, cuda), T(nb, cuda)
+        got = ops.gather_gemm(ta, pw, bias=tb, norm="affine", norm_w=tw, norm_b=th, act="relu").cpu().numpy()
+        np.testing.assert_allclose(got, O.gather_gemm(a, w, bias=b, norm="affine", norm_w=nw, norm_b=nb, act="relu"), rtol=RTOL, atol=ATOL)
+        tw.mul_(2.0)   # in-place update of a cached vector
+        got = ops.gather_gemm(ta, pw, bias=tb, norm="affine", norm_w=tw, norm_b=th, act="relu").cpu().numpy()
+        np.testing.assert_allclose(got, O.gather_gemm(a, w, bias=b, norm="affine", norm_w=2 * nw, norm_b=nb, act="relu"), rtol=RTOL, atol=ATOL)
+        del tb, tw, th
