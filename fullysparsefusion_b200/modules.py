@@ -315,7 +315,7 @@ class SIRLayer(nn.Module):
         else:
             if features_b is not None:
                 features = torch.cat([features, features_b], 1)
-            gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * 3)) if self.with_rel_mlp else None
+            gate = self.rel_mlp(ops.div_cols(f_cluster, [self.rel_dist_scaler] * f_cluster.size(1))) if self.with_rel_mlp else None
             x = ops.sir_input(features, self.xyz_normalizer, gate)   # cat(xyz/norm, feats) * gate, one pass
         ori = x
         cluster_list = []
@@ -608,3 +608,67 @@ class DynamicPointROIExtractor(nn.Module):
         p = max(int(num.item()), 1)   # the output-size read the reference performs as a boolean mask (:34-44)
         inds, roi_inds, info = out_pts_idx[:p], out_roi_idx[:p], out_feats[:p]
         return inds, roi_inds, dict(local_xyz=info[:, 3:6], boundary_offset=info[:, 6:12], is_in_margin=info[:, 12])
+
+
+# ------------------------------------------------------------------------------------------------
+# FullySparseBboxHead (query refinement)
+# ------------------------------------------------------------------------------------------------
+class FullySparseBboxHead(nn.Module):
+    """models/roi_heads/bbox_heads/fsd_bbox_head.py:22-151 (config single_refine_sir_layer, FSF_nuScenes_config.py:296-320):
+    num_blocks DynamicClusterVFE blocks (= SIRLayer with a 13-input relative-position MLP) over the RoI ids of the pooled
+    points; returns (roi feats [num_rois, sum of block widths], nonempty_roi_mask [num_rois]).
+
+    forward(pts_xyz [P,5], pts_features [P,C], pts_info dict(local_xyz, boundary_offset, is_in_margin), roi_inds [P] i64/i32,
+            rois [K,8] = (batch, x,y,z,w,l,h,rz)).  A roi id of -1 (the extractor's fake row) forms group -1, dropped by the
+    alignment step exactly as upstream (:178-197)."""
+
+    def __init__(self, num_classes=10, num_blocks=3, in_channels=(), feat_channels=(), with_distance=False, with_cluster_center=False,
+                 with_rel_mlp=True, rel_mlp_hidden_dims=(), rel_mlp_in_channels=(), reg_mlp=None, cls_mlp=None, mode="max",
+                 xyz_normalizer=(20, 20, 4), cat_voxel_feats=True, pos_fusion="mul", fusion="cat", act="gelu", geo_input=True,
+                 use_middle_cluster_feature=True, norm_cfg=dict(type="LN", eps=1e-3, momentum=0.01), dropout=0, unique_once=False,
+                 init_cfg=None, no_head=None):
+        super().__init__()
+        assert mode == "max" and pos_fusion == "mul" and fusion == "cat" and cat_voxel_feats and not dropout
+        self.num_blocks, self.geo_input, self.use_middle_cluster_feature = num_blocks, geo_input, use_middle_cluster_feature
+        self.block_list = nn.ModuleList([
+            SIRLayer(in_channels=in_channels[i], feat_channels=feat_channels[i], with_rel_mlp=with_rel_mlp,
+                     rel_mlp_hidden_dims=rel_mlp_hidden_dims[i], rel_mlp_in_channel=rel_mlp_in_channels[i], norm_cfg=norm_cfg, mode=mode,
+                     return_point_feats=i != num_blocks - 1, rel_dist_scaler=10.0, xyz_normalizer=xyz_normalizer, act=act)
+            for i in range(num_blocks)])
+
+    @torch.no_grad()
+    def forward(self, pts_xyz, pts_features, pts_info, roi_inds, rois):
+        assert pts_features.size(0) > 0
+        dev = pts_xyz.device
+        num_rois = rois.size(0)
+        ids32 = roi_inds.to(torch.int32).contiguous()
+        # rel_xyz = pts_xyz[:, :3] - roi_centers[roi_inds]  (:112): the fake row (-1) reads the last roi, as torch indexing does
+        idx = torch.where(ids32 < 0, ids32 + num_rois, ids32)
+        rel_xyz, _ = ops.cluster_delta(pts_xyz, rois[:, 1:4].contiguous(), idx)
+        f_cluster = torch.cat([pts_info["local_xyz"], pts_info["boundary_offset"], pts_info["is_in_margin"][:, None], rel_xyz], dim=-1)
+        plan = ScatterPlan(ids32.view(-1, 1))                      # unique_once: one ranking of the roi ids for all blocks
+        geo = ops.div_cols(f_cluster, [10.0] * f_cluster.size(1)) if self.geo_input else None
+        out_feats = pts_features
+        cluster_feat_list = []
+        out_coors = None
+        for i, block in enumerate(self.block_list):
+            parts = [pts_xyz, out_feats] + ([geo] if geo is not None else [])
+            in_feats = torch.cat(parts, 1)
+            if i < self.num_blocks - 1:
+                out_feats, c = block(in_feats, ids32, f_cluster, plan=plan)
+                if self.use_middle_cluster_feature:
+                    cluster_feat_list.append(c)
+            else:
+                c, out_coors = block(in_feats, ids32, f_cluster, plan=plan)
+                cluster_feat_list.append(c)
+        feats = torch.cat(cluster_feat_list, dim=1)
+        # get_nonempty_roi_mask + align_roi_feature_and_rois (:152-197): scatter the group rows to their roi slots
+        coors = out_coors.view(-1)
+        keep = ops.compact_indices(coors >= 0)
+        new_feature = torch.zeros((num_rois, feats.size(1)), dtype=torch.float32, device=dev)
+        mask = torch.zeros(num_rois, dtype=torch.bool, device=dev)
+        if keep.numel():
+            dst = ops.gather_int_rows(coors.view(-1, 1), keep).view(-1).long()
+            new_feature[dst] = ops.gather_rows(feats, keep)
+            mask[dst] = True
+        return new_feature, mask

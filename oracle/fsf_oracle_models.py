@@ -139,3 +139,28 @@ def vote_seg_head(feats, sd, eps=1e-5):
     logits = O.mlp_layer(x, sd["conv_seg.weight"], sd["conv_seg.bias"])
     votes = O.mlp_layer(x, sd["voting.weight"], sd["voting.bias"])
     return logits, votes
+
+
+def fully_sparse_bbox_head(pts_xyz, pts_features, local_xyz, boundary_offset, is_in_margin, roi_inds, rois, sd, num_blocks,
+                           xyz_normalizer=(20, 20, 4), eps=1e-3, act="gelu", geo_input=True):
+    """FullySparseBboxHead.forward (models/roi_heads/bbox_heads/fsd_bbox_head.py:95-151) with DynamicClusterVFE restated as the
+    SIRLayer above (PARITY UNPINNED: un-vendored registry type).  Returns (roi feats [K, C], nonempty mask [K])."""
+    pts_xyz = np.asarray(pts_xyz, F32)
+    rois = np.asarray(rois, F32)
+    roi_inds = np.asarray(roi_inds, np.int64)
+    rel_xyz = (pts_xyz[:, :3] - rois[:, 1:4][roi_inds]).astype(F32)
+    f_cluster = np.concatenate([local_xyz, boundary_offset, np.asarray(is_in_margin, F32)[:, None], rel_xyz], 1).astype(F32)
+    uniq, inv, _ = O.unique_rows(roi_inds[:, None])
+    out = np.asarray(pts_features, F32)
+    cl = []
+    for i in range(num_blocks):
+        parts = [pts_xyz, out] + ([(f_cluster / F32(10.0)).astype(F32)] if geo_input else [])
+        out, c = sir_layer(np.concatenate(parts, 1), inv, f_cluster, _sub(sd, f"block_list.{i}."), xyz_normalizer, 10.0, eps, act, len(uniq))
+        cl.append(c)
+    feats = np.concatenate(cl, 1)
+    new = np.zeros((rois.shape[0], feats.shape[1]), F32)
+    mask = np.zeros(rois.shape[0], bool)
+    ids = uniq[:, 0]
+    new[ids[ids >= 0]] = feats[ids >= 0]
+    mask[ids[ids >= 0]] = True
+    return new, mask

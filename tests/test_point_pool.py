@@ -93,3 +93,36 @@ def test_roi_extractor_and_shim(cuda):
     far[:, 1:4] = 1e4
     i2, r2, _ = ext(tp, torch.zeros(len(pts), dtype=torch.int64, device=cuda), far)
     assert i2.numel() == 1 and int(i2[0]) == -1 and int(r2[0]) == -1
+
+
+@pytest.mark.gpu
+def test_fully_sparse_bbox_head(cuda):
+    """Refine-stage head (fsd_bbox_head.py:95-151): point pooling → three SIR blocks over RoI ids → features aligned to
+    the RoIs, against the numpy restatement (features 1e-4 relative, the non-empty mask exact)."""
+    import torch
+    from fullysparsefusion_b200 import modules as M
+    from oracle import fsf_oracle_models as OM
+    from tests.test_gpu_modules import randomize, sd_np
+    pts, rois, extra = _scene(6000, 30, 11)
+    rois[-1, :3] = 1e3   # a RoI that pools nothing: stays zero, mask False
+    rng = np.random.default_rng(11)
+    pts5 = np.concatenate([pts, rng.uniform(0, 1, (len(pts), 2)).astype(np.float32)], 1)
+    feats = rng.standard_normal((len(pts), 24)).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    ext = M.DynamicPointROIExtractor(extra_wlh=extra, max_inbox_point=512)
+    rois8 = np.concatenate([np.zeros((len(rois), 1), np.float32), rois], 1)
+    inds, roi_inds, info = ext(T(pts5), torch.zeros(len(pts), dtype=torch.int64, device=cuda), T(rois8))
+    cin = 5 + 24 + 13
+    torch.manual_seed(3)
+    head = randomize(M.FullySparseBboxHead(num_blocks=3, in_channels=[cin, 5 + 32 + 13, 5 + 32 + 13], feat_channels=[[32, 32]] * 3,
+                                           rel_mlp_hidden_dims=[[16, 32]] * 3, rel_mlp_in_channels=[13] * 3, xyz_normalizer=[20, 20, 4],
+                                           act="gelu", norm_cfg=dict(type="LN", eps=1e-3), unique_once=True), seed=4).to(cuda)
+    ex_pts, ex_feats = T(pts5)[inds], T(feats)[inds]
+    got, mask = head(ex_pts, ex_feats, info, roi_inds, T(rois8))
+    want, wmask = OM.fully_sparse_bbox_head(ex_pts.cpu().numpy(), ex_feats.cpu().numpy(), info["local_xyz"].cpu().numpy(),
+                                            info["boundary_offset"].cpu().numpy(), info["is_in_margin"].cpu().numpy(),
+                                            roi_inds.cpu().numpy(), rois8, sd_np(head), 3)
+    assert got.shape == (len(rois), 3 * 64)
+    np.testing.assert_array_equal(mask.cpu().numpy(), wmask)
+    assert not wmask[-1] and wmask[:-1].any()
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=5e-5)
