@@ -102,14 +102,17 @@ __global__ void __launch_bounds__(kSrWarps * 32)
     auto flush = [&](int s) {
       const bool partial = (s == seg_prev) | (s == seg_next);
       if (!partial) {
-        const float denom = mean ? (float)max(1, run) : 1.f;
+        const int cnt_r = max(1, run);
+        const bool pow2 = (cnt_r & (cnt_r - 1)) == 0;  // exact multiply instead of the division sequence (same bits)
+        const float denom = mean ? (float)cnt_r : 1.f;
+        const float recip = 1.f / denom;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
           const int c = chan<VEC>(c0, lane, k, 0);
           if (c < C) {
             float r[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) r[e] = mean ? acc.val[k][e] / denom : acc.val[k][e];
+            for (int e = 0; e < VEC; ++e) r[e] = mean ? (pow2 ? acc.val[k][e] * recip : acc.val[k][e] / denom) : acc.val[k][e];
             float* o = out + (int64_t)s * C + c;
             if (VEC == 4) {
               stg_stream_f4(reinterpret_cast<float4*>(o),
@@ -273,14 +276,20 @@ __global__ void __launch_bounds__(kSrWarps * 32)
         }
       }
       const bool empty = end[j] == beg[j];
-      const float denom = mean ? (float)max(1, end[j] - beg[j]) : 1.f;
+      // mean = sum / count in IEEE fp32 (what the reference computes); counts that are powers of two (1 and 2 cover most
+      // voxels) take an exact multiply instead of the ~8-instruction division sequence: same bits, fewer instructions
+      const int cnt_j = max(1, end[j] - beg[j]);
+      const bool pow2 = (cnt_j & (cnt_j - 1)) == 0;
+      const float denom = mean ? (float)cnt_j : 1.f;
+      const float recip = 1.f / denom;  // exact when pow2
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int c = chan<VEC>(c0, lane, k, 0);
         if (c < C) {
           float r[VEC];
 #pragma unroll
-          for (int e = 0; e < VEC; ++e) r[e] = empty ? 0.f : (mean ? acc.val[k][e] / denom : acc.val[k][e]);
+          for (int e = 0; e < VEC; ++e)
+            r[e] = empty ? 0.f : (mean ? (pow2 ? acc.val[k][e] * recip : acc.val[k][e] / denom) : acc.val[k][e]);
           float* o = out + (s + j) * C + c;
           if (VEC == 4) {
             stg_stream_f4(reinterpret_cast<float4*>(o), make_float4(r[0], r[VEC > 1 ? 1 : 0], r[VEC > 2 ? 2 : 0], r[VEC > 3 ? 3 : 0]));
