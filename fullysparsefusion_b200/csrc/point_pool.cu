@@ -156,6 +156,43 @@ __global__ void __launch_bounds__(kPpWarps * 32)
 
 }  // namespace fsfb
 
+namespace fsfb {
+// BasePointBBoxCoder.decode (projects/mmdet3d_plugin/core/bbox/coders/base_point_bbox_coder.py:59-82) + the batch column of
+// FSF.decode_stage_bboxes (models/detectors/FSF.py:1085-1095): reg = (dxyz, log dims, sin, cos[, vx, vy])
+__global__ void __launch_bounds__(256)
+    k_decode_boxes(const float* __restrict__ reg, int64_t k, int code, int64_t reg_stride, const float* __restrict__ base,
+                   int64_t base_stride, const int32_t* __restrict__ batch, int64_t batch_stride, float eps, float* __restrict__ rois) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* r = reg + i * reg_stride;
+    float* o = rois + i * (code);  // 1 + (code - 1) columns
+    o[0] = batch ? (float)batch[i * batch_stride] : 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      o[1 + d] = __fadd_rn(__ldg(r + d), __ldg(base + i * base_stride + d));
+      o[4 + d] = __fsub_rn(expf(__ldg(r + 3 + d)), eps);
+    }
+    o[7] = atan2f(__ldg(r + 6), __ldg(r + 7));
+    if (code == 10) {
+      o[8] = __ldg(r + 8);
+      o[9] = __ldg(r + 9);
+    }
+  }
+}
+}  // namespace fsfb
+
+extern "C" int fsfb_decode_boxes(const float* reg, int64_t k, int code_size, int64_t reg_stride, const float* base_points,
+                                 int64_t base_stride, const int32_t* batch, int64_t batch_stride, float* rois, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(k >= 0 && (code_size == 8 || code_size == 10) && reg_stride >= code_size && base_stride >= 3,
+                 "decode_boxes: bad argument (code_size must be 8 or 10)");
+  if (k == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(reg && base_points && rois, "decode_boxes: null pointer");
+  const int grid = (int)std::min<int64_t>(ceil_div(k, 256), (int64_t)kNumSMs * 4);
+  FSFB_LAUNCH(k_decode_boxes, grid, 256, 0, (cudaStream_t)stream, reg, k, code_size, reg_stride, base_points, base_stride, batch,
+              batch_stride, 1e-6f, rois);
+  return FSFB_OK;
+}
+
 extern "C" int fsfb_dynamic_point_pool_workspace_bytes(int64_t k, int max_inbox_point, size_t* bytes) {
   using namespace fsfb;
   FSFB_CHECK_ARG(bytes && k >= 0 && max_inbox_point >= 1, "dynamic_point_pool_workspace_bytes: bad argument");

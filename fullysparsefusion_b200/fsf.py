@@ -10,8 +10,8 @@ combine_frustum_and_fsd (:657-692), with the segmentor of single_stage_fsd.py (V
   fsd          LiDAR queries: pre_voxelize, group_sample, ClusterAssigner (CCL), SIR, SparseClusterHeadV2
   combine      the two 1024-wide fusion MLPs
 
-The refine stage (dynamic_point_pool + FullySparseBboxHead) and box decode / NMS are SURVEY.md §8f "next"
-rows and are not part of this round.  One sample per call (samples_per_gpu = 1 in both stock configs).
+`FSF.refine` continues with the query-refinement stage (decode_stage_bboxes → dynamic point pooling →
+FullySparseBboxHead → query MLPs → refined head); final box decode / NMS (rank 3) are not built.  One sample per call (samples_per_gpu = 1 in both stock configs).
 All arithmetic goes through the C-ABI ops; torch is used for allocation, views and concatenation only.
 """
 from __future__ import annotations
@@ -125,6 +125,19 @@ class FSF(nn.Module):
         self.frustum_obj_head = _head(128 * 3 * 2 + 128, cfg["class_names"])
         self.combine_frustum_feat_mlp = M.build_mlp(128 * 3 * 2 + 128, [1024], LN3, act="gelu")
         self.combine_fsd_feat_mlp = M.build_mlp(128 * 3 * 2, [1024], LN3, act="gelu")
+        # query refinement (FSF.__init__ :144-164; configs :275-404): one extra stage in the stock config
+        self.num_extra_stages = int(cfg.get("num_extra_stages", 1))
+        self.roi_extractor = M.DynamicPointROIExtractor(extra_wlh=[1.0, 1.0, 1.0], max_inbox_point=512, debug=False)
+        embed = 1024
+        self.refine_sir_layers = nn.ModuleList([M.FullySparseBboxHead(
+            num_classes=nc, num_blocks=3, in_channels=[67 + 5 + 13 + 32 + 64, 131 + 13 + 2, 131 + 13 + 2], feat_channels=[[128, 128]] * 3,
+            rel_mlp_hidden_dims=[[16, 32]] * 3, rel_mlp_in_channels=[13] * 3, xyz_normalizer=[20, 20, 4], act="gelu", geo_input=True,
+            use_middle_cluster_feature=True, norm_cfg=LN3, unique_once=True) for _ in range(self.num_extra_stages)])
+        self.refine_img_mlp = nn.ModuleList([M.build_mlp(10, [32, 32], LN3, is_head=False, act="gelu") for _ in range(self.num_extra_stages)])
+        self.lidar_img_mlp = nn.ModuleList([M.build_mlp(128 * 3 * 2, [embed, embed], LN3, act="gelu") for _ in range(self.num_extra_stages)])
+        self.position_encoder = nn.ModuleList([M.build_mlp(3, [embed, embed], LN3, act="gelu") for _ in range(self.num_extra_stages)])
+        self.out_proj = nn.ModuleList([M.build_mlp(embed, [embed, embed], LN3, act="gelu", is_head=True) for _ in range(self.num_extra_stages)])
+        self.frustum_refined_head = nn.ModuleList([_head(embed, cfg["class_names"]) for _ in range(self.num_extra_stages)])
         self.fsd_begin_idx = 1000
         self.group_loop = False   # True: the reference's per-group Python loop (kept for the equivalence test)
         self.eval()
@@ -280,6 +293,40 @@ class FSF(nn.Module):
                       obj_reg=torch.cat([st["frustum_reg"], st["fsd_reg"]], dim=0))
 
         return [("segment", segment), ("enhance", enhance), ("frustum", frustum), ("fsd", fsd), ("combine", combine)], st
+
+    @torch.no_grad()
+    def refine(self, st: Dict[str, torch.Tensor], points: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Query refinement on the state a forward pass left behind: FSF.multi_stage_refine_test / each_stage_refine /
+        query_feat_refine (models/detectors/FSF.py:960-1083) up to the refined heads' logits and regressions (box decoding of
+        the final stage and NMS are SURVEY.md section 8f rank 3).  Not part of `stages()`: the benchmarked scope and its CPU
+        port end at combine_frustum_and_fsd."""
+        pts5 = points[:, :5].contiguous()
+        obj_centers, obj_reg, res_query_feat = st["obj_centers"], st["obj_reg"], st["obj_feats"]
+        out = {}
+        for i in range(self.num_extra_stages):
+            rois = ops.decode_boxes(obj_reg, obj_centers)                               # decode_stage_bboxes (:1085-1095)
+            obj_centers = rois[:, 1:4].contiguous()
+            inds, roi_inds, info = self.roi_extractor(pts5, None, rois[:, :8].contiguous())   # :1020-1024
+            fake = inds.numel() == 1 and int(inds[0]) < 0                               # nothing pooled: upstream's fake row
+            rows = (torch.full((1,), pts5.size(0) - 1, dtype=torch.int32, device=points.device) if fake   # points[-1], as upstream indexes
+                    else inds.to(torch.int32))
+            ex_pts = ops.gather_rows(pts5, rows)
+            ex_feats = ops.gather_rows(st["seg_feats"], rows)
+            img_feat = self.refine_img_mlp[i](ops.gather_rows(st["img_scores"], rows))   # img_cross_attn on the pooled points (:1029-1036)
+            feats = torch.cat([ex_feats, img_feat], dim=-1)
+            lidar_feat, lidar_mask = self.refine_sir_layers[i](ex_pts, feats, info, roi_inds, rois)
+            cur = self.lidar_img_mlp[i](lidar_feat)
+            pos = self.position_encoder[i](obj_centers)
+            query = self.out_proj[i](ops.add_(ops.add_(cur, res_query_feat), pos))     # :1077-1079
+            res = self.frustum_refined_head[i](query)
+            obj_reg, res_query_feat = res["reg_preds"][0], query
+            out.update({f"refine{i}_rois": rois, f"refine{i}_pts_inds": inds, f"refine{i}_roi_inds": roi_inds,
+                        f"refine{i}_lidar_feat": lidar_feat, f"refine{i}_mask": lidar_mask, f"refine{i}_query": query,
+                        f"refine{i}_cls": res["cls_logits"][0], f"refine{i}_reg": obj_reg, f"refine{i}_centers": obj_centers,
+                        f"refine{i}_local": info["local_xyz"], f"refine{i}_offset": info["boundary_offset"],
+                        f"refine{i}_margin": info["is_in_margin"]})
+        st.update(out)
+        return st
 
     @torch.no_grad()
     def forward(self, points, mask_data, mask_anno, lidar2img):

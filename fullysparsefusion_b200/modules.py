@@ -597,7 +597,7 @@ class DynamicPointROIExtractor(nn.Module):
 
     @torch.no_grad()
     def forward(self, pts_xyz: torch.Tensor, batch_inds: torch.Tensor, rois: torch.Tensor):
-        assert len(pts_xyz) > 0 and len(batch_inds) > 0 and len(rois) > 0
+        assert len(pts_xyz) > 0 and len(rois) > 0 and (batch_inds is None or len(batch_inds) > 0)   # one sample per call
         dev = pts_xyz.device
         cap = self.max_all_pts
         out_pts_idx = torch.full((cap,), -1, dtype=torch.int64, device=dev)

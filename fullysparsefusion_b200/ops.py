@@ -994,3 +994,18 @@ def group_cluster(score: torch.Tensor, centers: torch.Tensor, thresholds: Sequen
     check(lib.fsfb_group_relabel(_ptr(labels), _ptr(batch_c), 1, m, G, _ptr(inv_c), p, _ptr(small[16:]), _ptr(clu), st),
           "fsfb_group_relabel")
     return sel[:, 0].contiguous(), sel[:, 1].contiguous(), clu, ctr_k
+
+
+def decode_boxes(reg: torch.Tensor, base_points: torch.Tensor, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FSF.decode_stage_bboxes (FSF.py:1085-1095): rois [K, code] = (batch, xyz, dims, yaw[, vx, vy]) from regression rows."""
+    dev = _need_cuda(reg, base_points, batch)
+    reg = _rowmajor(reg)
+    base_points = _rowmajor(base_points)
+    k, code = reg.shape
+    rois = torch.empty((k, code), dtype=torch.float32, device=dev)
+    if batch is not None:
+        assert batch.dtype == torch.int32 and batch.dim() == 1
+    check(load().fsfb_decode_boxes(_ptr(reg), k, code, reg.stride(0) if k else code, _ptr(base_points),
+                                   base_points.stride(0) if k else 3, _ptr(batch), batch.stride(0) if batch is not None and k else 1,
+                                   _ptr(rois), _stream(dev)), "fsfb_decode_boxes")
+    return rois

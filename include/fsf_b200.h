@@ -474,6 +474,12 @@ int fsfb_connected_components_groups(const float* points, int64_t m, int64_t str
  *   num_out dev [1] i32: rows written.
  * ------------------------------------------------------------------------- */
 int fsfb_dynamic_point_pool_workspace_bytes(int64_t k, int max_inbox_point, size_t* bytes);
+/* FSF.decode_stage_bboxes (projects/mmdet3d_plugin/models/detectors/FSF.py:1085-1095) = BasePointBBoxCoder.decode
+ * (core/bbox/coders/base_point_bbox_coder.py:59-82) plus the batch column: reg dev [k, code_size] = (dxyz, log dims, sin, cos
+ * [, vx, vy]), base_points dev [k, >=3]; rois dev [k, code_size] = (batch, xyz = dxyz + base, dims = exp(.) - 1e-6,
+ * yaw = atan2(sin, cos)[, vx, vy]).  batch dev i32 (strided) or NULL = 0.  code_size 8 or 10. */
+int fsfb_decode_boxes(const float* reg, int64_t k, int code_size, int64_t reg_stride, const float* base_points,
+                      int64_t base_stride, const int32_t* batch, int64_t batch_stride, float* rois, void* stream);
 int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float* pts, int64_t n, int64_t pts_stride,
                             const float* extra_wlh, int max_inbox_point, int64_t capacity,
                             long long* out_pts_idx, long long* out_roi_idx, float* out_pts_feats,

@@ -575,3 +575,16 @@ def dynamic_point_pool(rois, pts, extra_wlh, max_inbox_point, capacity, margin=N
     res = (np.concatenate(out_p) if out_p else np.zeros(0, np.int64), np.concatenate(out_r) if out_r else np.zeros(0, np.int64),
            np.concatenate(out_f) if out_f else np.zeros((0, 13), F32))
     return res + (ambiguous,) if margin is not None else res
+
+
+def decode_boxes(reg, base_points, batch=None):
+    """BasePointBBoxCoder.decode (core/bbox/coders/base_point_bbox_coder.py:59-82) + FSF.decode_stage_bboxes' batch column
+    (models/detectors/FSF.py:1085-1095)."""
+    reg = np.asarray(reg, F32)
+    base = np.asarray(base_points, F32)[:, :3]
+    dims = (np.exp(reg[:, 3:6]) - F32(1e-6)).astype(F32)
+    xyz = (reg[:, :3] + base).astype(F32)
+    yaw = np.arctan2(reg[:, 6:7], reg[:, 7:8]).astype(F32)
+    b = np.zeros((reg.shape[0], 1), F32) if batch is None else np.asarray(batch, F32)[:, None]
+    out = [b, xyz, dims, yaw] + ([reg[:, 8:10]] if reg.shape[1] == 10 else [])
+    return np.concatenate(out, 1).astype(F32)

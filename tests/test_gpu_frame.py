@@ -189,3 +189,37 @@ def test_group_cluster_equals_loop(cuda, frame, thr):
     assert a["fsd_rows"].numel() > 0
     for k in ("fsd_rows", "pts_cluster_inds", "fsd_center_preds", "fsd_obj_coors", "fsd_obj_centers", "fsd_obj_feats", "fsd_cls"):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_refine_stage(cuda, frame):
+    """Query refinement (FSF.each_stage_refine / query_feat_refine, FSF.py:1009-1083) on the frame's combined queries, step by
+    step against the numpy restatement, each step fed the GPU path's inputs (teacher forcing)."""
+    model, sd, pts = frame["model"], frame["sd"], frame["pts"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    with torch.no_grad():
+        st = model(T(pts), T(frame["mask"]), T(frame["anno"]), T(frame["l2i"]))
+        st = model.refine(st, T(pts))
+    rois = N(st["refine0_rois"])
+    want_rois = O.decode_boxes(N(st["obj_reg"]), N(st["obj_centers"]))
+    np.testing.assert_allclose(rois, want_rois, rtol=2e-5, atol=2e-6)
+    # pooling: same (roi, point) pairs up to points that sit on a face of an enlarged box
+    wp, wr, wf, amb = O.dynamic_point_pool(rois[:, 1:8], pts[:, :3], [1.0, 1.0, 1.0], 512, 50000, margin=1e-4)
+    inds, roi_inds = N(st["refine0_pts_inds"]), N(st["refine0_roi_inds"])
+    assert inds.size > 1
+    assert (set(zip(roi_inds.tolist(), inds.tolist())) ^ set(zip(wr.tolist(), wp.tolist()))) <= amb
+    # RoI head on the GPU's pooled points
+    img_feat = O.mlp_from_state_dict(N(st["img_scores"])[inds], sub(sd, "refine_img_mlp.0."), "ln", "gelu", 1e-3)
+    feats = np.concatenate([N(st["seg_feats"])[inds], img_feat], 1)
+    want_feat, want_mask = OM.fully_sparse_bbox_head(pts[inds, :5], feats, N(st["refine0_local"]), N(st["refine0_offset"]),
+                                                     N(st["refine0_margin"]), roi_inds, rois, sub(sd, "refine_sir_layers.0."), 3)
+    np.testing.assert_array_equal(N(st["refine0_mask"]), want_mask)
+    close(st["refine0_lidar_feat"], want_feat, atol=1e-4)
+    # query update and refined head
+    cur = O.mlp_from_state_dict(N(st["refine0_lidar_feat"]), sub(sd, "lidar_img_mlp.0."), "ln", "gelu", 1e-3)
+    pos = O.mlp_from_state_dict(rois[:, 1:4], sub(sd, "position_encoder.0."), "ln", "gelu", 1e-3)
+    query = O.mlp_from_state_dict((cur + N(st["obj_feats"]) + pos).astype(np.float32), sub(sd, "out_proj.0."), "ln", "gelu", 1e-3)
+    scale = float(np.abs(query).max())
+    close(st["refine0_query"], query, atol=1e-4 * scale)
+    cls, reg = head_oracle(N(st["refine0_query"]), sd, "frustum_refined_head.0.")
+    close(st["refine0_cls"], cls, atol=1e-4 * max(1.0, float(np.abs(cls).max())))
+    close(st["refine0_reg"], reg, atol=1e-4 * max(1.0, float(np.abs(reg).max())))
