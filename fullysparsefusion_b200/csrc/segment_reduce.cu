@@ -309,6 +309,98 @@ __global__ void __launch_bounds__(kSrWarps * 32)
   }
 }
 
+// C == 132 (the 131-channel point features in their 16-byte padded rows: the widest scatter of the frame).  The generic
+// kernel would run it as K = 2 with one live lane in its second half: twice the load instructions and 70 registers.
+// Here the warp covers float4 0..31 of a row as above and the 33rd float4 of the (up to) four rows in flight is fetched by
+// lanes 0..3 in ONE instruction — lane 2j+i holds row i of segment j — and folded with a single shuffle step.
+template <bool IS_MAX>
+__global__ void __launch_bounds__(kSrWarps * 32)
+    k_segreduce_small_132(const float* __restrict__ feat, int64_t stride, const int32_t* __restrict__ perm,
+                          const int32_t* __restrict__ offsets, int m, int mean, float* __restrict__ out) {
+  constexpr int C = 132;
+  const int lane = lane_id();
+  const int64_t n_warps = (int64_t)gridDim.x * kSrWarps;
+  const int64_t w = (int64_t)blockIdx.x * kSrWarps + (threadIdx.x >> 5);
+  auto pair_base = [&](int64_t it) { return 2 * (w + it * n_warps); };
+  auto load_off = [&](int64_t s) -> int {
+    int v = 0;
+    if (lane < 3 && s + lane <= m) v = __ldg(offsets + s + lane);
+    return v;
+  };
+  auto load_perm = [&](int off, int64_t s) -> int {
+    const int b0 = __shfl_sync(0xffffffffu, off, 0), b1 = __shfl_sync(0xffffffffu, off, 1);
+    const int e1 = s + 1 < m ? __shfl_sync(0xffffffffu, off, 2) : b1;
+    int r = -1;
+    if (lane < 4 && s < m) {
+      const int p = (lane < 2 ? b0 : b1) + (lane & 1);
+      if (p < (lane < 2 ? b1 : e1)) r = perm ? __ldg(perm + p) : p;
+    }
+    return r;
+  };
+  auto comb = [&](float a, float b) { return IS_MAX ? fmaxf(a, b) : a + b; };
+  const float ident = IS_MAX ? -INFINITY : 0.f;
+  int off_a = load_off(pair_base(0));
+  int off_b = load_off(pair_base(1));
+  int prm_a = load_perm(off_a, pair_base(0));
+  for (int64_t it = 0;; ++it) {
+    const int64_t s = pair_base(it);
+    if (s >= m) break;
+    const int off_c = load_off(pair_base(it + 2));
+    const int prm_b = load_perm(off_b, pair_base(it + 1));
+    int beg[2], end[2], row[2][2];
+    beg[0] = __shfl_sync(0xffffffffu, off_a, 0);
+    end[0] = beg[1] = __shfl_sync(0xffffffffu, off_a, 1);
+    end[1] = s + 1 < m ? __shfl_sync(0xffffffffu, off_a, 2) : end[0];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) row[j][i] = __shfl_sync(0xffffffffu, prm_a, 2 * j + i);
+    float4 v[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        v[j][i] = make_float4(ident, ident, ident, ident);
+        if (row[j][i] >= 0) v[j][i] = ldg_stream_f4(reinterpret_cast<const float4*>(feat + (int64_t)row[j][i] * stride) + lane);
+      }
+    // 33rd float4: lane l < 4 owns row (l >> 1, l & 1); prm_a of that lane is exactly its row id
+    float4 tv = make_float4(ident, ident, ident, ident);
+    if (lane < 4 && prm_a >= 0) tv = ldg_stream_f4(reinterpret_cast<const float4*>(feat + (int64_t)prm_a * stride) + 32);
+    {
+      float4 o;
+      o.x = __shfl_xor_sync(0xffffffffu, tv.x, 1); o.y = __shfl_xor_sync(0xffffffffu, tv.y, 1);
+      o.z = __shfl_xor_sync(0xffffffffu, tv.z, 1); o.w = __shfl_xor_sync(0xffffffffu, tv.w, 1);
+      tv = make_float4(comb(tv.x, o.x), comb(tv.y, o.y), comb(tv.z, o.z), comb(tv.w, o.w));  // lanes 0 / 2: segments 0 / 1
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (s + j >= m) break;  // warp-uniform
+      float4 a = make_float4(comb(v[j][0].x, v[j][1].x), comb(v[j][0].y, v[j][1].y), comb(v[j][0].z, v[j][1].z), comb(v[j][0].w, v[j][1].w));
+      float4 t = make_float4(__shfl_sync(0xffffffffu, tv.x, 2 * j), __shfl_sync(0xffffffffu, tv.y, 2 * j),
+                             __shfl_sync(0xffffffffu, tv.z, 2 * j), __shfl_sync(0xffffffffu, tv.w, 2 * j));
+      for (int p = beg[j] + 2; p < end[j]; ++p) {  // longer segments: the rest, one row at a time
+        const int r = perm ? __ldg(perm + p) : p;
+        const float4 x = ldg_stream_f4(reinterpret_cast<const float4*>(feat + (int64_t)r * stride) + lane);
+        const float4 y = ldg_stream_f4(reinterpret_cast<const float4*>(feat + (int64_t)r * stride) + 32);  // same address in every lane
+        a = make_float4(comb(a.x, x.x), comb(a.y, x.y), comb(a.z, x.z), comb(a.w, x.w));
+        t = make_float4(comb(t.x, y.x), comb(t.y, y.y), comb(t.z, y.z), comb(t.w, y.w));
+      }
+      const bool empty = end[j] == beg[j];
+      const int cnt_j = max(1, end[j] - beg[j]);
+      const bool pow2 = (cnt_j & (cnt_j - 1)) == 0;
+      const float denom = mean ? (float)cnt_j : 1.f;
+      const float recip = 1.f / denom;
+      auto fin = [&](float x) { return empty ? 0.f : (mean ? (pow2 ? x * recip : x / denom) : x); };
+      float* o = out + (s + j) * C;
+      stg_stream_f4(reinterpret_cast<float4*>(o) + lane, make_float4(fin(a.x), fin(a.y), fin(a.z), fin(a.w)));
+      if (lane == 0) stg_stream_f4(reinterpret_cast<float4*>(o) + 32, make_float4(fin(t.x), fin(t.y), fin(t.z), fin(t.w)));
+    }
+    off_a = off_b;
+    off_b = off_c;
+    prm_a = prm_b;
+  }
+}
+
 // Fold partial rows of segments that cross chunk boundaries; zero-fill empty segments.
 // One warp per (chunk, block of 32 channels); the walk over the chunks a long segment spans is unrolled
 // four-wide so its loads are independent (instance-level segments can span hundreds of chunks).
@@ -495,7 +587,16 @@ int fsfb_segment_reduce(const float* feat, int64_t n, int c, int64_t feat_stride
   int rc;
   if (n <= (int64_t)kSrSmallAvg * m) {  // short segments on average: warp-per-segment kernel, single pass
 #define SRS_DISPATCH(VEC, K) rc = launch_segreduce_small<VEC, K>(feat, feat_stride, c, perm, offsets, (int)m, mode, n, out, argout, st)
-    if (vec4) {
+    if (vec4 && c == 132 && !argout) {  // 131-channel point features in padded rows: dedicated layout
+      static int resident132[2] = {0, 0};
+      const bool is_max = mode == FSFB_REDUCE_MAX;
+      auto kern = is_max ? k_segreduce_small_132<true> : k_segreduce_small_132<false>;
+      int& resident = resident132[is_max ? 1 : 0];
+      if (resident == 0) FSFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kSrWarps * 32, 0));
+      const int grid = (int)std::min<int64_t>(ceil_div(ceil_div(m, 2), kSrWarps), (int64_t)kNumSMs * std::max(1, resident));
+      FSFB_LAUNCH(kern, grid, kSrWarps * 32, 0, st, feat, feat_stride, perm, offsets, (int)m, mode == FSFB_REDUCE_MEAN ? 1 : 0, out);
+      rc = FSFB_OK;
+    } else if (vec4) {
       const int g = (int)ceil_div(c, 128);
       if (g <= 1) SRS_DISPATCH(4, 1);
       else if (g <= 2) SRS_DISPATCH(4, 2);

@@ -259,3 +259,31 @@ def test_ccl_oracle(cuda, m, batches, dist):
             got = ops.connected_components(T(pts, cuda), T(bb, cuda), dist).cpu().numpy()
             assert np.array_equal(got, O.connected_components(pts, bb, dist))
         assert len(np.unique(single)) == single.max() + 1              # the reference's own assert (:42)
+
+
+@pytest.mark.parametrize("n,m,kind", [(30000, None, "vox"), (20000, 3500, "ids"), (9000, 6000, "holes"), (5, 3, "ids")])
+def test_scatter_padded_131_rows(cuda, n, m, kind):
+    """The 131-channel point features live in 16-byte padded rows (ops.empty_rows → 132 floats): short segments take the
+    dedicated k_segreduce_small_132 kernel (33rd float4 of four rows in one load).  Same oracle, same exactness."""
+    rng = np.random.default_rng(n)
+    feat = rng.standard_normal((n, 131)).astype(np.float32)
+    feat[rng.random((n, 131)) < 0.2] = np.float32(0.5)
+    if kind == "vox":
+        _, index, _ = O.unique_rows(_coors(n, 5))
+        m = int(index.max()) + 1
+    elif kind == "holes":
+        index = rng.integers(0, m, n) * 2 % m
+        index[rng.random(n) < 0.05] = -1
+    else:
+        index = rng.integers(0, m, n)
+    index = index.astype(np.int64)
+    csr = ops.build_csr(T(index, cuda), m)
+    f = ops.empty_rows(n, 131, cuda)
+    f.copy_(T(feat, cuda))
+    assert f.stride(0) == 132
+    assert np.array_equal(ops.segment_reduce(f, csr, "max").cpu().numpy(), O.scatter_max(feat, index, m)[0])
+    np.testing.assert_allclose(ops.segment_reduce(f, csr, "mean").cpu().numpy(), O.scatter_mean(feat, index, m), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(ops.segment_reduce(f, csr, "sum").cpu().numpy(), O.scatter_sum(feat, index, m), rtol=RTOL, atol=1e-4)
+    g_max, g_arg = ops.segment_reduce(f, csr, "max", return_argmax=True)   # argmax keeps the generic kernel
+    w_max, w_arg = O.scatter_max(feat, index, m)
+    assert np.array_equal(g_max.cpu().numpy(), w_max) and np.array_equal(g_arg.cpu().numpy(), w_arg)
