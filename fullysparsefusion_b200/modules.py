@@ -662,13 +662,18 @@ class FullySparseBboxHead(nn.Module):
                 c, out_coors = block(in_feats, ids32, f_cluster, plan=plan)
                 cluster_feat_list.append(c)
         feats = torch.cat(cluster_feat_list, dim=1)
-        # get_nonempty_roi_mask + align_roi_feature_and_rois (:152-197): scatter the group rows to their roi slots
-        coors = out_coors.view(-1)
+        return self.align(feats, out_coors.view(-1), num_rois)
+
+    @staticmethod
+    def align(feats: torch.Tensor, coors: torch.Tensor, num_rois: int):
+        """get_nonempty_roi_mask + align_roi_feature_and_rois (fsd_bbox_head.py:152-197): group rows → their RoI slots; the
+        group of the fake row (-1) is dropped, RoIs without points stay zero."""
+        dev = feats.device
         keep = ops.compact_indices(coors >= 0)
         new_feature = torch.zeros((num_rois, feats.size(1)), dtype=torch.float32, device=dev)
         mask = torch.zeros(num_rois, dtype=torch.bool, device=dev)
         if keep.numel():
-            dst = ops.gather_int_rows(coors.view(-1, 1), keep).view(-1).long()
+            dst = ops.gather_int_rows(coors.to(torch.int32).view(-1, 1), keep).view(-1).long()
             new_feature[dst] = ops.gather_rows(feats, keep)
             mask[dst] = True
         return new_feature, mask

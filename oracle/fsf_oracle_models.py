@@ -141,6 +141,18 @@ def vote_seg_head(feats, sd, eps=1e-5):
     return logits, votes
 
 
+def align_roi_features(feats, out_coors, num_rois):
+    """FullySparseBboxHead.get_nonempty_roi_mask + align_roi_feature_and_rois (fsd_bbox_head.py:152-197) — pinned by
+    tests/golden/roi_align.npz (the reference's own methods)."""
+    feats = np.asarray(feats, F32)
+    ids = np.asarray(out_coors, np.int64)
+    new = np.zeros((num_rois, feats.shape[1]), F32)
+    mask = np.zeros(num_rois, bool)
+    new[ids[ids >= 0]] = feats[ids >= 0]
+    mask[ids[ids >= 0]] = True
+    return new, mask
+
+
 def fully_sparse_bbox_head(pts_xyz, pts_features, local_xyz, boundary_offset, is_in_margin, roi_inds, rois, sd, num_blocks,
                            xyz_normalizer=(20, 20, 4), eps=1e-3, act="gelu", geo_input=True):
     """FullySparseBboxHead.forward (models/roi_heads/bbox_heads/fsd_bbox_head.py:95-151) with DynamicClusterVFE restated as the
@@ -158,9 +170,4 @@ def fully_sparse_bbox_head(pts_xyz, pts_features, local_xyz, boundary_offset, is
         out, c = sir_layer(np.concatenate(parts, 1), inv, f_cluster, _sub(sd, f"block_list.{i}."), xyz_normalizer, 10.0, eps, act, len(uniq))
         cl.append(c)
     feats = np.concatenate(cl, 1)
-    new = np.zeros((rois.shape[0], feats.shape[1]), F32)
-    mask = np.zeros(rois.shape[0], bool)
-    ids = uniq[:, 0]
-    new[ids[ids >= 0]] = feats[ids >= 0]
-    mask[ids[ids >= 0]] = True
-    return new, mask
+    return align_roi_features(feats, uniq[:, 0], rois.shape[0])

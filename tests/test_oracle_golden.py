@@ -109,3 +109,33 @@ def test_ingroup():
 def test_vote_decode():
     g = load_golden("vote_decode")
     assert np.array_equal(O.decode_vote_targets(g["preds"]), g["offsets"])
+
+
+# ---- query refinement: goldens written by `python tools/make_golden.py refine` -------------------
+def test_box_decode_golden():
+    """BasePointBBoxCoder.decode / FSF.decode_stage_bboxes (the reference's own code) vs the oracle."""
+    g = load_golden("box_decode")
+    got = O.decode_boxes(g["reg"], g["base"])
+    np.testing.assert_allclose(got, g["rois"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(got[:, 1:], g["boxes"], rtol=1e-6, atol=1e-6)
+
+
+def test_roi_extractor_golden():
+    """The reference's DynamicPointROIExtractor (debug=True: its invariants were asserted when the golden was written) and
+    DynamicPointPoolFunction around the oracle's pooling semantics: buffer protocol, valid-row filter, field slicing."""
+    g = load_golden("roi_extractor")
+    p, r, f = O.dynamic_point_pool(g["rois"][:, 1:8], g["points"], [1.0, 1.0, 1.0], 512, 50000)
+    assert np.array_equal(p, g["inds"]) and np.array_equal(r, g["roi_inds"])
+    np.testing.assert_array_equal(f[:, 3:6], g["local_xyz"])
+    np.testing.assert_array_equal(f[:, 6:12], g["boundary_offset"])
+    np.testing.assert_array_equal(f[:, 12], g["is_in_margin"])
+    e = load_golden("roi_extractor_empty")   # nothing pooled: one fake row of -1 ids (dynamic_point_pool_op.py:36-40)
+    assert e["inds"].tolist() == [-1] and e["roi_inds"].tolist() == [-1] and e["local_xyz"].shape == (1, 3)
+
+
+def test_roi_align_golden():
+    from oracle import fsf_oracle_models as OM
+    g = load_golden("roi_align")
+    new, mask = OM.align_roi_features(g["feats"], g["out_coors"], int(g["num_rois"]))
+    assert np.array_equal(mask, g["mask"])
+    np.testing.assert_array_equal(new, g["aligned"])

@@ -126,3 +126,26 @@ def test_fully_sparse_bbox_head(cuda):
     np.testing.assert_array_equal(mask.cpu().numpy(), wmask)
     assert not wmask[-1] and wmask[:-1].any()
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.gpu
+def test_refine_goldens_gpu(cuda):
+    """The CUDA path against the goldens recorded from the reference's in-tree refine-stage Python (box decode, extractor
+    glue, RoI alignment)."""
+    import torch
+    from fullysparsefusion_b200 import modules as M, ops
+    from tests.conftest import load_golden
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    g = load_golden("box_decode")
+    np.testing.assert_allclose(ops.decode_boxes(T(g["reg"]), T(g["base"])).cpu().numpy(), g["rois"], rtol=2e-6, atol=2e-6)
+    g = load_golden("roi_extractor")
+    ext = M.DynamicPointROIExtractor(extra_wlh=[1.0, 1.0, 1.0], max_inbox_point=512)
+    inds, roi_inds, info = ext(T(g["points"]), None, T(g["rois"]))
+    assert np.array_equal(inds.cpu().numpy(), g["inds"]) and np.array_equal(roi_inds.cpu().numpy(), g["roi_inds"])
+    np.testing.assert_allclose(info["local_xyz"].cpu().numpy(), g["local_xyz"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(info["boundary_offset"].cpu().numpy(), g["boundary_offset"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(info["is_in_margin"].cpu().numpy(), g["is_in_margin"])
+    g = load_golden("roi_align")
+    new, mask = M.FullySparseBboxHead.align(T(g["feats"]), T(g["out_coors"]), int(g["num_rois"]))
+    assert np.array_equal(mask.cpu().numpy(), g["mask"])
+    np.testing.assert_array_equal(new.cpu().numpy(), g["aligned"])

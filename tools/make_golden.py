@@ -333,5 +333,76 @@ def main():
     save("vote_decode", preds=v, offsets=H.decode_vote_targets(types.SimpleNamespace(), v))
 
 
+def main_refine():
+    """Goldens of the query-refinement stage's IN-TREE Python (written by `python tools/make_golden.py refine`):
+      * BasePointBBoxCoder.decode + FSF.decode_stage_bboxes (core/bbox/coders/base_point_bbox_coder.py:59-82, FSF.py:1085-1095)
+      * DynamicPointROIExtractor.forward with debug=True (roi_extractors/dynamic_point_roi_extractor.py:30-100) around the
+        reference's DynamicPointPoolFunction (ops/dynamic_point_pool_op.py:7-57); the absent extension
+        dynamic_point_pool_ext.forward is served by oracle.fsf_oracle.dynamic_point_pool — so the extractor's own
+        assertions (:84-92) run on the oracle's semantics and the recorded outputs pin the glue (buffer protocol, valid-row
+        filtering, field slicing)
+      * FullySparseBboxHead.get_nonempty_roi_mask / align_roi_feature_and_rois (bbox_heads/fsd_bbox_head.py:152-197)."""
+    from oracle import fsf_oracle as O
+
+    import_reference()
+    torch.manual_seed(0)
+    coder_mod = importlib.import_module("projects.mmdet3d_plugin.core.bbox.coders.base_point_bbox_coder")
+    fsf = importlib.import_module("projects.mmdet3d_plugin.models.detectors.FSF")
+    pool_op = importlib.import_module("projects.mmdet3d_plugin.ops.dynamic_point_pool_op")
+    ext_mod = importlib.import_module("projects.mmdet3d_plugin.models.roi_heads.roi_extractors.dynamic_point_roi_extractor")
+    head_mod = importlib.import_module("projects.mmdet3d_plugin.models.roi_heads.bbox_heads.fsd_bbox_head")
+
+    # ---- box decode ----
+    g = torch.Generator().manual_seed(21)
+    k = 400
+    reg = torch.randn(k, 10, generator=g) * 0.7
+    base = torch.randn(k, 3, generator=g) * 20
+    coder = coder_mod.BasePointBBoxCoder(code_size=10)
+    boxes = coder.decode(reg, base)
+    self_ns = types.SimpleNamespace(bbox_coder=coder)
+    rois = fsf.FSF.decode_stage_bboxes(self_ns, base, torch.zeros(k), [reg])
+    save("box_decode", reg=reg, base=base, boxes=boxes, rois=rois)
+
+    # ---- extractor glue around the pooling op ----
+    def ext_forward(rois, pts, extra_wlh, max_inbox_point, out_pts_idx, out_roi_idx, out_pts_feats):
+        p, r, f = O.dynamic_point_pool(rois.numpy(), pts.numpy(), extra_wlh, max_inbox_point, out_pts_idx.numel())
+        out_pts_idx[: len(p)] = torch.from_numpy(p)
+        out_roi_idx[: len(r)] = torch.from_numpy(r)
+        out_pts_feats[: len(f)] = torch.from_numpy(f)
+
+    pool_op.dynamic_point_pool_ext.forward = ext_forward
+    rng = np.random.default_rng(22)
+    n, kk = 4000, 30
+    pts = np.concatenate([rng.uniform(-40, 40, (n, 2)), rng.uniform(-3, 1, (n, 1))], 1).astype(np.float32)
+    centers = pts[rng.integers(0, n, kk)] + rng.normal(0, 0.3, (kk, 3)).astype(np.float32)
+    dims = rng.uniform([1.5, 3.0, 1.2], [2.5, 6.0, 2.5], (kk, 3))
+    rois7 = np.concatenate([centers, dims, rng.uniform(-np.pi, np.pi, (kk, 1))], 1).astype(np.float32)
+    dense = (centers[:5, None, :] + rng.normal(0, 0.4, (5, 60, 3))).reshape(-1, 3).astype(np.float32)
+    pts = np.concatenate([pts, dense])
+    rois8 = np.concatenate([np.zeros((kk, 1), np.float32), rois7], 1)
+    ext = ext_mod.DynamicPointROIExtractor(debug=True, extra_wlh=[1.0, 1.0, 1.0], max_inbox_point=512)
+    inds, roi_inds, info = ext(torch.from_numpy(pts), torch.zeros(len(pts), dtype=torch.long), torch.from_numpy(rois8))
+    save("roi_extractor", points=pts, rois=rois8, inds=inds, roi_inds=roi_inds, local_xyz=info["local_xyz"],
+         boundary_offset=info["boundary_offset"], is_in_margin=info["is_in_margin"])
+    # nothing pooled: the fake row
+    far = rois8[:2].copy()
+    far[:, 1:4] = 1e4
+    ext_nd = ext_mod.DynamicPointROIExtractor(debug=False, extra_wlh=[1.0, 1.0, 1.0], max_inbox_point=512)   # the stock config's setting
+    i2, r2, info2 = ext_nd(torch.from_numpy(pts), torch.zeros(len(pts), dtype=torch.long), torch.from_numpy(far))
+    save("roi_extractor_empty", inds=i2, roi_inds=r2, local_xyz=info2["local_xyz"])
+
+    # ---- RoI alignment ----
+    Head = head_mod.FullySparseBboxHead
+    hs = types.SimpleNamespace(training=False)
+    feats = torch.randn(7, 12, generator=g)
+    out_coors = torch.tensor([-1, 0, 2, 3, 7, 8, 11])
+    mask = Head.get_nonempty_roi_mask(hs, out_coors, 13)
+    aligned = Head.align_roi_feature_and_rois(hs, feats, out_coors, 13)
+    save("roi_align", feats=feats, out_coors=out_coors, num_rois=13, mask=mask, aligned=aligned)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "refine":
+        main_refine()
+    else:
+        main()
