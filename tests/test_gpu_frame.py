@@ -223,3 +223,20 @@ def test_refine_stage(cuda, frame):
     cls, reg = head_oracle(N(st["refine0_query"]), sd, "frustum_refined_head.0.")
     close(st["refine0_cls"], cls, atol=1e-4 * max(1.0, float(np.abs(cls).max())))
     close(st["refine0_reg"], reg, atol=1e-4 * max(1.0, float(np.abs(reg).max())))
+
+
+def test_group_cluster_reference_golden(cuda):
+    """ops.group_sample + ops.group_cluster (all class groups in one pass) against the output of the reference's own
+    group_sample + ClusterAssigner (tests/golden/group_cluster.npz): rows and (cls, batch, cluster) ids bit-exact."""
+    from fullysparsefusion_b200 import ops
+    from fullysparsefusion_b200.fsf import NUSC
+    from tests.conftest import load_golden
+    g = load_golden("group_cluster")
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    groups = [[NUSC["class_names"].index(n) for n in grp] for grp in NUSC["group_names"]]
+    _, score, centers = ops.group_sample(T(g["logits"]), groups, xyz=T(g["points"]), offsets=T(g["offsets"]))
+    rows, cls, clu, ctr = ops.group_cluster(score, centers, NUSC["score_thresh"], NUSC["cluster_voxel_size"], NUSC["point_cloud_range"],
+                                            NUSC["connected_dist"], NUSC["min_points"])
+    assert np.array_equal(N(rows), g["rows"])
+    assert np.array_equal(np.stack([N(cls), np.zeros(len(g["rows"]), np.int64), N(clu)], 1), g["cluster_inds"])
+    np.testing.assert_allclose(N(ctr), g["center_preds"], rtol=1e-5, atol=1e-5)

@@ -139,3 +139,26 @@ def test_roi_align_golden():
     new, mask = OM.align_roi_features(g["feats"], g["out_coors"], int(g["num_rois"]))
     assert np.array_equal(mask, g["mask"])
     np.testing.assert_array_equal(new, g["aligned"])
+
+
+def test_group_cluster_golden():
+    """The reference's own group_sample + ClusterAssigner (six class groups, both fallbacks hit) vs the oracle's restatement."""
+    from fullysparsefusion_b200.fsf import NUSC
+    from oracle import fsf_oracle_frame as OF
+    g = load_golden("group_cluster")
+    groups = [[NUSC["class_names"].index(n) for n in grp] for grp in NUSC["group_names"]]
+    score, centers = OF.group_sample(g["logits"], g["points"], g["offsets"], groups, NUSC["score_thresh"])
+    rows, inds, ctrs = [], [], []
+    for gi in range(6):
+        idx = np.flatnonzero(score[:, gi] > np.float32(NUSC["score_thresh"][gi]))
+        if idx.size == 0:
+            idx = np.zeros(1, np.int64)
+        labels, keep = OF.cluster_assign_single(centers[idx, gi], NUSC["cluster_voxel_size"][gi], NUSC["point_cloud_range"],
+                                                NUSC["connected_dist"][gi], NUSC["min_points"])
+        rows.append(idx[keep])
+        inds.append(np.stack([np.full(keep.size, gi), np.zeros(keep.size, np.int64), labels], 1))
+        ctrs.append(centers[idx[keep], gi])
+    assert [len(r) for r in rows] == g["counts"].tolist()
+    assert np.array_equal(np.concatenate(rows), g["rows"])
+    assert np.array_equal(np.concatenate(inds), g["cluster_inds"])
+    np.testing.assert_allclose(np.concatenate(ctrs), g["center_preds"], rtol=1e-5, atol=1e-5)

@@ -401,8 +401,56 @@ def main_refine():
     save("roi_align", feats=feats, out_coors=out_coors, num_rois=13, mask=mask, aligned=aligned)
 
 
+def main_groups():
+    """Golden of the LiDAR-query clustering path (`python tools/make_golden.py groups`): the reference's own
+    SingleStageFSD.group_sample (single_stage_fsd.py:802-865, with get_fg_mask :740-781, get_offset_weight :867-874,
+    gather_group_by_names :891-904) followed by ClusterAssigner.forward (:921-982: filter_almost_empty, scatter_v2 'avg',
+    scipy connected components, modify_cluster_by_class) for the six nuScenes class groups.  The in-group index of the
+    'at least one point per sample' fallback comes from the reference's slow oracle get_inner_win_inds_slow."""
+    ref = import_reference()
+    fsd = ref["fsd"]
+    S = fsd.SingleStageFSD
+    L = ref["sst_in"].SSTInputLayer
+    fsd.get_inner_win_inds = lambda x: L.get_inner_win_inds_slow(types.SimpleNamespace(), x)
+    from fullysparsefusion_b200.fsf import NUSC
+    cfg = dict(score_thresh=NUSC["score_thresh"], group_names=NUSC["group_names"], class_names=NUSC["class_names"], offset_weight="max")
+    ns = types.SimpleNamespace(training=False, num_classes=10, test_cfg=cfg, train_cfg=None, cfg=cfg, runtime_info=None)
+    for name in ("gather_group_by_names", "get_fg_mask", "get_sample_beg_position", "get_offset_weight"):
+        setattr(ns, name, (lambda f: (lambda *a, **k: f(ns, *a, **k)))(getattr(S, name)))
+    g = torch.Generator().manual_seed(31)
+    n = 5000
+    pts = torch.cat([torch.rand(n, 2, generator=g) * 80 - 40, torch.rand(n, 1, generator=g) * 4 - 3], 1)
+    # clumps of foreground voxels so clusters exist; background logit dominant elsewhere
+    logits = torch.randn(n, 11, generator=g)
+    logits[:, 10] += 5.0
+    for c, (lo, hi) in enumerate([(0, 400), (400, 600), (600, 700), (700, 1000), (1000, 1003), (1003, 1300)]):
+        cls = NUSC["class_names"].index(NUSC["group_names"][c][0])
+        logits[lo:hi, cls] += 9.0
+        centre = pts[lo:hi].mean(0, keepdim=True)
+        k = hi - lo
+        pts[lo:hi] = centre + torch.randn(k, 3, generator=g) * torch.tensor([[1.5, 1.5, 0.3]])
+    logits[:, NUSC["class_names"].index("barrier")] -= 12.0      # group 3 (barrier): no candidate at all → row-0 fallback
+    pts[1000:1003] += torch.tensor([[0.0, 0.0, 0.0], [7.0, 0.0, 0.0], [0.0, 9.0, 0.0]])   # group 4: three isolated voxels → keep-all fallback
+    offsets = torch.randn(n, 33, generator=g) * 0.2
+    d = dict(seg_points=pts, seg_logits=logits, batch_idx=torch.zeros(n, dtype=torch.long))
+    out = S.group_sample(ns, d, offsets)
+    assigner = fsd.ClusterAssigner(cluster_voxel_size=[list(v) for v in NUSC["cluster_voxel_size"]], min_points=NUSC["min_points"],
+                                   point_cloud_range=NUSC["point_cloud_range"], connected_dist=NUSC["connected_dist"],
+                                   class_names=[f"g{i}" for i in range(6)], gpu_clustering=(False, False))
+    assigner.num_classes = 6
+    assigner.eval()
+    cluster_inds_list, valid_mask_list = assigner(out["center_preds"], out["batch_idx"], origin_points=out["seg_points"])
+    rows = [torch.nonzero(m).view(-1)[v] for m, v in zip(out["fg_mask_list"], valid_mask_list)]
+    centers = [c[v] for c, v in zip(out["center_preds"], valid_mask_list)]
+    save("group_cluster", points=pts, logits=logits, offsets=offsets, rows=torch.cat(rows), cluster_inds=torch.cat(cluster_inds_list),
+         center_preds=torch.cat(centers), counts=np.array([len(r) for r in rows]),
+         candidates=np.array([int(m.sum()) for m in out["fg_mask_list"]]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "refine":
         main_refine()
+    elif len(sys.argv) > 1 and sys.argv[1] == "groups":
+        main_groups()
     else:
         main()
