@@ -162,3 +162,52 @@ def test_group_cluster_golden():
     assert np.array_equal(np.concatenate(rows), g["rows"])
     assert np.array_equal(np.concatenate(inds), g["cluster_inds"])
     np.testing.assert_allclose(np.concatenate(ctrs), g["center_preds"], rtol=1e-5, atol=1e-5)
+
+
+# ---- more in-tree reference Python (`python tools/make_golden.py misc`) -----------------------------------------------
+def test_pre_voxelize_golden():
+    from oracle import fsf_oracle_frame as OF
+    g = load_golden("pre_voxelize")
+    data = dict(p=g["points"], l=g["logits"], v=g["votes"], f=g["feats"])
+    vox, uniq, inv = OF.pre_voxelize(data, g["points"], (0.1, 0.1, 0.1), [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0])
+    assert len(uniq) == len(g["v_points"])          # same voxel set, same (torch.unique) order
+    for k, want in (("p", "v_points"), ("l", "v_logits"), ("v", "v_votes"), ("f", "v_feats")):
+        np.testing.assert_allclose(vox[k], g[want], rtol=1e-4, atol=1e-5)
+
+
+def test_encode_preds_2d_golden():
+    from oracle import fsf_oracle_frame as OF
+    g = load_golden("encode_preds_2d")
+    preds, enc = OF.encode_preds_2d(g["anno"], g["obj_coors"][:, 2], int(g["img_w"]), int(g["img_h"]), 10)
+    np.testing.assert_array_equal(preds, g["preds_2d"])
+    np.testing.assert_allclose(enc, g["enc"], rtol=1e-6, atol=1e-7)
+
+
+def test_img_cross_attn_golden():
+    """FSF.img_cross_attn up to the MLP input (the per-point, per-class 2D scores of the selected camera)."""
+    from oracle import fsf_oracle_frame as OF
+    g = load_golden("img_cross_attn")
+    scores, ids, cam, fg, overlap = OF.img_scores(g["points"], g["mask"], g["lidar2img"], g["anno"])
+    flips = (scores != g["scores"]).any(1).mean()
+    assert flips <= 0.002, flips    # texel-boundary flips only (BLAS accumulation order of the K=4 projection, DESIGN.md §2)
+    same = ~(scores != g["scores"]).any(1)
+    np.testing.assert_array_equal(scores[same], g["scores"][same])
+
+
+def test_fg_weights_golden():
+    from oracle import fsf_oracle_frame as OF
+    g = load_golden("fg_weights")
+    np.testing.assert_allclose(OF.point_fg_weights(g["logits"]), g["weights"], rtol=1e-5, atol=1e-6)
+
+
+def test_combine_golden():
+    """combine_frustum_and_fsd's bookkeeping: concatenation order and the (batch, cls, id + fsd_begin_idx) rewrite of the
+    LiDAR queries' coordinates — what fsf.FSF.stages()['combine'] does with torch.cat / torch.stack."""
+    g = load_golden("combine")
+    fc = g["fsd_coors"]
+    fsd_re = np.stack([fc[:, 1], fc[:, 0], fc[:, 2] + 1000], 1)
+    assert np.array_equal(np.concatenate([g["fr_coors"], fsd_re]), g["obj_coors"])
+    assert np.array_equal(np.concatenate([g["fr_centers"], g["fsd_centers"]]), g["obj_centers"])
+    assert np.array_equal(np.concatenate([g["fr_cls"], g["fsd_cls"]]), g["obj_cls"])
+    assert np.array_equal(np.concatenate([g["fr_reg"], g["fsd_reg"]]), g["obj_reg"])
+    assert (g["preds_2d"][len(g["fr_coors"]):] == 0).all()

@@ -447,8 +447,75 @@ def main_groups():
          candidates=np.array([int(m.sum()) for m in out["fg_mask_list"]]))
 
 
+def main_misc():
+    """More of the hot path's IN-TREE Python, run as is (`python tools/make_golden.py misc`):
+      * SingleStageFSD.pre_voxelize (single_stage_fsd.py:585-605)
+      * FSF.get_single_cls_preds_2d + encode_preds_2d (FSF.py:449-504), as frustum_forward feeds encode_2d_mlp
+      * FSF.img_cross_attn up to the MLP input: frustum_gather → camera select → get_all_cls_preds_2d → encode_preds_2d
+        (FSF.py:694-728, 506-552)
+      * FSF.get_point_fg_weights (FSF.py:345-355)
+      * FSF.combine_frustum_and_fsd's index bookkeeping (FSF.py:657-692; the two MLPs are build_mlp, pinned separately)."""
+    from fullysparsefusion_b200 import synth
+    ref = import_reference()
+    FSF, S, sst_ops = ref["fsf"].FSF, ref["fsd"].SingleStageFSD, ref["sst_ops"]
+    g = torch.Generator().manual_seed(41)
+
+    # ---- pre_voxelize ----
+    n = 2000
+    pts = torch.from_numpy(synth.ring_points(n, sweeps=3, seed=41)[:, :5])
+    data = dict(seg_points=pts, seg_logits=torch.randn(n, 11, generator=g), seg_vote_preds=torch.randn(n, 33, generator=g),
+                seg_feats=torch.randn(n, 19, generator=g), batch_idx=torch.zeros(n, dtype=torch.long))
+    ns = types.SimpleNamespace(cfg=types.SimpleNamespace(pre_voxelization_size=(0.1, 0.1, 0.1)),
+                               cluster_assigner=types.SimpleNamespace(point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]))
+    vox = S.pre_voxelize(ns, data)
+    save("pre_voxelize", points=pts, logits=data["seg_logits"], votes=data["seg_vote_preds"], feats=data["seg_feats"],
+         v_points=vox["seg_points"], v_logits=vox["seg_logits"], v_votes=vox["seg_vote_preds"], v_feats=vox["seg_feats"])
+
+    # ---- 2D prediction encodings ----
+    H, W = 90, 160
+    mask = synth.mask_planes(6, 10, H, W, seed=42, overlap=True)
+    anno = synth.mask_anno(mask, seed=42)
+    l2i = synth.lidar2img(6, H, W)
+    fs = types.SimpleNamespace(num_classes=10, num_cams=6, encode_label_only=False, is_argo=False)
+    for name in ("prj_points_2d", "points_in_mask", "frustum_gather", "get_all_cls_preds_2d", "encode_preds_2d", "encode_2d_feats",
+                 "get_single_cls_preds_2d", "combine_by_batch"):
+        setattr(fs, name, (lambda f: (lambda *a, **k: f(fs, *a, **k)))(getattr(FSF, name)))
+    obj_coors = torch.stack([torch.zeros(40, dtype=torch.long), torch.zeros(40, dtype=torch.long),
+                             torch.randint(0, int(anno[:, 7].max()) + 1, (40,), generator=g)], 1)
+    preds = FSF.get_single_cls_preds_2d(fs, torch.from_numpy(anno)[None], obj_coors)
+    enc = FSF.encode_preds_2d(fs, preds, W, H)
+    save("encode_preds_2d", anno=anno, obj_coors=obj_coors, preds_2d=preds, enc=enc, img_w=W, img_h=H)
+
+    npts = 3000
+    p3 = torch.from_numpy(synth.ring_points(npts, sweeps=1, seed=43)[:, :3])
+    captured = {}
+    ident = lambda x: captured.setdefault("mlp_in", x.clone()) * 0 + x   # encode_mlp: record its input, pass it through
+    out = FSF.img_cross_attn(fs, [p3], torch.zeros(npts, dtype=torch.long), torch.from_numpy(anno)[None], torch.from_numpy(mask)[None],
+                             [dict(lidar2img=l2i)], ident)
+    save("img_cross_attn", points=p3, lidar2img=l2i, mask=mask, anno=anno, scores=captured["mlp_in"])
+
+    lg = torch.randn(500, 11, generator=g)
+    save("fg_weights", logits=lg, weights=FSF.get_point_fg_weights(fs, lg))
+
+    # ---- combine_frustum_and_fsd (identity MLPs: only the index bookkeeping is recorded) ----
+    cs = types.SimpleNamespace(fsd_begin_idx=1000, combine_frustum_feat_mlp=lambda x: x, combine_fsd_feat_mlp=lambda x: x)
+    kf, kl = 7, 11
+    fr = dict(centers=torch.randn(kf, 3, generator=g), coors=torch.randint(0, 50, (kf, 3), generator=g), feats=torch.randn(kf, 5, generator=g),
+              res=dict(cls_logits=[torch.randn(kf, 10, generator=g)], reg_preds=[torch.randn(kf, 10, generator=g)]),
+              preds_2d=torch.randn(kf, 9, generator=g))
+    ls = dict(centers=torch.randn(kl, 3, generator=g), coors=torch.randint(0, 50, (kl, 3), generator=g), feats=torch.randn(kl, 5, generator=g),
+              res=dict(cls_logits=[torch.randn(kl, 10, generator=g)], reg_preds=[torch.randn(kl, 10, generator=g)]))
+    oc, oco, ores, of, op2 = FSF.combine_frustum_and_fsd(cs, fr["centers"], fr["coors"], fr["res"], fr["feats"], fr["preds_2d"],
+                                                         ls["centers"], ls["coors"], ls["res"], ls["feats"])
+    save("combine", fr_centers=fr["centers"], fr_coors=fr["coors"], fr_cls=fr["res"]["cls_logits"][0], fr_reg=fr["res"]["reg_preds"][0],
+         fsd_centers=ls["centers"], fsd_coors=ls["coors"], fsd_cls=ls["res"]["cls_logits"][0], fsd_reg=ls["res"]["reg_preds"][0],
+         obj_centers=oc, obj_coors=oco, obj_cls=ores["cls_logits"][0], obj_reg=ores["reg_preds"][0], preds_2d=op2)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "refine":
+    if len(sys.argv) > 1 and sys.argv[1] == "misc":
+        main_misc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "refine":
         main_refine()
     elif len(sys.argv) > 1 and sys.argv[1] == "groups":
         main_groups()
