@@ -132,3 +132,15 @@ def test_compact_indices(cuda):
         mask = rng.random(n) < 0.3
         got = ops.compact_indices(T(mask, cuda))
         assert np.array_equal(got.cpu().numpy(), np.flatnonzero(mask).astype(np.int32))
+
+
+def test_cluster_head_reference_golden(cuda):
+    """fsf.SparseClusterHeadV2 with the state dict of the reference's own head: same logits / regressions (1e-4)."""
+    from tests.test_oracle_golden import _v2_head_from_golden
+    g, head, sd = _v2_head_from_golden()
+    head.load_state_dict(sd, strict=True)
+    head = head.eval().to(cuda)
+    with torch.no_grad():
+        out = head(torch.from_numpy(g["x"]).to(cuda))
+    np.testing.assert_allclose(out["cls_logits"][0].cpu().numpy(), g["cls"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(out["reg_preds"][0].cpu().numpy(), g["reg"], rtol=1e-4, atol=2e-5)

@@ -211,3 +211,30 @@ def test_combine_golden():
     assert np.array_equal(np.concatenate([g["fr_cls"], g["fsd_cls"]]), g["obj_cls"])
     assert np.array_equal(np.concatenate([g["fr_reg"], g["fsd_reg"]]), g["obj_reg"])
     assert (g["preds_2d"][len(g["fr_coors"]):] == 0).all()
+
+
+def _v2_head_from_golden():
+    import torch
+    from fullysparsefusion_b200 import fsf as FSFM
+    g = load_golden("cluster_head_v2")
+    names = ["car", "truck", "bus"]
+    head = FSFM.SparseClusterHeadV2(num_classes=3, in_channel=24, shared_mlp_dims=[32, 32], tasks=[dict(class_names=names)],
+                                    common_attrs=dict(center=(3, 2, 16), dim=(3, 2, 16), rot=(2, 2, 16), vel=(2, 2, 16)),
+                                    num_cls_layer=2, cls_hidden_dim=16, separate_head=dict(norm_cfg=dict(type="LN"), act="gelu"),
+                                    norm_cfg=dict(type="LN"), act="relu")
+    sd = {k.replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k not in ("x", "cls", "reg")}
+    return g, head, sd
+
+
+def test_cluster_head_state_dict_compat():
+    """A state dict saved by the REFERENCE's SparseClusterHeadV2 loads strictly into fsf.SparseClusterHeadV2 (same keys and
+    shapes: the checkpoint layout the stock configs produce), and the oracle reproduces the reference's outputs from it."""
+    g, head, sd = _v2_head_from_golden()
+    missing, unexpected = head.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    sdn = {k: v.numpy() for k, v in sd.items()}
+    h = O.mlp_from_state_dict(g["x"], {k[len("shared_mlp."):]: v for k, v in sdn.items() if k.startswith("shared_mlp.")}, "ln", "relu", 1e-5)
+    outs = {a: O.mlp_from_state_dict(h, {k[len(f"task_heads.0.{a}."):]: v for k, v in sdn.items() if k.startswith(f"task_heads.0.{a}.")},
+                                     "ln", "gelu", 1e-5) for a in ("center", "dim", "rot", "vel", "score")}
+    np.testing.assert_allclose(outs["score"], g["cls"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(np.concatenate([outs["center"], outs["dim"], outs["rot"], outs["vel"]], 1), g["reg"], rtol=1e-4, atol=1e-5)

@@ -512,8 +512,40 @@ def main_misc():
          obj_centers=oc, obj_coors=oco, obj_cls=ores["cls_logits"][0], obj_reg=ores["reg_preds"][0], preds_2d=op2)
 
 
+def main_heads():
+    """The reference's own SparseClusterHeadV2 / FSDSeparateHead (dense_heads/sparse_cluster_head_v2.py:17-168,
+    sparse_cluster_head.py:30-118) at reduced widths: state-dict keys (checkpoint compatibility of fsf.SparseClusterHeadV2) and
+    forward outputs (`python tools/make_golden.py heads`).  mmdet's builders are stubs here, so build_head / build_bbox_coder are
+    pointed at the in-tree classes they would resolve to."""
+    import_reference()
+    v2 = importlib.import_module("projects.mmdet3d_plugin.models.dense_heads.sparse_cluster_head_v2")
+    sch = importlib.import_module("projects.mmdet3d_plugin.models.dense_heads.sparse_cluster_head")
+    v2.builder.build_head = lambda cfg: v2.FSDSeparateHead(**{k: v for k, v in cfg.items() if k != "type"})
+    sch.build_bbox_coder = lambda cfg: types.SimpleNamespace(code_size=cfg["code_size"])
+    torch.manual_seed(51)
+    names = ["car", "truck", "bus"]
+    head = v2.SparseClusterHeadV2(
+        num_classes=3, bbox_coder=dict(type="BasePointBBoxCoder", code_size=10), loss_cls=dict(type="FocalLoss"),
+        loss_center=dict(type="L1Loss"), loss_size=dict(type="L1Loss"), loss_rot=dict(type="L1Loss"), in_channel=24,
+        shared_mlp_dims=[32, 32], tasks=[dict(class_names=names)], class_names=names,
+        common_attrs=dict(center=(3, 2, 16), dim=(3, 2, 16), rot=(2, 2, 16), vel=(2, 2, 16)), num_cls_layer=2, cls_hidden_dim=16,
+        separate_head=dict(type="FSDSeparateHead", norm_cfg=dict(type="LN"), act="gelu"), norm_cfg=dict(type="LN"), act="relu")
+    for mod in head.modules():
+        if isinstance(mod, nn.LayerNorm):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    head.eval()
+    x = torch.randn(50, 24)
+    with torch.no_grad():
+        out = head(x)
+    sd = {k.replace(".", "__"): v for k, v in head.state_dict().items()}
+    save("cluster_head_v2", x=x, cls=out["cls_logits"][0], reg=out["reg_preds"][0], **sd)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "misc":
+    if len(sys.argv) > 1 and sys.argv[1] == "heads":
+        main_heads()
+    elif len(sys.argv) > 1 and sys.argv[1] == "misc":
         main_misc()
     elif len(sys.argv) > 1 and sys.argv[1] == "refine":
         main_refine()
