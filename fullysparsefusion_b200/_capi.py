@@ -50,6 +50,10 @@ SIGNATURES = {
     "fsfb_group_keep": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p]),
     "fsfb_group_relabel": (_i, [_p, _p, _i64, _i64, _i, _p, _i64, _p, _p, _p]),
     "fsfb_connected_components_groups": (_i, [_p, _i64, _i64, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "fsfb_nms_flags": (_i, [_p, _i64, _i, _i64, _i, _f, _p, _p, _p, _p]),
+    "fsfb_nms_workspace_bytes": (_i, [_i64, _i, _p]),
+    "fsfb_nms_suppress": (_i, [_p, _i64, _i64, _p, _i, _p, _i64, _p, _i, _f, _p, _p, _sz, _p]),
+    "fsfb_nms_emit": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "fsfb_decode_boxes": (_i, [_p, _i64, _i, _i64, _p, _i64, _p, _i64, _p, _p]),
     "fsfb_dynamic_point_pool_workspace_bytes": (_i, [_i64, _i, _p]),
     "fsfb_dynamic_point_pool": (_i, [_p, _i64, _p, _i64, _i64, _p, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),

@@ -11,7 +11,8 @@ combine_frustum_and_fsd (:657-692), with the segmentor of single_stage_fsd.py (V
   combine      the two 1024-wide fusion MLPs
 
 `FSF.refine` continues with the query-refinement stage (decode_stage_bboxes → dynamic point pooling →
-FullySparseBboxHead → query MLPs → refined head); final box decode / NMS (rank 3) are not built.  One sample per call (samples_per_gpu = 1 in both stock configs).
+FullySparseBboxHead → query MLPs → refined head) and `FSF.get_bboxes` with the final box decode and
+rotated multi-class NMS (rank 3).  One sample per call (samples_per_gpu = 1 in both stock configs).
 All arithmetic goes through the C-ABI ops; torch is used for allocation, views and concatenation only.
 """
 from __future__ import annotations
@@ -327,6 +328,17 @@ class FSF(nn.Module):
                         f"refine{i}_margin": info["is_in_margin"]})
         st.update(out)
         return st
+
+    @torch.no_grad()
+    def get_bboxes(self, st: Dict[str, torch.Tensor], score_thr: float = 0.01, nms_thr: float = 0.35, max_num: int = 500):
+        """Detections of the last refine stage: FrustumClusterHead._get_bboxes_single (dense_heads/frustum_cluster_head.py:
+        595-698, test_cfg of FSF_nuScenes_config.py) = sigmoid, BasePointBBoxCoder.decode on the stage's centres, rotated
+        multi-class NMS → (boxes [n,9] (x,y,z,dx,dy,dz,yaw,vx,vy), scores [n], labels [n]).  Needs `refine` to have run."""
+        i = self.num_extra_stages - 1
+        rois = ops.decode_boxes(st[f"refine{i}_reg"], st[f"refine{i}_centers"])
+        boxes, scores, labels, rows = ops.multiclass_nms(rois[:, 1:], st[f"refine{i}_cls"], score_thr, nms_thr, max_num)
+        st.update(det_boxes=boxes, det_scores=scores, det_labels=labels, det_rows=rows)
+        return boxes, scores, labels
 
     @torch.no_grad()
     def forward(self, points, mask_data, mask_anno, lidar2img):

@@ -1009,3 +1009,44 @@ def decode_boxes(reg: torch.Tensor, base_points: torch.Tensor, batch: Optional[t
                                    base_points.stride(0) if k else 3, _ptr(batch), batch.stride(0) if batch is not None and k else 1,
                                    _ptr(rois), _stream(dev)), "fsfb_decode_boxes")
     return rois
+
+
+def multiclass_nms(boxes: torch.Tensor, logits: torch.Tensor, score_thr: float, nms_thr: float, max_num: int,
+                   apply_sigmoid: bool = True):
+    """box3d_multiclass_nms with rotated BEV IoU on sigmoid(logits) (frustum_cluster_head.py:595-698).
+    boxes [K, >=7] (x,y,z,dx,dy,dz,yaw,...), logits [K, C] → (boxes [n, D], scores [n], labels [n] i64, source rows [n] i32)."""
+    dev = _need_cuda(boxes, logits)
+    boxes, logits = _rowmajor(boxes), _rowmajor(logits)
+    k, nc = logits.shape
+    D = boxes.size(1)
+    lib, st = load(), _stream(dev)
+    empty = (torch.empty((0, D), device=dev), torch.empty(0, device=dev), torch.empty(0, dtype=torch.int64, device=dev),
+             torch.empty(0, dtype=torch.int32, device=dev))
+    if k == 0:
+        return empty
+    scores = torch.empty((k, nc), dtype=torch.float32, device=dev)
+    flags = torch.empty(nc * k, dtype=torch.uint8, device=dev)
+    counts = torch.empty(nc, dtype=torch.int32, device=dev)
+    check(lib.fsfb_nms_flags(_ptr(logits), k, nc, logits.stride(0), int(apply_sigmoid), float(score_thr), _ptr(scores), _ptr(flags),
+                             _ptr(counts), st), "fsfb_nms_flags")
+    flat = compact_indices(flags)
+    T = flat.numel()
+    if T == 0:
+        return empty
+    max_class = max(counts.tolist())
+    need = C.c_size_t(0)
+    check(lib.fsfb_nms_workspace_bytes(T, max_class, C.byref(need)), "fsfb_nms_workspace_bytes")
+    ws = _ws(need.value, dev)
+    keep = torch.empty(T, dtype=torch.uint8, device=dev)
+    check(lib.fsfb_nms_suppress(_ptr(boxes), k, boxes.stride(0), _ptr(scores), nc, _ptr(flat), T, _ptr(counts), max_class, float(nms_thr),
+                                _ptr(keep), _ptr(ws), ws.numel(), st), "fsfb_nms_suppress")
+    kept_idx = compact_indices(keep)
+    P = kept_idx.numel()
+    n = min(P, int(max_num))
+    out_boxes = torch.empty((n, D), dtype=torch.float32, device=dev)
+    out_scores = torch.empty(n, dtype=torch.float32, device=dev)
+    out_labels = torch.empty(n, dtype=torch.int64, device=dev)
+    out_rows = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib.fsfb_nms_emit(_ptr(boxes), boxes.stride(0), D, _ptr(kept_idx), P, T, max_class, int(max_num), _ptr(out_boxes),
+                            _ptr(out_scores), _ptr(out_labels), _ptr(out_rows), _ptr(ws), ws.numel(), st), "fsfb_nms_emit")
+    return out_boxes, out_scores, out_labels, out_rows

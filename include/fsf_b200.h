@@ -485,6 +485,31 @@ int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float* pts, int6
                             long long* out_pts_idx, long long* out_roi_idx, float* out_pts_feats,
                             int32_t* num_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * f3  Multi-class rotated BEV NMS: the tail of FrustumClusterHead._get_bboxes_single
+ * (projects/mmdet3d_plugin/models/dense_heads/frustum_cluster_head.py:595-698) = sigmoid, box3d_multiclass_nms with
+ * use_rotate_nms (mmdet3d fork / iou3d, un-vendored: rotated-rectangle IoU restated by polygon clipping).  Three steps with
+ * the two list lengths read by the caller in between (as fsfb_compact_indices reports them):
+ *   fsfb_nms_flags     scores dev [k, C] (sigmoid(logits) when apply_sigmoid), flags dev [C, k] u8 = score > score_thr,
+ *                      counts dev [C] i32
+ *   fsfb_nms_suppress  flat = ascending indices of the set flags (class-major candidates); per class: order by (score desc,
+ *                      box index asc), suppress later boxes whose rotated BEV IoU with a kept one exceeds nms_thr;
+ *                      keep dev [candidates] u8 in that order.  boxes dev rows (x, y, z, dx, dy, dz, yaw, ...).
+ *                      max_class = largest counts[c] (<= 8192).
+ *   fsfb_nms_emit      kept_idx = ascending indices of the set keep flags → boxes [n, box_dim], scores [n], labels [n] i64,
+ *                      source row [n] i32 (nullable), n = min(kept, max_num): class-major in descending score, or the max_num
+ *                      best scores in descending order when more survive.  Same workspace as fsfb_nms_suppress.
+ * ------------------------------------------------------------------------- */
+int fsfb_nms_flags(const float* logits, int64_t k, int num_classes, int64_t stride, int apply_sigmoid, float score_thr,
+                   float* scores, uint8_t* flags, int32_t* counts, void* stream);
+int fsfb_nms_workspace_bytes(int64_t candidates, int max_class, size_t* bytes);
+int fsfb_nms_suppress(const float* boxes, int64_t k, int64_t box_stride, const float* scores, int num_classes, const int32_t* flat,
+                      int64_t candidates, const int32_t* counts, int max_class, float nms_thr, uint8_t* keep, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int fsfb_nms_emit(const float* boxes, int64_t box_stride, int box_dim, const int32_t* kept_idx, int64_t kept, int64_t candidates,
+                  int max_class, int64_t max_num, float* out_boxes, float* out_scores, long long* out_labels, int32_t* out_box_idx,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -588,3 +588,72 @@ def decode_boxes(reg, base_points, batch=None):
     b = np.zeros((reg.shape[0], 1), F32) if batch is None else np.asarray(batch, F32)[:, None]
     out = [b, xyz, dims, yaw] + ([reg[:, 8:10]] if reg.shape[1] == 10 else [])
     return np.concatenate(out, 1).astype(F32)
+
+
+# ------------------------------------------------------------------------------------------
+# f3 multi-class rotated BEV NMS — PARITY UNPINNED (mmdet3d box3d_multiclass_nms / iou3d nms_gpu are un-vendored): the
+# published definition restated in float64; call site projects/mmdet3d_plugin/models/dense_heads/frustum_cluster_head.py:595-698.
+# ------------------------------------------------------------------------------------------
+def _rect_corners(b):
+    x, y, dx, dy, yaw = float(b[0]), float(b[1]), float(b[3]), float(b[4]), float(b[6])
+    c, s = np.cos(yaw), np.sin(yaw)
+    pts = np.array([[dx / 2, dy / 2], [-dx / 2, dy / 2], [-dx / 2, -dy / 2], [dx / 2, -dy / 2]])
+    return pts @ np.array([[c, s], [-s, c]]) + np.array([x, y])
+
+
+def rotated_iou_bev(a, b):
+    """IoU of two rotated BEV rectangles (x, y, z, dx, dy, dz, yaw): Sutherland-Hodgman clipping of a by b."""
+    poly = _rect_corners(a)
+    clip = _rect_corners(b)
+    for i in range(4):
+        p0, p1 = clip[i], clip[(i + 1) % 4]
+        edge = p1 - p0
+        out = []
+        for j in range(len(poly)):
+            q0, q1 = poly[j], poly[(j + 1) % len(poly)]
+            d0 = edge[0] * (q0[1] - p0[1]) - edge[1] * (q0[0] - p0[0])   # >= 0: left of the (counter-clockwise) edge = inside
+            d1 = edge[0] * (q1[1] - p0[1]) - edge[1] * (q1[0] - p0[0])
+            if d0 >= 0:
+                out.append(q0)
+            if (d0 >= 0) != (d1 >= 0):
+                out.append(q0 + (q1 - q0) * (d0 / (d0 - d1)))
+        poly = np.array(out) if out else np.zeros((0, 2))
+        if len(poly) == 0:
+            return 0.0
+    x, y = poly[:, 0], poly[:, 1]
+    inter = 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+    return inter / max(float(a[3]) * float(a[4]) + float(b[3]) * float(b[4]) - inter, 1e-8)
+
+
+def multiclass_nms(boxes, logits, score_thr, nms_thr, max_num, apply_sigmoid=True, margin=None):
+    """(boxes [n,D], scores [n], labels [n], source rows [n]); with `margin`, also whether any IoU that decided a
+    suppression or a survival lay within `margin` of nms_thr (then fp32 and fp64 may legitimately disagree)."""
+    boxes = np.asarray(boxes, F32)
+    x = np.asarray(logits, F32)
+    scores = (F32(1) / (F32(1) + np.exp(-x).astype(F32))).astype(F32) if apply_sigmoid else x
+    rows, sc, lb = [], [], []
+    close = False
+    for c in range(scores.shape[1]):
+        idx = np.flatnonzero(scores[:, c] > F32(score_thr))
+        idx = idx[np.lexsort((idx, -scores[idx, c].astype(np.float64)))]   # score desc, box index asc
+        kept = []
+        for i in idx:
+            ok = True
+            for j in kept:
+                v = rotated_iou_bev(boxes[j], boxes[i])
+                if margin is not None and abs(v - nms_thr) < margin:
+                    close = True
+                if v > nms_thr:
+                    ok = False
+                    break
+            if ok:
+                kept.append(i)
+        rows += kept
+        sc += [scores[i, c] for i in kept]
+        lb += [c] * len(kept)
+    rows, sc, lb = np.asarray(rows, np.int64), np.asarray(sc, F32), np.asarray(lb, np.int64)
+    if len(rows) > max_num:
+        order = np.lexsort((np.arange(len(sc)), -sc.astype(np.float64)))[:max_num]
+        rows, sc, lb = rows[order], sc[order], lb[order]
+    res = (boxes[rows], sc, lb, rows)
+    return res + (close,) if margin is not None else res

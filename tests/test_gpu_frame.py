@@ -240,3 +240,21 @@ def test_group_cluster_reference_golden(cuda):
     assert np.array_equal(N(rows), g["rows"])
     assert np.array_equal(np.stack([N(cls), np.zeros(len(g["rows"]), np.int64), N(clu)], 1), g["cluster_inds"])
     np.testing.assert_allclose(N(ctr), g["center_preds"], rtol=1e-5, atol=1e-5)
+
+
+def test_detections(cuda, frame):
+    """Forward → refine → get_bboxes: the final detections against decode + NMS of the oracle on the GPU's refined outputs."""
+    model, pts = frame["model"], frame["pts"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    with torch.no_grad():
+        st = model.refine(model(T(pts), T(frame["mask"]), T(frame["anno"]), T(frame["l2i"])), T(pts))
+        boxes, scores, labels = model.get_bboxes(st, score_thr=0.3, nms_thr=0.35, max_num=500)
+    rois = O.decode_boxes(N(st["refine0_reg"]), N(st["refine0_centers"]))
+    wb, ws, wl, wr, close = O.multiclass_nms(rois[:, 1:], N(st["refine0_cls"]), 0.3, 0.35, 500, margin=2e-4)
+    assert len(wb) > 0
+    if not close:   # no deciding IoU within 2e-4 of the threshold: the kept set is exact
+        assert np.array_equal(N(st["det_rows"]), wr) and np.array_equal(N(labels), wl)
+        np.testing.assert_allclose(N(scores), ws, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(N(boxes), wb, rtol=1e-5, atol=1e-5)
+    else:
+        assert abs(len(N(labels)) - len(wl)) <= 2

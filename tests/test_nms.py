@@ -1,0 +1,51 @@
+"""Multi-class rotated BEV NMS: oracle sanity on CPU, fsfb_nms_* parity on the GPU."""
+import numpy as np
+import pytest
+
+from oracle import fsf_oracle as O
+
+
+def _scene(k, c, seed):
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-30, 30, (max(3, k // 6), 2))
+    xy = centers[rng.integers(0, len(centers), k)] + rng.normal(0, 1.2, (k, 2))      # clumps: heavy overlap inside a clump
+    dims = rng.uniform([1.5, 3.5, 1.4], [2.2, 5.0, 2.0], (k, 3))
+    boxes = np.concatenate([xy, rng.uniform(-2, 0, (k, 1)), dims, rng.uniform(-np.pi, np.pi, (k, 1)), rng.normal(0, 1, (k, 2))], 1)
+    logits = rng.normal(-1.0, 2.0, (k, c))
+    return boxes.astype(np.float32), logits.astype(np.float32)
+
+
+def test_rotated_iou_oracle():
+    a = np.array([0, 0, 0, 4, 2, 1, 0.0])
+    assert abs(O.rotated_iou_bev(a, np.array([1, 0, 0, 4, 2, 1, 0.0])) - 0.6) < 1e-12
+    assert abs(O.rotated_iou_bev(a, np.array([0, 0, 0, 2, 4, 1, np.pi / 2])) - 1.0) < 1e-12
+    assert O.rotated_iou_bev(a, np.array([10, 0, 0, 4, 2, 1, 0.3])) == 0.0
+    b = np.array([0.3, -0.2, 0, 3, 1.5, 1, 0.7])
+    assert abs(O.rotated_iou_bev(a, b) - O.rotated_iou_bev(b, a)) < 1e-12   # symmetric
+    boxes, logits = _scene(60, 2, 0)
+    out = O.multiclass_nms(boxes, logits, 0.1, 0.35, 500)
+    assert len(out[0]) == len(out[1]) == len(out[2]) == len(out[3]) > 0
+    for c in range(2):   # survivors of a class do not overlap each other beyond the threshold, in descending score
+        rows = out[3][out[2] == c]
+        assert (np.diff(out[1][out[2] == c]) <= 0).all()
+        for i in range(len(rows)):
+            for j in range(i):
+                assert O.rotated_iou_bev(boxes[rows[j]], boxes[rows[i]]) <= 0.35
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,c,score_thr,max_num,seed", [(150, 3, 0.1, 500, 1), (200, 10, 0.01, 500, 2), (120, 2, 0.05, 20, 3),
+                                                        (50, 4, 0.999, 500, 4), (1, 1, 0.0, 5, 5), (300, 1, 0.2, 500, 6)])
+def test_multiclass_nms_parity(cuda, k, c, score_thr, max_num, seed):
+    import torch
+    from fullysparsefusion_b200 import ops
+    for attempt in range(12):   # a scene in which no deciding IoU sits within 2e-4 of the threshold (fp32 vs fp64)
+        boxes, logits = _scene(k, c, seed + 100 * attempt)
+        wb, ws, wl, wr, close = O.multiclass_nms(boxes, logits, score_thr, 0.35, max_num, margin=2e-4)
+        if not close:
+            break
+    assert not close
+    gb, gs, gl, gr = ops.multiclass_nms(torch.from_numpy(boxes).to(cuda), torch.from_numpy(logits).to(cuda), score_thr, 0.35, max_num)
+    assert np.array_equal(gr.cpu().numpy(), wr) and np.array_equal(gl.cpu().numpy(), wl)     # indices and labels bit-exact
+    np.testing.assert_allclose(gs.cpu().numpy(), ws, rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(gb.cpu().numpy(), wb)
