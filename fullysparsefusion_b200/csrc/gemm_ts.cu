@@ -866,10 +866,19 @@ int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t work
   }
   P.cpad = cpad;
   P.n_row_tiles = (int)ceil_div(P.rows, kTcRows);
-  static unsigned launch_seq = 0;
-  static unsigned sched_next[kTsSchedSlots] = {0};  // tickets drawn so far from each slot (wraps with the device counter)
-  P.sched_slot = (int)(launch_seq++ % kTsSchedSlots);
-  P.sched_base = sched_next[P.sched_slot];
+  // the counters are __device__ variables, i.e. one set per GPU: the host-side ticket bookkeeping is kept per device too
+  // (a process that launches on cuda:1 after cuda:0 must not carry cuda:0's totals over)
+  constexpr int kMaxDev = 64;
+  static unsigned launch_seq[kMaxDev] = {0};
+  static unsigned sched_next[kMaxDev][kTsSchedSlots] = {{0}};  // tickets drawn so far from each slot (wraps with the device counter)
+  int dev = 0;
+  FSFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) {
+    set_error("gather_gemm: device ordinal %d out of range", dev);
+    return FSFB_ERR_BADARG;
+  }
+  P.sched_slot = (int)(launch_seq[dev]++ % kTsSchedSlots);
+  P.sched_base = sched_next[dev][P.sched_slot];
   P.n_units = ceil_div(P.rows, kTcRows) * P.n_ct * P.splits;
   if (P.n_units >= (1ll << 31)) {
     set_error("gather_gemm: too many work units");
@@ -906,7 +915,7 @@ int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t work
     attr = true;
   }
   const unsigned grid = (unsigned)std::min<int64_t>(P.n_units, kNumSMs);
-  sched_next[P.sched_slot] += (unsigned)P.n_units + grid;
+  sched_next[dev][P.sched_slot] += (unsigned)P.n_units + grid;
   static const bool timed = [] { const char* e = getenv("FSFB_GEMM_TIMERS"); return e && atoi(e) != 0; }();
   // complete K chunks from 32-byte aligned rows: the 256-bit gather path
   const bool kfull = a_vec && P.cin % kGemmKChunk == 0 && P.cin <= kTsZeroRow && (uintptr_t)P.a % 32 == 0 && P.a_stride % 8 == 0;
