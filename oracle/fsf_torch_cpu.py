@@ -119,6 +119,132 @@ def sparse_conv(x, pairs, n_out, module, residual=None):
     return F.relu(out) if module.act else out
 
 
+# ---- query refinement + final boxes (FSF.py:960-1095, frustum_cluster_head.py:595-698) on the host ----------------
+def decode_boxes(reg, base):
+    """BasePointBBoxCoder.decode + the batch column of decode_stage_bboxes."""
+    dims = reg[:, 3:6].exp() - 1e-6
+    yaw = torch.atan2(reg[:, 6:7], reg[:, 7:8])
+    return torch.cat([reg.new_zeros((reg.size(0), 1)), reg[:, :3] + base[:, :3], dims, yaw, reg[:, 8:10]], 1)
+
+
+def dynamic_point_pool(rois7, pts, extra, max_inbox, capacity, chunk=64):
+    """dynamic_point_pool_ext.forward in canonical (roi, point) order (include/fsf_b200.h): brute force over roi chunks."""
+    out_p, out_r, out_f = [], [], []
+    total = 0
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    for r0 in range(0, rois7.size(0), chunk):
+        r = rois7[r0:r0 + chunk]
+        cosa, sina = torch.cos(-r[:, 6:7]), torch.sin(-r[:, 6:7])
+        sx, sy, lz = x[None] - r[:, 0:1], y[None] - r[:, 1:2], z[None] - r[:, 2:3]
+        lx = sx * cosa + sy * (-sina)
+        ly = sx * sina + sy * cosa
+        hl, hw, hh = r[:, 4:5] * 0.5, r[:, 3:4] * 0.5, r[:, 5:6] * 0.5
+        el, ew, eh = (r[:, 4:5] + extra[0]) * 0.5, (r[:, 3:4] + extra[1]) * 0.5, (r[:, 5:6] + extra[2]) * 0.5
+        hit = (lz.abs() <= eh) & (lx > -el) & (lx < el) & (ly > -ew) & (ly < ew)
+        for j in range(r.size(0)):
+            idx = torch.nonzero(hit[j])[:, 0][:max_inbox]
+            idx = idx[: max(0, capacity - total)]
+            if idx.numel() == 0:
+                continue
+            total += idx.numel()
+            a, b, c = lx[j, idx], ly[j, idx], lz[j, idx]
+            inner = (a.abs() < hl[j]) & (b.abs() < hw[j]) & (c.abs() <= hh[j])
+            out_f.append(torch.stack([x[idx], y[idx], z[idx], a, b, c, a + hl[j], b + hw[j], c + hh[j], hl[j] - a, hw[j] - b, hh[j] - c,
+                                      (~inner).float()], 1))
+            out_p.append(idx)
+            out_r.append(torch.full_like(idx, r0 + j))
+    if not out_p:
+        return (torch.full((1,), -1, dtype=torch.long), torch.full((1,), -1, dtype=torch.long), torch.zeros((1, 13)))
+    return torch.cat(out_p), torch.cat(out_r), torch.cat(out_f)
+
+
+def _corners(b):
+    """[n,4,2] counter-clockwise corners of BEV rectangles (x, y, dx, dy, yaw) in float64."""
+    c, s = np.cos(b[:, 4]), np.sin(b[:, 4])
+    sx = np.stack([b[:, 2], -b[:, 2], -b[:, 2], b[:, 2]], 1) * 0.5
+    sy = np.stack([b[:, 3], b[:, 3], -b[:, 3], -b[:, 3]], 1) * 0.5
+    return np.stack([b[:, 0:1] + sx * c[:, None] - sy * s[:, None], b[:, 1:2] + sx * s[:, None] + sy * c[:, None]], 2)
+
+
+def rotated_iou_pairs(a, b):
+    """IoU of rectangle pairs a[i] / b[i] ([P,5] = x, y, dx, dy, yaw): Sutherland-Hodgman clipping vectorised over the
+    pairs (polygons of at most 8 vertices in fixed-size buffers with a per-pair vertex count)."""
+    P = a.shape[0]
+    poly = np.zeros((P, 8, 2))
+    poly[:, :4] = _corners(a)
+    cnt = np.full(P, 4)
+    clip = _corners(b)
+    ar = np.arange(P)
+    for e in range(4):
+        p0, edge = clip[:, e], clip[:, (e + 1) % 4] - clip[:, e]
+        new = np.zeros((P, 8, 2))
+        ncnt = np.zeros(P, dtype=np.int64)
+        for j in range(8):
+            live = j < cnt
+            q0 = poly[:, j]
+            q1 = poly[ar, np.where(j + 1 < cnt, j + 1, 0)]
+            d0 = edge[:, 0] * (q0[:, 1] - p0[:, 1]) - edge[:, 1] * (q0[:, 0] - p0[:, 0])
+            d1 = edge[:, 0] * (q1[:, 1] - p0[:, 1]) - edge[:, 1] * (q1[:, 0] - p0[:, 0])
+            keep = live & (d0 >= 0)
+            sel = np.flatnonzero(keep & (ncnt < 8))
+            new[sel, ncnt[sel]] = q0[sel]
+            ncnt[sel] += 1
+            cross = live & ((d0 >= 0) != (d1 >= 0))
+            sel = np.flatnonzero(cross & (ncnt < 8))
+            t = d0[sel] / (d0[sel] - d1[sel])
+            new[sel, ncnt[sel]] = q0[sel] + (q1[sel] - q0[sel]) * t[:, None]
+            ncnt[sel] += 1
+        poly, cnt = new, ncnt
+    nxt = np.where(np.arange(8)[None] + 1 < cnt[:, None], np.arange(8)[None] + 1, 0)
+    x, y = poly[:, :, 0], poly[:, :, 1]
+    xn, yn = np.take_along_axis(x, nxt, 1), np.take_along_axis(y, nxt, 1)
+    valid = np.arange(8)[None] < cnt[:, None]
+    inter = 0.5 * np.abs(((x * yn - xn * y) * valid).sum(1))
+    return inter / np.maximum(a[:, 2] * a[:, 3] + b[:, 2] * b[:, 3] - inter, 1e-8)
+
+
+def multiclass_nms(boxes, logits, score_thr, nms_thr, max_num):
+    """box3d_multiclass_nms with rotated BEV IoU on sigmoid(logits): candidate pairs pre-filtered by centre distance, IoUs
+    vectorised, greedy pass per class in (score desc, box index asc) order."""
+    scores = torch.sigmoid(logits).numpy()
+    bx = boxes.numpy().astype(np.float64)
+    bev = bx[:, [0, 1, 3, 4, 6]]
+    rad = 0.5 * np.hypot(bev[:, 2], bev[:, 3])
+    rows, sc, lb = [], [], []
+    for c in range(scores.shape[1]):
+        idx = np.flatnonzero(scores[:, c] > np.float32(score_thr))
+        if idx.size == 0:
+            continue
+        idx = idx[np.lexsort((idx, -scores[idx, c].astype(np.float64)))]
+        b = bev[idx]
+        n = idx.size
+        sup = [[] for _ in range(n)]            # sup[i]: later boxes that i suppresses
+        for r0 in range(0, n, 512):
+            d = np.hypot(b[r0:r0 + 512, None, 0] - b[None, :, 0], b[r0:r0 + 512, None, 1] - b[None, :, 1])
+            near = d < (rad[idx][r0:r0 + 512, None] + rad[idx][None, :])
+            ii, jj = np.nonzero(near)
+            ii += r0
+            m = jj > ii
+            ii, jj = ii[m], jj[m]
+            if ii.size:
+                hitp = rotated_iou_pairs(b[ii], b[jj]) > nms_thr
+                for i, j in zip(ii[hitp], jj[hitp]):
+                    sup[i].append(j)
+        removed = np.zeros(n, bool)
+        for i in range(n):
+            if not removed[i]:
+                rows.append(idx[i])
+                sc.append(scores[idx[i], c])
+                lb.append(c)
+                if sup[i]:
+                    removed[sup[i]] = True
+    rows, sc, lb = np.asarray(rows, np.int64), np.asarray(sc, np.float32), np.asarray(lb, np.int64)
+    if rows.size > max_num:
+        order = np.lexsort((np.arange(rows.size), -sc.astype(np.float64)))[:max_num]
+        rows, sc, lb = rows[order], sc[order], lb[order]
+    return boxes[torch.from_numpy(rows)], torch.from_numpy(sc), torch.from_numpy(lb), torch.from_numpy(rows)
+
+
 class CpuFSF:
     def __init__(self, model):
         self.m = model
@@ -226,6 +352,7 @@ class CpuFSF:
             valid = ids_sel >= 1
             preds[valid] = mask_anno[ids_sel[valid] - 1]                             # get_all_cls_preds_2d
             img_feat = seq(m.segmentor_updated_mlp, preds[..., 4])
+            st["img_scores"] = preds[..., 4]
             feats = st["pts_lidar_feats"] + img_feat
             h = seq(m.segmentation_head.pre_seg_conv, feats)
             logits, votes = m.segmentation_head.conv_seg(h), m.segmentation_head.voting(h)
@@ -263,7 +390,7 @@ class CpuFSF:
             box[:, 1::2] /= mask_data.shape[-2]
             enc = torch.cat([box, pr[:, 4:5], F.one_hot(pr[:, 5].long(), m.num_classes + 1).float()], 1)
             obj = torch.cat([cl, seq(m.encode_2d_mlp, enc)], 1)
-            st.update(frustum_obj_feats=obj, frustum_out=head(m.frustum_obj_head, obj))
+            st.update(frustum_obj_feats=obj, frustum_out=head(m.frustum_obj_head, obj), frustum_centers=center)
 
         def fsd():
             pts5 = points[:, :5]
@@ -297,10 +424,49 @@ class CpuFSF:
             feats = torch.cat([v["l"][rows], v["v"][rows], v["f"][rows]], 1)
             cxyz, _, inv = scatter_v2(ctrs, inds, "avg")
             _, cl, _ = sir(m.backbone, v["p"][rows], feats, inds, v["p"][rows, :3] - cxyz[inv])
-            st.update(fsd_obj_feats=cl, fsd_out=head(m.bbox_head, cl), fsd_rows=rows)
+            st.update(fsd_obj_feats=cl, fsd_out=head(m.bbox_head, cl), fsd_rows=rows, fsd_centers=cxyz)
 
         def combine():
             st["obj_feats"] = torch.cat([seq(m.combine_frustum_feat_mlp, st["frustum_obj_feats"]),
                                          seq(m.combine_fsd_feat_mlp, st["fsd_obj_feats"])], 0)
 
+        def refine():
+            # each_stage_refine / query_feat_refine (FSF.py:1009-1083), one extra stage
+            pts5 = points[:, :5]
+            centers = torch.cat([st["frustum_centers"], st["fsd_centers"]], 0)
+            reg = torch.cat([st["frustum_out"][1], st["fsd_out"][1]], 0)
+            res = st["obj_feats"]
+            for i in range(m.num_extra_stages):
+                rois = decode_boxes(reg, centers)
+                centers = rois[:, 1:4]
+                inds, roi_inds, info = dynamic_point_pool(rois[:, 1:8], pts5[:, :3], m.roi_extractor.extra_wlh, m.roi_extractor.max_inbox_point,
+                                                          m.roi_extractor.max_all_pts)
+                ex_pts, ex_feats = pts5[inds], st["seg_feats"][inds]
+                feats = torch.cat([ex_feats, seq(m.refine_img_mlp[i], st["img_scores"][inds])], 1)
+                head_i = m.refine_sir_layers[i]
+                rel_xyz = ex_pts[:, :3] - centers[roi_inds]
+                f_cluster = torch.cat([info[:, 3:6], info[:, 6:12], info[:, 12:13], rel_xyz], 1)
+                unq, inv = torch.unique(roi_inds[:, None], return_inverse=True, dim=0)
+                out, cl = feats, []
+                for block in head_i.block_list:
+                    out, c = sir_layer(block, torch.cat([ex_pts, out, f_cluster / 10], 1), inv, unq, f_cluster)
+                    cl.append(c)
+                cl = torch.cat(cl, 1)
+                lidar = torch.zeros((rois.size(0), cl.size(1)))
+                ok = unq[:, 0] >= 0
+                lidar[unq[ok, 0]] = cl[ok]
+                query = seq(m.out_proj[i], seq(m.lidar_img_mlp[i], lidar) + res + seq(m.position_encoder[i], centers))
+                cls, reg = head(m.frustum_refined_head[i], query)
+                res = query
+                st.update({f"refine{i}_rois": rois, f"refine{i}_pts_inds": inds, f"refine{i}_roi_inds": roi_inds, f"refine{i}_lidar_feat": lidar,
+                           f"refine{i}_query": query, f"refine{i}_cls": cls, f"refine{i}_reg": reg, f"refine{i}_centers": centers})
+
+        def boxes():
+            # FrustumClusterHead._get_bboxes_single (frustum_cluster_head.py:595-698): sigmoid, decode, rotated multi-class NMS
+            i = m.num_extra_stages - 1
+            rois = decode_boxes(st[f"refine{i}_reg"], st[f"refine{i}_centers"])
+            b, s_, l_, r_ = multiclass_nms(rois[:, 1:], st[f"refine{i}_cls"], 0.01, 0.35, 500)
+            st.update(det_boxes=b, det_scores=s_, det_labels=l_, det_rows=r_)
+
+        self.extra_stages = [("refine", refine), ("boxes", boxes)]
         return [("segment", segment), ("enhance", enhance), ("frustum", frustum), ("fsd", fsd), ("combine", combine)], st
