@@ -542,9 +542,100 @@ def main_heads():
     save("cluster_head_v2", x=x, cls=out["cls_logits"][0], reg=out["reg_preds"][0], **sd)
 
 
+def main_loading():
+    """The reference's own LoadMaskFromFiles (datasets/pipelines/loading.py:22-339: load_nusc, load_argo + resize_img,
+    load_waymo + resize_img_waymo, reorg_anno_*) on sample directories written in the format of
+    tools/mask_tools/save_mask_nusc.py:138-171 (`python tools/make_golden.py loading`).  The sample directories are committed
+    under tests/golden/mask_samples/ (they are the INPUT fixtures); the outputs go to tests/golden/mask_loading.npz — full
+    planes for the small nuScenes sample, sha256 + strided rows for the full-size AV2 / Waymo stacks."""
+    import copy
+    import hashlib
+
+    from fullysparsefusion_b200 import loading as L
+    from fullysparsefusion_b200 import synth
+
+    import_reference()
+    ref = importlib.import_module("projects.mmdet3d_plugin.datasets.pipelines.loading")
+    root = os.path.join(OUT, "mask_samples")
+    out = {}
+
+    # nuScenes layout: 6 cameras x 10 classes, no resize
+    mask = synth.mask_planes(6, 10, 90, 160, seed=61, n_obj=120)
+    anno = synth.mask_anno(mask, seed=61, n_obj=250)
+    L.write_mask_sample(os.path.join(root, "nusc", "tok0"), mask, anno)
+    L.write_mask_sample(os.path.join(root, "nusc", "empty"), np.zeros((6, 10, 45, 80), np.uint8), np.zeros((0, 9), np.float32))
+    loader = ref.LoadMaskFromFiles(os.path.join(root, "nusc"))
+    for tok in ("tok0", "empty"):
+        res = loader(dict(sample_idx=tok))
+        out[f"nusc_{tok}_mask"] = res["mask_data"]
+        out[f"nusc_{tok}_anno"] = res["mask_anno"]
+        assert res["mask_data"].dtype == torch.uint8
+
+    def digest(t):
+        return np.frombuffer(hashlib.sha256(t.contiguous().numpy().tobytes()).digest(), dtype=np.uint8)
+
+    # AV2 layout: 7 single planes, the portrait front camera (2048 x 1550) resized to 1550 x 2048
+    rng = np.random.default_rng(62)
+    planes, rows = [], []
+    oid = 1
+    for cam in range(7):
+        H, W = (2048, 1550) if cam == 0 else (1550, 2048)
+        m = np.zeros((H, W), np.uint16)
+        for _ in range(12):
+            y0, x0 = int(rng.integers(0, H - 300)), int(rng.integers(0, W - 300))
+            h, w = int(rng.integers(20, 300)), int(rng.integers(20, 300))
+            m[y0:y0 + h, x0:x0 + w] = oid
+            rows.append([x0 + 0.25, y0 + 0.5, x0 + w - 0.25, y0 + h - 0.5, float(rng.uniform(0.3, 1)), int(rng.integers(0, 26)), cam, oid, 1])
+            oid += 1
+        planes.append(m)
+    sample = os.path.join(root, "argo", "uuid0")
+    os.makedirs(sample, exist_ok=True)
+    import cv2, json
+    anno = [[] for _ in range(7)]
+    for r in rows:
+        anno[r[6]].append(dict(bbox=r[:4], score=r[4], category=r[5], cam_id=r[6], obj_id=r[7]))
+    json.dump(anno, open(os.path.join(sample, "anno.json"), "w"), indent=2)
+    for cam, m in enumerate(planes):
+        cv2.imwrite(os.path.join(sample, f"{cam}.png"), m)
+    l2i = [synth.lidar2img(7, 1550, 2048)[c].astype(np.float64) for c in range(7)]
+    res = ref.LoadMaskFromFiles(os.path.join(root, "argo"), is_argo=True)(dict(img_info=dict(uuid="uuid0"), lidar2img=copy.deepcopy(l2i)))
+    out.update(argo_sha=digest(res["mask_data"]), argo_shape=np.array(res["mask_data"].shape), argo_anno=res["mask_anno"],
+               argo_l2i_in=np.stack(l2i), argo_l2i_out=np.stack(res["lidar2img"]), argo_rows=res["mask_data"][0, 0, ::97].clone(),
+               argo_cols=res["mask_data"][0, 0, :, ::89].clone())
+    assert res["mask_data"].dtype == torch.int32
+
+    # Waymo layout: 5 cameras x 3 classes, side cameras 886 x 1920 resized to 1280 x 1920
+    rows = []
+    oid = 1
+    sample = os.path.join(root, "waymo", "0001234")
+    os.makedirs(sample, exist_ok=True)
+    anno = [{n: [] for n in L.WAYMO_CLASSES} for _ in range(5)]
+    for cam in range(5):
+        H, W = (886, 1920) if cam >= 3 else (1280, 1920)
+        for ci, name in enumerate(L.WAYMO_CLASSES):
+            m = np.zeros((H, W), np.uint8)
+            for _ in range(5):
+                y0, x0 = int(rng.integers(0, H - 200)), int(rng.integers(0, W - 200))
+                h, w = int(rng.integers(10, 200)), int(rng.integers(10, 200))
+                m[y0:y0 + h, x0:x0 + w] = oid
+                anno[cam][name].append(dict(bbox=[x0 + 0.5, y0 + 0.25, x0 + w - 0.5, y0 + h - 0.25], score=float(rng.uniform(0.3, 1)),
+                                            category=ci, cam_id=cam, obj_id=oid))
+                oid += 1
+            cv2.imwrite(os.path.join(sample, f"{cam}_{name}.png"), m)
+    json.dump(anno, open(os.path.join(sample, "anno.json"), "w"), indent=2)
+    l2i = [synth.lidar2img(5, 1280, 1920)[c].astype(np.float64) for c in range(5)]
+    res = ref.LoadMaskFromFiles(os.path.join(root, "waymo"), is_waymo=True)(
+        dict(pts_filename="data/waymo/training/velodyne/0001234.bin", lidar2img=copy.deepcopy(l2i)))
+    out.update(waymo_sha=digest(res["mask_data"]), waymo_shape=np.array(res["mask_data"].shape), waymo_anno=res["mask_anno"],
+               waymo_l2i_in=np.stack(l2i), waymo_l2i_out=np.stack(res["lidar2img"]), waymo_rows=res["mask_data"][3:, :, ::61].clone())
+    save("mask_loading", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "heads":
         main_heads()
+    elif len(sys.argv) > 1 and sys.argv[1] == "loading":
+        main_loading()
     elif len(sys.argv) > 1 and sys.argv[1] == "misc":
         main_misc()
     elif len(sys.argv) > 1 and sys.argv[1] == "refine":
