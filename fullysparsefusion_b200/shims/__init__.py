@@ -5,8 +5,9 @@
     import projects.mmdet3d_plugin   # the plugin's `import torch_scatter` etc. now bind to the B200 path
 
 Every function is a thin wrapper over the C-ABI ops (no torch arithmetic on the hot path, no CPU
-fallback: CPU tensors raise).  Forward/inference only in this round — tensors that require grad raise
-NotImplementedError (training backward is SURVEY.md §8f row 4).
+fallback: CPU tensors raise).  torch_scatter carries autograd (torch_scatter's own gradient rules); the other shims return
+index tensors, which are non-differentiable upstream too.  The rest of training backward (sparse-conv dgrad / wgrad, SyncBN
+statistics) is SURVEY.md §8f row 4 and not built.
 """
 from __future__ import annotations
 
