@@ -1,6 +1,8 @@
 // gemm_common.cuh — packed-weight layout and the fused epilogue shared by the tensor-core
 // gather-GEMM (gemm_tc.cu), its CUDA-core cross-check (gemm_simt.cu) and fsfb_rownorm_act.
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fsfb {
@@ -33,7 +35,34 @@ struct GemmShape {
   __host__ __device__ size_t total_bytes() const {
     return tile_base(n_tiles() - 1) + (size_t)koff * kc() * block_bytes(n_tiles() - 1);
   }
+  // ---- fp16-split copy of the same blocks (experimental, FSFB_GEMM_F16=1): appended after the tf32 blocks ----
+  // Block (nt,k,kc) holds n_w rows of 128 bytes: halves [0,32) = fp16(w) of the chunk's 32 inputs, halves [32,64) =
+  // fp16((w - hi) * 2048), 16-byte chunks swizzled like the tf32 rows.
+  __host__ __device__ size_t f16_block_bytes(int nt) const { return (size_t)n_w(nt) * 128; }
+  __host__ __device__ size_t f16_tile_base(int nt) const { return total_bytes() + (size_t)nt * koff * kc() * kGemmNTile * 128; }
+  __host__ __device__ size_t f16_block_offset(int nt, int k, int kchunk) const {
+    return f16_tile_base(nt) + ((size_t)k * kc() + kchunk) * f16_block_bytes(nt);
+  }
+  __host__ __device__ size_t total_bytes_f16() const {
+    return f16_tile_base(n_tiles() - 1) + (size_t)koff * kc() * f16_block_bytes(n_tiles() - 1);
+  }
 };
+
+// byte offset of half j (0..63: 32 hi then 32 scaled lo) of row n inside an fp16-split block
+__host__ __device__ inline uint32_t sw128_offset_f16(int n, int j) {
+  return (uint32_t)n * 128u + (uint32_t)((((j >> 3) ^ (n & 7)) << 4) | ((j & 7) << 1));
+}
+constexpr float kF16LoScale = 2048.f;  // residuals are stored times 2^11 (keeps them in fp16's normal range); exact to undo
+
+// FSFB_GEMM_F16=1 (experimental): fsfb_gemm_prepack also writes the fp16-split blocks and the persistent gather-GEMM runs
+// kind::f16 MMAs on them (same 22-bit split precision as 3xTF32 at twice the tensor rate; inputs must stay below 65504).
+inline bool gemm_f16_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FSFB_GEMM_F16");
+    return e && atoi(e) != 0;
+  }();
+  return on;
+}
 
 // byte offset of element (n, j) inside a [rows][32 float] SWIZZLE_128B K-major block
 __host__ __device__ inline uint32_t sw128_offset(int n, int j) {

@@ -1,5 +1,7 @@
 // gemm_simt.cu — weight pre-packing, the standalone row norm/activation kernel, and the CUDA-core
 // fp32 cross-check of the gather-GEMM contract (tests only; the product path is gemm_tc.cu).
+#include <cuda_fp16.h>
+
 #include "gemm_common.cuh"
 
 namespace fsfb {
@@ -26,6 +28,29 @@ __global__ void __launch_bounds__(256)
     const uint32_t off = sw128_offset(nl, j);
     *reinterpret_cast<float*>(blk + off) = hi;
     *reinterpret_cast<float*>(blk + (size_t)S.n_w(nt) * 128 + off) = lo;
+  }
+}
+
+// fp16-split copy (FSFB_GEMM_F16=1): same walk, one 128-byte row per (n, K chunk) = [hi 32 halves | lo * 2048 32 halves]
+__global__ void __launch_bounds__(256)
+    k_gemm_prepack_f16(const float* __restrict__ w, GemmShape S, unsigned char* __restrict__ packed) {
+  const int kc = S.kc();
+  const int64_t per_k = (int64_t)S.n_pad() * kc * kGemmKChunk;
+  const int64_t total = per_k * S.koff;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(t / per_k);
+    int64_t r = t - (int64_t)k * per_k;
+    const int n = (int)(r / (kc * kGemmKChunk));
+    const int i = (int)(r - (int64_t)n * kc * kGemmKChunk);
+    const int kchunk = i / kGemmKChunk, j = i % kGemmKChunk;
+    const int nt = n / kGemmNTile, nl = n % kGemmNTile;
+    const float v = (n < S.cout && i < S.cin) ? w[((int64_t)k * S.cout + n) * S.cin + i] : 0.f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kF16LoScale);
+    unsigned char* blk = packed + S.f16_block_offset(nt, k, kchunk);
+    *reinterpret_cast<__half*>(blk + sw128_offset_f16(nl, j)) = hi;
+    *reinterpret_cast<__half*>(blk + sw128_offset_f16(nl, 32 + j)) = lo;
   }
 }
 
@@ -86,7 +111,7 @@ int fsfb_gemm_prepack_bytes(int koff, int cin, int cout, size_t* bytes) {
   using namespace fsfb;
   FSFB_CHECK_ARG(bytes && koff >= 1 && cin >= 1 && cout >= 1, "gemm_prepack_bytes: bad argument");
   GemmShape S{koff, cin, cout};
-  *bytes = S.total_bytes();
+  *bytes = gemm_f16_enabled() ? S.total_bytes_f16() : S.total_bytes();
   return FSFB_OK;
 }
 
@@ -98,6 +123,7 @@ int fsfb_gemm_prepack(const float* w, int koff, int cin, int cout, void* packed,
   const int64_t total = (int64_t)S.n_pad() * S.kc() * kGemmKChunk * koff;
   const int grid = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
   FSFB_LAUNCH(k_gemm_prepack, grid, 256, 0, (cudaStream_t)stream, w, S, (unsigned char*)packed);
+  if (gemm_f16_enabled()) FSFB_LAUNCH(k_gemm_prepack_f16, grid, 256, 0, (cudaStream_t)stream, w, S, (unsigned char*)packed);
   return FSFB_OK;
 }
 

@@ -31,6 +31,8 @@
 // (the 1 k- and 11 k-row levels of the U-Net, the 1024-wide cluster heads).
 #include <cstdlib>
 
+#include <cuda_fp16.h>
+
 #include "gemm_tc_ptx.cuh"
 
 namespace fsfb {
@@ -76,6 +78,23 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       "}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// kind::f16 twin (fp16-split operands, FSFB_GEMM_F16=1): A = 128 x 16 halves in 8 TMEM columns, B = 16 halves per row
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), K-major both
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
 }
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -163,7 +182,7 @@ __device__ __forceinline__ bool ts_unit(const TcParams& P, uint32_t u, TsUnit& U
 // per tcgen05.ld pair.  NORM / ACT / POST are compile-time so that a fully unrolled instance (UNROLL) is a few hundred
 // instructions whose vector operands are constant-bank immediates — no load instruction of any kind (measured: the same
 // body rolled, with ld.const indexing, was no faster than shared-memory vectors; GELU layers therefore keep that path).  Leaves the finished row in the staging row `my_row`; arrives on `acc_empty_bar` after the last TMEM read.
-template <int NORM, int ACT, bool POST, bool UNROLL>
+template <int NORM, int ACT, bool POST, bool UNROLL, bool F16 = false>
 __device__ __forceinline__ void ts_epi32(const TcParams& P, uint32_t t_row, uint32_t acc_cols, uint32_t my_row, int c_n, int n_sub,
                                          bool have_acc, bool use_res, bool valid, uint32_t acc_empty_bar, int lane) {
   float v[32];
@@ -172,8 +191,13 @@ __device__ __forceinline__ void ts_epi32(const TcParams& P, uint32_t t_row, uint
       float c2[32];
       tc_ld32(t_row + cb, v);
       tc_ld32(t_row + acc_cols + cb, c2);
+      if constexpr (F16) {  // the correction products carry the 2^11 of the scaled residuals
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) v[jj] += c2[jj];
+        for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(c2[jj], 1.f / kF16LoScale, v[jj]);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) v[jj] += c2[jj];
+      }
     } else {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
@@ -246,7 +270,10 @@ __device__ __forceinline__ void ts_epi32(const TcParams& P, uint32_t t_row, uint
 #define TS_ACC(var) do { if (TIMED) { const uint32_t t1_ = (uint32_t)clock(); var += t1_ - t0_; t0_ = t1_; } } while (0)
 // HV: the per-channel epilogue vectors travel in the kernel parameters (cout <= 128, host copies given): the epilogue reads
 // them as constant-bank operands of its FMAs, i.e. with no load instruction at all
-template <bool AVEC, bool KFULL, bool TIMED = false, bool HV = false>
+// F16 (FSFB_GEMM_F16=1, needs KFULL): fp16-split operands — a = hi + lo / 2048 with hi = fp16(a), lo = fp16((a - hi) * 2048),
+// the same 22 mantissa bits as the tf32 split — through kind::f16 MMAs (K = 16 per instruction, so 6 instead of 12 per stage
+// and half the TMEM / shared-memory operand bytes); the correction accumulator is scaled back by 2^-11 in the epilogue.
+template <bool AVEC, bool KFULL, bool TIMED = false, bool HV = false, bool F16 = false>
 __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -382,6 +409,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
       // hi = x with the 13 low mantissa bits cleared (what the tensor core keeps of a tf32 operand),
       // lo = x - hi exactly (the MMA truncates it to tf32 itself): 2 ALU ops per element
       // (two halves of 16 columns each keep the transient registers at 16)
+      if constexpr (F16) {
+        // column c of the hi half holds the chunk's inputs (2c, 2c+1) as fp16 (low half = even input); the lo half holds
+        // (x - hi) * 2048, exact in fp32 before its own rounding to fp16
+        uint32_t t16[16];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const __half2 h0 = __floats2half2_rn(cur[jj].x, cur[jj].y), h1 = __floats2half2_rn(cur[jj].z, cur[jj].w);
+          t16[2 * jj + 0] = *reinterpret_cast<const uint32_t*>(&h0);
+          t16[2 * jj + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        tc_st16(ta, t16);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&t16[2 * jj + 0]));
+          const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&t16[2 * jj + 1]));
+          const __half2 l0 = __floats2half2_rn((cur[jj].x - b0.x) * kF16LoScale, (cur[jj].y - b0.y) * kF16LoScale);
+          const __half2 l1 = __floats2half2_rn((cur[jj].z - b1.x) * kF16LoScale, (cur[jj].w - b1.y) * kF16LoScale);
+          t16[2 * jj + 0] = *reinterpret_cast<const uint32_t*>(&l0);
+          t16[2 * jj + 1] = *reinterpret_cast<const uint32_t*>(&l1);
+        }
+        tc_st16(ta + 16, t16);
+      } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t t16[16];
@@ -401,6 +450,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
           t16[4 * jj + 3] = __float_as_uint(cur[4 * h + jj].w - __uint_as_float(t16[4 * jj + 3]));
         }
         tc_st16(ta + 32 + 16 * h, t16);
+      }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
@@ -447,7 +497,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
         const int n_sub = __shfl_sync(0xffffffffu, U.n_sub, 0);
         if (lane == 0) mbar_arrive(smem_u32(&sh->nbr_empty[iter & 1]));
         const int n_active = __popc(m) * kc_n;
-        const uint32_t idesc = make_idesc_tf32(n_sub);
+        const uint32_t idesc = F16 ? make_idesc_f16(n_sub) : make_idesc_tf32(n_sub);
         if (iter > 0) {  // the epilogue has read the previous unit's accumulators out of TMEM
           mbar_wait(smem_u32(&sh->acc_empty), (uint32_t)(iter - 1) & 1u);
           tc_fence_after();
@@ -468,6 +518,23 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
           uint32_t elected;
           asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
           if (elected) {
+            if constexpr (F16) {
+              // slot layout: A hi in columns [0,16), lo in [16,32); W rows = [hi 64 bytes | lo 64 bytes]; two K = 16 steps
+              if (!(P.debug & 4)) {
+                const uint32_t a_lo16 = a_hi + 16;
+                if (is_main) {
+#pragma unroll
+                  for (int kk = 0; kk < 2; ++kk)
+                    tc_mma_f16_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int kk = 0; kk < 2; ++kk) {
+                    tc_mma_f16_ts(d_acc, a_lo16 + 8 * kk, make_sw128_desc(w_hi + 32u * kk), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                    tc_mma_f16_ts(d_acc, a_hi + 8 * kk, make_sw128_desc(w_hi + 64u + 32u * kk), idesc, 1u);
+                  }
+                }
+              }
+            } else
             if (!(P.debug & 4)) {
               if (is_main) {
 #pragma unroll
@@ -518,6 +585,12 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
         for (int it = 0; it < n_active; ++it) {
           mbar_wait(smem_u32(&sh->a_empty[s]), ph ^ 1u);
           const int want = (U.ct * P.koff + c.k) * kc_n + c.kc;
+          if (F16 && tag[s] != want && !(P.debug & 2)) {  // one 128-byte row per output channel holds hi and lo
+            const unsigned char* blk = P.w_packed + P.S.f16_block_offset(nt256, c.k, c.kc) + sub_off;
+            mbar_expect_tx(smem_u32(&sh->a_full[s]), sub_bytes);
+            bulk_g2s(base + (uint32_t)s * kTsWSlotBytes, blk, sub_bytes, smem_u32(&sh->a_full[s]));
+            tag[s] = want;
+          }
           if (tag[s] != want && !(P.debug & 2)) {
             const unsigned char* blk = P.w_packed + P.S.block_offset(nt256, c.k, c.kc) + sub_off;
             const uint32_t dst = base + (uint32_t)s * kTsWSlotBytes;
@@ -665,7 +738,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
         const int nrm = (HV && fused) ? E.norm : FSFB_NORM_NONE;
         const int ac = (HV && fused) ? act : FSFB_ACT_NONE;
         const int cn = (HV && fused) ? c_n : 0;  // raw sums (offset splits): no column is finished here
-#define TS_EPI(N, A, PO, UN) ts_epi32<N, A, PO, UN>(P, t_row, acc_cols, my_row, cn, U.n_sub, have_acc, use_res, valid, ae, lane)
+#define TS_EPI(N, A, PO, UN) ts_epi32<N, A, PO, UN, F16>(P, t_row, acc_cols, my_row, cn, U.n_sub, have_acc, use_res, valid, ae, lane)
         if (ac == FSFB_ACT_RELU) {
           if (nrm == FSFB_NORM_LAYERNORM) { if (post) TS_EPI(FSFB_NORM_LAYERNORM, FSFB_ACT_RELU, true, true); else TS_EPI(FSFB_NORM_LAYERNORM, FSFB_ACT_RELU, false, true); }
           else if (nrm == FSFB_NORM_AFFINE) { if (post) TS_EPI(FSFB_NORM_AFFINE, FSFB_ACT_RELU, true, true); else TS_EPI(FSFB_NORM_AFFINE, FSFB_ACT_RELU, false, true); }
@@ -688,7 +761,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) k_gather_gemm_ts(const __grid_c
         if (have_acc) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) v[jj] = __uint_as_float(a[jj]) + __uint_as_float(b[jj]);
+          for (int jj = 0; jj < 8; ++jj)
+            v[jj] = F16 ? fmaf(__uint_as_float(b[jj]), 1.f / kF16LoScale, __uint_as_float(a[jj])) : __uint_as_float(a[jj]) + __uint_as_float(b[jj]);
         } else {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) v[jj] = 0.f;
@@ -934,6 +1008,18 @@ int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t work
       FSFB_LAUNCH((k_gather_gemm_ts<true, true, true, true>), grid, kTsThreads, smem, st, P);
     } else {
       FSFB_LAUNCH((k_gather_gemm_ts<true, true, true, false>), grid, kTsThreads, smem, st, P);
+    }
+  } else if (kfull && gemm_f16_enabled()) {  // experimental fp16-split operands; P.w_packed carries the extra blocks (same switch)
+    static bool attr16 = false;
+    if (!attr16) {
+      FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, true, false, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ts<true, true, false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+      attr16 = true;
+    }
+    if (hv) {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true, false, true, true>), grid, kTsThreads, smem, st, P);
+    } else {
+      FSFB_LAUNCH((k_gather_gemm_ts<true, true, false, false, true>), grid, kTsThreads, smem, st, P);
     }
   } else if (kfull) {
     if (hv) {
