@@ -47,13 +47,17 @@ def parse():
     ap.add_argument("--points", type=int, default=300000)
     ap.add_argument("--sweeps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scope", default="hot", choices=["hot", "full"],
+                    help="hot: segment → combine (the driver's default, the measured scope); full: + query refinement and final "
+                         "boxes (decode + rotated NMS) on both arms")
     return ap.parse_args()
 
 
 def workload(args):
     return {"workload": f"FSF_nuScenes_config {args.sweeps}-sweep frame: {args.points} pts x 6 cams @1600x900, "
                         "10 class id planes (BASELINE configs[2] shape, one frame per GPU per step)",
-            "points": args.points, "sweeps": args.sweeps, "cams": 6, "classes": 10, "frames_per_step_per_gpu": 1}
+            "points": args.points, "sweeps": args.sweeps, "cams": 6, "classes": 10, "frames_per_step_per_gpu": 1,
+            "scope": "segment..combine" if args.scope == "hot" else "segment..combine + refine + boxes"}
 
 
 class ClockSampler:
@@ -155,6 +159,8 @@ def run_cpu_port(args, steps: int, warmup: int, model=None, frame=None):
     with torch.no_grad():
         for it in range(warmup + steps):
             stages, st = cpu.stages(frame["points"], frame["mask"], frame["anno"], frame["lidar2img"])
+            if args.scope == "full":
+                stages = stages + cpu.extra_stages
             t0 = time.perf_counter()
             for name, fn in stages:
                 t = time.perf_counter()
@@ -248,6 +254,8 @@ def main():
     def step(i, events=None):
         f = frames[i % n_frames]
         stages, st = model.stages(f["points"], f["mask"], f["anno"], f["lidar2img"])
+        if args.scope == "full":
+            stages = stages + [("refine", lambda: model.refine(st, f["points"])), ("boxes", lambda: model.get_bboxes(st))]
         for name, fn in stages:
             if events is not None:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
