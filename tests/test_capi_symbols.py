@@ -53,3 +53,22 @@ def test_ops_refuse_cpu_tensors():
         ops.voxelize(torch.zeros(4, 5), [0.2] * 3, [-1, -1, -1, 1, 1, 1])
     with pytest.raises(_capi.FsfbError):
         ops.unique_rows(torch.zeros(4, 3, dtype=torch.int64))
+
+
+def test_prepack_size_with_fp16_blocks():
+    """FSFB_GEMM_F16=1 (experimental, read once per process) appends the fp16-split blocks: half the bytes of the tf32 blocks."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import ctypes; from fullysparsefusion_b200 import _capi; lib = _capi.load(); n = ctypes.c_size_t(0); out = []\n"
+            "for k, ci, co in [(27, 128, 128), (1, 131, 11), (27, 64, 512), (1, 768, 1024)]:\n"
+            "    assert lib.fsfb_gemm_prepack_bytes(k, ci, co, ctypes.byref(n)) == 0; out.append(n.value)\n"
+            "print(*out)")
+    sizes = {}
+    for flag in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=str(REPO), env=dict(os.environ, FSFB_GEMM_F16=flag), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        sizes[flag] = [int(v) for v in r.stdout.split()]
+    assert all(b * 2 == a * 3 for a, b in zip(sizes["0"], sizes["1"])), sizes
