@@ -26,7 +26,10 @@ def _reference(src, index, m, mode):
 
 def _check(device):
     g = torch.Generator().manual_seed(3)
-    for n, c, m, hi in [(500, 7, 40, 40), (300, 33, 64, 50), (64, 4, 5, 5), (1, 3, 4, 2)]:       # m > hi: trailing empty segments
+    cases = [(500, 7, 40, 40), (300, 33, 64, 50), (64, 4, 5, 5)]                                # m > hi: trailing empty segments
+    if device == "cpu":
+        cases.append((1, 3, 4, 2))
+    for n, c, m, hi in cases:
         src = torch.randn(n, c, generator=g).to(device)
         index = torch.randint(0, hi, (n,), generator=g).to(device)
         weight = torch.randn(m, c, generator=g).to(device)
