@@ -30,3 +30,51 @@ def max_over_ranks(values: torch.Tensor) -> torch.Tensor:
 def throughput(units_per_rank: int, world: int, max_seconds: float) -> float:
     """Whole-job units/s: all ranks' units over the slowest rank's time."""
     return units_per_rank * world / max_seconds
+
+
+# ---- training-side collectives (SURVEY.md section 2.3 / 8f rank 4: host logic only, no backward kernels yet) --------------------
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def coalesced_all_reduce(tensors: List[torch.Tensor], op=None) -> List[torch.Tensor]:
+    """ONE all-reduce for a list of same-dtype tensors (flatten → reduce → views copied back in place).  NVSwitch collectives are
+    launch-latency bound at these sizes, so k small reductions cost k latencies; one bucket costs one."""
+    if not tensors or _world() == 1:
+        return tensors
+    op = dist.ReduceOp.SUM if op is None else op
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=op)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return tensors
+
+
+def reduce_means(values: List[torch.Tensor]) -> List[torch.Tensor]:
+    """mmdet.core.reduce_mean for several scalars at once: the heads call it once per loss normaliser (sparse_cluster_head.py:142,160;
+    sparse_cluster_head_v2.py:235,251; frustum_cluster_head.py:184,203 — six or more single-float all-reduces per step upstream).
+    Returns new tensors = mean over ranks, inputs untouched, exactly as reduce_mean does for each."""
+    w = _world()
+    if w == 1 or not values:
+        return [v.clone() for v in values]
+    flat = torch.stack([v.detach().reshape(()).to(torch.float32) for v in values]) / w
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return [flat[i].to(values[i].dtype) for i in range(len(values))]
+
+
+def naive_sync_bn_stats(x: torch.Tensor):
+    """Batch statistics of `naiveSyncBN1d` in training mode [UPSTREAM-RECALL: the fork's class is detectron2's NaiveSyncBatchNorm for
+    1-d inputs]: per-rank mean and mean of squares concatenated into ONE [2C] vector, all-reduced, divided by the world size (ranks
+    weigh equally whatever their row counts), var = E[x^2] - E[x]^2.  Layers are sequentially dependent, so the [2C] vector per
+    layer is the coalescing limit in the forward pass.  Returns (mean [C], var [C])."""
+    assert x.dim() == 2 and x.size(0) > 0
+    c = x.size(1)
+    vec = torch.cat([x.mean(0), (x * x).mean(0)])
+    w = _world()
+    if w > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        vec = vec / w
+    mean, meansq = vec[:c], vec[c:]
+    return mean, meansq - mean * mean

@@ -23,8 +23,17 @@ def _worker(rank, world, port, out):
     fdist.max_over_ranks(t)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
+    # training-side collectives: one bucket for k reductions, reduce_mean for several scalars, naive sync-BN statistics
+    a, b = torch.full((3,), float(rank + 1)), torch.arange(4, dtype=torch.float32).view(2, 2) * (rank + 1)
+    fdist.coalesced_all_reduce([a, b])
+    scal = [torch.tensor(2.0 * rank), torch.tensor(10.0 + rank, dtype=torch.float64)]
+    means = fdist.reduce_means(scal)
+    x = torch.arange(6, dtype=torch.float32).view(3, 2) + 10 * rank if rank == 0 else torch.ones(5, 2) * 4
+    mu, var = fdist.naive_sync_bn_stats(x)
+    extra = dict(a=a.tolist(), b=b.tolist(), means=[float(m) for m in means], scal=[float(v) for v in scal],
+                 dtypes=[str(m.dtype) for m in means], mu=mu.tolist(), var=var.tolist())
     if rank == 0:
-        out.put((gathered, t.tolist(), [fdist.frame_seed(r, i) for r in range(world) for i in range(3)]))
+        out.put((gathered, t.tolist(), [fdist.frame_seed(r, i) for r in range(world) for i in range(3)], extra))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -36,7 +45,7 @@ def test_two_rank_sharding_and_max_timing():
     procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    gathered, t, seeds = out.get(timeout=120)
+    gathered, t, seeds, extra = out.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -45,9 +54,22 @@ def test_two_rank_sharding_and_max_timing():
     assert t == [11.0, 5.0]                                        # MAX over ranks
     assert len(set(seeds)) == len(seeds)                           # disjoint synthetic streams
     assert fdist.throughput(10, 2, 0.5) == 40.0
+    assert extra["a"] == [3.0] * 3 and extra["b"] == [[0.0, 3.0], [6.0, 9.0]]        # sums over the two ranks, shapes kept
+    assert extra["means"] == [1.0, 10.5] and extra["scal"] == [0.0, 10.0]            # means over ranks; inputs untouched
+    assert extra["dtypes"] == ["torch.float32", "torch.float64"]
+    # rank 0 rows [[0,1],[2,3],[4,5]] (mean [2,3], mean sq [20/3, 35/3]); rank 1 all 4 (mean 4, mean sq 16): equal rank weights
+    import numpy as np
+    np.testing.assert_allclose(extra["mu"], [3.0, 3.5], rtol=1e-6)
+    np.testing.assert_allclose(extra["var"], [(20 / 3 + 16) / 2 - 9.0, (35 / 3 + 16) / 2 - 12.25], rtol=1e-5)
 
 
 def test_single_process_is_identity():
     t = torch.tensor([3.0])
     assert fdist.max_over_ranks(t).item() == 3.0
     assert fdist.frame_ids(0, 1, 3) == [0, 1, 2]
+    v = [torch.tensor(2.0), torch.tensor(5.0)]
+    assert [float(m) for m in fdist.reduce_means(v)] == [2.0, 5.0]
+    x = torch.tensor([[1.0, 2.0], [3.0, 6.0]])
+    mu, var = fdist.naive_sync_bn_stats(x)
+    assert mu.tolist() == [2.0, 4.0] and var.tolist() == [1.0, 4.0]
+    assert fdist.coalesced_all_reduce([x])[0] is x
