@@ -33,6 +33,40 @@ def test_rotated_iou_oracle():
                 assert O.rotated_iou_bev(boxes[rows[j]], boxes[rows[i]]) <= 0.35
 
 
+def test_rotated_iou_three_independent_ways():
+    """The NMS oracle is 'parity unpinned' (mmdet3d's iou3d is un-vendored), so its IoU is cross-checked against two independent
+    computations: the vectorised fixed-buffer clipper of the CPU port (different code, same published algorithm) and a
+    rasterised area estimate (different algorithm altogether), plus a closed form."""
+    from oracle import fsf_torch_cpu as P
+
+    # unit square against its 45-degree rotation: the intersection is a regular octagon of area 2 (sqrt 2 - 1)
+    sq, rot = np.array([0, 0, 0, 1, 1, 1, 0.0]), np.array([0, 0, 0, 1, 1, 1, np.pi / 4])
+    inter = 2 * (np.sqrt(2) - 1)
+    assert abs(O.rotated_iou_bev(sq, rot) - inter / (2 - inter)) < 1e-12
+    boxes, _ = _scene(90, 1, 21)
+    ii, jj = np.triu_indices(90, 1)
+    want = np.array([O.rotated_iou_bev(boxes[i], boxes[j]) for i, j in zip(ii, jj)])
+    bev = boxes[:, [0, 1, 3, 4, 6]].astype(np.float64)
+    got = P.rotated_iou_pairs(bev[ii], bev[jj])
+    assert (want > 0).sum() > 200
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+
+    def inside(b, x, y):
+        c, s = np.cos(b[6]), np.sin(b[6])
+        lx, ly = (x - b[0]) * c + (y - b[1]) * s, -(x - b[0]) * s + (y - b[1]) * c
+        return (np.abs(lx) <= b[3] / 2) & (np.abs(ly) <= b[4] / 2)
+
+    pairs = np.flatnonzero(want > 0.05)[:40]
+    for p in pairs:
+        a, b = boxes[ii[p]].astype(np.float64), boxes[jj[p]].astype(np.float64)
+        r = 0.5 * max(np.hypot(a[3], a[4]), np.hypot(b[3], b[4])) + np.hypot(a[0] - b[0], a[1] - b[1])
+        g = np.linspace(-r, r, 700)
+        x, y = np.meshgrid(a[0] + g, a[1] + g)
+        ia, ib = inside(a, x, y), inside(b, x, y)
+        est = (ia & ib).sum() / max((ia | ib).sum(), 1)
+        assert abs(est - want[p]) < 0.01, (est, want[p])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("k,c,score_thr,max_num,seed", [(150, 3, 0.1, 500, 1), (200, 10, 0.01, 500, 2), (120, 2, 0.05, 20, 3),
                                                         (50, 4, 0.999, 500, 4), (1, 1, 0.0, 5, 5), (300, 1, 0.2, 500, 6)])
