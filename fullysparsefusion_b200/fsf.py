@@ -17,7 +17,7 @@ All arithmetic goes through the C-ABI ops; torch is used for allocation, views a
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Tuple
 
 import torch
 import torch.nn.functional as F

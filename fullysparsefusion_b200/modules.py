@@ -14,7 +14,7 @@ inputs, 2x128 cluster features per SIR block → 768, 34 sparse convolutions).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional
 
 import torch
 from torch import nn

@@ -6,7 +6,6 @@ import torch
 from fullysparsefusion_b200 import fsf as FSFM
 from fullysparsefusion_b200 import synth
 from oracle import fsf_oracle as O
-from oracle import fsf_oracle_frame as OF
 from oracle import fsf_oracle_models as OM
 from oracle import fsf_torch_cpu as P
 

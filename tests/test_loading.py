@@ -3,7 +3,6 @@
 tests/golden/mask_samples/ holds sample directories in the on-disk format of tools/mask_tools/save_mask_nusc.py;
 tests/golden/mask_loading.npz holds what the reference's loader (datasets/pipelines/loading.py) returned for them
 (tools/make_golden.py loading).  Planes and lidar2img are bit-exact; the annotation table is exact (same float32 rounding)."""
-import copy
 import hashlib
 import os
 

@@ -1,5 +1,5 @@
 """Per-shape time of the sparse convolutions in one FSF frame (B200)."""
-import os, sys, json, collections
+import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench

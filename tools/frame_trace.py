@@ -1,6 +1,6 @@
 """Kernel-level trace of one FSF frame (torch.profiler / CUPTI): GPU busy time vs elapsed per stage, top kernels.
 Not a bench: profiler overhead inflates host time; use the busy/elapsed ratio and the kernel sums only."""
-import os, sys, json, collections
+import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity, record_function
