@@ -177,6 +177,25 @@ class LoadMaskFromFiles:
         return self._table(rows)
 
 
+class SaveNoAugPoints:
+    """Pipeline step of the same name (loading.py:342-354): appends a copy of xyz to every point, `[N,C]` → `[N,C+3]`, so the
+    un-augmented coordinates reach `FSF.split_points_last_3dim` (FSF.py:1123); with ground truth present it also keeps
+    `no_aug_gt_bboxes_3d` / `no_aug_gt_labels_3d`.  `results['points']` may be a tensor or an object with a `.tensor`."""
+
+    def __call__(self, results):
+        pts = results["points"]
+        t = pts.tensor if hasattr(pts, "tensor") else pts
+        out = torch.cat([t, t[:, :3].clone()], dim=-1)
+        if hasattr(pts, "tensor"):
+            pts.tensor = out
+        else:
+            results["points"] = out
+        if "gt_bboxes_3d" in results:
+            results["no_aug_gt_bboxes_3d"] = results["gt_bboxes_3d"].clone()
+            results["no_aug_gt_labels_3d"] = torch.from_numpy(np.asarray(results["gt_labels_3d"]))
+        return results
+
+
 def write_mask_sample(sample_dir: str, mask: np.ndarray, anno_rows: np.ndarray, class_names: Optional[Sequence[str]] = None,
                       single_cls: bool = False) -> None:
     """Store id planes [cams, classes, H, W] and annotation rows [(x1,y1,x2,y2,score,category,cam_id,obj_id,valid)] in the

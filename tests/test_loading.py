@@ -144,3 +144,15 @@ def test_disk_to_ids_on_device(gold):
         assert np.array_equal(ids.cpu().numpy(), O.points_in_mask(pts[:, 5:8], want_mask, l2i))
         assert np.array_equal(f["anno"].cpu().numpy(), gold["nusc_tok0_anno"])
     assert st.h2d_bytes == 4 * (6 * 10 * 90 * 160 + 250 * 9 * 4 + 6 * 16 * 4) + sum((3000 + 100 * i) * 8 * 4 for i in range(4))
+
+
+def test_save_no_aug_points():
+    import types
+
+    pts = torch.arange(20, dtype=torch.float32).view(4, 5)
+    res = L.SaveNoAugPoints()(dict(points=pts.clone()))
+    assert torch.equal(res["points"], torch.cat([pts, pts[:, :3]], 1))
+    holder = types.SimpleNamespace(tensor=pts.clone())                       # mmdet3d's LiDARPoints carries `.tensor`
+    res = L.SaveNoAugPoints()(dict(points=holder, gt_bboxes_3d=torch.ones(2, 9), gt_labels_3d=np.array([1, 3])))
+    assert torch.equal(holder.tensor, torch.cat([pts, pts[:, :3]], 1)) and res["points"] is holder
+    assert torch.equal(res["no_aug_gt_bboxes_3d"], torch.ones(2, 9)) and res["no_aug_gt_labels_3d"].tolist() == [1, 3]
