@@ -38,6 +38,7 @@ SIGNATURES = {
     "fsfb_ingroup_indices": (_i, [_p, _i64, _i64, _p, _p, _sz, _p]),
     "fsfb_project_sample": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "fsfb_project_sample_select": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "fsfb_project_sample_select_hwc": (_i, [_p, _i64, _i64, _p, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "fsfb_gemm_prepack_bytes": (_i, [_i, _i, _i, _psz]),
     "fsfb_gemm_prepack": (_i, [_p, _i, _i, _i, _p, _p]),
     "fsfb_gather_gemm": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _p]),

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- fused contract: camera-selected ids + fg flag --------------------------------------
-template <typename MaskT>
+// HWC (experimental, fsfb_project_sample_select_hwc): u8 planes stored class-interleaved [cams, H, W, 16] (classes padded to
+// 16 bytes), so the ids of a texel are ONE aligned 16-byte load instead of `classes` loads from as many planes (sectors).
+template <typename MaskT, bool HWC = false>
 __global__ void __launch_bounds__(256)
     k_project_sample_select(const float* __restrict__ xyz, int64_t n, int64_t stride,
                             const float* __restrict__ lidar2img, int cams,
@@ -130,14 +132,26 @@ __global__ void __launch_bounds__(256)
     for (int cam = 0; cam < cams; ++cam) {
       const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
       if (tex < 0) continue;
-      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
       int ids[kMaxClasses];
       long long sum = 0;
+      if constexpr (HWC) {
+        static_assert(kMaxClasses == 16, "one 16-byte texel");
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(mask) + ((int64_t)cam * plane + tex));
+        const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          ids[k] = (k < classes) ? (int)((w4[k >> 2] >> (8 * (k & 3))) & 0xffu) : 0;
+          sum += ids[k];
+          n_pos += ids[k] > 0;
+        }
+      } else {
+      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k) {
         ids[k] = (k < classes) ? (int)__ldg(m0 + k * plane) : 0;
         sum += ids[k];
         n_pos += ids[k] > 0;
+      }
       }
       if (sum > best_sum) {
         best_sum = sum;
@@ -235,6 +249,27 @@ int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
                 (const unsigned char*)mask, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows,
                 anno_cols, anno_col, scores);
   }
+  return FSFB_OK;
+}
+
+// Experimental twin of fsfb_project_sample_select for class-interleaved u8 planes: mask dev [cams, H, W, 16] u8 (texel = 16 bytes,
+// byte k = id of class k, bytes >= classes ignored), 16-byte aligned.  Same outputs.
+int fsfb_project_sample_select_hwc(const float* xyz, int64_t n, int64_t xyz_stride, const float* lidar2img, int cams,
+                                   const void* mask_hwc16, int classes, int H, int W, int32_t* ids_sel, uint8_t* cam_sel,
+                                   uint8_t* fg, uint8_t* overlap, const float* anno, int anno_rows, int anno_cols, int anno_col,
+                                   float* scores, void* stream) {
+  using namespace fsfb;
+  int rc = check_common(xyz, n, xyz_stride, lidar2img, cams, mask_hwc16, classes, H, W, "project_sample_select_hwc");
+  if (rc != FSFB_OK) return rc;
+  if (n == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(((uintptr_t)mask_hwc16 & 15) == 0, "project_sample_select_hwc: planes must be 16-byte aligned");
+  FSFB_CHECK_ARG(ids_sel || cam_sel || fg || overlap || scores, "project_sample_select_hwc: no output requested");
+  FSFB_CHECK_ARG(!scores || (anno && anno_rows >= 0 && anno_col >= 0 && anno_col < anno_cols),
+                 "project_sample_select_hwc: scores need a valid annotation table");
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
+  FSFB_LAUNCH((k_project_sample_select<unsigned char, true>), grid, 256, 0, (cudaStream_t)stream, xyz, n, xyz_stride, lidar2img,
+              cams, (const unsigned char*)mask_hwc16, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows, anno_cols,
+              anno_col, scores);
   return FSFB_OK;
 }
 

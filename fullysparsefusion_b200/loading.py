@@ -70,9 +70,16 @@ class LoadMaskFromFiles:
                  touched for the resized cameras).
     results out: 'mask_data' torch [cams, classes, H, W] (u8; AV2 int32 [7,1,H,W] as upstream's astype(np.int32)),
                  'mask_anno' torch f32 [obj_max_num, 9] = (x1,y1,x2,y2,score,category,cam_id,obj_id,valid) sorted by obj_id.
-    `out`: optional preallocated destination for mask_data (a numpy view of a pinned tensor); `workers`: decode threads."""
+    `out`: optional preallocated destination for mask_data (a numpy view of a pinned tensor); `workers`: decode threads.
+    `layout="hwc16"` (u8 samples only, EXPERIMENTAL consumer `ops.project_sample_select_hwc`): the planes are written
+    class-interleaved, `mask_data[cam, y, x, k]` = plane of class k, padded to 16 bytes per texel (pad bytes zero) — the sampling
+    kernel then reads the ids of a texel with one 16-byte load instead of one sector per class."""
 
-    def __init__(self, data_path, class_names=None, obj_max_num=250, is_argo=False, is_waymo=False, workers: int = 8):
+    def __init__(self, data_path, class_names=None, obj_max_num=250, is_argo=False, is_waymo=False, workers: int = 8,
+                 layout: str = "chw"):
+        if layout not in ("chw", "hwc16"):
+            raise ValueError("layout must be 'chw' (upstream's [cams, classes, H, W]) or 'hwc16' ([cams, H, W, 16] u8)")
+        self.layout = layout
         self.data_path = data_path
         self.obj_max_num = obj_max_num
         self.class_names = list(NUSC_CLASSES if class_names is None else class_names)
@@ -80,6 +87,7 @@ class LoadMaskFromFiles:
         self.is_waymo = is_waymo
         self.workers = max(1, int(workers))
         self._pool: Optional[ThreadPoolExecutor] = None
+        self._cleared = set()
 
     # ---- layout of one sample ------------------------------------------------------------------------------------------
     def _plan(self, results) -> Tuple[str, List[str], Tuple[int, int], Dict[int, Tuple[int, int]], np.dtype]:
@@ -109,10 +117,19 @@ class LoadMaskFromFiles:
         for cam, shape in resized.items():
             if tuple(shape) != (H, W):
                 raise ValueError(f"camera {cam} resizes to {shape} but camera {probe_cam} is {(H, W)}: planes cannot be stacked")
+        hwc = self.layout == "hwc16"
+        if hwc and (dtype != np.uint8 or classes > 16):
+            raise ValueError("layout='hwc16' needs uint8 planes and at most 16 classes")
+        shape = (cams, H, W, 16) if hwc else (cams, classes, H, W)
         if out is None:
-            out = np.empty((cams, classes, H, W), dtype=dtype)
-        elif out.shape != (cams, classes, H, W) or out.dtype != dtype:
-            raise ValueError(f"out must be {dtype} {(cams, classes, H, W)}, got {out.dtype} {out.shape}")
+            out = np.zeros(shape, dtype=dtype) if hwc else np.empty(shape, dtype=dtype)
+        elif out.shape != shape or out.dtype != dtype:
+            raise ValueError(f"out must be {dtype} {shape}, got {out.dtype} {out.shape}")
+        elif hwc and classes < 16:
+            addr = (out.__array_interface__["data"][0], shape)
+            if addr not in self._cleared:        # pad bytes of a caller's buffer are cleared once: nothing here writes them again
+                out[..., classes:] = 0
+                self._cleared.add(addr)
         if dtype == np.uint8 and first.dtype != np.uint8:
             raise ValueError(f"{paths[probe_cam * classes]}: {first.dtype} plane where uint8 ids are expected")
 
@@ -125,7 +142,7 @@ class LoadMaskFromFiles:
                 ori_shape[cam] = img.shape
             elif cam not in resized and img.shape != (H, W):
                 raise ValueError(f"{paths[p]}: shape {img.shape} differs from {(H, W)}")
-            _place(out[cam, cls], img)
+            _place(out[cam, :, :, cls] if hwc else out[cam, cls], img)
 
         if self.workers == 1:
             for p in range(len(paths)):

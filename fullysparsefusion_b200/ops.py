@@ -396,6 +396,46 @@ def project_sample_select(xyz: torch.Tensor, lidar2img: torch.Tensor, mask: torc
     return out
 
 
+def project_sample_select_hwc(xyz: torch.Tensor, lidar2img: torch.Tensor, mask_hwc16: torch.Tensor, classes: int,
+                              want_overlap: bool = False, anno: Optional[torch.Tensor] = None, anno_col: int = 4,
+                              want_ids: bool = True):
+    """EXPERIMENTAL twin of project_sample_select for class-interleaved planes: mask_hwc16 [cams, H, W, 16] u8 (byte k of a texel
+    = id of class k; `loading.LoadMaskFromFiles(layout="hwc16")` produces it).  Same outputs."""
+    dev = _need_cuda(xyz, lidar2img, mask_hwc16, anno)
+    assert xyz.dim() == 2 and xyz.size(1) >= 3 and xyz.dtype == torch.float32
+    if xyz.stride(1) != 1:
+        xyz = xyz.contiguous()
+    assert mask_hwc16.dim() == 4 and mask_hwc16.size(3) == 16 and mask_hwc16.dtype == torch.uint8 and mask_hwc16.is_contiguous()
+    assert 1 <= classes <= 16
+    cams, H, W, _ = mask_hwc16.shape
+    l2i = lidar2img.to(torch.float32).contiguous()
+    assert l2i.shape == (cams, 4, 4)
+    n = xyz.size(0)
+    ids = torch.empty((n, classes), dtype=torch.int32, device=dev) if want_ids else None
+    cam = torch.empty(n, dtype=torch.uint8, device=dev)
+    fg = torch.empty(n, dtype=torch.uint8, device=dev)
+    ov = torch.empty(n, dtype=torch.uint8, device=dev) if want_overlap else None
+    scores = None
+    a_rows = a_cols = 0
+    if anno is not None:
+        assert anno.dim() == 2 and anno.dtype == torch.float32
+        anno = anno.contiguous()
+        a_rows, a_cols = anno.shape
+        scores = torch.empty((n, classes), dtype=torch.float32, device=dev)
+    out_b = (4 * classes if want_ids else 0) + 2 + (1 if want_overlap else 0) + (4 * classes if anno is not None else 0)
+    with _Prof("project_sample_select_hwc", n * (12 + cams * classes + out_b)):
+        rc = load().fsfb_project_sample_select_hwc(_ptr(xyz), n, xyz.stride(0) if n else 3, _ptr(l2i), cams, _ptr(mask_hwc16),
+                                                   classes, H, W, _ptr(ids), _ptr(cam), _ptr(fg), _ptr(ov), _ptr(anno), a_rows,
+                                                   a_cols, int(anno_col), _ptr(scores), _stream(dev))
+    check(rc, "fsfb_project_sample_select_hwc")
+    out = (ids, cam, fg)
+    if want_overlap:
+        out += (ov,)
+    if anno is not None:
+        out += (scores,)
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # gather-GEMM (sparse conv / Linear) with fused epilogue
 # ------------------------------------------------------------------------------------------

@@ -180,6 +180,16 @@ int fsfb_project_sample_select(const float* xyz, int64_t n, int64_t xyz_stride,
                                uint8_t* overlap, const float* anno, int anno_rows, int anno_cols,
                                int anno_col, float* scores, void* stream);
 
+/* EXPERIMENTAL twin of fsfb_project_sample_select (same reference lines, same outputs) for u8 planes stored class-interleaved:
+ * mask_hwc16 dev [cams, H, W, 16] u8, 16-byte aligned — byte k of a texel = id plane of class k (FSF.py:202-226 samples the
+ * planes one by one; here a texel's ids are one 16-byte load).  fullysparsefusion_b200.loading.LoadMaskFromFiles(layout="hwc16")
+ * decodes the sample straight into this layout.  Not validated on hardware yet. */
+int fsfb_project_sample_select_hwc(const float* xyz, int64_t n, int64_t xyz_stride,
+                                   const float* lidar2img, int cams, const void* mask_hwc16,
+                                   int classes, int H, int W, int32_t* ids_sel, uint8_t* cam_sel,
+                                   uint8_t* fg, uint8_t* overlap, const float* anno, int anno_rows,
+                                   int anno_cols, int anno_col, float* scores, void* stream);
+
 /* ---------------------------------------------------------------------------
  * a5 / a9 / a10 / a16 / a17  Gather-GEMM with fused epilogue — the one dense
  * contraction of the path.  It serves nn.Linear stacks built by build_mlp

@@ -156,3 +156,37 @@ def test_save_no_aug_points():
     res = L.SaveNoAugPoints()(dict(points=holder, gt_bboxes_3d=torch.ones(2, 9), gt_labels_3d=np.array([1, 3])))
     assert torch.equal(holder.tensor, torch.cat([pts, pts[:, :3]], 1)) and res["points"] is holder
     assert torch.equal(res["no_aug_gt_bboxes_3d"], torch.ones(2, 9)) and res["no_aug_gt_labels_3d"].tolist() == [1, 3]
+
+
+def test_hwc16_layout_is_the_planes_interleaved(gold):
+    res = L.LoadMaskFromFiles(os.path.join(ROOT, "nusc"), layout="hwc16", workers=3)(dict(sample_idx="tok0"))
+    m = res["mask_data"].numpy()
+    assert m.shape == (6, 90, 160, 16) and m.dtype == np.uint8
+    assert np.array_equal(m[..., :10].transpose(0, 3, 1, 2), gold["nusc_tok0_mask"]) and not m[..., 10:].any()
+    buf = np.full((6, 90, 160, 16), 9, np.uint8)                       # a reused destination: pad bytes are cleared
+    L.LoadMaskFromFiles(os.path.join(ROOT, "nusc"), layout="hwc16")(dict(sample_idx="tok0"), out=buf)
+    assert np.array_equal(buf, m)
+    with pytest.raises(ValueError):
+        L.LoadMaskFromFiles(os.path.join(ROOT, "argo"), is_argo=True, layout="hwc16")(
+            dict(img_info=dict(uuid="uuid0"), lidar2img=[x.copy() for x in gold["argo_l2i_in"]]))
+    with pytest.raises(ValueError):
+        L.LoadMaskFromFiles(ROOT, layout="nhwc")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("FSFB_TEST_EXPERIMENTAL") != "1", reason="experimental path: set FSFB_TEST_EXPERIMENTAL=1")
+def test_hwc16_projection_matches_planar(gold):
+    """fsfb_project_sample_select_hwc (written without GPU access; gated until brought up) against the validated planar kernel."""
+    from fullysparsefusion_b200 import ops
+
+    dev = torch.device("cuda:0")
+    planar = torch.from_numpy(gold["nusc_tok0_mask"]).to(dev)
+    hwc = L.LoadMaskFromFiles(os.path.join(ROOT, "nusc"), layout="hwc16")(dict(sample_idx="tok0"))["mask_data"].to(dev)
+    anno = torch.from_numpy(gold["nusc_tok0_anno"]).to(dev)
+    l2i = torch.from_numpy(synth.lidar2img(6, 90, 160)).to(dev)
+    for n in (1, 777, 20000):
+        xyz = torch.from_numpy(synth.ring_points(n, seed=n)[:, :3].copy()).to(dev)
+        want = ops.project_sample_select(xyz, l2i, planar, want_overlap=True, anno=anno)
+        got = ops.project_sample_select_hwc(xyz, l2i, hwc, 10, want_overlap=True, anno=anno)
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)

@@ -6,9 +6,10 @@ mkdir -p gpurun_out
 timeout 120 tools/microbench/gather_paths > gpurun_out/gather_paths.txt 2>&1
 FSFB_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_gemm_f16.py -x -q > gpurun_out/f16_test.txt 2>&1
 echo "f16 test exit $?" >> gpurun_out/f16_test.txt
+FSFB_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_loading.py -x -q -k hwc16_projection > gpurun_out/hwc16_test.txt 2>&1
 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err
 if grep -q "F16 OK" gpurun_out/f16_test.txt || grep -q "1 passed" gpurun_out/f16_test.txt; then
   FSFB_GEMM_F16=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f16.json 2> gpurun_out/bench_f16.err
 fi
-tail -n 30 gpurun_out/gather_paths.txt gpurun_out/f16_test.txt
+tail -n 30 gpurun_out/gather_paths.txt gpurun_out/f16_test.txt gpurun_out/hwc16_test.txt
 cat gpurun_out/bench_tf32.json gpurun_out/bench_f16.json 2>/dev/null
