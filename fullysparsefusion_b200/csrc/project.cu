@@ -106,9 +106,7 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---- fused contract: camera-selected ids + fg flag --------------------------------------
-// HWC (experimental, fsfb_project_sample_select_hwc): u8 planes stored class-interleaved [cams, H, W, 16] (classes padded to
-// 16 bytes), so the ids of a texel are ONE aligned 16-byte load instead of `classes` loads from as many planes (sectors).
-template <typename MaskT, bool HWC = false>
+template <typename MaskT>
 __global__ void __launch_bounds__(256)
     k_project_sample_select(const float* __restrict__ xyz, int64_t n, int64_t stride,
                             const float* __restrict__ lidar2img, int cams,
@@ -132,26 +130,14 @@ __global__ void __launch_bounds__(256)
     for (int cam = 0; cam < cams; ++cam) {
       const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
       if (tex < 0) continue;
+      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
       int ids[kMaxClasses];
       long long sum = 0;
-      if constexpr (HWC) {
-        static_assert(kMaxClasses == 16, "one 16-byte texel");
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(mask) + ((int64_t)cam * plane + tex));
-        const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-          ids[k] = (k < classes) ? (int)((w4[k >> 2] >> (8 * (k & 3))) & 0xffu) : 0;
-          sum += ids[k];
-          n_pos += ids[k] > 0;
-        }
-      } else {
-      const MaskT* m0 = mask + (int64_t)cam * classes * plane + tex;
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k) {
         ids[k] = (k < classes) ? (int)__ldg(m0 + k * plane) : 0;
         sum += ids[k];
         n_pos += ids[k] > 0;
-      }
       }
       if (sum > best_sum) {
         best_sum = sum;
@@ -180,6 +166,70 @@ __global__ void __launch_bounds__(256)
           so[k] = (id >= 1 && id <= anno_rows) ? __ldg(anno + (int64_t)(id - 1) * anno_cols + anno_col) : 0.f;
         }
     }
+  }
+}
+
+// ---- fused contract on class-interleaved planes (EXPERIMENTAL, fsfb_project_sample_select_hwc) -----------------------------
+// mask [cams, H, W, 16] u8: the ids of a texel are ONE aligned 16-byte load instead of `classes` loads from as many planes
+// (= sectors).  The [32 points x classes] id and score blocks of a warp are staged in shared memory and leave as contiguous
+// 128-byte stores (the per-thread form writes 4 bytes every 40: ten partial-sector writes per point and output).
+__global__ void __launch_bounds__(256)
+    k_project_sample_select_hwc(const float* __restrict__ xyz, int64_t n, int64_t stride, const float* __restrict__ lidar2img, int cams,
+                                const uint4* __restrict__ mask, int classes, int H, int W, int32_t* __restrict__ ids_sel,
+                                uint8_t* __restrict__ cam_sel, uint8_t* __restrict__ fg, uint8_t* __restrict__ overlap,
+                                const float* __restrict__ anno, int anno_rows, int anno_cols, int anno_col,
+                                float* __restrict__ scores) {
+  static_assert(kMaxClasses == 16, "one 16-byte texel");
+  __shared__ CamSet s_cams;
+  __shared__ int32_t s_ids[8][32 * kMaxClasses];
+  __shared__ float s_sc[8][32 * kMaxClasses];
+  load_cams(s_cams, lidar2img, cams);
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * 32; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + lane;
+    if (i < n) {
+      const float* p = xyz + i * stride;
+      const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+      uint4 best = make_uint4(0u, 0u, 0u, 0u);
+      int best_sum = 0, best_cam = 0, n_pos = 0;  // an all-zero camera 0 wins ties, as torch.max returns the first maximum
+      for (int cam = 0; cam < cams; ++cam) {
+        const int tex = project_texel(s_cams.P[cam], x, y, z, W, H);
+        if (tex < 0) continue;
+        const uint4 t = __ldg(mask + ((int64_t)cam * plane + tex));
+        const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          const int id = (k < classes) ? (int)((w4[k >> 2] >> (8 * (k & 3))) & 0xffu) : 0;
+          sum += id;
+          n_pos += id > 0;
+        }
+        if (sum > best_sum) {
+          best_sum = sum;
+          best_cam = cam;
+          best = t;
+        }
+      }
+      const uint32_t b4[4] = {best.x, best.y, best.z, best.w};
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < classes) {
+          const int id = (int)((b4[k >> 2] >> (8 * (k & 3))) & 0xffu);
+          s_ids[warp][lane * classes + k] = id;
+          if (scores) s_sc[warp][lane * classes + k] = (id >= 1 && id <= anno_rows) ? __ldg(anno + (int64_t)(id - 1) * anno_cols + anno_col) : 0.f;
+        }
+      if (cam_sel) cam_sel[i] = (uint8_t)best_cam;
+      if (fg) fg[i] = (uint8_t)(best_sum > 0 || n_pos > 0);
+      if (overlap) overlap[i] = (uint8_t)min(n_pos, 255);
+    }
+    __syncwarp();
+    const int total = (int)min((int64_t)32, n - base) * classes;
+    if (ids_sel)
+      for (int e = lane; e < total; e += 32) ids_sel[base * classes + e] = s_ids[warp][e];
+    if (scores)
+      for (int e = lane; e < total; e += 32) scores[base * classes + e] = s_sc[warp][e];
+    __syncwarp();
   }
 }
 
@@ -267,9 +317,8 @@ int fsfb_project_sample_select_hwc(const float* xyz, int64_t n, int64_t xyz_stri
   FSFB_CHECK_ARG(!scores || (anno && anno_rows >= 0 && anno_col >= 0 && anno_col < anno_cols),
                  "project_sample_select_hwc: scores need a valid annotation table");
   const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
-  FSFB_LAUNCH((k_project_sample_select<unsigned char, true>), grid, 256, 0, (cudaStream_t)stream, xyz, n, xyz_stride, lidar2img,
-              cams, (const unsigned char*)mask_hwc16, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows, anno_cols,
-              anno_col, scores);
+  FSFB_LAUNCH(k_project_sample_select_hwc, grid, 256, 0, (cudaStream_t)stream, xyz, n, xyz_stride, lidar2img, cams,
+              (const uint4*)mask_hwc16, classes, H, W, ids_sel, cam_sel, fg, overlap, anno, anno_rows, anno_cols, anno_col, scores);
   return FSFB_OK;
 }
 
