@@ -11,5 +11,6 @@ timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out
 if grep -q "F16 OK" gpurun_out/f16_test.txt || grep -q "1 passed" gpurun_out/f16_test.txt; then
   FSFB_GEMM_F16=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f16.json 2> gpurun_out/bench_f16.err
 fi
+if grep -q "1 passed" gpurun_out/hwc16_test.txt; then timeout 200 python tools/op_bench_hwc.py > gpurun_out/op_bench_hwc.json 2>&1; fi
 tail -n 30 gpurun_out/gather_paths.txt gpurun_out/f16_test.txt gpurun_out/hwc16_test.txt
 cat gpurun_out/bench_tf32.json gpurun_out/bench_f16.json 2>/dev/null
