@@ -144,3 +144,16 @@ def test_cluster_head_reference_golden(cuda):
         out = head(torch.from_numpy(g["x"]).to(cuda))
     np.testing.assert_allclose(out["cls_logits"][0].cpu().numpy(), g["cls"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(out["reg_preds"][0].cpu().numpy(), g["reg"], rtol=1e-4, atol=2e-5)
+
+
+def test_vote_seg_head_reference_golden(cuda):
+    """modules.VoteSegHead with the state dict of the reference's own VoteSegHead (BN running statistics folded into the fused
+    Linear epilogue): same logits and votes (1e-4)."""
+    from tests.test_oracle_golden import _seg_head_from_golden
+    g, head, sd = _seg_head_from_golden()
+    head.load_state_dict(sd, strict=True)
+    head = head.eval().to(cuda)
+    with torch.no_grad():
+        logits, votes = head(torch.from_numpy(g["x"]).to(cuda))
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(votes.cpu().numpy(), g["votes"], rtol=1e-4, atol=2e-5)

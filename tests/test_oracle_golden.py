@@ -238,3 +238,28 @@ def test_cluster_head_state_dict_compat():
                                      "ln", "gelu", 1e-5) for a in ("center", "dim", "rot", "vel", "score")}
     np.testing.assert_allclose(outs["score"], g["cls"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(np.concatenate([outs["center"], outs["dim"], outs["rot"], outs["vel"]], 1), g["reg"], rtol=1e-4, atol=1e-5)
+
+
+def _seg_head_from_golden():
+    import torch
+    from fullysparsefusion_b200 import modules as M
+
+    g = load_golden("vote_seg_head")
+    head = M.VoteSegHead(in_channel=24, num_classes=4, hidden_dims=[16, 16], dropout_ratio=0.0, norm_cfg=dict(type="naiveSyncBN1d"),
+                         act_cfg=dict(type="ReLU"))
+    sd = {k.replace("__", "."): torch.from_numpy(np.asarray(v)) for k, v in g.items() if k not in ("x", "logits", "votes", "num_classes")}
+    return g, head, sd
+
+
+def test_vote_seg_head_state_dict_compat():
+    """A state dict saved by the REFERENCE's VoteSegHead (stock loss config: background class appended) loads strictly into
+    modules.VoteSegHead, and the oracle reproduces the reference's logits and votes from it."""
+    from oracle import fsf_oracle_models as OM
+
+    g, head, sd = _seg_head_from_golden()
+    missing, unexpected = head.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert int(g["num_classes"]) == head.num_classes == 5 and g["logits"].shape == (300, 5) and g["votes"].shape == (300, 15)
+    logits, votes = OM.vote_seg_head(g["x"], {k: v.numpy() for k, v in sd.items()})
+    np.testing.assert_allclose(logits, g["logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(votes, g["votes"], rtol=1e-4, atol=1e-5)

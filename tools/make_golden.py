@@ -542,6 +542,30 @@ def main_heads():
     save("cluster_head_v2", x=x, cls=out["cls_logits"][0], reg=out["reg_preds"][0], **sd)
 
 
+def main_seghead():
+    """The reference's own VoteSegHead (decode_heads/segmentation_head.py:16-104 over the in-tree Base3DDecodeHead,
+    decode_heads/decode_head.py:9-106) at reduced widths, eval mode, non-trivial BN running statistics: state-dict keys (checkpoint
+    compatibility of modules.VoteSegHead) and forward outputs (`python tools/make_golden.py seghead`)."""
+    ref = import_reference()
+    torch.manual_seed(71)
+    head = ref["seg_head"].VoteSegHead(in_channel=24, num_classes=4, hidden_dims=[16, 16], dropout_ratio=0.0,
+                                       norm_cfg=dict(type="naiveSyncBN1d"), act_cfg=dict(type="ReLU"),   # as FSF_nuScenes_config.py:78-95
+                                       loss_decode=dict(type="CrossEntropyLoss", use_sigmoid=False, class_weight=[1.0] * 4 + [0.1],
+                                                        loss_weight=10.0), loss_vote=dict(type="L1Loss", loss_weight=1.0))
+    for mod in head.modules():
+        if isinstance(mod, nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.normal_(0, 0.2)
+    head.eval()
+    x = torch.randn(300, 24)
+    with torch.no_grad():
+        logits, votes = head(x)
+    sd = {k.replace(".", "__"): v for k, v in head.state_dict().items()}
+    save("vote_seg_head", x=x, logits=logits, votes=votes, num_classes=np.int64(head.num_classes), **sd)
+
+
 def main_loading():
     """The reference's own LoadMaskFromFiles (datasets/pipelines/loading.py:22-339: load_nusc, load_argo + resize_img,
     load_waymo + resize_img_waymo, reorg_anno_*) on sample directories written in the format of
@@ -636,6 +660,8 @@ if __name__ == "__main__":
         main_heads()
     elif len(sys.argv) > 1 and sys.argv[1] == "loading":
         main_loading()
+    elif len(sys.argv) > 1 and sys.argv[1] == "seghead":
+        main_seghead()
     elif len(sys.argv) > 1 and sys.argv[1] == "misc":
         main_misc()
     elif len(sys.argv) > 1 and sys.argv[1] == "refine":
