@@ -340,6 +340,35 @@ class FSF(nn.Module):
         st.update(det_boxes=boxes, det_scores=scores, det_labels=labels, det_rows=rows)
         return boxes, scores, labels
 
+    # reference checkpoint prefix → attribute here (FSF.__init__ FSF.py:86-164; VoteSegmentor.__init__ single_stage_fsd.py:160-204)
+    REFERENCE_PREFIXES = (("segmentor.voxel_encoder.", "voxel_encoder."), ("segmentor.backbone.", "backbone_unet."),
+                          ("segmentor.segmentation_head.", "segmentation_head."), ("segmentor.decode_neck.", "decode_neck."))
+
+    def load_reference_state_dict(self, state_dict, strict: bool = False):
+        """Load a checkpoint saved by the reference detector: the segmentor's sub-modules live one level down there
+        (`segmentor.voxel_encoder.*`, `segmentor.backbone.*` = the sparse U-Net, `segmentor.segmentation_head.*`), every other
+        top-level name is the same.  Sparse-convolution kernels stored 5-d are brought to `[27, Cout, Cin]` (spconv 1.x
+        `[kz,ky,kx,Cin,Cout]`, spconv 2.x `[Cout,kz,ky,kx,Cin]`; told apart by the shape the target expects).  Returns
+        (missing, unexpected) like `load_state_dict`; the internal key names of the un-vendored blocks (SimpleSparseUNet,
+        DynamicScatterVFE, SIRLayer) are the recalled ones, so with strict=False check the two lists.  Calls `refresh()`."""
+        own = self.state_dict()
+        mapped = {}
+        for k, v in state_dict.items():
+            for a, b in self.REFERENCE_PREFIXES:
+                if k.startswith(a):
+                    k = b + k[len(a):]
+                    break
+            if k in own and v.dim() == 5 and own[k].dim() == 3:
+                koff, cout, cin = own[k].shape
+                if tuple(v.shape[3:]) == (cin, cout) and v.shape[:3].numel() == koff:        # spconv 1.x
+                    v = v.permute(0, 1, 2, 4, 3).reshape(koff, cout, cin)
+                elif v.shape[0] == cout and v.shape[4] == cin and v.shape[1:4].numel() == koff:  # spconv 2.x
+                    v = v.permute(1, 2, 3, 0, 4).reshape(koff, cout, cin)
+            mapped[k] = v
+        res = self.load_state_dict(mapped, strict=strict)
+        self.refresh()
+        return res
+
     @torch.no_grad()
     def forward(self, points, mask_data, mask_anno, lidar2img):
         stages, st = self.stages(points, mask_data, mask_anno, lidar2img)

@@ -85,3 +85,36 @@ def test_torch_cpu_port_refine_and_boxes_match_numpy_oracle():
     wb, ws, wl, wrow = O.multiclass_nms(boxes, st["refine0_cls"].numpy(), 0.01, 0.35, 500)
     assert np.array_equal(st["det_rows"].numpy(), wrow) and np.array_equal(st["det_labels"].numpy(), wl)
     np.testing.assert_allclose(st["det_scores"].numpy(), ws, rtol=1e-6)
+
+
+def test_reference_checkpoint_key_mapping():
+    """FSF.load_reference_state_dict: the reference nests the segmentor's modules (`segmentor.*`) and spconv stores kernels 5-d."""
+    torch.manual_seed(3)
+    src = FSFM.FSF()
+    ref_sd = {}
+    for k, v in src.state_dict().items():
+        for a, b in FSFM.FSF.REFERENCE_PREFIXES:
+            if k.startswith(b):
+                k = a + k[len(b):]
+                break
+        ref_sd[k] = v.clone()
+    n5 = 0
+    for k in list(ref_sd):
+        v = ref_sd[k]
+        if v.dim() == 3 and v.size(0) == 27:                        # conv kernels, alternately in the two spconv layouts
+            koff, cout, cin = v.shape
+            if n5 % 2 == 0:
+                ref_sd[k] = v.reshape(3, 3, 3, cout, cin).permute(0, 1, 2, 4, 3).contiguous()       # spconv 1.x [kz,ky,kx,Cin,Cout]
+            else:
+                ref_sd[k] = v.reshape(3, 3, 3, cout, cin).permute(3, 0, 1, 2, 4).contiguous()       # spconv 2.x [Cout,kz,ky,kx,Cin]
+            n5 += 1
+    assert n5 > 20 and any(k.startswith("segmentor.backbone.") for k in ref_sd)
+    torch.manual_seed(4)
+    dst = FSFM.FSF()
+    missing, unexpected = dst.load_reference_state_dict(ref_sd, strict=True)
+    assert not missing and not unexpected
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    ref_sd["segmentor.backbone.not_a_key"] = torch.zeros(1)
+    missing, unexpected = dst.load_reference_state_dict(ref_sd, strict=False)
+    assert unexpected == ["backbone_unet.not_a_key"] and not missing
