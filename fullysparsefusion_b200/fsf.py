@@ -340,6 +340,30 @@ class FSF(nn.Module):
         st.update(det_boxes=boxes, det_scores=scores, det_labels=labels, det_rows=rows)
         return boxes, scores, labels
 
+    @torch.no_grad()
+    def simple_test(self, points, img_metas, mask_data, mask_anno, score_thr: float = 0.01, nms_thr: float = 0.35,
+                    max_num: int = 500, **kwargs):
+        """The reference's test entry (FSF.simple_test, FSF.py:1114-1176) with its argument conventions: `points` a list of
+        per-sample `[N, 5+3]` tensors (or one tensor), `img_metas` a list of dicts carrying `lidar2img` (list of 4x4),
+        `mask_data [B, cams, classes, H, W]`, `mask_anno [B, obj_max_num, 9]`.  Returns mmdet3d's `bbox3d2result` layout, one dict per
+        sample with CPU tensors: `boxes_3d [n, 9]` (x, y, z, dx, dy, dz, yaw, vx, vy — the raw tensor a LiDARInstance3DBoxes would
+        wrap), `scores_3d [n]`, `labels_3d [n]`.  Samples are processed one after the other (samples_per_gpu = 1 upstream)."""
+        if torch.is_tensor(points):
+            points = [points]
+        results = []
+        for b, pts in enumerate(points):
+            l2i = img_metas[b]["lidar2img"]
+            if not torch.is_tensor(l2i):
+                import numpy as np
+
+                l2i = torch.from_numpy(np.asarray([np.asarray(m, dtype=np.float32) for m in l2i], dtype=np.float32))
+            l2i = l2i.to(device=pts.device, dtype=torch.float32)
+            st = self.forward(pts, mask_data[b], mask_anno[b], l2i)
+            st = self.refine(st, pts)
+            boxes, scores, labels = self.get_bboxes(st, score_thr, nms_thr, max_num)
+            results.append(dict(boxes_3d=boxes.cpu(), scores_3d=scores.cpu(), labels_3d=labels.cpu()))
+        return results
+
     # reference checkpoint prefix → attribute here (FSF.__init__ FSF.py:86-164; VoteSegmentor.__init__ single_stage_fsd.py:160-204)
     REFERENCE_PREFIXES = (("segmentor.voxel_encoder.", "voxel_encoder."), ("segmentor.backbone.", "backbone_unet."),
                           ("segmentor.segmentation_head.", "segmentation_head."), ("segmentor.decode_neck.", "decode_neck."))

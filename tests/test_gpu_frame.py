@@ -258,3 +258,21 @@ def test_detections(cuda, frame):
         np.testing.assert_allclose(N(boxes), wb, rtol=1e-5, atol=1e-5)
     else:
         assert abs(len(N(labels)) - len(wl)) <= 2
+
+
+def test_simple_test_entry(cuda, frame):
+    """FSF.simple_test (the reference's test entry and argument conventions) = forward → refine → get_bboxes on each sample."""
+    model, pts = frame["model"], frame["pts"]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    metas = [dict(lidar2img=[m for m in frame["l2i"].astype(np.float64)])]           # python-side 4x4 matrices, as the dataset gives
+    with torch.no_grad():
+        res = model.simple_test([T(pts)], metas, T(frame["mask"])[None], T(frame["anno"])[None], score_thr=0.3)
+        st = model.refine(model(T(pts), T(frame["mask"]), T(frame["anno"]), T(frame["l2i"])), T(pts))
+        boxes, scores, labels = model.get_bboxes(st, score_thr=0.3, nms_thr=0.35, max_num=500)
+    assert len(res) == 1 and set(res[0]) == {"boxes_3d", "scores_3d", "labels_3d"}
+    assert not res[0]["boxes_3d"].is_cuda and res[0]["boxes_3d"].shape[1] == 9
+    assert len(boxes) > 0 and abs(len(res[0]["labels_3d"]) - len(labels)) <= 2      # two passes over the same frame
+    if len(res[0]["labels_3d"]) == len(labels):
+        assert torch.equal(res[0]["labels_3d"], labels.cpu())
+        torch.testing.assert_close(res[0]["boxes_3d"], boxes.cpu(), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(res[0]["scores_3d"], scores.cpu(), rtol=1e-4, atol=1e-5)
