@@ -122,12 +122,12 @@ def test_frame_stager_cpu_rotation():
 
 
 @pytest.mark.gpu
-def test_disk_to_ids_on_device(gold):
+def test_disk_to_ids_on_device(cuda, gold):
     """sample directory → pinned slot → device → projection kernel: ids equal the oracle's on the reference-loaded planes."""
     from fullysparsefusion_b200 import ops
     from oracle import fsf_oracle as O
 
-    dev = torch.device("cuda:0")
+    dev = cuda
     st = L.FrameStager(dev, slots=2)
     loader = L.LoadMaskFromFiles(os.path.join(ROOT, "nusc"))
     l2i = synth.lidar2img(6, 90, 160)
@@ -175,11 +175,11 @@ def test_hwc16_layout_is_the_planes_interleaved(gold):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("FSFB_TEST_EXPERIMENTAL") != "1", reason="experimental path: set FSFB_TEST_EXPERIMENTAL=1")
-def test_hwc16_projection_matches_planar(gold):
+def test_hwc16_projection_matches_planar(cuda, gold):
     """fsfb_project_sample_select_hwc (written without GPU access; gated until brought up) against the validated planar kernel."""
     from fullysparsefusion_b200 import ops
 
-    dev = torch.device("cuda:0")
+    dev = cuda
     planar = torch.from_numpy(gold["nusc_tok0_mask"]).to(dev)
     hwc = L.LoadMaskFromFiles(os.path.join(ROOT, "nusc"), layout="hwc16")(dict(sample_idx="tok0"))["mask_data"].to(dev)
     anno = torch.from_numpy(gold["nusc_tok0_anno"]).to(dev)

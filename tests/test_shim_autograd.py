@@ -85,5 +85,5 @@ def test_backward_glue_on_cpu(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_backward_on_device():
+def test_backward_on_device(cuda):
     _check("cuda:0")
