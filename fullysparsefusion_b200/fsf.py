@@ -364,6 +364,13 @@ class FSF(nn.Module):
             results.append(dict(boxes_3d=boxes.cpu(), scores_3d=scores.cpu(), labels_3d=labels.cpu()))
         return results
 
+    def forward_test(self, points, img_metas, mask_data, mask_anno, **kwargs):
+        """FSF.forward_test (FSF.py:1096-1112): the outer lists are test-time augmentations; only the single-view case exists here
+        (aug_test is training-repo tooling)."""
+        if len(points) != 1:
+            raise NotImplementedError("test-time augmentation (aug_test) is outside the hot path")
+        return self.simple_test(points[0], img_metas[0], mask_data[0], mask_anno[0], **kwargs)
+
     # reference checkpoint prefix → attribute here (FSF.__init__ FSF.py:86-164; VoteSegmentor.__init__ single_stage_fsd.py:160-204)
     REFERENCE_PREFIXES = (("segmentor.voxel_encoder.", "voxel_encoder."), ("segmentor.backbone.", "backbone_unet."),
                           ("segmentor.segmentation_head.", "segmentation_head."), ("segmentor.decode_neck.", "decode_neck."))
