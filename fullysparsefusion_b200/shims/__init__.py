@@ -32,3 +32,39 @@ def patch_ccl(single_stage_fsd_module) -> None:
     single_stage_fsd_module.find_connected_componets = torchex.find_connected_componets
     single_stage_fsd_module.find_connected_componets_single_batch = torchex.find_connected_componets_single_batch
     single_stage_fsd_module.cc_gpu = torchex.connected_components
+
+
+def registry_table():
+    """(registry attribute in mmdet3d / mmdet, type string the configs use, class here) — the rows INTEGRATION.md section 3 lists."""
+    from .. import fsf, loading, modules
+
+    return [
+        ("VOXEL_ENCODERS", "DynamicScatterVFE", modules.DynamicScatterVFE),     # FSF_nuScenes_config.py:42-52
+        ("VOXEL_ENCODERS", "SIRLayer", modules.SIRLayer),                       # sir.py:61
+        ("BACKBONES", "SimpleSparseUNet", modules.SimpleSparseUNet),            # config :58-70
+        ("BACKBONES", "SIR", modules.SIR),                                      # config :113-124, :201-212
+        ("NECKS", "Voxel2PointScatterNeck", modules.Voxel2PointScatterNeck),    # config :72-76
+        ("HEADS", "VoteSegHead", modules.VoteSegHead),                          # config :78-95
+        ("HEADS", "SparseClusterHeadV2", fsf.SparseClusterHeadV2),              # config :126-160
+        ("HEADS", "FrustumClusterHead", fsf.SparseClusterHeadV2),               # same forward (inherits), config :214-273
+        ("HEADS", "FSDSeparateHead", fsf.FSDSeparateHead),
+        ("HEADS", "FullySparseBboxHead", modules.FullySparseBboxHead),          # config :296-320
+        ("ROI_EXTRACTORS", "DynamicPointROIExtractor", modules.DynamicPointROIExtractor),   # config :290-294
+        ("PIPELINES", "LoadMaskFromFiles", loading.LoadMaskFromFiles),
+        ("PIPELINES", "SaveNoAugPoints", loading.SaveNoAugPoints),
+    ]
+
+
+def register(registries, force: bool = True):
+    """Register the classes above in mmcv registries.  `registries`: a module or mapping that exposes the registry objects by the
+    attribute names of `registry_table()` (e.g. `mmdet3d.models.builder` for the model registries, `mmdet.datasets.builder` for
+    PIPELINES); registries it does not have are skipped.  Uses mmcv's `Registry.register_module(name=, force=, module=)`.
+    Returns the (registry, type) pairs that were registered."""
+    done = []
+    for reg_name, type_name, cls in registry_table():
+        reg = registries.get(reg_name) if isinstance(registries, dict) else getattr(registries, reg_name, None)
+        if reg is None:
+            continue
+        reg.register_module(name=type_name, force=force, module=cls)
+        done.append((reg_name, type_name))
+    return done

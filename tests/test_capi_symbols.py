@@ -72,3 +72,24 @@ def test_prepack_size_with_fp16_blocks():
         assert r.returncode == 0, r.stderr[-2000:]
         sizes[flag] = [int(v) for v in r.stdout.split()]
     assert all(b * 2 == a * 3 for a, b in zip(sizes["0"], sizes["1"])), sizes
+
+
+def test_registry_registration_with_a_stand_in_registry():
+    """shims.register drives mmcv's Registry API; mmcv is not installed here, so a registry with the same method stands in."""
+    from fullysparsefusion_b200 import shims
+
+    class Registry:
+        def __init__(self):
+            self.module_dict = {}
+
+        def register_module(self, name=None, force=False, module=None):
+            assert module is not None and (force or name not in self.module_dict)
+            self.module_dict[name] = module
+
+    regs = {n: Registry() for n in ("VOXEL_ENCODERS", "BACKBONES", "HEADS", "PIPELINES")}       # NECKS / ROI_EXTRACTORS absent: skipped
+    done = shims.register(regs)
+    assert ("HEADS", "VoteSegHead") in done and ("NECKS", "Voxel2PointScatterNeck") not in done
+    assert set(regs["VOXEL_ENCODERS"].module_dict) == {"DynamicScatterVFE", "SIRLayer"}
+    assert regs["PIPELINES"].module_dict["LoadMaskFromFiles"].__name__ == "LoadMaskFromFiles"
+    assert len(done) == len([r for r in shims.registry_table() if r[0] in regs])
+    shims.register(regs)        # force=True: a second registration replaces, as mmcv allows
