@@ -60,8 +60,15 @@ class SparseClusterHeadV2(nn.Module):
     (sparse_cluster_head_v2.py:134-168); FrustumClusterHead inherits this forward."""
 
     def __init__(self, num_classes, in_channel, shared_mlp_dims, tasks, common_attrs, num_cls_layer, cls_hidden_dim,
-                 separate_head, norm_cfg=LN5, act="relu"):
+                 separate_head, norm_cfg=LN5, act="relu", bbox_coder=None, class_names=None, train_cfg=None, test_cfg=None,
+                 shared_dropout=0, **training_only):
+        # `training_only` swallows what the stock configs also pass and inference never reads: loss_cls / loss_center / loss_size /
+        # loss_rot / loss_vel / loss_iou, cls_mlp / reg_mlp / iou_mlp (None in the configs), corner_loss_cfg, enlarge_width, as_rpn,
+        # init_cfg, and FrustumClusterHead's assigner / num_objs / vis_dir / use_one_to_one (sparse_cluster_head_v2.py:47-76,
+        # frustum_cluster_head.py:21-54)
         super().__init__()
+        assert not shared_dropout, "dropout is a training-time option"
+        self.bbox_coder_cfg, self.class_names, self.train_cfg, self.test_cfg = bbox_coder, class_names, train_cfg, test_cfg
         self.shared_mlp = M.build_mlp(in_channel, list(shared_mlp_dims), norm_cfg, act=act) if len(shared_mlp_dims) else None
         sep_in = shared_mlp_dims[-1] if len(shared_mlp_dims) else in_channel
         self.task_heads = nn.ModuleList()

@@ -93,3 +93,36 @@ def test_registry_registration_with_a_stand_in_registry():
     assert regs["PIPELINES"].module_dict["LoadMaskFromFiles"].__name__ == "LoadMaskFromFiles"
     assert len(done) == len([r for r in shims.registry_table() if r[0] in regs])
     shims.register(regs)        # force=True: a second registration replaces, as mmcv allows
+
+
+@pytest.mark.parametrize("cfg_file", ["nuScenes/FSF_nuScenes_config.py", "Argoverse2/FSF_AV2_config.py"])
+def test_stock_config_kwargs_construct_the_drop_in_classes(cfg_file):
+    """Every model sub-config of the reference's stock configs whose `type` is in shims.registry_table() constructs the class here
+    with its kwargs unchanged (build container only: reads the config from /root/reference)."""
+    import copy
+    import os
+
+    path = os.path.join("/root/reference/projects/configs", cfg_file)
+    if not os.path.exists(path):
+        pytest.skip("reference configs are not on this box")
+    from fullysparsefusion_b200 import shims
+
+    ns = {}
+    exec(compile(open(path).read(), path, "exec"), ns)
+    table = {t: c for _, t, c in shims.registry_table()}
+    found = []
+
+    def walk(d):
+        if isinstance(d, dict):
+            if d.get("type") in table and d.get("type") != "FSDSeparateHead":     # a partial spec its parent head completes
+                found.append(d)
+            for v in d.values():
+                walk(v)
+        elif isinstance(d, (list, tuple)):
+            for v in d:
+                walk(v)
+
+    walk(ns["model"])
+    assert len(found) >= 9
+    for d in found:
+        table[d["type"]](**{k: copy.deepcopy(v) for k, v in d.items() if k != "type"})
