@@ -3,6 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/bringup_f16.sh'
 # Everything is wrapped in its own timeout: a hang in an untested kernel must not hold the box.
 mkdir -p gpurun_out
+[ -x tools/microbench/gather_paths ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench/gather_paths tools/microbench/gather_paths.cu
 timeout 120 tools/microbench/gather_paths > gpurun_out/gather_paths.txt 2>&1
 FSFB_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_gemm_f16.py -x -q > gpurun_out/f16_test.txt 2>&1
 echo "f16 test exit $?" >> gpurun_out/f16_test.txt
