@@ -9,8 +9,9 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FSFB_TEST_EXPERIMENTAL") != "1", reason="experimental path: set FSFB_TEST_EXPERIMENTAL=1")]
+from tests.conftest import not_yet_on_hardware  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, not_yet_on_hardware]
 
 CHILD = r"""
 import numpy as np, torch

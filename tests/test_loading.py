@@ -12,6 +12,7 @@ import torch
 
 from fullysparsefusion_b200 import loading as L
 from fullysparsefusion_b200 import synth
+from tests.conftest import not_yet_on_hardware
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ROOT = os.path.join(GOLD, "mask_samples")
@@ -122,6 +123,7 @@ def test_frame_stager_cpu_rotation():
 
 
 @pytest.mark.gpu
+@not_yet_on_hardware
 def test_disk_to_ids_on_device(cuda, gold):
     """sample directory → pinned slot → device → projection kernel: ids equal the oracle's on the reference-loaded planes."""
     from fullysparsefusion_b200 import ops
@@ -174,7 +176,7 @@ def test_hwc16_layout_is_the_planes_interleaved(gold):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("FSFB_TEST_EXPERIMENTAL") != "1", reason="experimental path: set FSFB_TEST_EXPERIMENTAL=1")
+@not_yet_on_hardware
 def test_hwc16_projection_matches_planar(cuda, gold):
     """fsfb_project_sample_select_hwc (written without GPU access; gated until brought up) against the validated planar kernel."""
     from fullysparsefusion_b200 import ops
