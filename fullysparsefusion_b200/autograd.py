@@ -1,0 +1,68 @@
+"""Autograd for the gather-GEMM (sparse convolution / Linear without epilogue) — SURVEY.md section 8f rank 4, second step.
+
+    y = sparse_conv(a, w, nbr)        y[r] = sum_k a[nbr[k][r]] @ w[k].T        (nbr None: plain Linear, w [cout, cin])
+
+* forward and the input gradient run through the library's own persistent tcgen05 kernel: the input gradient of a sparse
+  convolution is the same gather-GEMM over the TRANSPOSED rulebook (`inv[k][nbr[k][r]] = r`, well defined because for a fixed
+  offset distinct outputs read distinct inputs — true for submanifold, strided and inverse convolutions alike) with `w[k]`
+  transposed:  da[j] = sum_k dy[inv[k][j]] @ w[k];
+* the weight gradient dw[k] = dy[rows_k].T @ a[nbr[k][rows_k]] is 27 library GEMMs (torch.matmul) for now — the baseline a native
+  split-K kernel has to beat, not the product;
+* the fused epilogues (folded BatchNorm, LayerNorm, activations, residual) are inference forms and have no backward: training
+  composes this function with torch's own norm / activation modules.
+Rulebook transposition uses torch indexing (backward only)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+def transpose_rulebook(nbr: torch.Tensor, n_in: int) -> torch.Tensor:
+    """nbr [koff, n_out] i32 (input row read by offset k of output r, < 0 none) → inv [koff, n_in] i32 (output row that reads
+    input j through offset k, -1 none)."""
+    inv = torch.full((nbr.size(0), n_in), -1, dtype=torch.int32, device=nbr.device)
+    k_idx, r_idx = torch.nonzero((nbr >= 0) & (nbr < n_in), as_tuple=True)
+    inv[k_idx, nbr[k_idx, r_idx].long()] = r_idx.to(torch.int32)
+    return inv
+
+
+class _SparseConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, w, nbr):
+        ctx.save_for_backward(a, w, nbr)
+        return ops.gather_gemm(a.contiguous(), ops.gemm_prepack(w.detach()), nbr=nbr)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, w, nbr = ctx.saved_tensors
+        w3 = w if w.dim() == 3 else w[None]
+        g = grad_out.contiguous()
+        grad_a = grad_w = None
+        if ctx.needs_input_grad[0]:
+            wt = w3.detach().transpose(1, 2).contiguous()                  # [koff, cin, cout]: the "weights" of the transposed conv
+            inv = transpose_rulebook(nbr, a.size(0)) if nbr is not None else None
+            grad_a = ops.gather_gemm(g, ops.gemm_prepack(wt), nbr=inv)
+            if grad_a.size(0) != a.size(0):                                # Linear: rows == a rows by construction
+                raise RuntimeError("sparse_conv backward: input gradient has the wrong number of rows")
+            grad_a = grad_a[:, : a.size(1)]
+        if ctx.needs_input_grad[1]:
+            grad_w3 = torch.zeros_like(w3)
+            for k in range(w3.size(0)):
+                if nbr is None:
+                    grad_w3[k] = g.t() @ a
+                else:
+                    rows = torch.nonzero((nbr[k] >= 0) & (nbr[k] < a.size(0)))[:, 0]
+                    if rows.numel():
+                        grad_w3[k] = g[rows].t() @ a[nbr[k][rows].long()]
+            grad_w = grad_w3.view_as(w)
+        return grad_a, grad_w, None
+
+
+def sparse_conv(a: torch.Tensor, w: torch.Tensor, nbr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable gather-GEMM: a [n_in, cin] f32, w [koff, cout, cin] (or [cout, cin] with nbr None), nbr [koff, n_out] i32."""
+    if nbr is None and w.dim() == 3 and w.size(0) != 1:
+        raise ValueError("a weight with several offsets needs a rulebook")
+    return _SparseConv.apply(a, w, nbr)

@@ -1,0 +1,85 @@
+"""Autograd of the gather-GEMM (fullysparsefusion_b200/autograd.py) against torch's own autograd of the same sum.
+
+The CPU test runs the backward glue (rulebook transposition, transposed weights, per-offset weight gradients) with
+`ops.gemm_prepack / gather_gemm` replaced by a torch stand-in (test-only; the product ops refuse CPU tensors); the GPU test runs
+the real kernels (gated: written after the GPU budget was spent)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from fullysparsefusion_b200 import autograd as AG
+from fullysparsefusion_b200 import ops
+from tests.conftest import not_yet_on_hardware
+
+
+def _reference(a, w, nbr):
+    w3 = w if w.dim() == 3 else w[None]
+    if nbr is None:
+        return a @ w3[0].t()
+    out = 0
+    for k in range(w3.size(0)):
+        src = nbr[k].long()
+        ok = (src >= 0) & (src < a.size(0))
+        rows = a[src.clamp(0, a.size(0) - 1)] * ok[:, None]
+        out = out + rows @ w3[k].t()
+    return out
+
+
+def _cases(device):
+    g = torch.Generator().manual_seed(5)
+    out = []
+    # submanifold-like: n_out == n_in, symmetric-ish random rulebook built from an injective map per offset
+    for n_in, n_out, cin, cout, koff in [(200, 200, 32, 64, 27), (150, 90, 64, 32, 8), (64, 300, 16, 16, 8)]:
+        nbr = torch.full((koff, n_out), -1, dtype=torch.int32)
+        for k in range(koff):
+            m = min(n_in, n_out)
+            src = torch.randperm(n_in, generator=g)[:m]                  # injective per offset, as real rulebooks are
+            dst = torch.randperm(n_out, generator=g)[:m]
+            keep = torch.rand(m, generator=g) < 0.4
+            nbr[k, dst[keep]] = src[keep].to(torch.int32)
+        a = torch.randn(n_in, cin, generator=g)
+        w = torch.randn(koff, cout, cin, generator=g) / (cin * koff) ** 0.5
+        out.append((a.to(device), w.to(device), nbr.to(device)))
+    a = torch.randn(300, 96, generator=g)
+    w = torch.randn(64, 96, generator=g) / 96 ** 0.5
+    out.append((a.to(device), w.to(device), None))                       # plain Linear
+    return out
+
+
+def _check(device, rtol, atol):
+    for a, w, nbr in _cases(device):
+        a1, w1 = a.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        a2, w2 = a.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = AG.sparse_conv(a1, w1, nbr)
+        want = _reference(a2, w2, nbr)
+        torch.testing.assert_close(y, want, rtol=rtol, atol=atol)
+        coef = torch.randn(want.shape, generator=torch.Generator().manual_seed(1)).to(device)
+        (y * coef).sum().backward()
+        (want * coef).sum().backward()
+        torch.testing.assert_close(a1.grad, a2.grad, rtol=rtol, atol=atol)
+        torch.testing.assert_close(w1.grad, w2.grad, rtol=rtol, atol=atol)
+        if nbr is not None:                                              # transposing twice gives the rulebook back
+            inv = AG.transpose_rulebook(nbr, a.size(0))
+            assert torch.equal(AG.transpose_rulebook(inv, nbr.size(1)), nbr)
+    # input gradient only / weight gradient only
+    a, w, nbr = _cases(device)[0]
+    a1 = a.clone().requires_grad_(True)
+    AG.sparse_conv(a1, w, nbr).sum().backward()
+    assert a1.grad is not None
+    w1 = w.clone().requires_grad_(True)
+    AG.sparse_conv(a, w1, nbr).sum().backward()
+    assert w1.grad is not None and w1.grad.shape == w.shape
+
+
+def test_backward_glue_on_cpu(monkeypatch):
+    monkeypatch.setattr(ops, "gemm_prepack", lambda w, keep_raw=False: types.SimpleNamespace(raw=w if w.dim() == 3 else w[None]))
+    monkeypatch.setattr(ops, "gather_gemm", lambda a, pw, nbr=None, **kw: _reference(a, pw.raw, nbr))
+    _check("cpu", 1e-5, 1e-5)
+
+
+@pytest.mark.gpu
+@not_yet_on_hardware
+def test_backward_on_device(cuda):
+    _check("cuda:0", 1e-4, 2e-5)

@@ -10,7 +10,7 @@ echo "f16 test exit $?" >> gpurun_out/f16_test.txt
 FSFB_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_loading.py -x -q -k hwc16_projection > gpurun_out/hwc16_test.txt 2>&1
 # the four tests of validated paths that were written after the GPU budget ran out (un-gate them once they pass)
 FSFB_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest -q -m gpu tests/test_loading.py tests/test_shim_autograd.py tests/test_gpu_frame.py \
-  tests/test_gpu_modules.py -k "disk_to_ids or backward_on_device or simple_test_entry or vote_seg_head_reference" > gpurun_out/new_tests.txt 2>&1
+  tests/test_gpu_modules.py tests/test_conv_autograd.py -k "disk_to_ids or backward_on_device or simple_test_entry or vote_seg_head_reference" > gpurun_out/new_tests.txt 2>&1
 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err
 if grep -q "F16 OK" gpurun_out/f16_test.txt || grep -q "1 passed" gpurun_out/f16_test.txt; then
   FSFB_GEMM_F16=1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f16.json 2> gpurun_out/bench_f16.err
