@@ -10,6 +10,8 @@
 //
 // Radix passes use up to 11 bits (2048 bins, 64 KB of per-warp counters in shared memory),
 // so <= 2048 segments sort in one pass and <= 4M segments in two.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fsfb {
@@ -216,26 +218,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Sort key of an output row: (number of present offsets, offset mask) packed into 31 bits, so rows with the same set of
-// neighbour offsets become adjacent AND tiles come out ordered by cost (the persistent gather-GEMM hands out tiles from
-// the end of the order: longest first).  koff <= 26: popc << koff | mask; koff == 27: the centre bit (13) is dropped
-// from the mask part to make room; koff > 27: the mask alone.
-__host__ __device__ inline uint32_t rulebook_key(uint32_t m, int koff) {
+// Sort key of an output row, so that rows with similar sets of neighbour offsets become adjacent AND tiles come out ordered by
+// cost (the persistent gather-GEMM hands out tiles from the end of the order: longest first).
+//   koff == 27 (3x3x3 kernels, offsets z-major), mode 1 (default): (any neighbour in the upper plane, any in the lower plane,
+//     the 27-bit mask) = 29 bits.  tools/tile_reuse_study.py: a 128-row tile then visits 9.2 offsets on the 160 k-voxel level
+//     of the synthetic frame against 11.1 with the popcount-major key (and 3-14 % fewer on the strided and coarser levels) —
+//     surfaces split into rows that only have in-plane neighbours and rows that also have vertical ones;
+//   mode 0 (FSFB_ROW_KEY=0, the key the round-1 measurements were taken with) and koff <= 26: popcount << koff | mask;
+//   koff > 27: the mask alone.
+__host__ __device__ inline uint32_t rulebook_key(uint32_t m, int koff, int mode) {
 #ifdef __CUDA_ARCH__
   const uint32_t pc = (uint32_t)__popc(m);
 #else
   const uint32_t pc = (uint32_t)__builtin_popcount(m);
 #endif
   if (koff <= 26) return (pc << koff) | m;
-  if (koff == 27) return (pc << 26) | (m & 0x1FFFu) | ((m >> 14) << 13);
+  if (koff == 27) {
+    if (mode == 0) return (pc << 26) | (m & 0x1FFFu) | ((m >> 14) << 13);  // centre bit (13) dropped to make room
+    const uint32_t up = (m >> 18) != 0u ? 1u : 0u, dn = (m & 0x1FFu) != 0u ? 1u : 0u;
+    return (up << 28) | (dn << 27) | m;
+  }
   return m;
 }
+inline int rulebook_key_mode() {
+  static const int mode = [] {
+    const char* e = getenv("FSFB_ROW_KEY");
+    return e ? atoi(e) : 1;
+  }();
+  return mode;
+}
 __global__ void __launch_bounds__(256)
-    k_rulebook_masks(const int32_t* __restrict__ nbr, int koff, int64_t rows, int32_t* __restrict__ mask) {
+    k_rulebook_masks(const int32_t* __restrict__ nbr, int koff, int64_t rows, int32_t* __restrict__ mask, int mode) {
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
     uint32_t m = 0;
     for (int k = 0; k < koff; ++k) m |= (__ldg(nbr + (int64_t)k * rows + r) >= 0 ? 1u : 0u) << k;
-    mask[r] = (int32_t)rulebook_key(m, koff);
+    mask[r] = (int32_t)rulebook_key(m, koff, mode);
   }
 }
 
@@ -357,7 +374,7 @@ int fsfb_rulebook_order_workspace_bytes(int64_t rows, int koff, size_t* bytes) {
   Workspace ws(nullptr, 0);
   ws.take<int32_t>(std::max<int64_t>(rows, 1));   // masks
   ws.take<uint32_t>(std::max<int64_t>(rows, 1));  // sorted keys
-  csr_ws_layout(rows, (int64_t)rulebook_key((1u << koff) - 1u, koff), ws, nullptr, nullptr, nullptr);
+  csr_ws_layout(rows, (int64_t)rulebook_key((1u << koff) - 1u, koff, 0), ws, nullptr, nullptr, nullptr);  // mode 0 has the larger maximum
   *bytes = ws.used;
   return FSFB_OK;
 }
@@ -373,15 +390,16 @@ int fsfb_rulebook_row_order(const int32_t* nbr, int koff, int64_t rows, int32_t*
   int32_t* mask = ws.take<int32_t>(rows);
   uint32_t* keys = ws.take<uint32_t>(rows);
   uint32_t *tk, *tv, *hist;
-  csr_ws_layout(rows, (int64_t)rulebook_key((1u << koff) - 1u, koff), ws, &tk, &tv, &hist);
+  csr_ws_layout(rows, (int64_t)rulebook_key((1u << koff) - 1u, koff, 0), ws, &tk, &tv, &hist);
   if (!ws.ok()) {
     set_error("rulebook_row_order: workspace too small (%zu given, %zu needed)", workspace_bytes, ws.used);
     return FSFB_ERR_CAPACITY;
   }
   const int grid = (int)std::min<int64_t>(ceil_div(rows, 256), (int64_t)kNumSMs * 8);
-  FSFB_LAUNCH(k_rulebook_masks, grid, 256, 0, st, nbr, koff, rows, mask);
+  const int mode = rulebook_key_mode();
+  FSFB_LAUNCH(k_rulebook_masks, grid, 256, 0, st, nbr, koff, rows, mask, mode);
   // stable LSD sort of the keys: rows with the same set of neighbour offsets become adjacent, fewest offsets first
-  return radix_sort_index<int>(mask, rows, rulebook_key((1u << koff) - 1u, koff), keys, (uint32_t*)order, tk, tv, hist, st);
+  return radix_sort_index<int>(mask, rows, rulebook_key((1u << koff) - 1u, koff, mode), keys, (uint32_t*)order, tk, tv, hist, st);
 }
 
 int fsfb_ingroup_workspace_bytes(int64_t n, int64_t m, size_t* bytes) {
