@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call for the experimental fp16-split gather-GEMM and the gather micro-benchmark:
-#   gpurun --timeout 900 -- 'bash tools/bringup_f16.sh'
+#   gpurun --timeout 1800 -- 'bash tools/bringup_f16.sh'
 # Everything is wrapped in its own timeout: a hang in an untested kernel must not hold the box.
 mkdir -p gpurun_out
 [ -x tools/microbench/gather_paths ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/microbench/gather_paths tools/microbench/gather_paths.cu
