@@ -14,13 +14,6 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-# GPU tests written after the round's GPU budget was spent: they have never run on hardware, so they stay out of the default
-# `-m gpu` run (a red suite must mean a regression, not a bring-up issue) until FSFB_TEST_EXPERIMENTAL=1 has been used to validate
-# them once (tools/bringup_f16.sh does that first).
-not_yet_on_hardware = pytest.mark.skipif(os.environ.get("FSFB_TEST_EXPERIMENTAL") != "1",
-                                         reason="not yet run on hardware: set FSFB_TEST_EXPERIMENTAL=1")
-
-
 def load_golden(name: str):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 

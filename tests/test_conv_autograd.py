@@ -11,7 +11,6 @@ import torch
 
 from fullysparsefusion_b200 import autograd as AG
 from fullysparsefusion_b200 import ops
-from tests.conftest import not_yet_on_hardware
 
 
 def _reference(a, w, nbr):
@@ -80,6 +79,5 @@ def test_backward_glue_on_cpu(monkeypatch):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_backward_on_device(cuda):
     _check("cuda:0", 1e-4, 2e-5)

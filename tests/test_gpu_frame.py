@@ -13,7 +13,6 @@ from oracle import fsf_oracle as O
 from oracle import fsf_oracle_frame as OF
 from oracle import fsf_oracle_models as OM
 from tests.test_gpu_modules import randomize, sd_np
-from tests.conftest import not_yet_on_hardware
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-4, 5e-5
@@ -261,7 +260,6 @@ def test_detections(cuda, frame):
         assert abs(len(N(labels)) - len(wl)) <= 2
 
 
-@not_yet_on_hardware
 def test_simple_test_entry(cuda, frame):
     """FSF.simple_test (the reference's test entry and argument conventions) = forward → refine → get_bboxes on each sample."""
     model, pts = frame["model"], frame["pts"]

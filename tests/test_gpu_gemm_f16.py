@@ -9,9 +9,8 @@ import sys
 
 import pytest
 
-from tests.conftest import not_yet_on_hardware  # noqa: E402
 
-pytestmark = [pytest.mark.gpu, not_yet_on_hardware]
+pytestmark = [pytest.mark.gpu]
 
 CHILD = r"""
 import numpy as np, torch

@@ -11,7 +11,6 @@ from fullysparsefusion_b200 import ops, synth
 from oracle import fsf_oracle as O
 from oracle import fsf_oracle_models as OM
 from tests.conftest import load_golden
-from tests.conftest import not_yet_on_hardware
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-4, 3e-5
@@ -147,7 +146,6 @@ def test_cluster_head_reference_golden(cuda):
     np.testing.assert_allclose(out["reg_preds"][0].cpu().numpy(), g["reg"], rtol=1e-4, atol=2e-5)
 
 
-@not_yet_on_hardware
 def test_vote_seg_head_reference_golden(cuda):
     """modules.VoteSegHead with the state dict of the reference's own VoteSegHead (BN running statistics folded into the fused
     Linear epilogue): same logits and votes (1e-4)."""

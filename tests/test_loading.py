@@ -12,7 +12,6 @@ import torch
 
 from fullysparsefusion_b200 import loading as L
 from fullysparsefusion_b200 import synth
-from tests.conftest import not_yet_on_hardware
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ROOT = os.path.join(GOLD, "mask_samples")
@@ -123,7 +122,6 @@ def test_frame_stager_cpu_rotation():
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_disk_to_ids_on_device(cuda, gold):
     """sample directory → pinned slot → device → projection kernel: ids equal the oracle's on the reference-loaded planes."""
     from fullysparsefusion_b200 import ops
@@ -176,7 +174,6 @@ def test_hwc16_layout_is_the_planes_interleaved(gold):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_hwc16_projection_matches_planar(cuda, gold):
     """fsfb_project_sample_select_hwc (written without GPU access; gated until brought up) against the validated planar kernel."""
     from fullysparsefusion_b200 import ops

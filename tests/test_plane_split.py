@@ -10,7 +10,6 @@ import torch
 from fullysparsefusion_b200 import modules as M
 from fullysparsefusion_b200 import ops, synth
 from oracle import fsf_oracle as O
-from tests.conftest import not_yet_on_hardware
 
 
 def _scene(n_pts, seed):
@@ -94,6 +93,5 @@ def test_plane_split_host_logic_on_cpu(monkeypatch):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_plane_split_on_device(cuda, monkeypatch):
     _compare("cuda:0", monkeypatch, 1e-4, 2e-5)

@@ -9,7 +9,6 @@ import torch
 from fullysparsefusion_b200 import ops
 from fullysparsefusion_b200.shims import torch_scatter as TS
 from oracle import fsf_oracle as O
-from tests.conftest import not_yet_on_hardware
 
 
 def _reference(src, index, m, mode):
@@ -86,6 +85,5 @@ def test_backward_glue_on_cpu(monkeypatch):
 
 
 @pytest.mark.gpu
-@not_yet_on_hardware
 def test_backward_on_device(cuda):
     _check("cuda:0")
