@@ -45,6 +45,11 @@ SIGNATURES = {
     "fsfb_gather_gemm_splitk_bytes": (_i, [_i64, _i, _i, _p]),
     "fsfb_gather_gemm_splitk": (_i, [_p, _i64, _i, _i64, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _i, _p, _sz, _p]),
     "fsfb_debug_gemm_timers": (_i, [_p]),
+    "fsfb_debug_gemm_ss_timers": (_i, [_p]),
+    "fsfb_gemm_f16_overflows": (_i, [_p]),
+    "fsfb_split_rows": (_i, [_p, _i64, _i, _i64, _p, _p]),
+    "fsfb_gather_gemm_split": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p, _i, _p, _i, _p, _p, _f, _p, _i64, _i, _p, _i64, _i, _p, _sz,
+                                   _p, _p, _p, _p]),
     "fsfb_group_flags": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p]),
     "fsfb_group_split": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p]),
     "fsfb_group_voxelize": (_i, [_p, _i64, _p, _p, _p, _i, _p, _p]),

@@ -54,12 +54,13 @@ __host__ __device__ inline uint32_t sw128_offset_f16(int n, int j) {
 }
 constexpr float kF16LoScale = 2048.f;  // residuals are stored times 2^11 (keeps them in fp16's normal range); exact to undo
 
-// FSFB_GEMM_F16=1 (experimental): fsfb_gemm_prepack also writes the fp16-split blocks and the persistent gather-GEMM runs
-// kind::f16 MMAs on them (same 22-bit split precision as 3xTF32 at twice the tensor rate; inputs must stay below 65504).
+// fp16-split operands (default; FSFB_GEMM_F16=0 restores the 3xTF32 kernels and the tf32-only packed weights):
+// fsfb_gemm_prepack also writes the fp16-split blocks and the persistent gather-GEMMs run kind::f16 MMAs on them (same
+// 22-bit split precision as 3xTF32 at twice the tensor rate; inputs must stay below 65504).
 inline bool gemm_f16_enabled() {
   static const bool on = [] {
     const char* e = getenv("FSFB_GEMM_F16");
-    return e && atoi(e) != 0;
+    return !e || atoi(e) != 0;
   }();
   return on;
 }

@@ -280,7 +280,7 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
                             int norm, const float* norm_w, const float* norm_b, float eps,
                             const float* residual, int64_t residual_stride, int act, float* out,
                             int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, const float* host_bias,
-                            const float* host_norm_w, const float* host_norm_b, void* stream) {
+                            const float* host_norm_w, const float* host_norm_b, void* stream, bool a_split = false) {
   int rc = check_epilogue(cout, bias, norm, norm_w, norm_b, act, "gather_gemm");
   if (rc != FSFB_OK) return rc;
   FSFB_CHECK_ARG(rows >= 0 && a_rows >= 0 && a_rows < (1ll << 31) && cin >= 1 && a_stride >= cin &&
@@ -320,6 +320,16 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
     // persistent A-through-TMEM kernel (gemm_ts.cu) whenever the output splits into column tiles of <= 128
     // channels; the kernel below remains for widths like 131 / 144 (one 256-wide tile) and fused LayerNorms wider
     // than 128.  FSFB_GEMM_TS=0 forces the kernel below (A/B experiments).
+    static const int ss_mode = [] { const char* e = getenv("FSFB_GEMM_SS"); return e ? atoi(e) : 1; }();
+    if (ss_mode) {  // fp16-split operands from shared memory (gemm_ss.cu); 1 = shape not served there
+      const int rc_ss = launch_gather_gemm_ss(P, a_vec, a_split, (float*)workspace, workspace_bytes, splits, host_bias, host_norm_w,
+                                              host_norm_b, (cudaStream_t)stream);
+      if (rc_ss != 1) return rc_ss;
+    }
+    if (a_split) {
+      set_error("gather_gemm_split: shape koff=%d cin=%d cout=%d is not served by the fp16-split kernel (or FSFB_GEMM_SS/F16=0)", koff, cin, cout);
+      return FSFB_ERR_BADARG;
+    }
     static const int ts_mode = [] { const char* e = getenv("FSFB_GEMM_TS"); return e ? atoi(e) : 1; }();
     const int n_pad = P.S.n_pad();
     // (31 or 32 offsets: two neighbour tables no longer fit next to the rings in shared memory)
@@ -408,4 +418,18 @@ extern "C" int fsfb_gather_gemm_hv(const float* a, int64_t a_rows, int cin, int6
   return gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b, eps,
                           residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, host_bias,
                           host_norm_w, host_norm_b, stream);
+}
+
+extern "C" int fsfb_gather_gemm_split(const void* a_split, int64_t a_rows, int cin, const int32_t* nbr, const int32_t* row_order, int koff,
+                                      int64_t rows, const void* w_packed, int cout, const float* bias, int norm, const float* norm_w,
+                                      const float* norm_b, float eps, const float* residual, int64_t residual_stride, int act, float* out,
+                                      int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, const float* host_bias,
+                                      const float* host_norm_w, const float* host_norm_b, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(splits >= 1 && splits <= koff, "gather_gemm_split: splits=%d must be in 1..koff", splits);
+  FSFB_CHECK_ARG(splits == 1 || ((uintptr_t)workspace & 15) == 0, "gather_gemm_split: workspace must be 16-byte aligned");
+  FSFB_CHECK_ARG(cin % 32 == 0, "gather_gemm_split: cin=%d must be a multiple of 32", cin);
+  return gather_gemm_impl(reinterpret_cast<const float*>(a_split), a_rows, cin, cin, nbr, row_order, koff, rows, w_packed, cout, bias, norm,
+                          norm_w, norm_b, eps, residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes,
+                          host_bias, host_norm_w, host_norm_b, stream, true);
 }

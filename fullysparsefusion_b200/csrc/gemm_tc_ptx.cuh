@@ -166,6 +166,11 @@ struct TcParams {
   // host copies of the per-channel epilogue vectors (cout <= 128): read as constant-bank operands by the epilogue warps
   float hv_bias[128], hv_w[128], hv_h[128];
   int debug;    // FSFB_GEMM_DEBUG bits (profiling experiments only): 1 no A loads, 2 no W copy, 4 no MMA, 8 no A stores
+  // shared-memory-operand persistent kernel (gemm_ss.cu): ring depths, column-tile width, accumulator buffers and the byte
+  // offsets of the regions behind the A / W rings
+  int ss_a_stages, ss_w_stages, ss_tile_w, ss_acc_cols, ss_bufs, ss_stage_stride;
+  uint32_t ss_w_slot, ss_off_w, ss_off_nbr, ss_off_stage, ss_off_vec, ss_off_sh;
+  unsigned int* ss_overflow;  // device counter: launches that saw an input outside fp16 range (|a| >= 65504)
 };
 
 
@@ -276,7 +281,11 @@ __device__ __forceinline__ void epilogue_phase2(const TcParams& P, uint32_t base
   }
 }
 
+// gemm_ss.cu: returns 1 when the shape is left to the kernels below
+int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspace, size_t workspace_bytes, int splits,
+                          const float* host_bias, const float* host_norm_w, const float* host_norm_b, cudaStream_t st);
 // gemm_ts.cu
+int launch_splitk_epilogue(const TcParams& P, cudaStream_t st);
 int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, const float* host_bias,
                           const float* host_norm_w, const float* host_norm_b, cudaStream_t st);
 

@@ -7,6 +7,7 @@ tensor is not on a CUDA device — there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -493,6 +494,20 @@ def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
     return (_ptr(bias), _NORMS[norm], _ptr(norm_w), _ptr(norm_b))
 
 
+_SPLIT_ON = os.environ.get("FSFB_CONV_SPLIT", "1") != "0" and os.environ.get("FSFB_GEMM_SS", "1") != "0" \
+    and os.environ.get("FSFB_GEMM_F16", "1") != "0"
+
+
+def split_rows(a: torch.Tensor) -> torch.Tensor:
+    """fp32 rows [n, c] (c % 32 == 0) → the fp16-split operand rows of fsfb_gather_gemm_split (uint8 [n, 4 c])."""
+    dev = _need_cuda(a)
+    assert a.dim() == 2 and a.dtype == torch.float32 and a.stride(1) == 1 and a.size(1) % 32 == 0
+    out = torch.empty((a.size(0), 4 * a.size(1)), dtype=torch.uint8, device=dev)
+    with _Prof("split_rows", 8 * a.size(0) * a.size(1)):
+        check(load().fsfb_split_rows(_ptr(a), a.size(0), a.size(1), a.stride(0), _ptr(out), _stream(dev)), "fsfb_split_rows")
+    return out
+
+
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
                 out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False,
@@ -547,6 +562,19 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         units = ((rows + 127) // 128) * (cpad // 128)
         if tileable and w.koff >= 6 and cpad <= 1024 and units * 2 <= 148 and w.koff * ((w.cin + 31) // 32) >= 32:
             splits = max(1, min(w.koff // 3, 148 // units))
+    # 27-offset convolutions: every input row is gathered by ~6 offsets, so the fp32 → fp16-split conversion is done once per
+    # row up front (fsfb_split_rows) and the kernel's gather is pure data movement (include/fsf_b200.h)
+    if (_SPLIT_ON and nbr is not None and w.koff > 1 and w.koff <= 27 and w.cin % 32 == 0 and tileable and a.data_ptr() % 16 == 0
+            and a.stride(0) % 4 == 0 and a.size(0) > 0):
+        a_s = split_rows(a)
+        ws = torch.empty(splits * rows * cpad, dtype=torch.float32, device=dev) if splits > 1 else None
+        hv = w.cout <= 128 and splits == 1
+        with prof:
+            check(lib.fsfb_gather_gemm_split(_ptr(a_s), a.size(0), w.cin, _ptr(nbr), _ptr(row_order), w.koff, rows, _ptr(w.data), *tail[:-1],
+                                             splits, _ptr(ws), ws.numel() * 4 if ws is not None else 0,
+                                             _host_vec(bias) if hv else None, _host_vec(norm_w) if hv else None,
+                                             _host_vec(norm_b) if hv else None, tail[-1]), "fsfb_gather_gemm_split")
+        return out
     with prof:
         if splits > 1:
             ws = torch.empty(splits * rows * cpad, dtype=torch.float32, device=dev)

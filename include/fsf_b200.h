@@ -257,9 +257,34 @@ int fsfb_gather_gemm_hv(const float* a, int64_t a_rows, int cin, int64_t a_strid
                         size_t workspace_bytes, const float* host_bias, const float* host_norm_w,
                         const float* host_norm_b, void* stream);
 
+/* Pre-split operands for the 27-offset convolutions.  fsfb_split_rows converts fp32 rows [rows, c] (c % 32 == 0, 16-byte
+ * aligned rows) into the fp16-split row format of the tensor-core operand: per 32 channels one 128-byte block
+ * [32 x fp16(a) | 32 x fp16((a - hi) * 2048)], out dev [rows * c * 4] bytes (HBM-bound: 8 c bytes per row).
+ * fsfb_gather_gemm_split is fsfb_gather_gemm_hv reading such rows (dense, 4 * cin bytes per row): the gather then is pure data
+ * movement (16-byte cp.async copies into the operand ring, no conversion per gathered row), which matters when every row is
+ * gathered by ~6 of the 27 offsets.  Results are bit-identical to fsfb_gather_gemm on the fp32 rows. */
+int fsfb_split_rows(const float* a, int64_t rows, int c, int64_t a_stride, void* out, void* stream);
+int fsfb_gather_gemm_split(const void* a_split, int64_t a_rows, int cin,
+                           const int32_t* nbr, const int32_t* row_order, int koff, int64_t rows,
+                           const void* w_packed, int cout,
+                           const float* bias, int norm, const float* norm_w, const float* norm_b,
+                           float eps, const float* residual, int64_t residual_stride, int act,
+                           float* out, int64_t out_stride, int splits, void* workspace,
+                           size_t workspace_bytes, const float* host_bias, const float* host_norm_w,
+                           const float* host_norm_b, void* stream);
+
+/* The default arithmetic of fsfb_gather_gemm* is the fp16-split form (csrc/gemm_ss.cu: a = hi + lo / 2048 with fp16 hi and
+ * lo, three kind::f16 MMAs per product, the same 22 mantissa bits as 3xTF32; FSFB_GEMM_F16=0 in the environment restores
+ * 3xTF32).  Inputs must lie inside fp16 range (|a| < 65504; the reference's features are normalised activations and metric
+ * coordinates).  A launch that meets a larger magnitude produces Inf/NaN in the affected rows and bumps this counter:
+ * *count = number of such launches on the current device since the library was loaded (synchronises the device). */
+int fsfb_gemm_f16_overflows(unsigned int* count);
+
 /* Diagnostics only: per-CTA role cycle counters [148][32] u32 of the last fsfb_gather_gemm launch made with
  * FSFB_GEMM_TIMERS=1 in the environment (layout in csrc/gemm_ts.cu). */
 int fsfb_debug_gemm_timers(unsigned int* out);
+/* Same for the shared-memory-operand kernel (layout in csrc/gemm_ss.cu). */
+int fsfb_debug_gemm_ss_timers(unsigned int* out);
 
 /* Same contract evaluated with plain fp32 FMAs on CUDA cores from the UNPACKED weights
  * (w dev [koff,cout,cin]).  Independent cross-check of the tensor-core path at sizes the
