@@ -10,11 +10,11 @@
 //     warp instruction, every sector fully used), up to three stages of loads in flight per thread in registers; fp32 →
 //     fp16 hi + fp16 (residual * 2048) in registers, lane pairs exchange halves so that every lane writes one 16-byte
 //     piece of the SWIZZLE_128B K-major row [hi 64 B | lo 64 B] (conflict-free 128-bit shared stores);
-//   * warp 20     single MMA issuer: per stage two K = 16 steps x (hi*hi → main accumulator; lo*hi + hi*lo → correction
-//     accumulator, scaled back by 2^-11 in the epilogue) = 6 kind::f16 MMAs instead of the 12 kind::tf32 ones of 3xTF32;
-//   * warp 21     W loader: one bulk-async copy per stage (fp16 blocks of fsfb_gemm_prepack: 128 B per output channel);
+//   * warps 20,21 MMA issuers: per stage two K = 16 steps x (hi*hi → main accumulator, first warp; lo*hi + hi*lo → correction
+//     accumulator, second warp, scaled back by 2^-11 in the epilogue) = 6 kind::f16 MMAs instead of the 12 kind::tf32 ones;
+//   * warp 22     W loader: one bulk-async copy per stage (fp16 blocks of fsfb_gemm_prepack: 128 B per output channel);
 //     slots that already hold the wanted block are not re-copied (Linear layers keep W resident);
-//   * warp 22     scheduler: unit ids from a global ticket counter, the unit's 27 x 128 neighbour table (4-byte
+//   * warp 23     scheduler: unit ids from a global ticket counter, the unit's 27 x 128 neighbour table (4-byte
 //     cp.async) and its active-offset mask, published through an 8-deep info ring;
 //   * warps 16-19 epilogue: accumulators are DOUBLE-BUFFERED in tensor memory (2 x (main + correction) x <= 128
 //     columns), so the drain of unit i overlaps the MMAs of unit i+1 (the Linear layers of the TS kernel were epilogue
@@ -35,9 +35,9 @@ namespace fsfb {
 
 constexpr int kSsProducerWarps = 16;
 constexpr int kSsEpiWarp = kSsProducerWarps;   // warps 16-19 (TMEM lane quarter = warp % 4)
-constexpr int kSsMmaWarp = kSsEpiWarp + 4;     // warp 20
-constexpr int kSsLoaderWarp = kSsMmaWarp + 1;  // warp 21
-constexpr int kSsSchedWarp = kSsMmaWarp + 2;   // warp 22 (warp 23 idles: setmaxnreg works on whole warpgroups)
+constexpr int kSsMmaWarp = kSsEpiWarp + 4;     // warps 20, 21: MMA issuers (main / correction accumulator)
+constexpr int kSsLoaderWarp = kSsMmaWarp + 2;  // warp 22
+constexpr int kSsSchedWarp = kSsMmaWarp + 3;   // warp 23
 constexpr int kSsThreads = 768;
 constexpr int kSsInfo = 8;                     // info ring depth (> prefetch depth + accumulator buffers: see header)
 constexpr int kSsMaxA = 6, kSsMaxW = 4;
@@ -142,19 +142,19 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
     if (base & 1023u) __trap();
     for (int s = 0; s < kSsMaxA; ++s) {
       mbar_init(smem_u32(&sh->a_full[s]), LOAD == 3 ? kSsSplitWarps * 32 : kSsProducerWarps);
-      mbar_init(smem_u32(&sh->a_empty[s]), 1);
+      mbar_init(smem_u32(&sh->a_empty[s]), 2);  // both MMA issuers commit
     }
     for (int s = 0; s < kSsMaxW; ++s) {
       mbar_init(smem_u32(&sh->w_full[s]), 1);
-      mbar_init(smem_u32(&sh->w_empty[s]), 1);
+      mbar_init(smem_u32(&sh->w_empty[s]), 2);
     }
     for (int s = 0; s < kSsInfo; ++s) {
       mbar_init(smem_u32(&sh->info_full[s]), 1);
-      mbar_init(smem_u32(&sh->info_empty[s]), (LOAD == 3 ? kSsSplitWarps : kSsProducerWarps) + 1 + 1 + 4);
+      mbar_init(smem_u32(&sh->info_empty[s]), (LOAD == 3 ? kSsSplitWarps : kSsProducerWarps) + 2 + 1 + 4);  // + MMA warps, loader, epilogue
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&sh->tbl_empty[s]), LOAD == 3 ? kSsSplitWarps : kSsProducerWarps);
-      mbar_init(smem_u32(&sh->acc_full[s]), 1);
+      mbar_init(smem_u32(&sh->acc_full[s]), 2);
       mbar_init(smem_u32(&sh->acc_empty[s]), 4);
     }
     for (int w = 0; w < 4; ++w) mbar_init(smem_u32(&sh->res_full[w]), 1);
@@ -442,11 +442,18 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
     }  // producing warp
   } else if (warp >= kSsMmaWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-    if (warp == kSsMmaWarp) {
-      // ================= MMA issuer =================
+    if (warp == kSsMmaWarp || warp == kSsMmaWarp + 1) {
+      // ================= two MMA issuers =================
+      // first warp: main accumulator (a_hi * w_hi); second warp: correction accumulator (a_lo * w_hi + a_hi * w_lo).  Two warps
+      // because the per-stage instruction latency of ONE issuing warp (waits, descriptors, 6 MMAs, 3 commits: ~650 clk measured)
+      // exceeded the 384 clk of tensor work of a stage.  Whole-warp loop with warp-uniform operands, one elected lane issues.
+      const bool is_main = warp == kSsMmaWarp;
       const uint32_t u_tmem_d = __shfl_sync(0xffffffffu, tmem_d, 0);
-      const uint32_t u_base = __shfl_sync(0xffffffffu, base, 0);
-      const uint32_t u_w = __shfl_sync(0xffffffffu, s_w, 0);
+      // low words of the SWIZZLE_128B K-major descriptors of slot 0 (high word constant: SBO = 1024, version 1, layout 2)
+      const uint32_t a_d0 = __shfl_sync(0xffffffffu, ((base & 0x3FFFFu) >> 4) | 0x10000u, 0);
+      const uint32_t w_d0 = __shfl_sync(0xffffffffu, ((s_w & 0x3FFFFu) >> 4) | 0x10000u, 0);
+      const uint32_t w_dstep = __shfl_sync(0xffffffffu, P.ss_w_slot >> 4, 0);
+      constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;
       const uint32_t a_full0 = __shfl_sync(0xffffffffu, smem_u32(&sh->a_full[0]), 0);
       const uint32_t a_empty0 = __shfl_sync(0xffffffffu, smem_u32(&sh->a_empty[0]), 0);
       const uint32_t w_full0 = __shfl_sync(0xffffffffu, smem_u32(&sh->w_full[0]), 0);
@@ -461,56 +468,54 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
         TsUnit U;
         if (!ss_unit(P, __shfl_sync(0xffffffffu, u, 0), U)) break;
         const uint32_t m = __shfl_sync(0xffffffffu, m0, 0) & U.k_keep;
-        const int n_sub = U.n_sub;
         const int n_active = __popc(m) * kc_n;
-        const uint32_t idesc = make_idesc_f16(n_sub);
+        const uint32_t idesc = make_idesc_f16(U.n_sub);
         const uint32_t buf = P.ss_bufs == 2 ? (seq & 1u) : 0u;
         const uint32_t use = P.ss_bufs == 2 ? (seq >> 1) : seq;  // earlier uses of this accumulator buffer
-        const uint32_t d_main = u_tmem_d + buf * 2u * acc_cols, d_corr = d_main + acc_cols;
+        const uint32_t d_acc = u_tmem_d + buf * 2u * acc_cols + (is_main ? 0u : acc_cols);
+        const uint32_t acc_full_bar = smem_u32(&sh->acc_full[buf]);
         if (use > 0) {  // the epilogue has read the buffer's previous unit out of TMEM
           if (lane == 0) mbar_wait(smem_u32(&sh->acc_empty[buf]), (use - 1u) & 1u);
           __syncwarp();
           tc_fence_after();
         }
         SS_ACC(tm_open);
-        StageCursor c;
-        c.init(m);
+        int kc = 0;
         for (int it = 0; it < n_active; ++it) {
           if (lane == 0) mbar_wait(w_full0 + 8u * w_s, w_ph);
-          __syncwarp();
           SS_ACC(tm_w);
           if (lane == 0) mbar_wait(a_full0 + 8u * a_s, a_ph);
           __syncwarp();
-          // (LOAD == 3: the slot was written by cp.async copies whose completion the mbarrier tracked — the pairing CUTLASS's
-          //  sm100 cp.async + UMMA mainloop uses without a proxy fence; a fence.proxy.async here compiles to MEMBAR.ALL.CTA per stage)
           tc_fence_after();
           SS_ACC(tm_a);
-          const uint32_t a_slot = u_base + (uint32_t)a_s * kSsASlot;
-          const uint32_t w_slot = u_w + (uint32_t)w_s * P.ss_w_slot;
-          const int k_valid = min(kGemmKChunk, P.cin - c.kc * kGemmKChunk);
-          const int ksteps = (k_valid + 15) >> 4;
+          const uint32_t a_d = a_d0 + (uint32_t)a_s * (kSsASlot >> 4);
+          const uint32_t w_d = w_d0 + (uint32_t)w_s * w_dstep;
+          int ksteps = 2;
+          if (LOAD != 0 && LOAD != 3) ksteps = (min(kGemmKChunk, P.cin - kc * kGemmKChunk) + 15) >> 4;
           uint32_t elected;
           asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
           if (elected) {
             if (!(P.debug & 4)) {
+              // 16-byte units inside the 128-byte row: K step +2, lo half +4
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 if (kk < ksteps) {
                   const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-                  const uint64_t a_hi = make_sw128_desc(a_slot + 32u * kk), a_lo = make_sw128_desc(a_slot + 64u + 32u * kk);
-                  const uint64_t w_hi = make_sw128_desc(w_slot + 32u * kk), w_lo = make_sw128_desc(w_slot + 64u + 32u * kk);
-                  tc_mma_f16_ss(d_main, a_hi, w_hi, idesc, acc);
-                  tc_mma_f16_ss(d_corr, a_lo, w_hi, idesc, acc);
-                  tc_mma_f16_ss(d_corr, a_hi, w_lo, idesc, 1u);
+                  if (is_main) {
+                    tc_mma_f16_ss(d_acc, kDescHi | (a_d + 2u * kk), kDescHi | (w_d + 2u * kk), idesc, acc);
+                  } else {
+                    tc_mma_f16_ss(d_acc, kDescHi | (a_d + 4u + 2u * kk), kDescHi | (w_d + 2u * kk), idesc, acc);
+                    tc_mma_f16_ss(d_acc, kDescHi | (a_d + 2u * kk), kDescHi | (w_d + 4u + 2u * kk), idesc, 1u);
+                  }
                 }
               }
             }
             tc_commit(a_empty0 + 8u * a_s);
             tc_commit(w_empty0 + 8u * w_s);
-            if (it == n_active - 1) tc_commit(smem_u32(&sh->acc_full[buf]));
+            if (it == n_active - 1) tc_commit(acc_full_bar);
           }
           __syncwarp();
-          c.next(kc_n);
+          if (++kc == kc_n) kc = 0;
           if (++a_s == a_stages) {
             a_s = 0;
             a_ph ^= 1u;
@@ -521,9 +526,9 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
           }
           SS_ACC(tm_issue);
         }
-        if (n_active == 0 && lane == 0) mbar_arrive(smem_u32(&sh->acc_full[buf]));  // the epilogue writes zeros
+        if (n_active == 0 && lane == 0) mbar_arrive(acc_full_bar);  // the epilogue writes zeros
       }
-      if (timed && lane == 0) {
+      if (timed && lane == 0 && is_main) {
         uint32_t* t = P.timers + (size_t)blockIdx.x * 32 + 4;
         t[0] = tm_open; t[1] = tm_w; t[2] = tm_a; t[3] = tm_issue;
       }
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
       // ================= W loader =================
       int w_s = 0;
       uint32_t w_ph = 0;
-      int tag[kSsMaxW] = {-1, -1, -1, -1};
+      int t0 = -1, t1 = -1, t2 = -1, t3 = -1;  // block held by each slot (registers: no dynamically indexed array)
       for (uint32_t seq = 0;; ++seq) {
         uint32_t u, m;
         open_info(seq, u, m);
@@ -541,23 +546,25 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
         const int n_active = __popc(m) * kc_n;
         const int c0 = U.ct * P.ss_tile_w;
         const int nt256 = c0 / kGemmNTile;
-        const uint32_t sub_off = (uint32_t)(c0 % kGemmNTile) * 128u;
+        const size_t blk_bytes = P.S.f16_block_bytes(nt256);
+        const unsigned char* w_unit = P.w_packed + P.S.f16_tile_base(nt256) + (size_t)(c0 % kGemmNTile) * 128u;
         const uint32_t sub_bytes = (uint32_t)U.n_sub * 128u;
+        const int tag_base = U.ct * P.koff * kc_n;
         StageCursor c;
         c.init(m);
         for (int it = 0; it < n_active; ++it) {
+          const int blk = c.k * kc_n + c.kc;
+          const int want = tag_base + blk;
+          const int have = w_s == 0 ? t0 : (w_s == 1 ? t1 : (w_s == 2 ? t2 : t3));
           if (lane == 0) {
             mbar_wait(smem_u32(&sh->w_empty[w_s]), w_ph ^ 1u);
-            const int want = (U.ct * P.koff + c.k) * kc_n + c.kc;
-            if (tag[w_s] != want && !(P.debug & 2)) {
-              const unsigned char* blk = P.w_packed + P.S.f16_block_offset(nt256, c.k, c.kc) + sub_off;
+            if (have != want && !(P.debug & 2)) {
               mbar_expect_tx(smem_u32(&sh->w_full[w_s]), sub_bytes);
-              bulk_g2s(s_w + (uint32_t)w_s * P.ss_w_slot, blk, sub_bytes, smem_u32(&sh->w_full[w_s]));
+              bulk_g2s(s_w + (uint32_t)w_s * P.ss_w_slot, w_unit + (size_t)blk * blk_bytes, sub_bytes, smem_u32(&sh->w_full[w_s]));
             }
             mbar_arrive(smem_u32(&sh->w_full[w_s]));
           }
-          // (tags are tracked by every lane so that the array stays in registers of a converged warp)
-          tag[w_s] = (U.ct * P.koff + c.k) * kc_n + c.kc;
+          if (w_s == 0) t0 = want; else if (w_s == 1) t1 = want; else if (w_s == 2) t2 = want; else t3 = want;
           __syncwarp();
           c.next(kc_n);
           if (++w_s == w_stages) {
@@ -662,7 +669,10 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
       const int c_n = min(U.n_sub, P.S.cout - c0);  // real channels in this column tile
       const bool split = P.splits > 1;
       const bool fast = split || ((c_n & 3) == 0 && P.out_vec && res_vec);
-      const bool fused = fast && !split;
+      // odd widths / unaligned rows (33, 11, 131 ... channel heads): the same fused thread-per-row epilogue into the staging
+      // tile, then a flat element walk with 4-byte stores that are contiguous within each row
+      const bool generic = !fast && E.residual == nullptr && E.norm != FSFB_NORM_LAYERNORM;
+      const bool fused = (fast && !split) || generic;
       const bool valid = r_cur < P.rows;
       // the previous unit's bulk stores have read this thread's staging row
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -828,6 +838,23 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(my_row), "r"(bytes) : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      } else if (generic) {
+        __syncwarp();  // this warp's 32 staging rows are complete
+        const int dq = 32 / c_n, dr = 32 - dq * c_n;  // element e = 32 it + lane of the warp's [32, c_n] block
+        int r = lane / c_n, c = lane - r * c_n;
+        for (int it = 0; it < c_n; ++it) {  // 32 c_n elements / 32 lanes: every lane has exactly c_n of them
+          const int64_t rr = __shfl_sync(0xffffffffu, r_cur, r);
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(my_stage + (uint32_t)(r * (int)stage_stride + c) * 4u));
+          if (rr < P.rows) P.out[rr * P.out_stride + c0 + c] = x;
+          r += dq;
+          c += dr;
+          if (c >= c_n) {
+            c -= c_n;
+            ++r;
+          }
+        }
+        __syncwarp();  // reads of the staging rows finish before the next unit overwrites them
       } else {
         __syncwarp();  // this warp's staging rows are complete
         Epilogue Es = E;
