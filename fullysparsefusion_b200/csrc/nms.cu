@@ -21,11 +21,15 @@ struct Rect {  // rotated BEV rectangle: centre, half sizes, rotation
   float cx, cy, hx, hy, c, s;
 };
 
-__device__ __forceinline__ Rect rect_from_box(const float* __restrict__ b) {  // box = (x, y, z, dx, dy, dz, yaw, ...)
+// box = (x, y, z, dx, dy, dz, yaw, ...).  Geometry of mmdet3d 0.x (the reference pins mmcv-full 1.3.9 / mmdet 2.14, README.md:
+// 20-22): xywhr2xyxyr keeps dx along x and dy along y, and iou3d's rotate_around_center turns the axis-aligned corners by
+// x' = dx cos + dy sin, y' = -dx sin + dy cos, i.e. CLOCKWISE by yaw — the same frame the point pooling uses (rot_angle = rz + pi/2
+// with l along local x; in-tree anchor of that convention: fsd_bbox_head_fsd.py:307-309, rotation_3d_in_axis(local, roi_ry + pi/2)).
+__device__ __forceinline__ Rect rect_from_box(const float* __restrict__ b) {
   Rect r;
   r.cx = b[0]; r.cy = b[1];
   r.hx = 0.5f * b[3]; r.hy = 0.5f * b[4];
-  r.c = cosf(b[6]); r.s = sinf(b[6]);
+  r.c = cosf(b[6]); r.s = -sinf(b[6]);
   return r;
 }
 

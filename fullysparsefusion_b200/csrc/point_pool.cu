@@ -37,8 +37,13 @@ __device__ __forceinline__ PpBox pp_box(const float* __restrict__ roi, float e0,
   const float w = roi[3], l = roi[4], h = roi[5], rz = roi[6];
   b.hl = l * 0.5f; b.hw = w * 0.5f; b.hh = h * 0.5f;
   b.el = (l + e0) * 0.5f; b.ew = (w + e1) * 0.5f; b.eh = (h + e2) * 0.5f;
-  b.cosa = cosf(-rz);
-  b.sina = sinf(-rz);
+  // mmdet3d 0.x lidar_to_local_coords (roiaware_pool3d / the fork's dynamic_point_pool): rotate the offset by rz + pi/2, l along
+  // local x, w along local y — the rectangle is the axis-aligned (w along x, l along y) box turned CLOCKWISE by rz, the same
+  // footprint nms.cu's rect_from_box gives the box (in-tree anchor: fsd_bbox_head_fsd.py:307-309 maps local → global with
+  // rotation_3d_in_axis(local, roi_ry + pi/2))
+  const float rot = __fadd_rn(rz, 1.57079632679489661923f);
+  b.cosa = cosf(rot);
+  b.sina = sinf(rot);
   return b;
 }
 

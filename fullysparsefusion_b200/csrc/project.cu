@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256)
     k_gather_overlap(const uint8_t* __restrict__ overlap, const int32_t* __restrict__ idx_fg, int64_t n_fg,
                      int32_t* __restrict__ ov32) {
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_fg; j += (int64_t)gridDim.x * blockDim.x)
-    ov32[j] = min((int)overlap[idx_fg[j]], kMaxOverlap);
+    ov32[j] = min((int)overlap[idx_fg[j]], kMaxOverlap + 1);  // group kMaxOverlap + 1 = "more than the kernels keep": the host raises
 }
 
 }  // namespace fsfb

@@ -391,6 +391,7 @@ class FSF(nn.Module):
         DynamicScatterVFE, SIRLayer) are the recalled ones, so with strict=False check the two lists.  Calls `refresh()`."""
         own = self.state_dict()
         mapped = {}
+        odd_kernels = []
         for k, v in state_dict.items():
             for a, b in self.REFERENCE_PREFIXES:
                 if k.startswith(a):
@@ -402,8 +403,18 @@ class FSF(nn.Module):
                     v = v.permute(0, 1, 2, 4, 3).reshape(koff, cout, cin)
                 elif v.shape[0] == cout and v.shape[4] == cin and v.shape[1:4].numel() == koff:  # spconv 2.x
                     v = v.permute(1, 2, 3, 0, 4).reshape(koff, cout, cin)
+                else:
+                    odd_kernels.append(f"{k}: {tuple(v.shape)} matches neither spconv layout of [{koff}, {cout}, {cin}]")
             mapped[k] = v
         res = self.load_state_dict(mapped, strict=strict)
+        # a non-strict load that leaves parameters at their random initial values must not pass silently
+        missing = [k for k in res.missing_keys if own[k].is_floating_point()]
+        if missing or res.unexpected_keys or odd_kernels:
+            import warnings
+            warnings.warn(f"load_reference_state_dict: {len(missing)} floating-point tensor(s) of this model were NOT loaded "
+                          f"(first: {missing[:5]}), {len(res.unexpected_keys)} checkpoint key(s) have no counterpart (first: "
+                          f"{list(res.unexpected_keys)[:5]}), {len(odd_kernels)} 5-d kernel(s) of unknown layout {odd_kernels[:3]}",
+                          RuntimeWarning, stacklevel=2)
         self.refresh()
         return res
 

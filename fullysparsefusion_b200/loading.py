@@ -269,6 +269,8 @@ class FrameStager:
         self._ready: List[Optional["torch.cuda.Event"]] = [None] * self.slots
         self._free: List[Optional["torch.cuda.Event"]] = [None] * self.slots
         self._stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self._unreleased: List[bool] = [False] * self.slots
+        self._fetched_stream = None
         self._head = 0          # next slot to fill
         self._queued: List[int] = []
         self._shapes: List[Optional[dict]] = [None] * self.slots
@@ -292,6 +294,10 @@ class FrameStager:
         return self._buf(self._host, self._head, key, tuple(shape), dtype, pinned=True)
 
     def _wait_free(self, slot):
+        if self.cuda and self._unreleased[slot]:
+            # the frame fetched from this slot was never release()d: the only safe free point is "everything queued so far"
+            self._fetched_stream.synchronize()
+            self._unreleased[slot] = False
         ev = self._free[slot]
         if ev is not None:
             ev.synchronize()      # the frame that last used this slot has been consumed
@@ -321,6 +327,8 @@ class FrameStager:
         # would tie the blocks to that stream)
         devs = {key: self._buf(self._dev, slot, key, tuple(h.shape), h.dtype, pinned=False) for key, h in staged.items()}
         if self.cuda:
+            # a (re)allocated block may still be in use by work queued on the caller's stream: the copy stream starts after it
+            self._stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._stream):
                 for key, h in staged.items():
                     devs[key].copy_(h, non_blocking=True)
@@ -344,6 +352,12 @@ class FrameStager:
             torch.cuda.current_stream(self.device).wait_event(self._ready[slot])
         frame = {k: self._buf(self._dev, slot, k, shape, dtype, pinned=False) for k, (shape, dtype) in self._shapes[slot].items()}
         frame["_slot"] = slot
+        if self.cuda:
+            # default free point for callers that never call release(): everything queued on the current stream up to this
+            # get() — release() moves it behind the frame's own consumers (call it; without it the slot is only protected
+            # against work queued BEFORE the frame was fetched, and the next put() into it waits on the stream below)
+            self._fetched_stream = torch.cuda.current_stream(self.device)
+            self._unreleased[slot] = True
         return frame
 
     def release(self, frame: Dict[str, torch.Tensor]) -> None:
@@ -352,3 +366,4 @@ class FrameStager:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._free[frame["_slot"]] = ev
+            self._unreleased[frame["_slot"]] = False

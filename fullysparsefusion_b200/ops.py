@@ -186,9 +186,14 @@ def unique_rows(rows: torch.Tensor, lo: Optional[Sequence[int]] = None, ext: Opt
     assert rows.dim() == 2 and rows.dtype in (torch.int64, torch.int32), (rows.shape, rows.dtype)
     rows = rows.contiguous()
     n, d = rows.shape
-    if n == 0:
-        return (rows.new_empty((0, d)), torch.empty(0, dtype=inv_dtype, device=dev),
-                torch.empty(0, dtype=torch.int64, device=dev) if return_counts else None)
+    if n == 0:   # torch.unique survives empty input: empty unique / inverse / counts (and an index over zero rows)
+        res = (rows.new_empty((0, d)) if return_unique else None, torch.empty(0, dtype=inv_dtype, device=dev),
+               torch.empty(0, dtype=torch.int32 if inv_dtype == torch.int32 else torch.int64, device=dev) if return_counts else None)
+        if return_index:
+            lo0 = tuple(int(v) for v in lo) if lo is not None else (0,) * d
+            ext0 = tuple(int(v) for v in ext) if ext is not None else (1,) * d
+            return res + (VoxelIndex(_ws(0, dev), lo0, ext0, 0),)
+        return res
     if lo is None or ext is None:
         mn, mx = rows_minmax(rows)
         lo = mn
@@ -494,6 +499,7 @@ def _epilogue_args(cout, bias, norm, norm_w, norm_b, residual, act, dev):
     return (_ptr(bias), _NORMS[norm], _ptr(norm_w), _ptr(norm_b))
 
 
+_CHECK_STATUS = os.environ.get("FSFB_CHECK_STATUS", "0") != "0"
 _SPLIT_ON = os.environ.get("FSFB_CONV_SPLIT", "1") != "0" and os.environ.get("FSFB_GEMM_SS", "1") != "0" \
     and os.environ.get("FSFB_GEMM_F16", "1") != "0"
 
@@ -850,16 +856,21 @@ def frustum_rows(xyz_noaug, lidar2img, mask, fg: torch.Tensor, overlap: torch.Te
     lib = load()
     ov32 = torch.empty(n_fg, dtype=torch.int32, device=dev)
     check(lib.fsfb_gather_overlap(_ptr(overlap), _ptr(idx_fg), n_fg, _ptr(ov32), _stream(dev)), "fsfb_gather_overlap")
-    csr = build_csr(ov32, 17)
-    off = csr.offsets.tolist()  # 18 ints: the one sync that sizes the output (the reference syncs per overlap count)
+    csr = build_csr(ov32, 18)
+    off = csr.offsets.tolist()  # 19 ints: the one sync that sizes the output (the reference syncs per overlap count)
+    if off[18] - off[17] > 0:
+        raise _capi.FsfbError(f"frustum_rows: {off[18] - off[17]} point(s) lie in more than 16 (camera, class) masks; the expansion "
+                              "keeps at most 16 object ids per point (csrc/project.cu kMaxOverlap)")
     extra = sum((off[k + 1] - off[k]) * (k - 1) for k in range(2, 17))
     rows = n_fg + extra
     xyz_noaug = _rowmajor(xyz_noaug)
     mask, is_i32 = _mask_args(mask)
     cams, classes, H, W = mask.shape
     l2i = lidar2img.to(torch.float32).contiguous()
-    rows_point = torch.empty(rows, dtype=torch.int32, device=dev)
-    sir_coors = torch.empty((rows, 3), dtype=torch.int32, device=dev)
+    # zero-filled: should the kernel ever skip a row (status bit 4: re-sampled ids disagree with the overlap counts given) the
+    # row points at point 0 / object 0 instead of at uninitialised memory
+    rows_point = torch.zeros(rows, dtype=torch.int32, device=dev)
+    sir_coors = torch.zeros((rows, 3), dtype=torch.int32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     if batch_idx is not None:
         batch_idx = batch_idx.to(torch.int32).contiguous()
@@ -867,6 +878,8 @@ def frustum_rows(xyz_noaug, lidar2img, mask, fg: torch.Tensor, overlap: torch.Te
                                  _ptr(idx_fg), n_fg, _ptr(csr.perm), _ptr(csr.seg), _ptr(csr.offsets), _ptr(batch_idx),
                                  _ptr(rows_point), _ptr(sir_coors), _ptr(status), _stream(dev))
     check(rc, "fsfb_frustum_expand")
+    if _CHECK_STATUS and int(status.item()) & 4:   # FSFB_CHECK_STATUS=1 (tests): costs a device sync per call
+        raise _capi.FsfbError("frustum_rows: re-sampled object ids disagree with the overlap counts (status bit 4)")
     return rows_point, sir_coors, n_fg
 
 

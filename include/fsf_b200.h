@@ -427,7 +427,9 @@ int fsfb_group_sample(const float* logits, int64_t n, int num_classes_with_bg, c
                       float* fg_weight, float* group_score, float* group_center, void* stream);
 
 /* FSF.extract_fg_pts + double_overlap_pts + get_sir_coors (FSF.py:260-308, 357-365).
- * gather_overlap: ov32[j] = overlap[idx_fg[j]] (input of fsfb_csr_build with m = 17 groups).
+ * gather_overlap: ov32[j] = min(overlap[idx_fg[j]], 17) (input of fsfb_csr_build with m = 18 groups; group 17 = a point seen by
+ * more than the 16 (camera, class) masks frustum_expand keeps per point — the caller must treat a non-empty group 17 as an error:
+ * the reference appends overlap - 1 rows for any count).
  * frustum_expand: given that CSR (perm/seg/offsets over overlap counts), writes for every output row
  * the source point (rows_point, index into the full point array) and sir_coors (batch, 0, object id)
  * in the reference's row order; total rows = n_fg + sum_k cnt_k*(k-1).  status bit 2 = a point's

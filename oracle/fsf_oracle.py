@@ -551,7 +551,8 @@ def dynamic_point_pool(rois, pts, extra_wlh, max_inbox_point, capacity, margin=N
         cx, cy, cz, w, l, h, rz = rois[r]
         hl, hw, hh = F32(l * F32(0.5)), F32(w * F32(0.5)), F32(h * F32(0.5))
         el, ew, eh = F32((l + e[0]) * F32(0.5)), F32((w + e[1]) * F32(0.5)), F32((h + e[2]) * F32(0.5))
-        cosa, sina = F32(np.cos(F32(-rz))), F32(np.sin(F32(-rz)))
+        rot = F32(F32(rz) + F32(np.pi / 2))      # mmdet3d 0.x lidar_to_local_coords: rot_angle = rz + pi / 2
+        cosa, sina = F32(np.cos(rot)), F32(np.sin(rot))
         sx, sy = (pts[:, 0] - cx).astype(F32), (pts[:, 1] - cy).astype(F32)
         lz = (pts[:, 2] - cz).astype(F32)
         lx = ((sx * cosa).astype(F32) + (sy * (-sina)).astype(F32)).astype(F32)
@@ -598,7 +599,8 @@ def _rect_corners(b):
     x, y, dx, dy, yaw = float(b[0]), float(b[1]), float(b[3]), float(b[4]), float(b[6])
     c, s = np.cos(yaw), np.sin(yaw)
     pts = np.array([[dx / 2, dy / 2], [-dx / 2, dy / 2], [-dx / 2, -dy / 2], [dx / 2, -dy / 2]])
-    return pts @ np.array([[c, s], [-s, c]]) + np.array([x, y])
+    # mmdet3d 0.x iou3d rotate_around_center: x' = dx cos + dy sin, y' = -dx sin + dy cos (clockwise by yaw)
+    return pts @ np.array([[c, -s], [s, c]]) + np.array([x, y])
 
 
 def rotated_iou_bev(a, b):

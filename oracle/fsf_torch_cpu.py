@@ -134,7 +134,8 @@ def dynamic_point_pool(rois7, pts, extra, max_inbox, capacity, chunk=64):
     x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
     for r0 in range(0, rois7.size(0), chunk):
         r = rois7[r0:r0 + chunk]
-        cosa, sina = torch.cos(-r[:, 6:7]), torch.sin(-r[:, 6:7])
+        rot = r[:, 6:7] + torch.tensor(np.pi / 2, dtype=torch.float32)   # mmdet3d 0.x: rot_angle = rz + pi / 2
+        cosa, sina = torch.cos(rot), torch.sin(rot)
         sx, sy, lz = x[None] - r[:, 0:1], y[None] - r[:, 1:2], z[None] - r[:, 2:3]
         lx = sx * cosa + sy * (-sina)
         ly = sx * sina + sy * cosa
@@ -160,7 +161,7 @@ def dynamic_point_pool(rois7, pts, extra, max_inbox, capacity, chunk=64):
 
 def _corners(b):
     """[n,4,2] counter-clockwise corners of BEV rectangles (x, y, dx, dy, yaw) in float64."""
-    c, s = np.cos(b[:, 4]), np.sin(b[:, 4])
+    c, s = np.cos(b[:, 4]), -np.sin(b[:, 4])      # clockwise by yaw (mmdet3d 0.x iou3d)
     sx = np.stack([b[:, 2], -b[:, 2], -b[:, 2], b[:, 2]], 1) * 0.5
     sy = np.stack([b[:, 3], b[:, 3], -b[:, 3], -b[:, 3]], 1) * 0.5
     return np.stack([b[:, 0:1] + sx * c[:, None] - sy * s[:, None], b[:, 1:2] + sx * s[:, None] + sy * c[:, None]], 2)

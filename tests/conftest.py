@@ -4,6 +4,8 @@ import sys
 import numpy as np
 import pytest
 
+os.environ.setdefault("FSFB_CHECK_STATUS", "1")   # ops.frustum_rows reads the kernel's status word back (one sync per call)
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)

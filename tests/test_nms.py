@@ -33,6 +33,36 @@ def test_rotated_iou_oracle():
                 assert O.rotated_iou_bev(boxes[rows[j]], boxes[rows[i]]) <= 0.35
 
 
+def test_rotated_iou_rotation_direction():
+    """mmdet3d 0.x iou3d turns the (dx along x, dy along y) rectangle CLOCKWISE by yaw.  Two 4 x 1 boxes at yaw = pi/4 have their long
+    axis along (1, -1); shifted by 0.5 along (1, 1) — across the long axis — they overlap in a 4 x 0.5 strip: IoU = 2 / 6.  The
+    counter-clockwise reading would slide them along their length instead (IoU 3.5 / 4.5)."""
+    d = 0.5 / np.sqrt(2)
+    a = np.array([0, 0, 0, 4, 1, 1, np.pi / 4])
+    b = np.array([d, d, 0, 4, 1, 1, np.pi / 4])
+    assert abs(O.rotated_iou_bev(a, b) - 1 / 3) < 1e-9
+    from oracle import fsf_torch_cpu as P
+    assert abs(P.rotated_iou_pairs(a[None, [0, 1, 3, 4, 6]], b[None, [0, 1, 3, 4, 6]])[0] - 1 / 3) < 1e-9
+
+
+def test_pool_box_and_nms_rectangle_share_one_footprint():
+    """The refine stage hands the SAME decoded boxes to the point pooling and to the NMS: a point the pooling puts inside a box
+    (no margin) must lie inside the rectangle the NMS intersects, for an elongated box at a generic yaw."""
+    rng = np.random.default_rng(5)
+    box = np.array([1.0, -2.0, 0.0, 1.2, 6.0, 2.0, 0.7], np.float32)      # w (x size) 1.2, l (y size) 6.0
+    pts = (rng.uniform(-5, 5, (4000, 3)) + box[:3]).astype(np.float32)
+    pi, ri, f = O.dynamic_point_pool(box[None], pts, [0.0, 0.0, 0.0], 4096, 100000)
+    assert 50 < pi.size < 4000
+    corners = O._rect_corners(box)
+    inside = np.ones(len(pts), bool)
+    for i in range(4):      # counter-clockwise polygon: inside = left of every edge
+        p0, p1 = corners[i], corners[(i + 1) % 4]
+        inside &= (p1[0] - p0[0]) * (pts[:, 1] - p0[1]) - (p1[1] - p0[1]) * (pts[:, 0] - p0[0]) >= -1e-4
+    assert inside[pi].all()
+    near = np.abs(pts[:, 2] - box[2]) <= 0.999      # pooled set == rectangle set wherever the z test passes
+    assert set(np.flatnonzero(inside & near & (np.abs(pts[:, 2] - box[2]) < 1.0))) >= set(pi.tolist()) - set(np.flatnonzero(~near).tolist())
+
+
 def test_rotated_iou_three_independent_ways():
     """The NMS oracle is 'parity unpinned' (mmdet3d's iou3d is un-vendored), so its IoU is cross-checked against two independent
     computations: the vectorised fixed-buffer clipper of the CPU port (different code, same published algorithm) and a
@@ -52,8 +82,8 @@ def test_rotated_iou_three_independent_ways():
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
 
     def inside(b, x, y):
-        c, s = np.cos(b[6]), np.sin(b[6])
-        lx, ly = (x - b[0]) * c + (y - b[1]) * s, -(x - b[0]) * s + (y - b[1]) * c
+        c, s = np.cos(b[6]), np.sin(b[6])      # box frame = axes turned clockwise by yaw (mmdet3d 0.x): local = R(+yaw) shift
+        lx, ly = (x - b[0]) * c - (y - b[1]) * s, (x - b[0]) * s + (y - b[1]) * c
         return (np.abs(lx) <= b[3] / 2) & (np.abs(ly) <= b[4] / 2)
 
     pairs = np.flatnonzero(want > 0.05)[:40]

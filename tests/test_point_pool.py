@@ -32,8 +32,8 @@ def test_oracle_invariants():
     assert (np.abs(f[:, 4]) < roi[:, 3] + extra[1] + 1e-5).all()
     assert (np.abs(f[:, 5]) < roi[:, 5] + extra[2] + 1e-5).all()
     # local coordinates really are the roi frame: rotating back recovers the offset to the centre
-    c, s = np.cos(roi[:, 6]), np.sin(roi[:, 6])
-    back = np.stack([f[:, 3] * c - f[:, 4] * s, f[:, 3] * s + f[:, 4] * c], 1)
+    c, s = np.cos(roi[:, 6] + np.pi / 2), np.sin(roi[:, 6] + np.pi / 2)      # local = R(rz + pi/2) shift (mmdet3d 0.x)
+    back = np.stack([f[:, 3] * c + f[:, 4] * s, -f[:, 3] * s + f[:, 4] * c], 1)
     np.testing.assert_allclose(back, pts[pi][:, :2] - roi[:, :2], atol=2e-4)
     assert set(np.unique(f[:, 12])) <= {0.0, 1.0} and 0 < f[:, 12].mean() < 1
     # caps
