@@ -70,11 +70,37 @@ def scatter_v2(feat, coors, mode, return_inv=True, min_points=0, unq_inv=None, n
 # ------------------------------------------------------------------------------------------------
 # build_mlp
 # ------------------------------------------------------------------------------------------------
+class naiveSyncBN1d(nn.BatchNorm1d):
+    """Norm type 'naiveSyncBN1d' of the stock configs (FSF_nuScenes_config.py:50,63,85; built through mmcv's build_norm_layer in
+    ops/sst_ops.py:814).  Source un-vendored [UPSTREAM-RECALL: detectron2's NaiveSyncBatchNorm for [N, C] inputs]: in training
+    with an initialised process group the batch statistics are the rank-mean of (mean, mean of squares) — `dist.naive_sync_bn_stats`,
+    one [2C] all-reduce per layer; otherwise exactly nn.BatchNorm1d.  Eval mode (the inference path) is folded into the GEMM
+    epilogue by FusedLinear / SparseConvModule and never runs this forward."""
+
+    def forward(self, x):
+        import torch.distributed as tdist
+
+        if not self.training or not (tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1):
+            return super().forward(x)
+        from . import dist as fdist
+
+        mean, var = fdist.naive_sync_bn_stats(x)
+        with torch.no_grad():
+            m = self.momentum if self.momentum is not None else 0.1
+            self.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
+            self.running_var.mul_(1 - m).add_(var.detach(), alpha=m)
+            self.num_batches_tracked += 1
+        scale = self.weight * torch.rsqrt(var + self.eps)
+        return x * scale + (self.bias - mean * scale)
+
+
 def build_norm_layer(cfg: dict, num_features: int):
     t = cfg["type"]
     if t == "LN":
         return "ln", nn.LayerNorm(num_features, eps=cfg.get("eps", 1e-5))
-    if t in ("BN1d", "naiveSyncBN1d", "BN", "SyncBN"):
+    if t == "naiveSyncBN1d":
+        return "bn", naiveSyncBN1d(num_features, eps=cfg.get("eps", 1e-5), momentum=cfg.get("momentum", 0.1))
+    if t in ("BN1d", "BN", "SyncBN"):
         return "bn", nn.BatchNorm1d(num_features, eps=cfg.get("eps", 1e-5), momentum=cfg.get("momentum", 0.1))
     raise NotImplementedError(t)
 
@@ -339,6 +365,31 @@ class SIRLayer(nn.Module):
                 return point_feats, cluster_feats, plan.new_coors
             return point_feats, cluster_feats
         return cluster_feats, plan.new_coors
+
+
+class DynamicClusterVFE(SIRLayer):
+    """Registry type 'DynamicClusterVFE' (VOXEL_ENCODERS): the block the reference's FullySparseBboxHead builds through
+    builder.build_voxel_encoder (models/roi_heads/bbox_heads/fsd_bbox_head.py:62-87) and calls as
+    block(in_feats, roi_inds [P], f_cluster, unq_inv_once=, new_coors_once=) (:135,140).  Same computation as SIRLayer; it takes
+    the extra constructor kwargs of that call site (fusion='cat', pos_fusion='mul', cat_voxel_feats=True: the only combination
+    the configs use), accepts 1-d group ids and returns the group coordinates in the shape / dtype they came in (the head indexes
+    RoI slots with them, :178-197).  The once-computed unique of the caller is not needed: the ranking is recomputed here (or
+    shared through `plan`)."""
+
+    def __init__(self, *args, fusion="cat", pos_fusion="mul", cat_voxel_feats=True, **kwargs):
+        if fusion != "cat" or pos_fusion != "mul" or not cat_voxel_feats:
+            raise NotImplementedError("DynamicClusterVFE: only fusion='cat', pos_fusion='mul', cat_voxel_feats=True is on the FSF path")
+        super().__init__(*args, **kwargs)
+
+    def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_both=False,
+                unq_inv_once=None, new_coors_once=None, plan: Optional[ScatterPlan] = None, features_b=None):
+        one_d = coors.dim() == 1
+        if plan is None:
+            plan = ScatterPlan(coors.view(-1, 1) if one_d else coors)
+        out = super().forward(features, coors, f_cluster, return_both=return_both, plan=plan, features_b=features_b)
+        if one_d and (return_both or not self.return_point_feats):   # the last element is the group coordinates
+            out = out[:-1] + (out[-1].view(-1).to(coors.dtype),)
+        return out
 
 
 class SIR(nn.Module):

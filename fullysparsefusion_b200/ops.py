@@ -249,6 +249,9 @@ def build_csr(index: torch.Tensor, m: int) -> SegmentCSR:
     assert index.dim() == 1 and index.dtype in (torch.int64, torch.int32)
     index = index.contiguous()
     n = index.numel()
+    if n == 0:   # nothing to sort: every segment is empty
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return SegmentCSR(torch.zeros(m + 1, dtype=torch.int32, device=dev), z, z, 0, m)
     lib = load()
     need = C.c_size_t(0)
     check(lib.fsfb_csr_workspace_bytes(n, m, C.byref(need)), "fsfb_csr_workspace_bytes")

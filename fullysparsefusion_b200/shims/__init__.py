@@ -23,6 +23,20 @@ def install(force: bool = False) -> None:
                       ("dynamic_point_pool_ext", dynamic_point_pool_ext)):
         if force or name not in sys.modules:
             sys.modules[name] = mod
+    # mmdet3d.ops (Voxelization, furthest_point_sample, spconv: single_stage_fsd.py:13, sst_ops.py:5): with an mmdet3d package
+    # importable the three names are patched INTO its `ops` package (the plugin also imports mmdet3d.ops.roiaware_pool3d /
+    # iou3d submodules at load time, which stay the fork's); without mmdet3d the shim module stands in under that name
+    try:
+        import importlib
+
+        real = importlib.import_module("mmdet3d.ops")
+    except Exception:
+        real = None
+    if real is not None and real is not mmdet3d_ops:
+        for attr in ("Voxelization", "furthest_point_sample", "spconv"):
+            setattr(real, attr, getattr(mmdet3d_ops, attr))
+    else:
+        sys.modules["mmdet3d.ops"] = mmdet3d_ops
 
 
 def patch_ccl(single_stage_fsd_module) -> None:
@@ -41,6 +55,8 @@ def registry_table():
     return [
         ("VOXEL_ENCODERS", "DynamicScatterVFE", modules.DynamicScatterVFE),     # FSF_nuScenes_config.py:42-52
         ("VOXEL_ENCODERS", "SIRLayer", modules.SIRLayer),                       # sir.py:61
+        ("VOXEL_ENCODERS", "DynamicClusterVFE", modules.DynamicClusterVFE),     # fsd_bbox_head.py:62-87
+        ("NORM_LAYERS", "naiveSyncBN1d", modules.naiveSyncBN1d),                # mmcv.cnn NORM_LAYERS; sst_ops.py:814
         ("BACKBONES", "SimpleSparseUNet", modules.SimpleSparseUNet),            # config :58-70
         ("BACKBONES", "SIR", modules.SIR),                                      # config :113-124, :201-212
         ("NECKS", "Voxel2PointScatterNeck", modules.Voxel2PointScatterNeck),    # config :72-76

@@ -43,9 +43,14 @@ def scatter_v2(feat, coors, mode, unq=None):
     return out, new_coors, inv
 
 
-def floor_coors(points, voxel, rng):
+def floor_coors(points, voxel, rng, kernel_rule=False):
+    """kernel_rule=False: the in-tree formula torch.div(p - min, vs, rounding_mode='floor') (single_stage_fsd.py:270, 444, 591-593,
+    948).  kernel_rule=True: floor((p - min) / vs) in fp32, the rule of mmdet3d's dynamic Voxelization kernel behind
+    VoteSegmentor.voxelize (single_stage_fsd.py:206-226) — the two differ for a few points per 100 k that sit on a voxel face."""
     lo = torch.tensor(rng[:3], dtype=torch.float32)
     vs = torch.tensor(voxel, dtype=torch.float32)
+    if kernel_rule:
+        return torch.floor((points[:, :3] - lo[None]) / vs[None]).long()
     return torch.div(points[:, :3] - lo[None], vs[None], rounding_mode="floor").long()
 
 
@@ -284,7 +289,7 @@ class CpuFSF:
 
         def segment():
             pts5 = points[:, :5]
-            c = floor_coors(points, cfg["seg_voxel_size"], rng)[:, [2, 1, 0]]
+            c = floor_coors(points, cfg["seg_voxel_size"], rng, kernel_rule=True)[:, [2, 1, 0]]
             coors = F.pad(c, (1, 0), value=0)
             unq, inv = torch.unique(coors, return_inverse=True, dim=0)
             vfe = m.voxel_encoder

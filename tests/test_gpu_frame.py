@@ -276,3 +276,52 @@ def test_simple_test_entry(cuda, frame):
         assert torch.equal(res[0]["labels_3d"], labels.cpu())
         torch.testing.assert_close(res[0]["boxes_3d"], boxes.cpu(), rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(res[0]["scores_3d"], scores.cpu(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("points,sweeps", [(34000, 1), (300000, 10)])
+def test_full_frame_against_cpu_port_at_benchmark_sizes(cuda, points, sweeps):
+    """BASELINE configs[1] (single sweep, 34 k points) and configs[2] (10 sweeps, 300 k points: the benchmarked shape) at the real
+    1600 x 900 image size, every stage of FSF.simple_test including refinement and the final boxes, against the torch-CPU port
+    on the same frame and weights (the numpy oracle is too slow here; the port itself is pinned to it in
+    tests/test_cpu_port_vs_oracle.py).  Same comparison bench.py prints as `parity`."""
+    import copy
+
+    import bench
+    from oracle import fsf_torch_cpu as P
+
+    frame = bench.synth_frame(points, sweeps, seed=3)
+    dev_frame = {k: v.to(cuda) for k, v in frame.items()}
+    model = bench.make_model().to(cuda)
+    with torch.no_grad():
+        st0 = model(dev_frame["points"], dev_frame["mask"], dev_frame["anno"], dev_frame["lidar2img"])
+        bench.calibrate_seg_head(model, st0["seg_logits"])
+        stages, st = model.stages(dev_frame["points"], dev_frame["mask"], dev_frame["anno"], dev_frame["lidar2img"])
+        for _, fn in stages:
+            fn()
+        model.refine(st, dev_frame["points"])
+        model.get_bboxes(st)
+        torch.cuda.synchronize()
+        cpu_model = copy.deepcopy(model).cpu()
+        cpu = P.CpuFSF(cpu_model)
+        cstages, cst = cpu.stages(frame["points"], frame["mask"], frame["anno"], frame["lidar2img"])
+        for _, fn in cstages + cpu.extra_stages:
+            fn()
+    par = bench.frame_parity(st, cst)
+    assert not par["breach"], par
+    assert par["rel_p999_by_tensor"]["seg_logits"] < 5e-4 and par["rel_p999_by_tensor"]["voxel_feats"] < 5e-4, par
+    assert not par["shape_mismatch"] or all("det_" in s for s in par["shape_mismatch"]), par      # same voxels, rows, queries
+    # the selection steps agree (a handful of near-tie flips at most) and the detections are the same set
+    assert par["index_mismatches"].get("fsd_rows", 0) <= 0.005 * cst["fsd_rows"].numel() + 2, par
+    assert abs(int(st["det_boxes"].size(0)) - int(cst["det_boxes"].size(0))) <= 0.02 * cst["det_boxes"].size(0) + 2, par
+
+
+def test_scatter_plan_on_empty_input(cuda):
+    """torch.unique survives empty input (an empty frame / every point filtered out); so does the ranking path."""
+    from fullysparsefusion_b200 import modules as M, ops
+    empty = torch.zeros((0, 4), dtype=torch.int32, device=cuda)
+    u, inv, cnt = ops.unique_rows(empty, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], return_counts=True)
+    assert u.shape == (0, 4) and inv.numel() == 0 and cnt.numel() == 0
+    res = ops.unique_rows(empty, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], return_unique=False, return_index=True)
+    assert res[0] is None and res[3].m == 0
+    plan = M.ScatterPlan(empty, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], want_index=True)
+    assert plan.m == 0

@@ -401,6 +401,103 @@ def main_refine():
     save("roi_align", feats=feats, out_coors=out_coors, num_rois=13, mask=mask, aligned=aligned)
 
 
+def main_wiring():
+    """Goldens of the IN-TREE control flow around the un-vendored blocks (`python tools/make_golden.py wiring`): the reference's own
+    SIR.forward (models/backbones/sir.py:65-85) and FullySparseBboxHead.forward (models/roi_heads/bbox_heads/fsd_bbox_head.py:
+    95-151) run here, on CPU, with the registry types they build through builder.build_voxel_encoder ('SIRLayer', sir.py:41-62;
+    'DynamicClusterVFE', fsd_bbox_head.py:62-87) served by the repo's OWN block classes — constructed from the reference's own
+    kwargs, forward restated in plain torch below (the block's source is un-vendored; its parameters and state-dict names are the
+    repo's).  What the goldens pin: which rows feed which block (points ‖ features ‖ f_cluster / 10), the order of the
+    concatenated group features, use_middle_cluster_feature, the group coordinates handed to the RoI alignment, and that every
+    kwarg the reference passes is accepted."""
+    import torch.nn.functional as F
+
+    from fullysparsefusion_b200 import modules as M
+    from fullysparsefusion_b200.shims import registry_table
+
+    class _CpuBlock:   # mixin: forward of modules.SIRLayer in stock torch ops (same arithmetic, CPU)
+        def forward(self, features, coors, f_cluster=None, points=None, img_feats=None, img_metas=None, return_both=False,
+                    unq_inv_once=None, new_coors_once=None):
+            new_coors, inv = torch.unique(coors, return_inverse=True, dim=0)
+            x = torch.cat([features[:, :3] / torch.tensor(self.xyz_normalizer), features[:, 3:]], 1)
+            if self.with_rel_mlp:
+                x = x * nn.Sequential.forward(self.rel_mlp, f_cluster / self.rel_dist_scaler)
+            ori, cl, pf = x, [], None
+            for i, vfe in enumerate(self.vfe_layers):
+                y = vfe.norm(vfe.linear(x))
+                pf = F.gelu(y) if vfe.act == "gelu" else F.relu(y)
+                c = torch.full((new_coors.size(0), pf.size(1)), float("-inf")).scatter_reduce_(
+                    0, inv[:, None].expand_as(pf), pf, reduce="amax", include_self=True)
+                cl.append(c)
+                if i != len(self.vfe_layers) - 1:
+                    x = torch.cat([pf, c[inv]], 1)
+            cluster = torch.cat(cl, 1)
+            if return_both or self.return_point_feats:
+                if self.with_shortcut and pf.shape == ori.shape:
+                    pf = pf + ori
+                return (pf, cluster, new_coors) if return_both else (pf, cluster)
+            return cluster, new_coors
+
+    table = {t: c for reg, t, c in registry_table() if reg == "VOXEL_ENCODERS"}
+    cpu_types = {t: type("Cpu" + t, (_CpuBlock, c), {}) for t, c in table.items()}
+    built = []
+
+    def build_voxel_encoder(cfg):
+        cfg = dict(cfg)
+        cls = cpu_types[cfg.pop("type")]
+        built.append((cls.__name__, sorted(cfg)))
+        return cls(**cfg)
+
+    _SPECIAL[("mmdet3d.models", "builder")] = types.SimpleNamespace(build_voxel_encoder=build_voxel_encoder)
+    _SPECIAL[("mmdet3d.models.builder", "build_voxel_encoder")] = build_voxel_encoder   # when the submodule was imported first
+    import_reference()
+    sir_mod = importlib.import_module("projects.mmdet3d_plugin.models.backbones.sir")
+    head_mod = importlib.import_module("projects.mmdet3d_plugin.models.roi_heads.bbox_heads.fsd_bbox_head")
+
+    g = torch.Generator().manual_seed(31)
+    torch.manual_seed(31)
+    # ---- SIR backbone over (class, batch, cluster) ids ----
+    n, cf = 1500, 13
+    sir_kw = dict(num_blocks=3, in_channels=[3 + cf, 3 + 32, 3 + 32], feat_channels=[[32, 32]] * 3, rel_mlp_hidden_dims=[[16, 32]] * 3,
+                  with_rel_mlp=True, norm_cfg=dict(type="LN", eps=1e-3), mode="max", xyz_normalizer=[20, 20, 4], act="gelu",
+                  unique_once=True)
+    sir = sir_mod.SIR(**sir_kw).eval()
+    pts = torch.randn(n, 3, generator=g) * 10
+    feats = torch.randn(n, cf, generator=g)
+    coors = torch.stack([torch.randint(0, 3, (n,), generator=g), torch.zeros(n, dtype=torch.long), torch.randint(0, 40, (n,), generator=g)], 1)
+    f_cluster = torch.randn(n, 3, generator=g)
+    with torch.no_grad():
+        out_feats, cluster_feats, out_coors = sir(pts, feats, coors, f_cluster)
+    sd = {"sir_sd__" + k.replace(".", "__"): v for k, v in sir.state_dict().items()}
+    save("wiring_sir", points=pts, features=feats, coors=coors, f_cluster=f_cluster, out_feats=out_feats, cluster_feats=cluster_feats,
+         out_coors=out_coors, **sd)
+
+    # ---- RoI head over pooled points (roi ids with the -1 fake group and empty rois) ----
+    p, k, c0 = 900, 25, 16
+    head_kw = dict(num_classes=10, num_blocks=3, in_channels=[3 + c0 + 13, 3 + 32 + 13, 3 + 32 + 13], feat_channels=[[32, 32]] * 3,
+                   with_distance=False, with_cluster_center=False, with_rel_mlp=True, rel_mlp_hidden_dims=[[16, 32]] * 3,
+                   rel_mlp_in_channels=[13] * 3, reg_mlp=None, cls_mlp=None, xyz_normalizer=[20, 20, 4], act="gelu", geo_input=True,
+                   use_middle_cluster_feature=True, norm_cfg=dict(type="LN", eps=1e-3, momentum=0.01), unique_once=True)
+    head = head_mod.FullySparseBboxHead(**head_kw).eval()
+    xyz = torch.randn(p, 3, generator=g) * 10
+    pf = torch.randn(p, c0, generator=g)
+    roi_inds = torch.randint(0, k - 4, (p,), generator=g)       # the last rois stay empty
+    roi_inds[:7] = -1                                             # rows of the extractor's fake group
+    info = dict(local_xyz=torch.randn(p, 3, generator=g), boundary_offset=torch.rand(p, 6, generator=g),
+                is_in_margin=(torch.rand(p, generator=g) < 0.3).float())
+    rois = torch.cat([torch.zeros(k, 1), torch.randn(k, 3, generator=g) * 10, torch.rand(k, 3, generator=g) * 3 + 1,
+                      torch.rand(k, 1, generator=g) * 6 - 3], 1)
+    with torch.no_grad():
+        roi_feats, nonempty = head(xyz, pf, info, roi_inds, rois)
+    sd = {"head_sd__" + kk.replace(".", "__"): v for kk, v in head.state_dict().items()}
+    save("wiring_roi_head", pts_xyz=xyz, pts_features=pf, roi_inds=roi_inds, rois=rois, local_xyz=info["local_xyz"],
+         boundary_offset=info["boundary_offset"], is_in_margin=info["is_in_margin"], roi_feats=roi_feats, nonempty=nonempty, **sd)
+    import json
+    with open(os.path.join(OUT, "wiring_kwargs.json"), "w") as fh:   # the kwargs the reference passed to the registry builds
+        json.dump(dict(sir=sir_kw, head=head_kw, built=built), fh, indent=1)
+    print("registry builds:", [b[0] for b in built])
+
+
 def main_groups():
     """Golden of the LiDAR-query clustering path (`python tools/make_golden.py groups`): the reference's own
     SingleStageFSD.group_sample (single_stage_fsd.py:802-865, with get_fg_mask :740-781, get_offset_weight :867-874,
@@ -664,6 +761,8 @@ if __name__ == "__main__":
         main_seghead()
     elif len(sys.argv) > 1 and sys.argv[1] == "misc":
         main_misc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "wiring":
+        main_wiring()
     elif len(sys.argv) > 1 and sys.argv[1] == "refine":
         main_refine()
     elif len(sys.argv) > 1 and sys.argv[1] == "groups":
