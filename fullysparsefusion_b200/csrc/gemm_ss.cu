@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
   const uint32_t tmem_d = sh->tmem_base;
   const uint32_t acc_cols = (uint32_t)P.ss_acc_cols;
   const int kc_n = P.S.kc();
-  // role cycle counters (FSFB_GEMM_TIMERS=1, tools/gemm_timers.py): phases partition each role's time
+  // role cycle counters (FSFB_GEMM_TIMERS=1, tools/gemm_role_timers.py): phases partition each role's time
   const bool timed = P.timers != nullptr;
   uint32_t t_last = 0;
 #define SS_T0() do { if (timed) t_last = (uint32_t)clock(); } while (0)
@@ -1070,7 +1070,7 @@ extern "C" int fsfb_split_rows(const float* a, int64_t rows, int c, int64_t a_st
   return FSFB_OK;
 }
 
-// Diagnostics (tools/gemm_timers.py; not part of the product path): per-CTA role counters of the last launch made under
+// Diagnostics (tools/gemm_role_timers.py; not part of the product path): per-CTA role counters of the last launch made under
 // FSFB_GEMM_TIMERS=1, out[148][32] u32.  Per CTA: [0..3] producer warp 0 {wait slot empty, convert + store, advance + issue
 // gathers, stages}; [4..7] MMA {open unit + wait accumulators free, wait W, wait A, issue}; [8..12] epilogue warp 16 {open +
 // residual / vectors, wait accumulators full, drain + epilogue math, rows out, units}; [31] producer total.

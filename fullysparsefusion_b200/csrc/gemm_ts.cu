@@ -7,7 +7,7 @@
 // One CTA per SM pulls work units from a global counter (heaviest row tiles first: fsfb_rulebook_row_order sorts
 // rows by the number of present offsets, and units are handed out from the end of that order); a unit is (row tile
 // of 128 output rows, column tile of <= 128 channels, offset split).  Measured on the previous one-tile-per-CTA kernel
-// (tools/conv_real_experiments.py): launch + neighbour-tile prologue (~13 k clk) and the drain + epilogue
+// (round-1 experiments, profiles/r1_ncu_summary.md): launch + neighbour-tile prologue (~13 k clk) and the drain + epilogue
 // (~23 k clk) of a tile cost more than its ~43 MMA stages (33 k clk) and nothing overlapped, because TMEM and
 // shared memory admit one CTA per SM.  Here the roles run ahead of each other across units:
 //   * warps 0-15  A producers (stage-striped groups of 4 warps, thread = row): gather 128 B of their row with

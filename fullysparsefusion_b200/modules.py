@@ -426,28 +426,12 @@ class SIR(nn.Module):
 # ------------------------------------------------------------------------------------------------
 # SimpleSparseUNet
 # ------------------------------------------------------------------------------------------------
-# EXPERIMENTAL (FSFB_PLANE_SPLIT=1, not yet timed on hardware): run a big 3x3x3 convolution as three passes over its z-planes
-# (offsets 0-8 / 9-17 / 18-26), each with the row order of its own 9-bit mask.  tools/tile_reuse_study.py: 6.3 offsets per 128-row
-# tile-equivalent instead of 9.2 (one order for all 27 offsets), at the price of two extra [rows, cout] round trips.  Only existing
-# entry points are used: each pass is an ordinary gather-GEMM on a slice of the rulebook and of the packed weights, the running
-# sum travels as the next pass's residual and the BatchNorm scale is applied to every pass (s*(p0+p1+p2)+h = s*p0 + s*p1 + (s*p2+h)).
-PLANE_SPLIT = os.environ.get("FSFB_PLANE_SPLIT") == "1"
-PLANE_SPLIT_MIN_ROWS = 50000
-
-
 class Rulebook:
     """Neighbour table of one indice_key plus the mask-sorted row order the gather-GEMM tiles walk."""
-    __slots__ = ("nbr", "order", "_planes")
-
-    def planes(self):
-        """[(rulebook rows 9p..9p+8, their own mask-sorted row order)] for the three z-planes of a 27-offset rulebook."""
-        if self._planes is None:
-            self._planes = [(self.nbr[9 * p:9 * p + 9], ops.rulebook_row_order(self.nbr[9 * p:9 * p + 9])) for p in range(3)]
-        return self._planes
+    __slots__ = ("nbr", "order")
 
     def __init__(self, nbr: torch.Tensor, sort_rows: bool = True):
         self.nbr = nbr
-        self._planes = None
         # rows with the same set of present offsets become adjacent: a 128-row tile then skips every offset none of
         # its rows has (21 → ~11 of 27 offsets per tile on LiDAR voxel sets); results do not depend on the order
         # (the sort is ~12 small launches: only worth it for the big levels)
@@ -480,29 +464,8 @@ class SparseConvModule(nn.Module):
             shift = n.bias.detach().float() - n.running_mean.float() * scale
             self._pack = (ops.gemm_prepack(self.weight.detach().float()), scale.contiguous(), shift.contiguous())
         w, scale, shift = self._pack
-        if (PLANE_SPLIT and isinstance(rb, Rulebook) and nbr.size(0) == 27 and nbr.size(1) >= PLANE_SPLIT_MIN_ROWS and w.cout <= 256
-                and not residual_post):
-            return self._forward_planes(feats, rb, out, residual)
         return ops.gather_gemm(feats, w, nbr=nbr, norm="affine", norm_w=scale, norm_b=shift, residual=residual,
                                act=self.act, out=out, residual_post=residual_post, row_order=order)
-
-    def _forward_planes(self, feats, rb, out, residual):
-        w, scale, shift = self._pack
-        if getattr(self, "_plane_packs", None) is None or self._plane_packs[0] is not w:
-            # cout <= 256 = one column tile: the packed blocks are ordered [offset][K chunk], so a plane's 9 offsets are one
-            # contiguous byte range that is itself a valid 9-offset pack (csrc/gemm_common.cuh GemmShape)
-            per_plane = 9 * ((w.cin + 31) // 32) * 2 * ((w.cout + 15) // 16 * 16) * 128
-            packs = [ops.PackedWeight(w.data[p * per_plane:(p + 1) * per_plane], 9, w.cin, w.cout,
-                                      None if w.raw is None else w.raw[9 * p:9 * p + 9]) for p in range(3)]
-            self._plane_packs = (w, packs, torch.zeros_like(shift))
-        _, packs, zero = self._plane_packs
-        planes = rb.planes()
-        acc = residual
-        for p in (0, 2):   # the vertical planes first; the in-plane one (every row has work there) carries shift and activation
-            acc = ops.gather_gemm(feats, packs[p], nbr=planes[p][0], norm="affine", norm_w=scale, norm_b=zero, residual=acc,
-                                  row_order=planes[p][1])
-        return ops.gather_gemm(feats, packs[1], nbr=planes[1][0], norm="affine", norm_w=scale, norm_b=shift, residual=acc,
-                               act=self.act, out=out, row_order=planes[1][1])
 
 
 class SparseBasicBlock(nn.Module):

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 90 python tools/ss_smoke.py > gpurun_out/ss_smoke.txt 2>&1; echo "exit $?" >> gpurun_out/ss_smoke.txt
 tail -n 4 gpurun_out/ss_smoke.txt
 grep -q "SMOKE OK" gpurun_out/ss_smoke.txt || exit 0
-timeout 120 python tools/gemm_ss_timers.py > gpurun_out/ss_timers.txt 2>&1
+timeout 120 python tools/gemm_role_timers.py > gpurun_out/ss_timers.txt 2>&1
 cat gpurun_out/ss_timers.txt
 if [ "$1" != "quick" ]; then
 timeout 300 python -m pytest tests/test_gpu_gemm.py -x -q > gpurun_out/ss_gemm_test.txt 2>&1; echo "exit $?" >> gpurun_out/ss_gemm_test.txt

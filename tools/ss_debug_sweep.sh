@@ -3,6 +3,6 @@
 mkdir -p gpurun_out
 for d in 0 1 2 4 3 5 6 7; do
   echo "=== FSFB_GEMM_DEBUG=$d"
-  FSFB_GEMM_DEBUG=$d timeout 120 python tools/gemm_ss_timers.py 2>&1 | grep -A13 "conv sorted" | grep -v "^--"
+  FSFB_GEMM_DEBUG=$d timeout 120 python tools/gemm_role_timers.py 2>&1 | grep -A13 "conv sorted" | grep -v "^--"
 done > gpurun_out/ss_debug_sweep.txt 2>&1
 cat gpurun_out/ss_debug_sweep.txt
