@@ -358,10 +358,10 @@ def main():
         _capi.check(_capi.load().fsfb_gemm_f16_overflows(ctypes.byref(cnt)), "fsfb_gemm_f16_overflows")
         return int(cnt.value)
 
-    def step(i, events=None):
+    def step(i, events=None, scope=None):
         f = frames[i % n_frames]
         stages, st = model.stages(f["points"], f["mask"], f["anno"], f["lidar2img"])
-        if args.scope == "full":   # FSF.simple_test's tail (FSF.py:1158-1171; frustum_cluster_head.py:595-698)
+        if (scope or args.scope) == "full":   # FSF.simple_test's tail (FSF.py:1158-1171; frustum_cluster_head.py:595-698)
             stages = stages + [("refine", lambda: model.refine(st, f["points"])), ("boxes", lambda: model.get_bboxes(st))]
         for name, fn in stages:
             if events is not None:
@@ -397,6 +397,17 @@ def main():
         prof_dom, ops.PROFILER, ops.PROFILE_ONLY = ops.PROFILER, None, None
         launches = _capi.launch_count() - launches0
         ms_total = t_start.elapsed_time(t_end)
+        # the round-1 scope (segment → combine) timed the same way, for continuity with BENCH_r01 (not the headline)
+        ms_hot = None
+        if args.scope == "full":
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            h0.record()
+            for i in range(args.steps):
+                step(i, scope="hot")
+            h1.record()
+            barrier()
+            ms_hot = h0.elapsed_time(h1)
 
         # ---- profile pass (not part of `value`): per-stage and per-op events ---------------------------
         events = []
@@ -429,7 +440,8 @@ def main():
         ms_e2e = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
-    ms_total, ms_e2e = fdist.max_over_ranks(torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)).tolist()
+    ms_total, ms_e2e, ms_hot = fdist.max_over_ranks(torch.tensor([ms_total, ms_e2e, ms_hot if ms_hot is not None else 0.0],
+                                                                 dtype=torch.float64, device=dev)).tolist()
 
     if rank == 0:
         per_stage = {}
@@ -522,6 +534,8 @@ def main():
                                 "wire format in front of it — 60 PNG planes per frame — costs ~0.38 core-seconds of inflate per frame "
                                 "(DESIGN.md section 6: ~12 frames/s on 8 decode threads), so from disk the decode, not this path, "
                                 "bounds the rate"},
+                "hot_scope": ({"value": fdist.throughput(args.steps, world, ms_hot * 1e-3), "ms_per_step": ms_hot / args.steps,
+                               "scope": "segment..combine (the scope of the round-1 bench lines)"} if ms_hot else None),
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm, "kernels": table,
                 "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}}
         if world == 1 and not args.no_cpu_baseline:

@@ -17,8 +17,8 @@
 
 namespace fsfb {
 
-struct Rect {  // rotated BEV rectangle: centre, half sizes, rotation
-  float cx, cy, hx, hy, c, s;
+struct Rect {  // rotated BEV rectangle: centre, half sizes, rotation, half diagonal
+  float cx, cy, hx, hy, c, s, rad;
 };
 
 // box = (x, y, z, dx, dy, dz, yaw, ...).  Geometry of mmdet3d 0.x (the reference pins mmcv-full 1.3.9 / mmdet 2.14, README.md:
@@ -30,6 +30,7 @@ __device__ __forceinline__ Rect rect_from_box(const float* __restrict__ b) {
   r.cx = b[0]; r.cy = b[1];
   r.hx = 0.5f * b[3]; r.hy = 0.5f * b[4];
   r.c = cosf(b[6]); r.s = -sinf(b[6]);
+  r.rad = sqrtf(r.hx * r.hx + r.hy * r.hy);
   return r;
 }
 
@@ -81,6 +82,9 @@ __device__ float rect_intersection(const Rect& A, const Rect& B) {
 }
 
 __device__ __forceinline__ float rect_iou(const Rect& A, const Rect& B) {
+  // circumscribed circles apart: no intersection (most pairs of a scene; skips the polygon clipping)
+  const float dx = A.cx - B.cx, dy = A.cy - B.cy, rr = A.rad + B.rad;
+  if (dx * dx + dy * dy >= rr * rr) return 0.f;
   const float inter = rect_intersection(A, B);
   const float ua = 4.f * A.hx * A.hy + 4.f * B.hx * B.hy - inter;
   return inter / fmaxf(ua, 1e-8f);
@@ -116,26 +120,62 @@ __global__ void k_nms_offsets(const int32_t* __restrict__ counts, int C, int32_t
   }
 }
 
-// candidate t (flat = c * k + i, ascending) → slot offsets[c] + rank among its class by (score desc, box index asc)
+// candidate t (flat = c * k + i, ascending) → slot offsets[c] + rank among its class by (score desc, box index asc).
+// A block of 256 candidates walks the candidates of the classes it touches in shared-memory tiles (score, box index): the
+// counting rank is O(T * T_c) compares but only O(T * T_c / 256) gathered loads.
 __global__ void __launch_bounds__(256)
     k_nms_rank(const int32_t* __restrict__ flat, int64_t T, int64_t k, int C, const float* __restrict__ scores,
                const int32_t* __restrict__ offsets, int32_t* __restrict__ sorted_box, int32_t* __restrict__ sorted_cls,
                float* __restrict__ sorted_score) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t f = flat[t];
-    const int c = (int)(f / k);
-    const int i = (int)(f - (int64_t)c * k);
-    const float s = scores[(int64_t)i * C + c];
-    const int beg = offsets[c], end = offsets[c + 1];
-    int rank = 0;
-    for (int u = beg; u < end; ++u) {  // candidates of a class are contiguous in `flat` (class-major, box ascending)
-      const int j = (int)(flat[u] - (int64_t)c * k);
-      const float sj = scores[(int64_t)j * C + c];
-      rank += (sj > s) | ((sj == s) & (j < i));
+  __shared__ float s_score[256];
+  __shared__ int s_box[256];
+  __shared__ int s_lo, s_hi;
+  for (int64_t t0 = (int64_t)blockIdx.x * 256; t0 < T; t0 += (int64_t)gridDim.x * 256) {   // block-uniform
+    const int64_t t = t0 + threadIdx.x;
+    const bool live = t < T;
+    int c = 0, i = 0, beg = 0, end = 0;
+    float s = 0.f;
+    if (live) {
+      const int64_t f = flat[t];
+      c = (int)(f / k);
+      i = (int)(f - (int64_t)c * k);
+      s = scores[(int64_t)i * C + c];
+      beg = offsets[c];
+      end = offsets[c + 1];
     }
-    sorted_box[beg + rank] = i;
-    sorted_cls[beg + rank] = c;
-    sorted_score[beg + rank] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {   // candidates are class-major: the block's classes span [class of t0, class of its last candidate]
+      const int64_t tl = min(t0 + 255, T - 1);
+      s_lo = offsets[(int)(flat[t0] / k)];
+      s_hi = offsets[(int)(flat[tl] / k) + 1];
+    }
+    __syncthreads();
+    const int lo = s_lo, hi = s_hi;
+    int rank = 0;
+    for (int u0 = lo; u0 < hi; u0 += 256) {
+      __syncthreads();
+      const int u = u0 + (int)threadIdx.x;
+      if (u < hi) {
+        const int64_t fu = flat[u];
+        const int cu = (int)(fu / k);
+        const int ju = (int)(fu - (int64_t)cu * k);
+        s_box[threadIdx.x] = ju;
+        s_score[threadIdx.x] = scores[(int64_t)ju * C + cu];
+      }
+      __syncthreads();
+      if (live) {
+        const int a = max(beg, u0) - u0, b = min(end, min(hi, u0 + 256)) - u0;   // this thread's class inside the tile
+        for (int x = a; x < b; ++x) {
+          const float sj = s_score[x];
+          rank += (sj > s) | ((sj == s) & (s_box[x] < i));
+        }
+      }
+    }
+    if (live) {
+      sorted_box[beg + rank] = i;
+      sorted_cls[beg + rank] = c;
+      sorted_score[beg + rank] = s;
+    }
   }
 }
 
@@ -164,7 +204,7 @@ __global__ void __launch_bounds__(kNmsCols)
     __syncthreads();
     if (cls == c && col0 < ce) {
       unsigned long long bits = 0;
-      const int ncol = min(kNmsCols, ce - col0);
+      const int ncol = (col0 + kNmsCols - 1 > row) ? min(kNmsCols, ce - col0) : 0;   // columns up to `row` never count
       for (int j = 0; j < ncol; ++j) {
         const int64_t col = col0 + j;
         if (col > row && rect_iou(me, s_col[j]) > thr) bits |= 1ull << j;
@@ -181,8 +221,18 @@ __global__ void __launch_bounds__(32)
                  uint8_t* __restrict__ keep) {
   const int c = blockIdx.x, lane = threadIdx.x;
   const int beg = offsets[c], end = offsets[c + 1];
-  unsigned long long removed[4] = {0, 0, 0, 0};
+  unsigned long long removed[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
+  auto load_row = [&](int i, unsigned long long (&m)[4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int w = lane + 32 * s;
+      m[s] = w < words ? mask[(int64_t)i * words + w] : 0ull;
+    }
+  };
+  if (beg < end) load_row(beg, nxt);
   for (int i = beg; i < end; ++i) {
+    unsigned long long cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+    if (i + 1 < end) load_row(i + 1, nxt);   // in flight while row i is decided: the chain is one shuffle per row, not one load
     const int li = i - beg;
     const int wi = li >> 6;
     const unsigned long long word = __shfl_sync(0xffffffffu, removed[wi >> 5 & 3], wi & 31);
@@ -191,10 +241,7 @@ __global__ void __launch_bounds__(32)
     if (lane == 0) keep[i] = gone ? 0 : 1;
     if (!gone) {
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int w = lane + 32 * s;
-        if (w < words) removed[s] |= mask[(int64_t)i * words + w];
-      }
+      for (int s = 0; s < 4; ++s) removed[s] |= cur[s];
     }
   }
 }
@@ -205,19 +252,29 @@ __global__ void __launch_bounds__(256)
                const int32_t* __restrict__ sorted_cls, const float* __restrict__ sorted_score, const float* __restrict__ boxes,
                int64_t box_stride, int box_dim, int64_t max_num, float* __restrict__ out_boxes, float* __restrict__ out_scores,
                long long* __restrict__ out_labels, int32_t* __restrict__ out_box_idx) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < P; t += (int64_t)gridDim.x * blockDim.x) {
-    const int r = kept_idx[t];
-    const float s = sorted_score[r];
+  __shared__ float s_tile[256];
+  for (int64_t t0 = (int64_t)blockIdx.x * 256; t0 < P; t0 += (int64_t)gridDim.x * 256) {   // block-uniform
+    const int64_t t = t0 + threadIdx.x;
+    const bool live = t < P;
+    const int r = live ? kept_idx[t] : 0;
+    const float s = live ? sorted_score[r] : 0.f;
     int64_t dst = t;
-    if (P > max_num) {  // global top max_num by (score desc, emitted position asc)
+    if (P > max_num) {  // global top max_num by (score desc, emitted position asc): counting rank over shared-memory tiles
       int rank = 0;
-      for (int64_t u = 0; u < P; ++u) {
-        const float su = sorted_score[kept_idx[u]];
-        rank += (su > s) | ((su == s) & (u < t));
+      for (int64_t u0 = 0; u0 < P; u0 += 256) {
+        __syncthreads();
+        if (u0 + threadIdx.x < P) s_tile[threadIdx.x] = sorted_score[kept_idx[u0 + threadIdx.x]];
+        __syncthreads();
+        const int n = (int)min((int64_t)256, P - u0);
+        for (int x = 0; x < n; ++x) {
+          const float su = s_tile[x];
+          rank += (su > s) | ((su == s) & (u0 + x < t));
+        }
       }
       if (rank >= max_num) continue;
       dst = rank;
     }
+    if (!live) continue;
     const float* b = boxes + (int64_t)sorted_box[r] * box_stride;
     for (int d = 0; d < box_dim; ++d) out_boxes[dst * box_dim + d] = b[d];
     out_scores[dst] = s;

@@ -17,6 +17,7 @@ with torch.no_grad():
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(2):
             stages, st = model.stages(f["points"], f["mask"], f["anno"], f["lidar2img"])
+            stages = stages + [("refine", lambda: model.refine(st, f["points"])), ("boxes", lambda: model.get_bboxes(st))]
             for name, fn in stages:
                 with record_function("stage:" + name):
                     fn()
