@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
       const bool fast = split || ((c_n & 3) == 0 && P.out_vec && res_vec);
       // odd widths / unaligned rows (33, 11, 131 ... channel heads): the same fused thread-per-row epilogue into the staging
       // tile, then a flat element walk with 4-byte stores that are contiguous within each row
-      const bool generic = !fast && E.residual == nullptr && E.norm != FSFB_NORM_LAYERNORM;
+      const bool generic = !fast && E.residual == nullptr;
       const bool fused = (fast && !split) || generic;
       const bool valid = r_cur < P.rows;
       // the previous unit's bulk stores have read this thread's staging row
@@ -723,6 +723,73 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
           else SS_EPI(FSFB_NORM_NONE, FSFB_ACT_NONE, false);
         }
 #undef SS_EPI
+      } else if (fused && !use_res) {
+        // Vectors from shared memory (GELU layers, wide tiles, device-only vectors), no residual: ONE pass over tensor memory
+        // (32 columns per tcgen05.ld pair) that parks the biased sums in the thread's own staging row and hands the
+        // accumulators back; LayerNorm statistics and the norm / activation then run from shared memory.  (The three-pass form
+        // below re-read TMEM for mean, variance and output, 8 columns per round trip: 40-50 k clk per unit on LN + GELU layers.)
+        const bool has_bias = E.bias != nullptr;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < U.n_sub; cb += 32) {
+          float v[32];
+          if (have_acc) {
+            float c2[32];
+            tc_ld32(t_row + cb, v);
+            tc_ld32(t_row + acc_cols + cb, c2);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = fmaf(c2[jj], 1.f / kF16LoScale, v[jj]);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+          }
+          if (cb + 32 >= U.n_sub) {  // last TMEM read of this unit
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 4) {
+            float4 y = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+            if (has_bias) {
+              const float4 bb = lds_f4(s_vec + (uint32_t)(cb + jj) * 4u);
+              y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
+            }
+            // columns in [c_n, n_sub) are exact zeros (zero weight rows, default bias 0); beyond n_sub the 32-column load
+            // returns whatever the tensor memory held
+            if (cb + jj < U.n_sub) sum += (y.x + y.y) + (y.z + y.w);
+            sts_f4(my_row + (uint32_t)(cb + jj) * 4u, y);
+          }
+        }
+        float mean = 0.f, rstd = 1.f;
+        if (E.norm == FSFB_NORM_LAYERNORM) {
+          mean = sum / (float)c_n;
+          float qq = 0.f;
+#pragma unroll 4
+          for (int c = 0; c < c_n; c += 4) {
+            const float4 x = lds_f4(my_row + (uint32_t)c * 4u);
+            const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
+            qq += d0 * d0 + (c + 1 < c_n ? d1 * d1 : 0.f) + (c + 2 < c_n ? d2 * d2 : 0.f) + (c + 3 < c_n ? d3 * d3 : 0.f);
+          }
+          rstd = 1.f / sqrtf(qq / (float)c_n + E.eps);
+        }
+        if (E.norm != FSFB_NORM_NONE || act != FSFB_ACT_NONE) {
+#pragma unroll 2
+          for (int c = 0; c < c_n; c += 4) {
+            float4 y = lds_f4(my_row + (uint32_t)c * 4u);
+            if (E.norm != FSFB_NORM_NONE) {
+              const float4 w4 = lds_f4(s_vec + (uint32_t)(256 + c) * 4u), h4 = lds_f4(s_vec + (uint32_t)(512 + c) * 4u);
+              if (E.norm == FSFB_NORM_LAYERNORM) {
+                y.x = (y.x - mean) * rstd * w4.x + h4.x; y.y = (y.y - mean) * rstd * w4.y + h4.y;
+                y.z = (y.z - mean) * rstd * w4.z + h4.z; y.w = (y.w - mean) * rstd * w4.w + h4.w;
+              } else {
+                y.x = fmaf(y.x, w4.x, h4.x); y.y = fmaf(y.y, w4.y, h4.y); y.z = fmaf(y.z, w4.z, h4.z); y.w = fmaf(y.w, w4.w, h4.w);
+              }
+            }
+            y.x = apply_act(y.x, act); y.y = apply_act(y.y, act); y.z = apply_act(y.z, act); y.w = apply_act(y.w, act);
+            sts_f4(my_row + (uint32_t)c * 4u, y);
+          }
+        }
       } else {
         float v[8];
         auto ld_issue = [&](int cb, uint32_t(&a)[8], uint32_t(&b)[8]) {  // warp-collective; pair with ld_wait
@@ -750,7 +817,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
             ld_issue(cb, a, b);
             ld_wait(a, b);
 #pragma unroll
-            for (int jj = 0; jj < 8; jj += 4) {
+            for (int jj = 0; jj < 8; jj += 4) {   // columns >= c_n hold exact zeros (zero weight rows, default bias 0)
               float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
               if (has_bias) bb = lds_f4(s_vec + (uint32_t)(cb + jj) * 4u);
               if (cb + jj < c_n) sum += (v[jj] + bb.x) + (v[jj + 1] + bb.y) + (v[jj + 2] + bb.z) + (v[jj + 3] + bb.w);
@@ -766,9 +833,9 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
             for (int jj = 0; jj < 8; jj += 4) {
               float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
               if (has_bias) bb = lds_f4(s_vec + (uint32_t)(cb + jj) * 4u);
-              if (cb + jj < c_n) {
+              if (cb + jj < c_n) {   // a width that is not a multiple of 4 ends inside this group: its tail columns do not count
                 const float d0 = v[jj] + bb.x - mean, d1 = v[jj + 1] + bb.y - mean, d2 = v[jj + 2] + bb.z - mean, d3 = v[jj + 3] + bb.w - mean;
-                qq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+                qq += d0 * d0 + (cb + jj + 1 < c_n ? d1 * d1 : 0.f) + (cb + jj + 2 < c_n ? d2 * d2 : 0.f) + (cb + jj + 3 < c_n ? d3 * d3 : 0.f);
               }
             }
           }

@@ -215,33 +215,73 @@ __global__ void __launch_bounds__(kNmsCols)
   (void)beg; (void)end;
 }
 
-// one warp per class: greedy pass in score order; the removed set lives in registers (4 words per lane: classes up to 8192)
+// one warp per class: greedy pass in score order; the removed set is a bit vector in shared memory (words <= kNmsMaxWords: 65 536
+// candidates per class), lane l owns words l, l + 32, ...; the next row's mask words are loaded while the current row is decided
+constexpr int kNmsMaxWords = 1024;
 __global__ void __launch_bounds__(32)
     k_nms_reduce(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ offsets, int words,
                  uint8_t* __restrict__ keep) {
+  __shared__ unsigned long long removed[kNmsMaxWords];
   const int c = blockIdx.x, lane = threadIdx.x;
   const int beg = offsets[c], end = offsets[c + 1];
-  unsigned long long removed[4] = {0, 0, 0, 0}, nxt[4] = {0, 0, 0, 0};
-  auto load_row = [&](int i, unsigned long long (&m)[4]) {
+  for (int w = lane; w < words; w += 32) removed[w] = 0ull;
+  __syncwarp();
+  if (words <= 32) {   // classes of <= 2048 candidates: one word per lane and row, eight rows of loads in flight
+    constexpr int kAhead = 8;
+    unsigned long long ring[kAhead];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int w = lane + 32 * s;
-      m[s] = w < words ? mask[(int64_t)i * words + w] : 0ull;
+    for (int d = 0; d < kAhead; ++d) ring[d] = (beg + d < end && lane < words) ? mask[(int64_t)(beg + d) * words + lane] : 0ull;
+    for (int i0 = beg; i0 < end; i0 += kAhead) {
+#pragma unroll
+      for (int d = 0; d < kAhead; ++d) {
+        const int i = i0 + d;
+        if (i < end) {   // warp-uniform
+          const unsigned long long cur = ring[d];
+          ring[d] = (i + kAhead < end && lane < words) ? mask[(int64_t)(i + kAhead) * words + lane] : 0ull;
+          const int li = i - beg;
+          const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
+          __syncwarp();
+          if (lane == 0) keep[i] = gone ? 0 : 1;
+          if (!gone && lane < words) removed[lane] |= cur;
+          __syncwarp();
+        }
+      }
     }
-  };
-  if (beg < end) load_row(beg, nxt);
-  for (int i = beg; i < end; ++i) {
-    unsigned long long cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-    if (i + 1 < end) load_row(i + 1, nxt);   // in flight while row i is decided: the chain is one shuffle per row, not one load
-    const int li = i - beg;
-    const int wi = li >> 6;
-    const unsigned long long word = __shfl_sync(0xffffffffu, removed[wi >> 5 & 3], wi & 31);
-    // removed[] of lane l holds words l, l+32, l+64, l+96: word wi lives in lane wi & 31, slot wi >> 5
-    const bool gone = (word >> (li & 63)) & 1ull;
-    if (lane == 0) keep[i] = gone ? 0 : 1;
-    if (!gone) {
+  } else if (words <= 128) {   // four words per lane stay in registers between rows
+    unsigned long long nxt[4] = {0, 0, 0, 0};
+    auto load_row = [&](int i, unsigned long long (&m)[4]) {
 #pragma unroll
-      for (int s = 0; s < 4; ++s) removed[s] |= cur[s];
+      for (int s = 0; s < 4; ++s) {
+        const int w = lane + 32 * s;
+        m[s] = w < words ? mask[(int64_t)i * words + w] : 0ull;
+      }
+    };
+    if (beg < end) load_row(beg, nxt);
+    for (int i = beg; i < end; ++i) {
+      unsigned long long cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+      if (i + 1 < end) load_row(i + 1, nxt);   // in flight while row i is decided
+      const int li = i - beg;
+      const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
+      __syncwarp();
+      if (lane == 0) keep[i] = gone ? 0 : 1;
+      if (!gone) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const int w = lane + 32 * s;
+          if (w < words) removed[w] |= cur[s];
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    for (int i = beg; i < end; ++i) {
+      const int li = i - beg;
+      const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
+      __syncwarp();
+      if (lane == 0) keep[i] = gone ? 0 : 1;
+      if (!gone)
+        for (int w = lane; w < words; w += 32) removed[w] |= mask[(int64_t)i * words + w];
+      __syncwarp();
     }
   }
 }
@@ -324,8 +364,8 @@ int fsfb_nms_suppress(const float* boxes, int64_t k, int64_t box_stride, const f
                       size_t workspace_bytes, void* stream) {
   using namespace fsfb;
   FSFB_CHECK_ARG(k >= 0 && box_stride >= 7 && num_classes >= 1 && num_classes <= 64 && candidates >= 0 && max_class >= 0 &&
-                     max_class <= 8192,
-                 "nms_suppress: bad argument (at most 8192 candidates per class)");
+                     max_class <= 65536,
+                 "nms_suppress: bad argument (at most 65536 candidates per class)");
   if (candidates == 0) return FSFB_OK;
   FSFB_CHECK_ARG(boxes && scores && flat && counts && keep, "nms_suppress: null pointer");
   cudaStream_t st = (cudaStream_t)stream;

@@ -532,7 +532,7 @@ int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float* pts, int6
  *   fsfb_nms_suppress  flat = ascending indices of the set flags (class-major candidates); per class: order by (score desc,
  *                      box index asc), suppress later boxes whose rotated BEV IoU with a kept one exceeds nms_thr;
  *                      keep dev [candidates] u8 in that order.  boxes dev rows (x, y, z, dx, dy, dz, yaw, ...).
- *                      max_class = largest counts[c] (<= 8192).
+ *                      max_class = largest counts[c] (<= 65536).
  *   fsfb_nms_emit      kept_idx = ascending indices of the set keep flags → boxes [n, box_dim], scores [n], labels [n] i64,
  *                      source row [n] i32 (nullable), n = min(kept, max_num): class-major in descending score, or the max_num
  *                      best scores in descending order when more survive.  Same workspace as fsfb_nms_suppress.

@@ -12,7 +12,9 @@ with torch.no_grad():
     st = model(f["points"], f["mask"], f["anno"], f["lidar2img"])
     bench.calibrate_seg_head(model, st["seg_logits"])
     for _ in range(3):
-        model(f["points"], f["mask"], f["anno"], f["lidar2img"])
+        st = model(f["points"], f["mask"], f["anno"], f["lidar2img"])
+        model.refine(st, f["points"])
+        model.get_bboxes(st)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for _ in range(2):
