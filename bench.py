@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--points", type=int, default=300000)
     ap.add_argument("--sweeps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="nuscenes", choices=["nuscenes", "av2"],
+                    help="nuscenes: FSF_nuScenes_config (the BASELINE metric's configuration); av2: FSF_AV2_config (BASELINE configs[3]: "
+                         "~107 k 4-d points, 7 ring cameras with one int32 id plane, 26 classes, the 32 x 2048 x 2048 grid)")
     ap.add_argument("--scope", default="full", choices=["hot", "full"],
                     help="full (default): FSF.simple_test = segment → combine + query refinement + final boxes (decode + rotated "
                          "NMS) on both arms; hot: segment → combine only (the scope of the round-1 numbers)")
@@ -55,9 +58,15 @@ def parse():
 
 def workload(args):
     """The `config` of the JSON line: byte-identical for both arms (static description of the workload, nothing measured)."""
-    return {"workload": f"FSF_nuScenes_config {args.sweeps}-sweep frame: {args.points} pts x 6 cams @1600x900, "
-                        "10 class id planes (BASELINE configs[2] shape, one frame per GPU per step)",
-            "points": args.points, "sweeps": args.sweeps, "cams": 6, "classes": 10, "frames_per_step_per_gpu": 1,
+    if args.config == "av2":
+        head = {"workload": f"FSF_AV2_config frame: {args.points} 4-d pts x 7 ring cams @2048x1550, one int32 id plane per camera, "
+                            "26 classes, +-204.8 m range (BASELINE configs[3] shape, one frame per GPU per step)",
+                "points": args.points, "sweeps": 1, "cams": 7, "classes": 26}
+    else:
+        head = {"workload": f"FSF_nuScenes_config {args.sweeps}-sweep frame: {args.points} pts x 6 cams @1600x900, "
+                            "10 class id planes (BASELINE configs[2] shape, one frame per GPU per step)",
+                "points": args.points, "sweeps": args.sweeps, "cams": 6, "classes": 10}
+    return {**head, "frames_per_step_per_gpu": 1,
             "scope": "FSF.simple_test: segment, enhance, frustum, fsd, combine" + (", refine, boxes (decode + rotated NMS)"
                                                                                     if args.scope == "full" else ""),
             "l2": "3 distinct frames rotate (288 MB of inputs > 126 MB L2)"}
@@ -98,7 +107,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_model(seed: int = 0):
+def make_model(seed: int = 0, config: str = "nuscenes"):
     """Random-init FSF (stock nuScenes architecture).  The segmentation logits are calibrated so that the
     synthetic scene behaves like a busy real one: ~5 % of voxels per class pass the 0.1 group-score
     threshold (a constant-logit random head would pass none or all of them)."""
@@ -107,7 +116,7 @@ def make_model(seed: int = 0):
     from fullysparsefusion_b200 import fsf as FSFM
 
     torch.manual_seed(seed)
-    model = FSFM.FSF()
+    model = FSFM.FSF(config)
     g = torch.Generator().manual_seed(seed + 1)
     for m in model.modules():  # non-trivial eval-mode BN statistics
         if isinstance(m, torch.nn.BatchNorm1d):
@@ -133,11 +142,16 @@ def calibrate_seg_head(model, logits) -> None:
     model.segmentation_head.refresh()
 
 
-def synth_frame(points: int, sweeps: int, seed: int):
+def synth_frame(points: int, sweeps: int, seed: int, config: str = "nuscenes"):
     import torch
 
     from fullysparsefusion_b200 import synth
 
+    if config == "av2":   # 7 ring cameras, one int32 id plane each (loading.py:169-186), 4-d points + un-augmented xyz
+        mask = synth.mask_planes(cams=7, classes=1, H=1550, W=2048, seed=seed, dtype="int32")
+        return dict(points=torch.from_numpy(synth.av2_points(points, seed=seed)), mask=torch.from_numpy(mask),
+                    anno=torch.from_numpy(synth.mask_anno(mask, seed=seed, categories=26)),
+                    lidar2img=torch.from_numpy(synth.lidar2img(7, 1550, 2048)))
     mask = synth.mask_planes(seed=seed)
     return dict(points=torch.from_numpy(synth.ring_points(points, sweeps=sweeps, seed=seed)), mask=torch.from_numpy(mask),
                 anno=torch.from_numpy(synth.mask_anno(mask, seed=seed)), lidar2img=torch.from_numpy(synth.lidar2img()))
@@ -152,9 +166,9 @@ def run_cpu_port(args, steps: int, warmup: int, model=None, frame=None):
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     if model is None:
-        model = make_model()
+        model = make_model(config=args.config)
     model = model.cpu()
-    frame = frame or synth_frame(args.points, args.sweeps, seed=0)
+    frame = frame or synth_frame(args.points, args.sweeps, seed=0, config=args.config)
     cpu = P.CpuFSF(model)
     per_stage = {}
     n_run = 0
@@ -334,10 +348,10 @@ def main():
     # three distinct frames rotate through the steps: 3 x 96 MB of inputs plus > 1 GB of per-frame
     # intermediates exceed the 126 MB L2, so no step starts on a warm cache
     n_frames = 3
-    hosts = [{k: v.pin_memory() for k, v in synth_frame(args.points, args.sweeps, seed=fdist.frame_seed(rank, i)).items()}
+    hosts = [{k: v.pin_memory() for k, v in synth_frame(args.points, args.sweeps, seed=fdist.frame_seed(rank, i), config=args.config).items()}
              for i in range(n_frames)]
     frames = [{k: v.to(dev) for k, v in h.items()} for h in hosts]
-    model = make_model().to(dev)
+    model = make_model(config=args.config).to(dev)
     with torch.no_grad():
         st0 = model(frames[0]["points"], frames[0]["mask"], frames[0]["anno"], frames[0]["lidar2img"])
         calibrate_seg_head(model, st0["seg_logits"])

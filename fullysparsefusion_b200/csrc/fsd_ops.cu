@@ -13,7 +13,7 @@ namespace fsfb {
 
 constexpr int kGsMaxClasses = 32;
 constexpr int kGsMaxGroups = 8;
-constexpr int kGsMaxPerGroup = 4;
+constexpr int kGsMaxPerGroup = 12;  // AV2 groups hold up to 9 classes (FSF_AV2_config.py:40-45)
 
 struct GroupSpec {
   int n_groups;

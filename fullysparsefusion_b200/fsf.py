@@ -37,6 +37,37 @@ NUSC = dict(
     cluster_voxel_size=[(0.3, 0.3, 8), (0.3, 0.3, 8), (0.3, 0.3, 8), (0.1, 0.1, 8), (0.2, 0.2, 8), (0.05, 0.05, 8)],
     connected_dist=[0.6, 0.6, 0.6, 0.2, 0.4, 0.1], min_points=2, num_cams=6,
 )
+NUSC.update(
+    point_dim=5, is_argo=False, code_size=10,
+    unet=dict(base_channels=64, output_channels=128,
+              encoder_channels=((128,), (128, 128, 128), (128, 128, 128), (256, 256, 256), (512, 512, 512)),
+              encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1), (1, 1, 1)),
+              decoder_channels=((512, 512, 256), (256, 256, 128), (128, 128, 128), (128, 128, 128), (128, 128, 128)),
+              decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1))))
+
+# ---- the stock Argoverse 2 configuration (projects/configs/Argoverse2/FSF_AV2_config.py): 4-d points, the +-204.8 m grid
+# [32, 2048, 2048] (:11,86), a four-stage 64-channel U-Net (:83-95), 26 classes in six groups (:12-49), seven ring cameras
+# with ONE int32 id plane each (datasets/pipelines/loading.py:169-186), per-point 2-D encoding of the selected object
+# (is_argo: bbox / score / one-hot category = 32 channels, FSF.py:449-474,537-552), no velocity (code_size 8, :164,259)
+_AV2_CLASSES = ["Regular_vehicle", "Pedestrian", "Bicyclist", "Motorcyclist", "Wheeled_rider", "Bollard", "Construction_cone", "Sign",
+                "Construction_barrel", "Stop_sign", "Mobile_pedestrian_crossing_sign", "Large_vehicle", "Bus", "Box_truck", "Truck",
+                "Vehicular_trailer", "Truck_cab", "School_bus", "Articulated_bus", "Message_board_trailer", "Bicycle", "Motorcycle",
+                "Wheeled_device", "Wheelchair", "Stroller", "Dog"]
+AV2 = dict(
+    class_names=_AV2_CLASSES,
+    group_names=[_AV2_CLASSES[:1], _AV2_CLASSES[1:5], _AV2_CLASSES[5:11], _AV2_CLASSES[11:20], _AV2_CLASSES[20:25], _AV2_CLASSES[25:]],
+    seg_voxel_size=(0.2, 0.2, 0.2), point_cloud_range=[-204.8, -204.8, -3.2, 204.8, 204.8, 3.2], sparse_shape=[32, 2048, 2048],
+    score_thresh=[0.4, 0.25, 0.25, 0.25, 0.25, 0.25], pre_voxelization_size=(0.1, 0.1, 0.1),
+    cluster_voxel_size=[(0.3, 0.3, 6.4), (0.05, 0.05, 6.4), (0.08, 0.08, 6.4), (0.5, 0.5, 6.4), (0.1, 0.1, 6.4), (0.08, 0.08, 6.4)],
+    connected_dist=[0.6, 0.1, 0.15, 1.0, 0.2, 0.15], min_points=2, num_cams=7,
+    point_dim=4, is_argo=True, code_size=8,
+    unet=dict(base_channels=64, output_channels=64,
+              encoder_channels=((64,), (64, 64, 64), (64, 64, 64), (128, 128, 128)),
+              encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)),
+              decoder_channels=((128, 128, 64), (64, 64, 64), (64, 64, 64), (64, 64, 64)),
+              decoder_paddings=((1, 0), (1, 0), (0, 0), (0, 1))))
+CONFIGS = {"nuscenes": NUSC, "av2": AV2}
+
 BN = dict(type="naiveSyncBN1d", eps=1e-3, momentum=0.01)
 LN3 = dict(type="LN", eps=1e-3)
 LN5 = dict(type="LN")
@@ -90,62 +121,73 @@ class SparseClusterHeadV2(nn.Module):
         return dict(cls_logits=cls_list, reg_preds=reg_list)
 
 
-def _head(in_channel, class_names):
+def _head(in_channel, class_names, code_size=10):
+    attrs = dict(center=(3, 2, 128), dim=(3, 2, 128), rot=(2, 2, 128))
+    if code_size == 10:   # nuScenes regresses a velocity; the AV2 config (code_size 8) has no `vel` attribute
+        attrs["vel"] = (2, 2, 128)
     return SparseClusterHeadV2(
         num_classes=len(class_names), in_channel=in_channel, shared_mlp_dims=[1024, 1024],
         tasks=[dict(num_class=len(class_names), class_names=class_names)],
-        common_attrs=dict(center=(3, 2, 128), dim=(3, 2, 128), rot=(2, 2, 128), vel=(2, 2, 128)), num_cls_layer=2,
+        common_attrs=attrs, num_cls_layer=2,
         cls_hidden_dim=128, separate_head=dict(norm_cfg=LN5, act="gelu"), norm_cfg=LN5, act="relu")
 
 
 class FSF(nn.Module):
     """The FSF detector's inference forward on synthetic or real frames (random init unless weights are loaded)."""
 
-    def __init__(self, cfg: dict = NUSC):
+    def __init__(self, cfg=NUSC):
+        """cfg: one of CONFIGS' dicts (or its name, "nuscenes" / "av2"): every width below is derived from it the way the stock
+        config files spell them out (point dims P, classes nc, U-Net output → point feature width F = out + 3)."""
         super().__init__()
+        if isinstance(cfg, str):
+            cfg = CONFIGS[cfg]
         self.cfg = cfg
         nc = len(cfg["class_names"])
         self.num_classes = nc
+        self.is_argo = bool(cfg.get("is_argo", False))
+        P = self.point_dim = int(cfg.get("point_dim", 5))
+        code = int(cfg.get("code_size", 10))
+        unet = cfg.get("unet", NUSC["unet"])
+        F_pt = unet["output_channels"] + 3            # neck output: voxel feature ‖ xyz - voxel centre (131 / 67)
+        enc2d = 5 + nc + 1                             # bbox (4) + score + one-hot category incl. "none" (16 / 32)
+        pt2d = enc2d if self.is_argo else nc           # per-point image input: the 32-channel encoding (AV2) or nc class scores
         self.groups = [[cfg["class_names"].index(n) for n in g] for g in cfg["group_names"]]
-        # segmentor (FSF_nuScenes_config.py:33-102)
-        self.voxel_encoder = M.DynamicScatterVFE(in_channels=5, feat_channels=[64, 64], voxel_size=cfg["seg_voxel_size"],
+        # segmentor (FSF_nuScenes_config.py:33-102; FSF_AV2_config.py:60-132)
+        self.voxel_encoder = M.DynamicScatterVFE(in_channels=P, feat_channels=[64, 64], voxel_size=cfg["seg_voxel_size"],
                                                  with_cluster_center=True, with_voxel_center=True,
                                                  point_cloud_range=cfg["point_cloud_range"], norm_cfg=BN, unique_once=True)
-        self.backbone_unet = M.SimpleSparseUNet(
-            in_channels=64, sparse_shape=cfg["sparse_shape"], norm_cfg=BN, base_channels=64, output_channels=128,
-            encoder_channels=((128,), (128, 128, 128), (128, 128, 128), (256, 256, 256), (512, 512, 512)),
-            encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1), (1, 1, 1)),
-            decoder_channels=((512, 512, 256), (256, 256, 128), (128, 128, 128), (128, 128, 128), (128, 128, 128)),
-            decoder_paddings=((1, 1), (1, 0), (1, 0), (0, 0), (0, 1)))
+        self.backbone_unet = M.SimpleSparseUNet(in_channels=64, sparse_shape=cfg["sparse_shape"], norm_cfg=BN, **unet)
         self.decode_neck = M.Voxel2PointScatterNeck(voxel_size=cfg["seg_voxel_size"], point_cloud_range=cfg["point_cloud_range"])
-        self.segmentation_head = M.VoteSegHead(in_channel=67 + 64, hidden_dims=[128, 128], num_classes=nc,
+        self.segmentation_head = M.VoteSegHead(in_channel=F_pt, hidden_dims=[128, 128], num_classes=nc,
                                                norm_cfg=dict(type="naiveSyncBN1d"), act_cfg=dict(type="ReLU"))
         # FSF.__init__ (FSF.py:100-164)
-        self.segmentor_updated_mlp = M.build_mlp(10, [128, 131], LN3, is_head=True, act="gelu")
+        self.segmentor_updated_mlp = M.build_mlp(pt2d, [128, F_pt], LN3, is_head=True, act="gelu")
         nn.init.constant_(self.segmentor_updated_mlp[-1].weight, 0.0)   # FSF.py:142-143
         nn.init.constant_(self.segmentor_updated_mlp[-1].bias, 0.0)
-        self.encode_2d_mlp = M.build_mlp(16, [128, 128], LN3, is_head=False, act="gelu")
+        self.encode_2d_mlp = M.build_mlp(enc2d, [128, 128], LN3, is_head=False, act="gelu")
         sir_kw = dict(num_blocks=3, feat_channels=[[128, 128]] * 3, rel_mlp_hidden_dims=[[16, 32]] * 3, norm_cfg=LN3, mode="max",
                       xyz_normalizer=[20, 20, 4], act="gelu", unique_once=True)
-        self.backbone = M.SIR(in_channels=[116 + 64, 133, 133], **sir_kw)          # LiDAR queries (:113-124)
-        self.frustum_sir = M.SIR(in_channels=[67 + 64 + 5, 133, 133], **sir_kw)    # camera queries (:201-212)
-        self.bbox_head = _head(128 * 3 * 2, cfg["class_names"])
-        self.frustum_obj_head = _head(128 * 3 * 2 + 128, cfg["class_names"])
+        fsd_feat = (nc + 1) + 3 * (nc + 1) + F_pt      # pre-voxel logits ‖ votes ‖ features (175 on nuScenes)
+        self.fsd_feat_dims = (nc + 1, 3 * (nc + 1), F_pt)
+        self.backbone = M.SIR(in_channels=[P + fsd_feat, P + 128, P + 128], **sir_kw)       # LiDAR queries (:113-124; AV2 :150-161)
+        self.frustum_sir = M.SIR(in_channels=[P + F_pt, P + 128, P + 128], **sir_kw)          # camera queries (:201-212; AV2 :241-252)
+        self.bbox_head = _head(128 * 3 * 2, cfg["class_names"], code)
+        self.frustum_obj_head = _head(128 * 3 * 2 + 128, cfg["class_names"], code)
         self.combine_frustum_feat_mlp = M.build_mlp(128 * 3 * 2 + 128, [1024], LN3, act="gelu")
         self.combine_fsd_feat_mlp = M.build_mlp(128 * 3 * 2, [1024], LN3, act="gelu")
-        # query refinement (FSF.__init__ :144-164; configs :275-404): one extra stage in the stock config
+        # query refinement (FSF.__init__ :144-164; configs :275-404 / AV2 :318-426): one extra stage in the stock configs
         self.num_extra_stages = int(cfg.get("num_extra_stages", 1))
         self.roi_extractor = M.DynamicPointROIExtractor(extra_wlh=[1.0, 1.0, 1.0], max_inbox_point=512, debug=False)
         embed = 1024
         self.refine_sir_layers = nn.ModuleList([M.FullySparseBboxHead(
-            num_classes=nc, num_blocks=3, in_channels=[67 + 5 + 13 + 32 + 64, 131 + 13 + 2, 131 + 13 + 2], feat_channels=[[128, 128]] * 3,
+            num_classes=nc, num_blocks=3, in_channels=[P + F_pt + 32 + 13, P + 128 + 13, P + 128 + 13], feat_channels=[[128, 128]] * 3,
             rel_mlp_hidden_dims=[[16, 32]] * 3, rel_mlp_in_channels=[13] * 3, xyz_normalizer=[20, 20, 4], act="gelu", geo_input=True,
             use_middle_cluster_feature=True, norm_cfg=LN3, unique_once=True) for _ in range(self.num_extra_stages)])
-        self.refine_img_mlp = nn.ModuleList([M.build_mlp(10, [32, 32], LN3, is_head=False, act="gelu") for _ in range(self.num_extra_stages)])
+        self.refine_img_mlp = nn.ModuleList([M.build_mlp(pt2d, [32, 32], LN3, is_head=False, act="gelu") for _ in range(self.num_extra_stages)])
         self.lidar_img_mlp = nn.ModuleList([M.build_mlp(128 * 3 * 2, [embed, embed], LN3, act="gelu") for _ in range(self.num_extra_stages)])
         self.position_encoder = nn.ModuleList([M.build_mlp(3, [embed, embed], LN3, act="gelu") for _ in range(self.num_extra_stages)])
         self.out_proj = nn.ModuleList([M.build_mlp(embed, [embed, embed], LN3, act="gelu", is_head=True) for _ in range(self.num_extra_stages)])
-        self.frustum_refined_head = nn.ModuleList([_head(embed, cfg["class_names"]) for _ in range(self.num_extra_stages)])
+        self.frustum_refined_head = nn.ModuleList([_head(embed, cfg["class_names"], code) for _ in range(self.num_extra_stages)])
         self.fsd_begin_idx = 1000
         self.group_loop = False   # True: the reference's per-group Python loop (kept for the equivalence test)
         self.eval()
@@ -189,16 +231,19 @@ class FSF(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def stages(self, points: torch.Tensor, mask_data: torch.Tensor, mask_anno: torch.Tensor, lidar2img: torch.Tensor
                ) -> Tuple[List[Tuple[str, Callable[[], None]]], Dict[str, torch.Tensor]]:
-        """points [N,8] f32 (x,y,z,intensity,dt + un-augmented xyz), mask_data u8 [cams,classes,H,W],
-        mask_anno f32 [250,9], lidar2img f32 [cams,4,4].  Returns ([(stage name, fn)], state)."""
+        """points [N,P+3] f32 (nuScenes: x,y,z,intensity,dt; AV2: x,y,z,intensity; + un-augmented xyz), mask_data
+        [cams,classes,H,W] u8 (nuScenes: 10 class planes) or i32 (AV2: one plane), mask_anno f32 [250,9], lidar2img f32 [cams,4,4].
+        Returns ([(stage name, fn)], state)."""
         st: Dict[str, torch.Tensor] = {}
         cfg = self.cfg
         dev = points.device
+        P = self.point_dim
+        noaug = slice(P, P + 3)
         rng, vs = cfg["point_cloud_range"], cfg["seg_voxel_size"]
         grid_zyx = cfg["sparse_shape"]
 
         def segment():
-            pts5 = points[:, :5]
+            pts5 = points[:, :P]
             coors3 = ops.voxelize(points, vs, rng, floor_mode=0)                       # single_stage_fsd.py:217-219
             coors4 = F.pad(coors3, (1, 0), value=0)                                    # batch pad (:222-225)
             plan = M.ScatterPlan(coors4, lo=[0, 0, 0, 0], ext=[1] + list(grid_zyx), want_index=True)
@@ -211,8 +256,12 @@ class FSF(nn.Module):
 
         def enhance():
             # img_cross_attn (FSF.py:694-728): the whole gather/select/lookup chain is one kernel
-            _, cam, fg, ov, scores = ops.project_sample_select(points[:, 5:8], lidar2img, mask_data, want_overlap=True,
-                                                               anno=mask_anno, anno_col=4, want_ids=False)
+            if self.is_argo:   # one id plane: the selected object's annotation row → bbox / score / one-hot category (FSF.py:449-474,537-552)
+                ids, cam, fg, ov = ops.project_sample_select(points[:, noaug], lidar2img, mask_data, want_overlap=True, want_ids=True)
+                _, scores = ops.encode_preds_2d(mask_anno, ids, mask_data.shape[-1], mask_data.shape[-2], self.num_classes, coor_col=0)
+            else:
+                _, cam, fg, ov, scores = ops.project_sample_select(points[:, noaug], lidar2img, mask_data, want_overlap=True,
+                                                                   anno=mask_anno, anno_col=4, want_ids=False)
             img_feat = self.segmentor_updated_mlp(scores)
             st["img_scores"] = scores
             pts_feats = ops.add_(img_feat, st["pts_lidar_feats"])                      # :790
@@ -222,11 +271,11 @@ class FSF(nn.Module):
                       offsets=offsets)
 
         def frustum():
-            pts5 = points[:, :5]
+            pts5 = points[:, :P]
             fgw, _, _ = ops.group_sample(st["seg_logits"], want_fg_weight=True)         # get_point_fg_weights (:345-355)
-            rows, sir_coors, n_fg = ops.frustum_rows(points[:, 5:8], lidar2img, mask_data, st["fg"], st["overlap"])
+            rows, sir_coors, n_fg = ops.frustum_rows(points[:, noaug], lidar2img, mask_data, st["fg"], st["overlap"])
             if rows.numel() == 0:   # fake one object (FSF.py:407-414)
-                r_pts = torch.zeros((1, 5), device=dev)
+                r_pts = torch.zeros((1, P), device=dev)
                 r_feat = torch.zeros((1, st["seg_feats"].size(1)), device=dev)
                 sir_coors = torch.zeros((1, 3), dtype=torch.int32, device=dev)
                 f_cluster = torch.zeros((1, 3), device=dev)
@@ -251,7 +300,7 @@ class FSF(nn.Module):
                       point_fg_weights=fgw)
 
         def fsd():
-            pts5 = points[:, :5].contiguous()
+            pts5 = points[:, :P].contiguous()
             # pre_voxelize (single_stage_fsd.py:585-605)
             c3 = ops.voxelize(pts5, cfg["pre_voxelization_size"], rng, floor_mode=1)
             c4 = F.pad(c3, (1, 0), value=0)
@@ -272,10 +321,11 @@ class FSF(nn.Module):
                 pts_cluster_inds = torch.stack([cls, torch.zeros_like(cls), clu], dim=1)   # (cls, batch, cluster) (:145-152)
             n = rows.numel()
             s_pts = ops.gather_rows(v_pts, rows)
-            pts_feats = torch.empty((n, 11 + 33 + 131), dtype=torch.float32, device=dev)
-            ops.gather_rows(v_logits, rows, out=pts_feats[:, :11])
-            ops.gather_rows(v_votes, rows, out=pts_feats[:, 11:44])
-            ops.gather_rows(v_feats, rows, out=pts_feats[:, 44:])
+            d0, d1, d2 = self.fsd_feat_dims                                           # logits ‖ votes ‖ point features
+            pts_feats = torch.empty((n, d0 + d1 + d2), dtype=torch.float32, device=dev)
+            ops.gather_rows(v_logits, rows, out=pts_feats[:, :d0])
+            ops.gather_rows(v_votes, rows, out=pts_feats[:, d0:d0 + d1])
+            ops.gather_rows(v_feats, rows, out=pts_feats[:, d0 + d1:])
             # extract_feat (:458-474)
             plan_q = M.ScatterPlan(pts_cluster_inds)
             cluster_xyz_mean = plan_q.reduce(center_preds, "mean")
@@ -308,7 +358,7 @@ class FSF(nn.Module):
         query_feat_refine (models/detectors/FSF.py:960-1083) up to the refined heads' logits and regressions (box decoding of
         the final stage and NMS are SURVEY.md section 8f rank 3).  Not part of `stages()`: the benchmarked scope and its CPU
         port end at combine_frustum_and_fsd."""
-        pts5 = points[:, :5].contiguous()
+        pts5 = points[:, :self.point_dim].contiguous()
         obj_centers, obj_reg, res_query_feat = st["obj_centers"], st["obj_reg"], st["obj_feats"]
         out = {}
         for i in range(self.num_extra_stages):

@@ -134,8 +134,9 @@ def mask_planes(cams: int = 6, classes: int = 10, H: int = 900, W: int = 1600, s
     return mask
 
 
-def mask_anno(mask: np.ndarray, seed: int = 0, n_obj: int = 250) -> np.ndarray:
-    """[n_obj,9] f32 rows (x1,y1,x2,y2,score,category,cam_id,obj_id,valid) sorted by obj_id."""
+def mask_anno(mask: np.ndarray, seed: int = 0, n_obj: int = 250, categories=None) -> np.ndarray:
+    """[n_obj,9] f32 rows (x1,y1,x2,y2,score,category,cam_id,obj_id,valid) sorted by obj_id.  categories: number of classes to
+    draw the category from when the planes are not per class (AV2: one id plane per camera, 26 classes)."""
     rng = np.random.default_rng(seed + 2000)
     cams, classes, H, W = mask.shape
     anno = np.zeros((n_obj, 9), dtype=np.float32)
@@ -144,7 +145,8 @@ def mask_anno(mask: np.ndarray, seed: int = 0, n_obj: int = 250) -> np.ndarray:
             ids = np.unique(mask[cam, cls])
             for oid in ids[ids > 0]:
                 ys, xs = np.nonzero(mask[cam, cls] == oid)
-                anno[int(oid) - 1] = (xs.min(), ys.min(), xs.max(), ys.max(), rng.uniform(0.3, 1.0), cls, cam, oid, 1)
+                cat = cls if categories is None else int(rng.integers(0, categories))
+                anno[int(oid) - 1] = (xs.min(), ys.min(), xs.max(), ys.max(), rng.uniform(0.3, 1.0), cat, cam, oid, 1)
     return anno
 
 
@@ -162,3 +164,12 @@ def cluster_points(m: int, seed: int = 0, batches: int = 1, n_clusters: int = 40
         perm = rng.permutation(m)
         b = b[perm]
     return np.concatenate([xy, z], 1).astype(np.float32), b
+
+
+def av2_points(n: int, seed: int = 0) -> np.ndarray:
+    """[n,7] f32 Argoverse-2-shaped sweep: x,y,z,intensity + un-augmented xyz (4-d points, FSF_AV2_config.py:70), spread over the
+    +-204.8 m / +-3.2 m range of that config (the spinning-LiDAR pattern of ring_points stretched to a 200 m horizon)."""
+    p = ring_points(n, sweeps=max(1, round(n / 50000)), seed=seed, clip=(-200.0, -200.0, -3.19, 200.0, 200.0, 3.19), beams=64,
+                    n_boxes=96, max_range=190.0)
+    out = np.concatenate([p[:, :4], p[:, :3]], axis=1)
+    return np.ascontiguousarray(out, dtype=np.float32)

@@ -259,6 +259,8 @@ class CpuFSF:
     def stages(self, points, mask_data, mask_anno, lidar2img) -> Tuple[List[Tuple[str, Callable[[], None]]], Dict]:
         m, cfg, st = self.m, self.cfg, {}
         rng = cfg["point_cloud_range"]
+        P = int(cfg.get("point_dim", 5))          # nuScenes: x,y,z,intensity,dt; AV2: x,y,z,intensity; then the un-augmented xyz
+        is_argo = bool(cfg.get("is_argo", False))
 
         def sir_layer(layer, feats, inv, unq, f_cluster, return_pts=True):
             x = torch.cat([feats[:, :3] / torch.tensor(layer.xyz_normalizer), feats[:, 3:]], 1)
@@ -285,10 +287,10 @@ class CpuFSF:
         def head(h, x):
             x = seq(h.shared_mlp, x)
             r = {k: seq(getattr(h.task_heads[0], k), x) for k in h.task_heads[0].attrs}
-            return r["score"], torch.cat([r["center"], r["dim"], r["rot"], r["vel"]], 1)
+            return r["score"], torch.cat([r["center"], r["dim"], r["rot"]] + ([r["vel"]] if "vel" in r else []), 1)
 
         def segment():
-            pts5 = points[:, :5]
+            pts5 = points[:, :P]
             c = floor_coors(points, cfg["seg_voxel_size"], rng, kernel_rule=True)[:, [2, 1, 0]]
             coors = F.pad(c, (1, 0), value=0)
             unq, inv = torch.unique(coors, return_inverse=True, dim=0)
@@ -350,22 +352,31 @@ class CpuFSF:
             st.update(voxel_feats=x, pts_lidar_feats=torch.cat([pts_feats, pts5[:, :3] - centre], 1))
 
         def enhance():
-            ids = points_in_mask(points[:, 5:8], mask_data, lidar2img)               # frustum_gather (FSF.py:228-258)
+            ids = points_in_mask(points[:, P:P + 3], mask_data, lidar2img)           # frustum_gather (FSF.py:228-258)
             cam = ids.sum(-1).max(-1)[1]
             sel = F.one_hot(cam, ids.size(1)).bool().unsqueeze(-1)
             ids_sel = ids.masked_select(sel).reshape(-1, ids.size(2))
             preds = torch.zeros((len(ids_sel), ids.size(2), mask_anno.size(1)))
             valid = ids_sel >= 1
             preds[valid] = mask_anno[ids_sel[valid] - 1]                             # get_all_cls_preds_2d
-            img_feat = seq(m.segmentor_updated_mlp, preds[..., 4])
-            st["img_scores"] = preds[..., 4]
+            if is_argo:   # encode_2d_feats with encode_single_cls (FSF.py:449-474, 537-552): bbox / w,h ‖ score ‖ one-hot category
+                pr = preds.reshape(-1, mask_anno.size(1)).clone()
+                pr[~valid.reshape(-1), 5] = m.num_classes                            # invalid rows: category = "none"
+                box = pr[:, :4].clone()
+                box[:, 0::2] /= mask_data.shape[-1]
+                box[:, 1::2] /= mask_data.shape[-2]
+                pt2d = torch.cat([box, pr[:, 4:5], F.one_hot(pr[:, 5].long(), m.num_classes + 1).float()], 1)
+            else:
+                pt2d = preds[..., 4]
+            img_feat = seq(m.segmentor_updated_mlp, pt2d)
+            st["img_scores"] = pt2d
             feats = st["pts_lidar_feats"] + img_feat
             h = seq(m.segmentation_head.pre_seg_conv, feats)
             logits, votes = m.segmentation_head.conv_seg(h), m.segmentation_head.voting(h)
             st.update(ids=ids, seg_feats=feats, seg_logits=logits, seg_vote_preds=votes, offsets=votes * votes.abs())
 
         def frustum():
-            pts5, ids = points[:, :5], st["ids"]
+            pts5, ids = points[:, :P], st["ids"]
             fgw = 1 - st["seg_logits"].softmax(1)[:, -1]
             fg = ids.sum((-2, -1)) > 0                                              # extract_fg_pts
             feat, p, o, w = st["seg_feats"][fg], pts5[fg], ids[fg].reshape(int(fg.sum()), -1), fgw[fg]
@@ -399,7 +410,7 @@ class CpuFSF:
             st.update(frustum_obj_feats=obj, frustum_out=head(m.frustum_obj_head, obj), frustum_centers=center)
 
         def fsd():
-            pts5 = points[:, :5]
+            pts5 = points[:, :P]
             c = F.pad(floor_coors(pts5, cfg["pre_voxelization_size"], rng)[:, [2, 1, 0]], (1, 0), value=0)
             unq = torch.unique(c, return_inverse=True, dim=0)
             v = {k: scatter_v2(t, None, "avg", unq=unq)[0] for k, t in dict(p=pts5, l=st["seg_logits"], v=st["seg_vote_preds"],
@@ -438,7 +449,7 @@ class CpuFSF:
 
         def refine():
             # each_stage_refine / query_feat_refine (FSF.py:1009-1083), one extra stage
-            pts5 = points[:, :5]
+            pts5 = points[:, :P]
             centers = torch.cat([st["frustum_centers"], st["fsd_centers"]], 0)
             reg = torch.cat([st["frustum_out"][1], st["fsd_out"][1]], 0)
             res = st["obj_feats"]

@@ -323,3 +323,36 @@ def test_scatter_plan_on_empty_input(cuda):
     assert res[0] is None and res[3].m == 0
     plan = M.ScatterPlan(empty, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], want_index=True)
     assert plan.m == 0
+
+
+def test_av2_frame_against_cpu_port(cuda):
+    """BASELINE configs[3]: the stock Argoverse 2 configuration (FSF_AV2_config.py) — ~107 k 4-d points, seven ring cameras with ONE
+    int32 id plane each, 26 classes in six groups, the 32 x 2048 x 2048 grid, a four-stage 64-channel U-Net, the 32-channel per-point
+    encoding of the selected 2-D object (is_argo) and no velocity head — every stage of simple_test against the torch-CPU port."""
+    import copy
+
+    import bench
+    from oracle import fsf_torch_cpu as P
+
+    frame = bench.synth_frame(107000, 1, seed=4, config="av2")
+    dev_frame = {k: v.to(cuda) for k, v in frame.items()}
+    model = bench.make_model(config="av2").to(cuda)
+    with torch.no_grad():
+        st0 = model(dev_frame["points"], dev_frame["mask"], dev_frame["anno"], dev_frame["lidar2img"])
+        bench.calibrate_seg_head(model, st0["seg_logits"])
+        stages, st = model.stages(dev_frame["points"], dev_frame["mask"], dev_frame["anno"], dev_frame["lidar2img"])
+        for _, fn in stages:
+            fn()
+        model.refine(st, dev_frame["points"])
+        model.get_bboxes(st)
+        torch.cuda.synchronize()
+        cpu = P.CpuFSF(copy.deepcopy(model).cpu())
+        cstages, cst = cpu.stages(frame["points"], frame["mask"], frame["anno"], frame["lidar2img"])
+        for _, fn in cstages + cpu.extra_stages:
+            fn()
+    assert st["seg_logits"].shape[1] == 27 and st["seg_feats"].shape[1] == 67 and st["img_scores"].shape[1] == 32
+    assert st["refine0_reg"].shape[1] == 8 and st["det_boxes"].shape[1] == 7          # no velocity
+    par = bench.frame_parity(st, cst)
+    assert not par["breach"], par
+    assert par["counts_gpu_cpu"]["voxels"][0] == par["counts_gpu_cpu"]["voxels"][1], par
+    assert par["rel_p999_by_tensor"]["seg_logits"] < 5e-4, par
