@@ -216,8 +216,49 @@ __global__ void __launch_bounds__(kNmsCols)
 }
 
 // one warp per class: greedy pass in score order; the removed set is a bit vector in shared memory (words <= kNmsMaxWords: 65 536
-// candidates per class), lane l owns words l, l + 32, ...; the next row's mask words are loaded while the current row is decided
+// candidates per class), lane l owns words l, l + 32, ...  The mask rows of the next AHEAD candidates are already in registers
+// (a static ring: the loop body is unrolled over it), so the chain per row is one shared-memory read, not one global load.
 constexpr int kNmsMaxWords = 1024;
+
+template <int WPL, int AHEAD>
+__device__ __forceinline__ void nms_reduce_ring(const unsigned long long* __restrict__ mask, int beg, int end, int words, int lane,
+                                                unsigned long long* removed, uint8_t* __restrict__ keep) {
+  unsigned long long ring[AHEAD][WPL];
+  auto load_row = [&](int i, unsigned long long (&m)[WPL]) {
+#pragma unroll
+    for (int s = 0; s < WPL; ++s) {
+      const int w = lane + 32 * s;
+      m[s] = (i < end && w < words) ? mask[(int64_t)i * words + w] : 0ull;
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < AHEAD; ++d) load_row(beg + d, ring[d]);
+  for (int i0 = beg; i0 < end; i0 += AHEAD) {
+#pragma unroll
+    for (int d = 0; d < AHEAD; ++d) {
+      const int i = i0 + d;
+      if (i < end) {   // warp-uniform
+        unsigned long long cur[WPL];
+#pragma unroll
+        for (int s = 0; s < WPL; ++s) cur[s] = ring[d][s];
+        load_row(i + AHEAD, ring[d]);
+        const int li = i - beg;
+        const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
+        __syncwarp();
+        if (lane == 0) keep[i] = gone ? 0 : 1;
+        if (!gone) {
+#pragma unroll
+          for (int s = 0; s < WPL; ++s) {
+            const int w = lane + 32 * s;
+            if (w < words) removed[w] |= cur[s];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(32)
     k_nms_reduce(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ offsets, int words,
                  uint8_t* __restrict__ keep) {
@@ -226,53 +267,12 @@ __global__ void __launch_bounds__(32)
   const int beg = offsets[c], end = offsets[c + 1];
   for (int w = lane; w < words; w += 32) removed[w] = 0ull;
   __syncwarp();
-  if (words <= 32) {   // classes of <= 2048 candidates: one word per lane and row, eight rows of loads in flight
-    constexpr int kAhead = 8;
-    unsigned long long ring[kAhead];
-#pragma unroll
-    for (int d = 0; d < kAhead; ++d) ring[d] = (beg + d < end && lane < words) ? mask[(int64_t)(beg + d) * words + lane] : 0ull;
-    for (int i0 = beg; i0 < end; i0 += kAhead) {
-#pragma unroll
-      for (int d = 0; d < kAhead; ++d) {
-        const int i = i0 + d;
-        if (i < end) {   // warp-uniform
-          const unsigned long long cur = ring[d];
-          ring[d] = (i + kAhead < end && lane < words) ? mask[(int64_t)(i + kAhead) * words + lane] : 0ull;
-          const int li = i - beg;
-          const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
-          __syncwarp();
-          if (lane == 0) keep[i] = gone ? 0 : 1;
-          if (!gone && lane < words) removed[lane] |= cur;
-          __syncwarp();
-        }
-      }
-    }
-  } else if (words <= 128) {   // four words per lane stay in registers between rows
-    unsigned long long nxt[4] = {0, 0, 0, 0};
-    auto load_row = [&](int i, unsigned long long (&m)[4]) {
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int w = lane + 32 * s;
-        m[s] = w < words ? mask[(int64_t)i * words + w] : 0ull;
-      }
-    };
-    if (beg < end) load_row(beg, nxt);
-    for (int i = beg; i < end; ++i) {
-      unsigned long long cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-      if (i + 1 < end) load_row(i + 1, nxt);   // in flight while row i is decided
-      const int li = i - beg;
-      const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
-      __syncwarp();
-      if (lane == 0) keep[i] = gone ? 0 : 1;
-      if (!gone) {
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const int w = lane + 32 * s;
-          if (w < words) removed[w] |= cur[s];
-        }
-      }
-      __syncwarp();
-    }
+  if (words <= 32) {
+    nms_reduce_ring<1, 8>(mask, beg, end, words, lane, removed, keep);
+  } else if (words <= 64) {
+    nms_reduce_ring<2, 8>(mask, beg, end, words, lane, removed, keep);
+  } else if (words <= 128) {
+    nms_reduce_ring<4, 4>(mask, beg, end, words, lane, removed, keep);
   } else {
     for (int i = beg; i < end; ++i) {
       const int li = i - beg;

@@ -28,7 +28,7 @@ constexpr int kPpWarps = 8;
 constexpr int kPpTile = 2048;  // points per shared-memory tile (24 KB)
 
 struct PpBox {
-  float cx, cy, cz, hl, hw, hh, el, ew, eh, cosa, sina;
+  float cx, cy, cz, hl, hw, hh, el, ew, eh, cosa, sina, r2;
 };
 
 __device__ __forceinline__ PpBox pp_box(const float* __restrict__ roi, float e0, float e1, float e2) {
@@ -44,12 +44,19 @@ __device__ __forceinline__ PpBox pp_box(const float* __restrict__ roi, float e0,
   const float rot = __fadd_rn(rz, 1.57079632679489661923f);
   b.cosa = cosf(rot);
   b.sina = sinf(rot);
+  b.r2 = (b.el * b.el + b.ew * b.ew) * 1.0001f + 1e-6f;   // circumscribed circle of the enlarged footprint (with rounding slack)
   return b;
 }
 
 __device__ __forceinline__ bool pp_local(const PpBox& b, float x, float y, float z, float& lx, float& ly, float& lz) {
   const float sx = __fsub_rn(x, b.cx), sy = __fsub_rn(y, b.cy);
   lz = __fsub_rn(z, b.cz);
+  // a point outside the footprint's circumscribed circle cannot be inside the box: the brute-force K x N scan rejects almost every
+  // pair here, before the rotation (the accepted pairs run the exact test below, unchanged)
+  if (sx * sx + sy * sy > b.r2) {
+    lx = ly = 0.f;
+    return false;
+  }
   // no FMA contraction: the oracle evaluates the same four products and two sums in fp32
   lx = __fadd_rn(__fmul_rn(sx, b.cosa), __fmul_rn(sy, -b.sina));
   ly = __fadd_rn(__fmul_rn(sx, b.sina), __fmul_rn(sy, b.cosa));
