@@ -43,7 +43,10 @@ constexpr int kSsInfo = 8;                     // info ring depth (> prefetch de
 constexpr int kSsMaxA = 6, kSsMaxW = 4;
 constexpr uint32_t kSsASlot = kTcRows * 128;   // 128 rows x [hi 64 B | lo 64 B]
 constexpr int kSsPrefetch = 4;                 // stages of gathers in flight per producer thread
-constexpr int kSsSplitWarps = 4;                 // producer warps of the pre-split input mode (LOAD == 3)
+constexpr int kSsSplitWarps = 4;                 // producer warps of the cp.async pre-split mode (LOAD == 3)
+// producer warps / items per thread and stage / register-ring depth of each load mode (an item = 16 bytes of one row's K chunk)
+__host__ __device__ constexpr int ss_prod_warps(int load) { return load == 3 ? kSsSplitWarps : (load == 4 ? 8 : kSsProducerWarps); }
+__host__ __device__ constexpr int ss_items(int load) { return 1024 / (32 * ss_prod_warps(load)); }
 
 struct SsShared {
   uint64_t a_full[kSsMaxA], a_empty[kSsMaxA];
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
   if (tid == 0) {
     if (base & 1023u) __trap();
     for (int s = 0; s < kSsMaxA; ++s) {
-      mbar_init(smem_u32(&sh->a_full[s]), LOAD == 3 ? kSsSplitWarps * 32 : kSsProducerWarps);
+      mbar_init(smem_u32(&sh->a_full[s]), LOAD == 3 ? kSsSplitWarps * 32 : ss_prod_warps(LOAD));
       mbar_init(smem_u32(&sh->a_empty[s]), 2);  // both MMA issuers commit
     }
     for (int s = 0; s < kSsMaxW; ++s) {
@@ -150,10 +153,10 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
     }
     for (int s = 0; s < kSsInfo; ++s) {
       mbar_init(smem_u32(&sh->info_full[s]), 1);
-      mbar_init(smem_u32(&sh->info_empty[s]), (LOAD == 3 ? kSsSplitWarps : kSsProducerWarps) + 2 + 1 + 4);  // + MMA warps, loader, epilogue
+      mbar_init(smem_u32(&sh->info_empty[s]), ss_prod_warps(LOAD) + 2 + 1 + 4);  // + MMA warps, loader, epilogue
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&sh->tbl_empty[s]), LOAD == 3 ? kSsSplitWarps : kSsProducerWarps);
+      mbar_init(smem_u32(&sh->tbl_empty[s]), ss_prod_warps(LOAD));
       mbar_init(smem_u32(&sh->acc_full[s]), 2);
       mbar_init(smem_u32(&sh->acc_empty[s]), 4);
     }
@@ -191,16 +194,21 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
 
   if (warp < kSsProducerWarps) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;" ::: "memory");
-    if (LOAD != 3 || warp < kSsSplitWarps) {
+    if (warp < ss_prod_warps(LOAD)) {
     // ================= A producers =================
     const int chunk = tid & 7;    // 16-byte piece (4 floats) of the 128-byte K chunk
-    const int row_a = tid >> 3;   // this thread's rows: row_a and row_a + 64
+    constexpr int kItems = ss_items(LOAD);               // 2 (sixteen warps) or 4 (eight warps: LOAD == 4)
+    constexpr int kRowStep = kTcRows / kItems;           // this thread's rows: row_a + kRowStep * p
+    constexpr int kRing = kItems == 2 ? kSsPrefetch : 3;  // register-ring depth: 8 / 12 float4 per thread
+    const int row_a = tid >> 3;
     const bool odd = (chunk & 1) != 0;
-    const uint32_t piece = (uint32_t)(odd ? 4 + (chunk >> 1) : (chunk >> 1));  // 16-byte piece of the fp16 row this lane writes
-    uint32_t dst_off[2];
+    // 16-byte piece of the fp16 row this lane writes: converted modes pair lanes (even lane: both hi halves, odd: both lo);
+    // the pre-split copy (LOAD == 4) moves piece `chunk` as it is
+    const uint32_t piece = LOAD == 4 ? (uint32_t)chunk : (uint32_t)(odd ? 4 + (chunk >> 1) : (chunk >> 1));
+    uint32_t dst_off[kItems];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
-      const int row = row_a + 64 * p;
+    for (int p = 0; p < kItems; ++p) {
+      const int row = row_a + kRowStep * p;
       dst_off[p] = (uint32_t)row * 128u + ((piece ^ (uint32_t)(row & 7)) << 4);
     }
     // ---- load-side iterator over (unit, active offset, K chunk) ----
@@ -318,17 +326,17 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
         t[31] = (uint32_t)clock() - tm_start;
       }
     } else {
-    // one prefetched stage: two items (rows row_a, row_a + 64) and its K chunk (-1: empty slot)
+    // one prefetched stage: kItems items (rows row_a + kRowStep * p) and its K chunk (-1: empty slot)
     struct Pref {
-      float4 v[2];
+      float4 v[kItems];
       int kc;
     };
     auto load_stage = [&](Pref& q, int k, int kc, int64_t row0, uint32_t tbl) {
       q.kc = kc;
       const int col = kc * kGemmKChunk + chunk * 4;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int row = row_a + 64 * p;
+      for (int p = 0; p < kItems; ++p) {
+        const int row = row_a + kRowStep * p;
         int32_t src;
         if (P.nbr) {
           src = lds_i32(tbl + (uint32_t)(k * kTcRows + row) * 4u);
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
         }
         if ((uint32_t)src >= (uint32_t)P.a_rows || (P.debug & 1)) src = -1;  // also catches negative entries
         const float* g = P.a + (int64_t)(src >= 0 ? src : 0) * P.a_stride + col;
-        if (LOAD == 0) {
+        if (LOAD == 0 || LOAD == 4) {   // (LOAD == 4: the row is fp16-split bytes of the same size and chunking)
           q.v[p] = ldg_pred_f4_na(g, src >= 0);
         } else if (LOAD == 1) {
           q.v[p] = ldg_pred_f4_na(g, src >= 0 && col < P.cin);  // the row's stride covers round_up(cin, 4)
@@ -361,8 +369,12 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
       SS_ACC(tm_empty);
       const uint32_t slot = base + a_s * kSsASlot;
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < kItems; ++p) {
         float4 v = q.v[p];
+        if constexpr (LOAD == 4) {   // pre-split rows: a plain copy into the swizzled slot
+          if (!(P.debug & 8)) sts_f4(slot + dst_off[p], v);
+          continue;
+        }
         if (LOAD == 1) {  // columns past cin inside the last 128-bit piece hold whatever follows the row: zero them
           const int nv = P.cin - (q.kc * kGemmKChunk + chunk * 4);
           if (nv < 4) {
@@ -401,14 +413,14 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
     // moves, so nothing waits for a load before its own store).  Visit d: store the stage slot d holds (fetched
     // kSsPrefetch visits ago), then fetch the next stage into it; stages are therefore stored in fetch order whatever
     // bubbles the non-blocking fetches leave.  A fetch blocks only while no slot holds a stage.
-    Pref q[kSsPrefetch];
+    Pref q[kRing];
 #pragma unroll
-    for (int d = 0; d < kSsPrefetch; ++d) q[d].kc = -1;
+    for (int d = 0; d < kRing; ++d) q[d].kc = -1;
     int n_held = 0;
     SS_T0();
     while (!(ended && n_held == 0)) {
 #pragma unroll
-      for (int d = 0; d < kSsPrefetch; ++d) {
+      for (int d = 0; d < kRing; ++d) {
         if (q[d].kc >= 0) {
           store_stage(q[d]);
           q[d].kc = -1;
@@ -491,7 +503,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
           const uint32_t a_d = a_d0 + (uint32_t)a_s * (kSsASlot >> 4);
           const uint32_t w_d = w_d0 + (uint32_t)w_s * w_dstep;
           int ksteps = 2;
-          if (LOAD != 0 && LOAD != 3) ksteps = (min(kGemmKChunk, P.cin - kc * kGemmKChunk) + 15) >> 4;
+          if (LOAD != 0 && LOAD != 3 && LOAD != 4) ksteps = (min(kGemmKChunk, P.cin - kc * kGemmKChunk) + 15) >> 4;
           uint32_t elected;
           asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
           if (elected) {
@@ -1100,10 +1112,20 @@ int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspac
     FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ss<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ss<3, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ss<3, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ss<4, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    FSFB_CUDA(cudaFuncSetAttribute((k_gather_gemm_ss<4, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     attr = true;
   }
-  const int load = a_split ? 3 : (!a_vec ? 2 : (P.cin % kGemmKChunk == 0 ? 0 : 1));
-  if (load == 3) {
+  // pre-split rows: 16-byte cp.async copies by four warps (LOAD 3).  Measured alternatives (profiles/r2_ncu_summary.md section 2):
+  // register-staged 128-bit loads + plain stores by eight warps (LOAD 4, FSFB_GEMM_SPLIT_LDG=1) 389 vs 297 us on the 160 k-voxel
+  // layer — the per-warp bookkeeping costs more issue slots than the cp.async form's lower copy rate (1,180 clk per 128-row stage
+  // with nothing else running); TMA tile::gather4 2,510 clk per stage (tools/microbench/tma_gather4.cu)
+  static const bool split_ldg = [] { const char* e = getenv("FSFB_GEMM_SPLIT_LDG"); return e && atoi(e) != 0; }();
+  const int load = a_split ? (split_ldg ? 4 : 3) : (!a_vec ? 2 : (P.cin % kGemmKChunk == 0 ? 0 : 1));
+  if (load == 4) {
+    if (hv) FSFB_LAUNCH((k_gather_gemm_ss<4, true>), grid, kSsThreads, smem, st, P);
+    else FSFB_LAUNCH((k_gather_gemm_ss<4, false>), grid, kSsThreads, smem, st, P);
+  } else if (load == 3) {
     if (hv) FSFB_LAUNCH((k_gather_gemm_ss<3, true>), grid, kSsThreads, smem, st, P);
     else FSFB_LAUNCH((k_gather_gemm_ss<3, false>), grid, kSsThreads, smem, st, P);
   } else if (load == 0) {
