@@ -215,74 +215,56 @@ __global__ void __launch_bounds__(kNmsCols)
   (void)beg; (void)end;
 }
 
-// one warp per class: greedy pass in score order; the removed set is a bit vector in shared memory (words <= kNmsMaxWords: 65 536
-// candidates per class), lane l owns words l, l + 32, ...  The mask rows of the next AHEAD candidates are already in registers
-// (a static ring: the loop body is unrolled over it), so the chain per row is one shared-memory read, not one global load.
+// one warp per class: greedy pass in score order, 64 candidates (one mask word) at a time.  Inside a block the chain runs over
+// the 64 diagonal words staged in shared memory (registers + broadcast reads, no global load on the chain); the surviving rows
+// of the block are then OR-ed into the removed set with independent loads (lane l owns words l, l + 32, ...), so the only
+// serial global-memory latency is two round trips per 64 candidates.  The removed set lives in shared memory
+// (words <= kNmsMaxWords: 65 536 candidates per class).
 constexpr int kNmsMaxWords = 1024;
-
-template <int WPL, int AHEAD>
-__device__ __forceinline__ void nms_reduce_ring(const unsigned long long* __restrict__ mask, int beg, int end, int words, int lane,
-                                                unsigned long long* removed, uint8_t* __restrict__ keep) {
-  unsigned long long ring[AHEAD][WPL];
-  auto load_row = [&](int i, unsigned long long (&m)[WPL]) {
-#pragma unroll
-    for (int s = 0; s < WPL; ++s) {
-      const int w = lane + 32 * s;
-      m[s] = (i < end && w < words) ? mask[(int64_t)i * words + w] : 0ull;
-    }
-  };
-#pragma unroll
-  for (int d = 0; d < AHEAD; ++d) load_row(beg + d, ring[d]);
-  for (int i0 = beg; i0 < end; i0 += AHEAD) {
-#pragma unroll
-    for (int d = 0; d < AHEAD; ++d) {
-      const int i = i0 + d;
-      if (i < end) {   // warp-uniform
-        unsigned long long cur[WPL];
-#pragma unroll
-        for (int s = 0; s < WPL; ++s) cur[s] = ring[d][s];
-        load_row(i + AHEAD, ring[d]);
-        const int li = i - beg;
-        const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
-        __syncwarp();
-        if (lane == 0) keep[i] = gone ? 0 : 1;
-        if (!gone) {
-#pragma unroll
-          for (int s = 0; s < WPL; ++s) {
-            const int w = lane + 32 * s;
-            if (w < words) removed[w] |= cur[s];
-          }
-        }
-        __syncwarp();
-      }
-    }
-  }
-}
 
 __global__ void __launch_bounds__(32)
     k_nms_reduce(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ offsets, int words,
                  uint8_t* __restrict__ keep) {
   __shared__ unsigned long long removed[kNmsMaxWords];
+  __shared__ unsigned long long s_diag[64];
   const int c = blockIdx.x, lane = threadIdx.x;
   const int beg = offsets[c], end = offsets[c + 1];
   for (int w = lane; w < words; w += 32) removed[w] = 0ull;
   __syncwarp();
-  if (words <= 32) {
-    nms_reduce_ring<1, 8>(mask, beg, end, words, lane, removed, keep);
-  } else if (words <= 64) {
-    nms_reduce_ring<2, 8>(mask, beg, end, words, lane, removed, keep);
-  } else if (words <= 128) {
-    nms_reduce_ring<4, 4>(mask, beg, end, words, lane, removed, keep);
-  } else {
-    for (int i = beg; i < end; ++i) {
-      const int li = i - beg;
-      const bool gone = (removed[li >> 6] >> (li & 63)) & 1ull;
-      __syncwarp();
-      if (lane == 0) keep[i] = gone ? 0 : 1;
-      if (!gone)
-        for (int w = lane; w < words; w += 32) removed[w] |= mask[(int64_t)i * words + w];
-      __syncwarp();
+  for (int b0 = beg; b0 < end; b0 += 64) {
+    const int wb = (b0 - beg) >> 6;
+    const int nb = min(64, end - b0);
+    const unsigned long long* rows = mask + (int64_t)b0 * words;
+    s_diag[lane] = lane < nb ? rows[(int64_t)lane * words + wb] : 0ull;
+    s_diag[lane + 32] = lane + 32 < nb ? rows[(int64_t)(lane + 32) * words + wb] : 0ull;
+    __syncwarp();
+    unsigned long long rem = removed[wb], kept = 0ull;   // every lane runs the same chain: no divergence, no shuffle
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) {
+      const unsigned long long d = s_diag[r];
+      const bool alive = !((rem >> r) & 1ull) && r < nb;
+      kept |= alive ? (1ull << r) : 0ull;
+      rem |= alive ? d : 0ull;
     }
+    if (lane < nb) keep[b0 + lane] = (uint8_t)((kept >> lane) & 1ull);
+    if (lane + 32 < nb) keep[b0 + lane + 32] = (uint8_t)((kept >> (lane + 32)) & 1ull);
+    // words up to wb are final (columns before a row never count); OR the surviving rows into the later ones
+    for (int w = (wb & ~31) + lane; w < words; w += 32) {
+      if (w <= wb) continue;
+      unsigned long long acc = 0ull, k = kept;
+      while (k) {   // warp-uniform; four independent loads per trip
+        unsigned long long v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = k ? __ffsll((long long)k) - 1 : -1;
+          k = k ? (k & (k - 1)) : 0ull;
+          v[u] = r >= 0 ? rows[(int64_t)r * words + w] : 0ull;
+        }
+        acc |= (v[0] | v[1]) | (v[2] | v[3]);
+      }
+      removed[w] |= acc;
+    }
+    __syncwarp();
   }
 }
 
@@ -292,7 +274,7 @@ __global__ void __launch_bounds__(256)
                const int32_t* __restrict__ sorted_cls, const float* __restrict__ sorted_score, const float* __restrict__ boxes,
                int64_t box_stride, int box_dim, int64_t max_num, float* __restrict__ out_boxes, float* __restrict__ out_scores,
                long long* __restrict__ out_labels, int32_t* __restrict__ out_box_idx) {
-  __shared__ float s_tile[256];
+  __shared__ __align__(16) float s_tile[256];
   for (int64_t t0 = (int64_t)blockIdx.x * 256; t0 < P; t0 += (int64_t)gridDim.x * 256) {   // block-uniform
     const int64_t t = t0 + threadIdx.x;
     const bool live = t < P;
@@ -303,12 +285,15 @@ __global__ void __launch_bounds__(256)
       int rank = 0;
       for (int64_t u0 = 0; u0 < P; u0 += 256) {
         __syncthreads();
-        if (u0 + threadIdx.x < P) s_tile[threadIdx.x] = sorted_score[kept_idx[u0 + threadIdx.x]];
+        s_tile[threadIdx.x] = u0 + threadIdx.x < P ? sorted_score[kept_idx[u0 + threadIdx.x]] : -INFINITY;   // never counts
         __syncthreads();
         const int n = (int)min((int64_t)256, P - u0);
-        for (int x = 0; x < n; ++x) {
-          const float su = s_tile[x];
-          rank += (su > s) | ((su == s) & (u0 + x < t));
+        for (int x = 0; x < n; x += 4) {
+          const float4 su = *reinterpret_cast<const float4*>(&s_tile[x]);
+          rank += (su.x > s) | ((su.x == s) & (u0 + x < t));
+          rank += (su.y > s) | ((su.y == s) & (u0 + x + 1 < t));
+          rank += (su.z > s) | ((su.z == s) & (u0 + x + 2 < t));
+          rank += (su.w > s) | ((su.w == s) & (u0 + x + 3 < t));
         }
       }
       if (rank >= max_num) continue;
