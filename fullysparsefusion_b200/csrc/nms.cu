@@ -215,96 +215,131 @@ __global__ void __launch_bounds__(kNmsCols)
   (void)beg; (void)end;
 }
 
-// one warp per class: greedy pass in score order, 64 candidates (one mask word) at a time.  Inside a block the chain runs over
-// the 64 diagonal words staged in shared memory (registers + broadcast reads, no global load on the chain); the surviving rows
-// of the block are then OR-ed into the removed set with independent loads (lane l owns words l, l + 32, ...), so the only
-// serial global-memory latency is two round trips per 64 candidates.  The removed set lives in shared memory
-// (words <= kNmsMaxWords: 65 536 candidates per class).
+// one CTA of 8 warps per class: greedy pass in score order, 64 candidates (one mask word) at a time.
+//   1. the block's 64 diagonal words wait in shared memory (prefetched during the previous block: they are plain mask entries);
+//      warp 0 runs the 64-step chain on registers + broadcast shared-memory reads (every lane the same work: no shuffle);
+//   2. all 8 warps OR the surviving rows into the removed set (shared memory, words <= kNmsMaxWords: 65 536 candidates per
+//      class): warp j takes survivors j, j + 8, ..., up to 8 independent loads in flight per lane.
+// Two global-memory round trips per 64 candidates are on the serial path instead of one per candidate.
 constexpr int kNmsMaxWords = 1024;
+constexpr int kNmsReduceWarps = 8;
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kNmsReduceWarps * 32)
     k_nms_reduce(const unsigned long long* __restrict__ mask, const int32_t* __restrict__ offsets, int words,
                  uint8_t* __restrict__ keep) {
   __shared__ unsigned long long removed[kNmsMaxWords];
-  __shared__ unsigned long long s_diag[64];
-  const int c = blockIdx.x, lane = threadIdx.x;
+  __shared__ unsigned long long s_diag[2][64];
+  __shared__ unsigned long long s_kept;
+  const int c = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int beg = offsets[c], end = offsets[c + 1];
-  for (int w = lane; w < words; w += 32) removed[w] = 0ull;
-  __syncwarp();
-  for (int b0 = beg; b0 < end; b0 += 64) {
+  for (int w = tid; w < words; w += kNmsReduceWarps * 32) removed[w] = 0ull;
+  auto load_diag = [&](int b0, int slot) {   // threads 0..63 of the callers' range: row r of the block starting at b0
+    const int r = tid & 63;
+    s_diag[slot][r] = b0 + r < end ? mask[(int64_t)(b0 + r) * words + ((b0 - beg) >> 6)] : 0ull;
+  };
+  if (tid < 64 && beg < end) load_diag(beg, 0);
+  __syncthreads();
+  int slot = 0;
+  for (int b0 = beg; b0 < end; b0 += 64, slot ^= 1) {
     const int wb = (b0 - beg) >> 6;
     const int nb = min(64, end - b0);
-    const unsigned long long* rows = mask + (int64_t)b0 * words;
-    s_diag[lane] = lane < nb ? rows[(int64_t)lane * words + wb] : 0ull;
-    s_diag[lane + 32] = lane + 32 < nb ? rows[(int64_t)(lane + 32) * words + wb] : 0ull;
-    __syncwarp();
-    unsigned long long rem = removed[wb], kept = 0ull;   // every lane runs the same chain: no divergence, no shuffle
+    if (warp == 0) {
+      unsigned long long rem = removed[wb], kept = 0ull;
 #pragma unroll 8
-    for (int r = 0; r < 64; ++r) {
-      const unsigned long long d = s_diag[r];
-      const bool alive = !((rem >> r) & 1ull) && r < nb;
-      kept |= alive ? (1ull << r) : 0ull;
-      rem |= alive ? d : 0ull;
-    }
-    if (lane < nb) keep[b0 + lane] = (uint8_t)((kept >> lane) & 1ull);
-    if (lane + 32 < nb) keep[b0 + lane + 32] = (uint8_t)((kept >> (lane + 32)) & 1ull);
-    // words up to wb are final (columns before a row never count); OR the surviving rows into the later ones
-    for (int w = (wb & ~31) + lane; w < words; w += 32) {
-      if (w <= wb) continue;
-      unsigned long long acc = 0ull, k = kept;
-      while (k) {   // warp-uniform; four independent loads per trip
-        unsigned long long v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = k ? __ffsll((long long)k) - 1 : -1;
-          k = k ? (k & (k - 1)) : 0ull;
-          v[u] = r >= 0 ? rows[(int64_t)r * words + w] : 0ull;
-        }
-        acc |= (v[0] | v[1]) | (v[2] | v[3]);
+      for (int r = 0; r < 64; ++r) {
+        const unsigned long long d = s_diag[slot][r];
+        const bool alive = !((rem >> r) & 1ull) && r < nb;
+        kept |= alive ? (1ull << r) : 0ull;
+        rem |= alive ? d : 0ull;
       }
-      removed[w] |= acc;
+      if (lane == 0) s_kept = kept;
+      if (lane < nb) keep[b0 + lane] = (uint8_t)((kept >> lane) & 1ull);
+      if (lane + 32 < nb) keep[b0 + lane + 32] = (uint8_t)((kept >> (lane + 32)) & 1ull);
+    } else if (warp >= 2 && warp < 4 && b0 + 64 < end) {
+      load_diag(b0 + 64, slot ^ 1);   // 64 threads (warps 2, 3): the next block's diagonal words
     }
-    __syncwarp();
+    __syncthreads();
+    // words up to wb are final (columns before a row never count); OR the surviving rows into the later ones
+    unsigned long long mine = 0ull, k = s_kept;
+    for (int j = 0; k; ++j, k &= k - 1)   // survivors j = warp (mod 8), as a bit set of row numbers
+      if ((j & (kNmsReduceWarps - 1)) == warp) mine |= k & (~k + 1ull);
+    if (mine) {   // warp-uniform
+      const unsigned long long* rows = mask + (int64_t)b0 * words;
+      int r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {   // a warp owns at most 8 of the 64 rows
+        r[u] = mine ? __ffsll((long long)mine) - 1 : -1;
+        mine = mine ? (mine & (mine - 1)) : 0ull;
+      }
+      for (int w = (wb & ~31) + lane; w < words; w += 32) {
+        if (w <= wb) continue;
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc |= r[u] >= 0 ? rows[(int64_t)r[u] * words + w] : 0ull;
+        if (acc) atomicOr(&removed[w], acc);
+      }
+    }
+    __syncthreads();
   }
 }
 
-// kept rows → outputs (order of `kept_idx`: class-major, score descending)
-__global__ void __launch_bounds__(256)
+// kept rows → outputs (order of `kept_idx`: class-major, score descending).  When more than max_num survive, the output is the
+// max_num best by (score desc, emitted position asc): a counting rank, P x P compares.  A CTA ranks 32 candidates; its 8 warps
+// each take one eighth of every 256-entry shared-memory tile (broadcast 128-bit reads, four independent counters).
+constexpr int kNmsEmitWarps = 8;
+constexpr int kNmsEmitTile = 2048;   // scores per shared-memory tile
+__global__ void __launch_bounds__(kNmsEmitWarps * 32)
     k_nms_emit(const int32_t* __restrict__ kept_idx, int64_t P, const int32_t* __restrict__ sorted_box,
                const int32_t* __restrict__ sorted_cls, const float* __restrict__ sorted_score, const float* __restrict__ boxes,
                int64_t box_stride, int box_dim, int64_t max_num, float* __restrict__ out_boxes, float* __restrict__ out_scores,
                long long* __restrict__ out_labels, int32_t* __restrict__ out_box_idx) {
-  __shared__ __align__(16) float s_tile[256];
-  for (int64_t t0 = (int64_t)blockIdx.x * 256; t0 < P; t0 += (int64_t)gridDim.x * 256) {   // block-uniform
-    const int64_t t = t0 + threadIdx.x;
+  __shared__ __align__(16) float s_tile[kNmsEmitTile];
+  __shared__ int s_rank[kNmsEmitWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t t0 = (int64_t)blockIdx.x * 32; t0 < P; t0 += (int64_t)gridDim.x * 32) {   // block-uniform
+    const int64_t t = t0 + lane;
     const bool live = t < P;
     const int r = live ? kept_idx[t] : 0;
     const float s = live ? sorted_score[r] : 0.f;
     int64_t dst = t;
-    if (P > max_num) {  // global top max_num by (score desc, emitted position asc): counting rank over shared-memory tiles
-      int rank = 0;
-      for (int64_t u0 = 0; u0 < P; u0 += 256) {
+    if (P > max_num) {
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      for (int64_t u0 = 0; u0 < P; u0 += kNmsEmitTile) {
         __syncthreads();
-        s_tile[threadIdx.x] = u0 + threadIdx.x < P ? sorted_score[kept_idx[u0 + threadIdx.x]] : -INFINITY;   // never counts
+#pragma unroll
+        for (int e = 0; e < kNmsEmitTile / (kNmsEmitWarps * 32); ++e) {   // independent gathers: one latency per tile
+          const int64_t u = u0 + e * (kNmsEmitWarps * 32) + threadIdx.x;
+          s_tile[e * (kNmsEmitWarps * 32) + threadIdx.x] = u < P ? sorted_score[kept_idx[u]] : -INFINITY;   // never counts
+        }
         __syncthreads();
-        const int n = (int)min((int64_t)256, P - u0);
-        for (int x = 0; x < n; x += 4) {
-          const float4 su = *reinterpret_cast<const float4*>(&s_tile[x]);
-          rank += (su.x > s) | ((su.x == s) & (u0 + x < t));
-          rank += (su.y > s) | ((su.y == s) & (u0 + x + 1 < t));
-          rank += (su.z > s) | ((su.z == s) & (u0 + x + 2 < t));
-          rank += (su.w > s) | ((su.w == s) & (u0 + x + 3 < t));
+        constexpr int kPer = kNmsEmitTile / kNmsEmitWarps;   // this warp's share of the tile
+        const int64_t xb = u0 + warp * kPer;
+#pragma unroll 4
+        for (int x = 0; x < kPer; x += 4) {
+          const float4 su = *reinterpret_cast<const float4*>(&s_tile[warp * kPer + x]);
+          r0 += (su.x > s) | ((su.x == s) & (xb + x < t));
+          r1 += (su.y > s) | ((su.y == s) & (xb + x + 1 < t));
+          r2 += (su.z > s) | ((su.z == s) & (xb + x + 2 < t));
+          r3 += (su.w > s) | ((su.w == s) & (xb + x + 3 < t));
         }
       }
-      if (rank >= max_num) continue;
+      s_rank[warp][lane] = (r0 + r1) + (r2 + r3);
+      __syncthreads();
+      int rank = 0;
+#pragma unroll
+      for (int w = 0; w < kNmsEmitWarps; ++w) rank += s_rank[w][lane];
+      __syncthreads();
       dst = rank;
     }
-    if (!live) continue;
+    if (!live || (P > max_num && dst >= max_num)) continue;
+    // warp w writes the fields d = w, w + 8, ... of the 32 candidates
     const float* b = boxes + (int64_t)sorted_box[r] * box_stride;
-    for (int d = 0; d < box_dim; ++d) out_boxes[dst * box_dim + d] = b[d];
-    out_scores[dst] = s;
-    out_labels[dst] = sorted_cls[r];
-    if (out_box_idx) out_box_idx[dst] = sorted_box[r];
+    for (int d = warp; d < box_dim; d += kNmsEmitWarps) out_boxes[dst * box_dim + d] = b[d];
+    if (warp == 0) {
+      out_scores[dst] = s;
+      out_labels[dst] = sorted_cls[r];
+      if (out_box_idx) out_box_idx[dst] = sorted_box[r];
+    }
   }
 }
 
@@ -371,7 +406,7 @@ int fsfb_nms_suppress(const float* boxes, int64_t k, int64_t box_stride, const f
   FSFB_CUDA(cudaMemsetAsync(mask, 0, (size_t)candidates * words * sizeof(unsigned long long), st));
   dim3 mgrid((unsigned)ceil_div(candidates, kNmsCols), (unsigned)words);
   FSFB_LAUNCH(k_nms_mask, mgrid, kNmsCols, 0, st, boxes, box_stride, sorted_box, sorted_cls, offsets, candidates, words, nms_thr, mask);
-  FSFB_LAUNCH(k_nms_reduce, num_classes, 32, 0, st, mask, offsets, words, keep);
+  FSFB_LAUNCH(k_nms_reduce, num_classes, kNmsReduceWarps * 32, 0, st, mask, offsets, words, keep);
   return FSFB_OK;
 }
 
@@ -395,8 +430,8 @@ int fsfb_nms_emit(const float* boxes, int64_t box_stride, int box_dim, const int
     set_error("nms_emit: workspace does not match the one given to nms_suppress");
     return FSFB_ERR_CAPACITY;
   }
-  const int grid = (int)std::min<int64_t>(ceil_div(kept, 256), (int64_t)kNumSMs * 8);
-  FSFB_LAUNCH(k_nms_emit, grid, 256, 0, (cudaStream_t)stream, kept_idx, kept, sorted_box, sorted_cls, sorted_score, boxes, box_stride,
+  const int grid = (int)std::min<int64_t>(ceil_div(kept, 32), (int64_t)kNumSMs * 8);
+  FSFB_LAUNCH(k_nms_emit, grid, kNmsEmitWarps * 32, 0, (cudaStream_t)stream, kept_idx, kept, sorted_box, sorted_cls, sorted_score, boxes, box_stride,
               box_dim, max_num, out_boxes, out_scores, out_labels, out_box_idx);
   return FSFB_OK;
 }

@@ -16,16 +16,15 @@
 // run-dependent.  Canonical order here: roi-major, point index ascending; the per-roi cap keeps the lowest point
 // indices, the global cap (the caller's buffer length, 50000 upstream) keeps the first entries of that order.
 //
-// B200 design: one warp owns a roi and scans the points in index order (ballot + popcount prefix = ordered
-// compaction, no atomics); a CTA of 8 warps streams point tiles through shared memory so the 3.6 MB of xyz is read
-// from L2 once per 8 rois.  The first pass leaves <= max_inbox point ids per roi in a scratch table, a one-CTA scan
-// turns counts into output offsets, and the second pass (warp per roi) writes ids and the 13 features.
+// B200 design: the K x N scan runs thread-per-roi over point slices (k_pp_scan: a count pass and a store pass, broadcast
+// shared-memory reads, no atomics, canonical order by construction) and leaves <= max_inbox point ids per roi in a
+// scratch table; a one-CTA scan turns counts into output offsets, and k_pp_write (warp per roi) writes ids and the 13
+// features.
 #include "common.cuh"
 
 namespace fsfb {
 
 constexpr int kPpWarps = 8;
-constexpr int kPpTile = 2048;  // points per shared-memory tile (24 KB)
 
 struct PpBox {
   float cx, cy, cz, hl, hw, hh, el, ew, eh, cosa, sina, r2;
@@ -63,39 +62,101 @@ __device__ __forceinline__ bool pp_local(const PpBox& b, float x, float y, float
   return (fabsf(lz) <= b.eh) & (lx > -b.el) & (lx < b.el) & (ly > -b.ew) & (ly < b.ew);
 }
 
-__global__ void __launch_bounds__(kPpWarps * 32)
+// Thread = 4 rois, CTA = 256 rois x one slice of the points.  The slice streams through shared memory as (x, y, z, x^2 + y^2)
+// tiles; every thread reads the same point (one broadcast 128-bit read per 128 rois) and rejects it per roi with
+// |p|^2 - 2 p.c <= r^2 - |c|^2 + slack — two FMAs and a compare, deliberately loose: it may only over-select — and the rare
+// survivors run pp_local, the exact test (which starts with the tight circle).  A thread meets its points in ascending order
+// and slices are ascending ranges, so (slice, local order) is the canonical ascending point order with no sort and no atomics:
+//   pass 1 (WRITE = false) counts the hits of every (slice, roi); k_pp_slice_prefix turns them into exclusive prefixes;
+//   pass 2 (WRITE = true) re-scans and stores the ids at prefix + local rank, while below max_inbox.
+constexpr int kPpThreads = 64;
+constexpr int kPpPerThread = 4;
+constexpr int kPpRois = kPpThreads * kPpPerThread;   // rois per CTA
+constexpr int kPpTile = 1024;                        // points per shared-memory tile (16 KB)
+constexpr int kPpMaxSlices = 256;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kPpThreads)
     k_pp_scan(const float* __restrict__ rois, int64_t k, const float* __restrict__ pts, int64_t n, int64_t pts_stride,
-              float e0, float e1, float e2, int max_inbox, int32_t* __restrict__ scratch, int32_t* __restrict__ counts) {
-  __shared__ float s_pts[kPpTile * 3];
-  const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int64_t r = (int64_t)blockIdx.x * kPpWarps + warp;
-  const bool have = r < k;
-  PpBox b = pp_box(rois + (have ? r : 0) * 7, e0, e1, e2);
-  int cnt = 0;
-  for (int64_t t0 = 0; t0 < n; t0 += kPpTile) {
-    const int tn = (int)min((int64_t)kPpTile, n - t0);
+              float e0, float e1, float e2, int max_inbox, int64_t slice_len, int32_t* __restrict__ slice_counts,
+              int32_t* __restrict__ scratch) {
+  __shared__ float4 s_pts[kPpTile];
+  const int slice = blockIdx.y;
+  PpBox b[kPpPerThread];
+  float m2x[kPpPerThread], m2y[kPpPerThread], lim[kPpPerThread];
+  int64_t r[kPpPerThread];
+  int before[kPpPerThread], cnt[kPpPerThread];
+  bool on[kPpPerThread];
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kPpPerThread; ++j) {
+    r[j] = (int64_t)blockIdx.x * kPpRois + j * kPpThreads + threadIdx.x;   // warp-contiguous rois per j: coalesced tables
+    const bool have = r[j] < k;
+    b[j] = pp_box(rois + (have ? r[j] : 0) * 7, e0, e1, e2);
+    m2x[j] = -2.f * b[j].cx;
+    m2y[j] = -2.f * b[j].cy;
+    // slack: the two forms differ by rounding of terms of size |p|^2, |c|^2 (<= ~1e5 m^2 in a +-200 m scene: ~1e-2 absolute)
+    const float cc = b[j].cx * b[j].cx + b[j].cy * b[j].cy;
+    lim[j] = b[j].r2 - cc + 1e-6f * (cc + b[j].r2) + 0.05f;
+    before[j] = (WRITE && have) ? slice_counts[(int64_t)slice * k + r[j]] : 0;
+    cnt[j] = 0;
+    on[j] = have && (!WRITE || before[j] < max_inbox);
+    if (WRITE && on[j]) {   // nothing to store when this (slice, roi) had no hit in pass 1
+      const int nxt = slice + 1 < (int)gridDim.y ? slice_counts[(int64_t)(slice + 1) * k + r[j]] : -1;
+      if (nxt == before[j]) on[j] = false;
+    }
+    if (!on[j]) lim[j] = -INFINITY;
+    any |= on[j];
+  }
+  if (WRITE && !__syncthreads_or(any)) return;
+  const int64_t p0 = (int64_t)slice * slice_len, p1 = min(n, p0 + slice_len);
+  for (int64_t t0 = p0; t0 < p1; t0 += kPpTile) {
+    const int tn = (int)min((int64_t)kPpTile, p1 - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn; i += kPpWarps * 32) {
+    for (int i = threadIdx.x; i < tn; i += kPpThreads) {
       const float* p = pts + (t0 + i) * pts_stride;
-      s_pts[3 * i] = __ldg(p);
-      s_pts[3 * i + 1] = __ldg(p + 1);
-      s_pts[3 * i + 2] = __ldg(p + 2);
+      const float x = __ldg(p), y = __ldg(p + 1);
+      s_pts[i] = make_float4(x, y, __ldg(p + 2), x * x + y * y);
     }
     __syncthreads();
-    if (!have || cnt >= max_inbox) continue;  // warp-uniform; the barriers above are still reached by everyone
-    for (int i0 = 0; i0 < tn && cnt < max_inbox; i0 += 32) {
-      const int i = i0 + lane;
-      float lx, ly, lz;
-      const bool hit = i < tn && pp_local(b, s_pts[3 * i], s_pts[3 * i + 1], s_pts[3 * i + 2], lx, ly, lz);
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = cnt + __popc(bal & lanemask_lt());
-        if (pos < max_inbox) scratch[r * max_inbox + pos] = (int32_t)(t0 + i);
+    if (!any) continue;
+#pragma unroll 2
+    for (int i = 0; i < tn; ++i) {
+      const float4 q = s_pts[i];
+#pragma unroll
+      for (int j = 0; j < kPpPerThread; ++j) {
+        if (fmaf(q.x, m2x[j], fmaf(q.y, m2y[j], q.w)) > lim[j]) continue;
+        float lx, ly, lz;
+        if (pp_local(b[j], q.x, q.y, q.z, lx, ly, lz)) {
+          if (WRITE) {
+            const int pos = before[j] + cnt[j];
+            if (pos < max_inbox) scratch[r[j] * max_inbox + pos] = (int32_t)(t0 + i);
+            else lim[j] = -INFINITY;
+          }
+          ++cnt[j];
+        }
       }
-      cnt += __popc(bal);
     }
   }
-  if (have && lane == 0) counts[r] = min(cnt, max_inbox);
+  if (!WRITE) {
+#pragma unroll
+    for (int j = 0; j < kPpPerThread; ++j)
+      if (r[j] < k) slice_counts[(int64_t)slice * k + r[j]] = cnt[j];
+  }
+}
+
+// per roi: hits per slice -> exclusive prefix over the slices (in place), total -> counts (capped)
+__global__ void __launch_bounds__(256)
+    k_pp_slice_prefix(int32_t* __restrict__ slice_counts, int64_t k, int slices, int max_inbox, int32_t* __restrict__ counts) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= k) return;
+  int run = 0;
+  for (int s = 0; s < slices; ++s) {
+    const int c = slice_counts[(int64_t)s * k + r];
+    slice_counts[(int64_t)s * k + r] = run;
+    run += c;
+  }
+  counts[r] = min(run, max_inbox);
 }
 
 // exclusive scan of the per-roi counts (k is a few thousand: one CTA), clipped to the output capacity
@@ -209,6 +270,7 @@ extern "C" int fsfb_dynamic_point_pool_workspace_bytes(int64_t k, int max_inbox_
   using namespace fsfb;
   FSFB_CHECK_ARG(bytes && k >= 0 && max_inbox_point >= 1, "dynamic_point_pool_workspace_bytes: bad argument");
   Workspace ws(nullptr, 0);
+  ws.take<int32_t>((size_t)std::max<int64_t>(k, 1) * kPpMaxSlices);     // hits per (slice, roi)
   ws.take<int32_t>((size_t)std::max<int64_t>(k, 1) * max_inbox_point);  // scratch
   ws.take<int32_t>(std::max<int64_t>(k, 1));                             // counts
   ws.take<int32_t>(std::max<int64_t>(k, 1));                             // offsets
@@ -232,6 +294,7 @@ extern "C" int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float
   }
   FSFB_CHECK_ARG(rois && pts && out_pts_idx && out_roi_idx && out_pts_feats, "dynamic_point_pool: null device pointer");
   Workspace ws(workspace, workspace_bytes);
+  int32_t* slice_counts = ws.take<int32_t>((size_t)k * kPpMaxSlices);
   int32_t* scratch = ws.take<int32_t>((size_t)k * max_inbox_point);
   int32_t* counts = ws.take<int32_t>(k);
   int32_t* offsets = ws.take<int32_t>(k);
@@ -240,8 +303,17 @@ extern "C" int fsfb_dynamic_point_pool(const float* rois, int64_t k, const float
     return FSFB_ERR_CAPACITY;
   }
   const int grid = (int)ceil_div(k, kPpWarps);
-  FSFB_LAUNCH(k_pp_scan, grid, kPpWarps * 32, 0, st, rois, k, pts, n, pts_stride, extra_wlh[0], extra_wlh[1], extra_wlh[2],
-              max_inbox_point, scratch, counts);
+  // enough (roi block, slice) CTAs of two warps for ~24 warps per SM; slices are whole tiles
+  const int rblocks = (int)ceil_div(k, kPpRois);
+  int slices = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(kNumSMs * 12, rblocks), 1), kPpMaxSlices);
+  const int64_t slice_len = ceil_div(ceil_div(n, slices), kPpTile) * kPpTile;
+  slices = (int)ceil_div(n, slice_len);
+  const dim3 sgrid((unsigned)rblocks, (unsigned)slices);
+  FSFB_LAUNCH(k_pp_scan<false>, sgrid, kPpThreads, 0, st, rois, k, pts, n, pts_stride, extra_wlh[0], extra_wlh[1], extra_wlh[2],
+              max_inbox_point, slice_len, slice_counts, scratch);
+  FSFB_LAUNCH(k_pp_slice_prefix, (int)ceil_div(k, 256), 256, 0, st, slice_counts, k, slices, max_inbox_point, counts);
+  FSFB_LAUNCH(k_pp_scan<true>, sgrid, kPpThreads, 0, st, rois, k, pts, n, pts_stride, extra_wlh[0], extra_wlh[1], extra_wlh[2],
+              max_inbox_point, slice_len, slice_counts, scratch);
   FSFB_LAUNCH(k_pp_offsets, 1, 1024, 0, st, counts, k, capacity, offsets, num_out);
   FSFB_LAUNCH(k_pp_write, grid, kPpWarps * 32, 0, st, rois, k, pts, pts_stride, extra_wlh[0], extra_wlh[1], extra_wlh[2],
               max_inbox_point, scratch, counts, offsets, capacity, out_pts_idx, out_roi_idx, out_pts_feats);

@@ -47,6 +47,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
+template <int NT>   // 32-channel groups per lane: ceil(c / 32), so that no unrolled slot is a predicated-off instruction
 __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P) {
   extern __shared__ float s_w[];
   // layout: w1t [3][32] | w2t [32][32] | w3t [32][cpad] | g1,b1 [32] | g2,b2 [32] | g3,b3 [cpad]
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
   float* b2 = g2 + 32;
   float* g3 = b2 + 32;
   float* b3 = g3 + cpad;
+  float4* hx = reinterpret_cast<float4*>(b3 + cpad) + (threadIdx.x >> 5) * 32;   // this warp's [32 hidden units] x [4 points]
   for (int t = threadIdx.x; t < 3 * 32; t += blockDim.x) {
     const int i = t / 32, j = t % 32;
     w1t[t] = j < P.h1 ? __ldg(P.w1 + j * 3 + i) : 0.f;
@@ -85,10 +87,22 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
   __syncthreads();
 
   const int lane = lane_id();
-  const int nt = cpad / 32;  // channel groups per lane (<= 8)
-  constexpr int PT = 4;      // points in flight per warp: independent dependency chains for ILP
+  constexpr int PT = 4;      // points in flight per warp: independent dependency chains for ILP (hx holds float4 = PT values)
   const int64_t warps = (int64_t)gridDim.x * kGateWarps;
   for (int64_t i0 = ((int64_t)blockIdx.x * kGateWarps + (threadIdx.x >> 5)) * PT; i0 < P.n; i0 += warps * PT) {
+    // the gated rows themselves: requested first, consumed last (their latency hides behind the three layers)
+    float xin[PT][NT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) {
+      const int64_t i = min(i0 + p, P.n - 1);
+      const float* fr = P.feats + i * P.feat_stride;
+      const float* fb = P.feats_b ? P.feats_b + i * P.feats_b_stride - P.c_a : fr;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int c = lane + 32 * t;
+        xin[p][t] = c < P.c ? __ldg((c < P.c_a ? fr : fb) + c) : 0.f;
+      }
+    }
     // ---- layer 1: 3 → h1, LN, act (lane j owns hidden unit j) ----
     float h[PT];
 #pragma unroll
@@ -124,12 +138,15 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
     float h2[PT];
 #pragma unroll
     for (int p = 0; p < PT; ++p) h2[p] = 0.f;
+    __syncwarp();
+    hx[lane] = make_float4(h[0], h[1], h[2], h[3]);   // lanes >= h1 hold zeros
+    __syncwarp();
 #pragma unroll 8
     for (int k = 0; k < kGateMaxH; ++k) {
       if (k < P.h1) {
         const float w = w2t[k * 32 + lane];
-#pragma unroll
-        for (int p = 0; p < PT; ++p) h2[p] = fmaf(__shfl_sync(0xffffffffu, h[p], k), w, h2[p]);
+        const float4 hv = hx[k];   // broadcast: one shared-memory read instead of four shuffles
+        h2[0] = fmaf(hv.x, w, h2[0]); h2[1] = fmaf(hv.y, w, h2[1]); h2[2] = fmaf(hv.z, w, h2[2]); h2[3] = fmaf(hv.w, w, h2[3]);
       }
     }
     {
@@ -155,21 +172,23 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
         h2[p] = on ? apply_act(d[p] * (1.f / sqrtf(var[p] / (float)P.h2 + P.eps)) * g2[lane] + b2[lane], P.act) : 0.f;
     }
     // ---- layer 3: h2 → c (lane owns channels lane + 32 t) ----
-    float g[PT][kGateMaxC / 32];
+    float g[PT][NT];
 #pragma unroll
     for (int p = 0; p < PT; ++p)
 #pragma unroll
-      for (int t = 0; t < kGateMaxC / 32; ++t) g[p][t] = 0.f;
+      for (int t = 0; t < NT; ++t) g[p][t] = 0.f;
+    __syncwarp();
+    hx[lane] = make_float4(h2[0], h2[1], h2[2], h2[3]);
+    __syncwarp();
 #pragma unroll 2
     for (int k = 0; k < kGateMaxH; ++k) {
       if (k < P.h2) {
-        float hv[PT];
-#pragma unroll
-        for (int p = 0; p < PT; ++p) hv[p] = __shfl_sync(0xffffffffu, h2[p], k);
+        const float4 hq = hx[k];
+        const float hv[PT] = {hq.x, hq.y, hq.z, hq.w};
         const float* wr = w3t + k * cpad + lane;
 #pragma unroll
-        for (int t = 0; t < kGateMaxC / 32; ++t)
-          if (t < nt) {
+        for (int t = 0; t < NT; ++t)
+          {
             const float w = wr[32 * t];
 #pragma unroll
             for (int p = 0; p < PT; ++p) g[p][t] = fmaf(hv[p], w, g[p][t]);
@@ -181,8 +200,8 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
     for (int p = 0; p < PT; ++p) {
       mu[p] = 0.f;
 #pragma unroll
-      for (int t = 0; t < kGateMaxC / 32; ++t)
-        if (t < nt && lane + 32 * t < P.c) mu[p] += g[p][t];
+      for (int t = 0; t < NT; ++t)
+        if (lane + 32 * t < P.c) mu[p] += g[p][t];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -193,8 +212,8 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
       mu[p] /= (float)P.c;
       q[p] = 0.f;
 #pragma unroll
-      for (int t = 0; t < kGateMaxC / 32; ++t)
-        if (t < nt && lane + 32 * t < P.c) {
+      for (int t = 0; t < NT; ++t)
+        if (lane + 32 * t < P.c) {
           const float d = g[p][t] - mu[p];
           q[p] += d * d;
         }
@@ -208,15 +227,13 @@ __global__ void __launch_bounds__(kGateWarps * 32) k_sir_gate(const GateParams P
       const int64_t i = i0 + p;
       if (i >= P.n) break;
       const float rstd = 1.f / sqrtf(q[p] / (float)P.c + P.eps);
-      const float* fr = P.feats + i * P.feat_stride;
-      const float* fb = P.feats_b ? P.feats_b + i * P.feats_b_stride - P.c_a : fr;
       float* o = P.out + i * P.out_stride;
 #pragma unroll
-      for (int t = 0; t < kGateMaxC / 32; ++t) {
+      for (int t = 0; t < NT; ++t) {
         const int c = lane + 32 * t;
-        if (t < nt && c < P.c) {
+        if (c < P.c) {
           const float gate = apply_act((g[p][t] - mu[p]) * rstd * g3[c] + b3[c], P.act);
-          float x = __ldg((c < P.c_a ? fr : fb) + c);
+          float x = xin[p][t];
           if (c < 3) x = __fdiv_rn(x, P.nrm[c]);
           o[c] = __fmul_rn(x, gate);
         }
@@ -252,13 +269,25 @@ extern "C" int fsfb_sir_gate_input(const float* feats, int64_t n, int c, int64_t
   P.w1 = w1; P.g1 = ln1_w; P.b1 = ln1_b; P.w2 = w2; P.g2 = ln2_w; P.b2 = ln2_b; P.w3 = w3; P.g3 = ln3_w; P.b3 = ln3_b;
   P.eps = eps; P.act = act; P.out = out; P.out_stride = out_stride;
   const int cpad = (c + 31) & ~31;
-  const size_t smem = (size_t)(3 * 32 + 32 * 32 + 32 * cpad + 4 * 32 + 2 * cpad) * 4;
-  static bool attr = false;
-  if (!attr) {
-    FSFB_CUDA(cudaFuncSetAttribute(k_sir_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
+  const size_t smem = (size_t)(3 * 32 + 32 * 32 + 32 * cpad + 4 * 32 + 2 * cpad + kGateWarps * 32 * 4) * 4;
+  const int grid = (int)std::min<int64_t>(ceil_div(n, kGateWarps * 4), (int64_t)kNumSMs * 3);  // 3 CTAs of 256 threads fit an SM
+  auto go = [&](auto kern) -> int {
+    static bool attr = false;   // one per instantiation of this generic lambda
+    if (!attr) {
+      FSFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    FSFB_LAUNCH(kern, grid, kGateWarps * 32, smem, (cudaStream_t)stream, P);
+    return FSFB_OK;
+  };
+  switch (cpad / 32) {
+    case 1: return go(k_sir_gate<1>);
+    case 2: return go(k_sir_gate<2>);
+    case 3: return go(k_sir_gate<3>);
+    case 4: return go(k_sir_gate<4>);
+    case 5: return go(k_sir_gate<5>);
+    case 6: return go(k_sir_gate<6>);
+    case 7: return go(k_sir_gate<7>);
+    default: return go(k_sir_gate<8>);
   }
-  const int grid = (int)std::min<int64_t>(ceil_div(n, kGateWarps * 4), (int64_t)kNumSMs * 3);  // 3 CTAs of 256 threads fit an SM at 70 registers
-  FSFB_LAUNCH(k_sir_gate, grid, kGateWarps * 32, smem, (cudaStream_t)stream, P);
-  return FSFB_OK;
 }
