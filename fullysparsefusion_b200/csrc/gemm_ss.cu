@@ -72,29 +72,6 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ float4 ldg_pred_f4_na(const float* p, bool pred) {  // read-only path, no L1 allocation
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
-      : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
-      : "l"(p), "r"((int)pred));
-  return v;
-}
-
 // unit → (row tile, column tile, offset split); column tiles are P.ss_tile_w wide
 __device__ __forceinline__ bool ss_unit(const TcParams& P, uint32_t u, TsUnit& U) {
   if (u >= (uint32_t)P.n_units) return false;
@@ -1003,6 +980,33 @@ uint32_t* g_ss_timers = nullptr;  // FSFB_GEMM_TIMERS=1: role counters of the la
 
 // Launch helper called from fsfb_gather_gemm (gemm_tc.cu).  Returns 1 when the shape is not served by this kernel (the
 // caller falls back to gemm_ts.cu / gemm_tc.cu), FSFB_OK after a launch, a negative status on errors.
+// FSFB_GEMM_TIMERS=1: the zeroed [148][32] u32 counter block of this launch (nullptr otherwise)
+int ss_timers_buffer(uint32_t** out, cudaStream_t st) {
+  *out = nullptr;
+  static const bool timed = [] { const char* e = getenv("FSFB_GEMM_TIMERS"); return e && atoi(e) != 0; }();
+  if (timed) {
+    if (!g_ss_timers) FSFB_CUDA(cudaMalloc(&g_ss_timers, (size_t)kNumSMs * 32 * 4));
+    FSFB_CUDA(cudaMemsetAsync(g_ss_timers, 0, (size_t)kNumSMs * 32 * 4, st));
+    *out = g_ss_timers;
+  }
+  return FSFB_OK;
+}
+
+// device address of the fp16-overflow counter on the current device (shared with gemm_lin.cu)
+int ss_overflow_counter(unsigned int** out) {
+  constexpr int kMaxDev = 64;
+  static unsigned int* ptr[kMaxDev] = {nullptr};
+  int dev = 0;
+  FSFB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) {
+    set_error("gather_gemm: device ordinal %d out of range", dev);
+    return FSFB_ERR_BADARG;
+  }
+  if (!ptr[dev]) FSFB_CUDA(cudaGetSymbolAddress((void**)&ptr[dev], g_ss_overflow));
+  *out = ptr[dev];
+  return FSFB_OK;
+}
+
 int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspace, size_t workspace_bytes, int splits,
                           const float* host_bias, const float* host_norm_w, const float* host_norm_b, cudaStream_t st) {
   const int n_pad = P.S.n_pad();
@@ -1083,12 +1087,9 @@ int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspac
   P.sched_base = sched_next[dev][P.sched_slot];
   const unsigned grid = (unsigned)std::min<int64_t>(P.n_units, kNumSMs);
   sched_next[dev][P.sched_slot] += (unsigned)P.n_units + grid;
-  P.timers = nullptr;
-  static const bool timed = [] { const char* e = getenv("FSFB_GEMM_TIMERS"); return e && atoi(e) != 0; }();
-  if (timed) {
-    if (!g_ss_timers) FSFB_CUDA(cudaMalloc(&g_ss_timers, (size_t)kNumSMs * 32 * 4));
-    FSFB_CUDA(cudaMemsetAsync(g_ss_timers, 0, (size_t)kNumSMs * 32 * 4, st));
-    P.timers = g_ss_timers;
+  {
+    const int rc = ss_timers_buffer(&P.timers, st);
+    if (rc != FSFB_OK) return rc;
   }
 
   static const bool hv_on = [] { const char* e = getenv("FSFB_GEMM_HV"); return !e || atoi(e) != 0; }();

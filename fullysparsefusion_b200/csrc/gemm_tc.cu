@@ -321,6 +321,10 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
     // channels; the kernel below remains for widths like 131 / 144 (one 256-wide tile) and fused LayerNorms wider
     // than 128.  FSFB_GEMM_TS=0 forces the kernel below (A/B experiments).
     static const int ss_mode = [] { const char* e = getenv("FSFB_GEMM_SS"); return e ? atoi(e) : 1; }();
+    if (ss_mode && !a_split && splits <= 1) {  // dense Linear over many rows: one CTA per row tile (gemm_lin.cu)
+      const int rc_lin = launch_linear_ss(P, a_vec, (cudaStream_t)stream);
+      if (rc_lin != 1) return rc_lin;
+    }
     if (ss_mode) {  // fp16-split operands from shared memory (gemm_ss.cu); 1 = shape not served there
       const int rc_ss = launch_gather_gemm_ss(P, a_vec, a_split, (float*)workspace, workspace_bytes, splits, host_bias, host_norm_w,
                                               host_norm_b, (cudaStream_t)stream);

@@ -181,3 +181,41 @@ def test_epilogue_vectors_not_cached_by_address(cuda):
         got = ops.gather_gemm(ta, pw, bias=tb, norm="affine", norm_w=tw, norm_b=th, act="relu").cpu().numpy()
         np.testing.assert_allclose(got, O.gather_gemm(a, w, bias=b, norm="affine", norm_w=2 * nw, norm_b=nb, act="relu"), rtol=RTOL, atol=ATOL)
         del tb, tw, th
+
+
+@pytest.mark.parametrize("rows,cin,cout,norm,act,res,post", [
+    (9000, 128, 128, "ln", "gelu", False, False),      # the SIR point MLP
+    (8200, 256, 128, "ln", "gelu", True, False),       # residual before the activation, 8 K chunks
+    (10001, 133, 128, "ln", "gelu", False, False),     # unaligned rows: scalar loads, partial last chunk
+    (8193, 10, 128, "affine", "relu", False, False),   # one partial chunk (one K step), BatchNorm-as-affine
+    (9000, 128, 131, None, None, False, False),        # two column tiles, odd width
+    (9000, 128, 33, None, "relu", True, True),         # narrow odd tile, residual after the activation
+    (8500, 11, 64, "ln", "relu", False, False),        # 64-column accumulators
+    (9100, 32, 146, None, "gelu", True, False),        # two column tiles + residual
+    (12345, 181, 128, "ln", None, True, True),
+])
+def test_linear_row_tile_kernel(cuda, rows, cin, cout, norm, act, res, post):
+    """Dense Linear over >= 8192 rows runs csrc/gemm_lin.cu (one CTA per 128-row tile); same oracle, same tolerance."""
+    rng = np.random.default_rng(rows + 7 * cin + cout)
+    a = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    nw = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    nb = rng.standard_normal(cout).astype(np.float32)
+    r = rng.standard_normal((rows, cout)).astype(np.float32) if res else None
+    want = O.gather_gemm(a, w, bias=b, norm=norm, norm_w=nw, norm_b=nb, eps=1e-3, residual=None if post else r, act=act)
+    if post and res:
+        want = want + r
+    pw = ops.gemm_prepack(T(w, cuda), keep_raw=True)
+    kw = dict(bias=T(b, cuda), norm=norm, norm_w=T(nw, cuda) if norm else None, norm_b=T(nb, cuda) if norm else None, eps=1e-3,
+              residual=T(r, cuda) if res else None, act=act, residual_post=post)
+    got = ops.gather_gemm(T(a, cuda), pw, **kw).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+    # the same rows as a strided view (row stride 192 floats, 16-byte aligned) and into a strided output
+    if cin <= 160:
+        wide = torch.zeros(rows, 192, device=cuda)
+        wide[:, :cin] = T(a, cuda)
+        out = torch.full((rows, cout + 5), -7.0, device=cuda)
+        ops.gather_gemm(wide[:, :cin], pw, out=out[:, :cout], **kw)
+        np.testing.assert_allclose(out[:, :cout].cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+        assert float(out[:, cout:].min()) == -7.0 and float(out[:, cout:].max()) == -7.0   # nothing written past the row

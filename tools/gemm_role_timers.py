@@ -33,7 +33,8 @@ for label, fn in (("split_rows only (timers below are stale)", lambda: ops.split
                   ("linear 128x128 bias relu", lambda: ops.gather_gemm(a, lin_w, bias=bias, act="relu")),
                   ("linear 128x128 plain", lambda: ops.gather_gemm(a, lin_w)),
                   ("linear 128x33", lambda: ops.gather_gemm(a, lin33)),
-                  ("linear 133x128", lambda: ops.gather_gemm(a133, lin133))):
+                  ("linear 133x128", lambda: ops.gather_gemm(a133, lin133)),
+                  ("linear 128x128 ln gelu", lambda: ops.gather_gemm(a, lin_w, bias=bias, norm="ln", norm_w=bias, norm_b=bias, eps=1e-3, act="gelu"))):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -46,6 +47,11 @@ for label, fn in (("split_rows only (timers below are stale)", lambda: ops.split
         continue
     t = out.astype(np.float64)
     print(f"== {label}: {e0.elapsed_time(e1):.3f} ms; producer total clk mean {t[:,31].mean():.0f} max {t[:,31].max():.0f}")
+    if t[:, 22].max() > 0:   # the row-tile Linear kernel (csrc/gemm_lin.cu): thread 0 of CTAs 1000..1147
+        for i, n in enumerate(["prologue", "main loop", "last MMA", "phase 1", "statistics", "phase 2", "whole CTA"]):
+            col = t[:, 16 + i]
+            print(f"   lin {n:10s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f}")
+        continue
     for i, n in enumerate(names):
         col = t[:, i]
         print(f"   {n:12s} mean {col.mean():10.0f}  min {col.min():10.0f}  max {col.max():10.0f}")
