@@ -10,12 +10,12 @@
 // 128 x 128 tile in ~13 k clk while sixteen producer warps share their issue slots; a Linear layer has four K chunks of tensor
 // work per tile, so the layer ran at the epilogue's pace (profiles/r2_ss_role_timers.txt: 160 k rows x 128 -> 128 in 107 us,
 // 4x its HBM time).  Here a CTA is one 128-row tile and 256 threads that do everything in turn — load + split the A chunk
-// (coalesced 128-bit loads, the next two chunks' loads in flight across the barriers), one elected thread issues the MMAs, then all
+// (coalesced 128-bit loads, the next three chunks' loads in flight across the barriers), one elected thread issues the MMAs, then all
 // eight warps run the epilogue — and two CTAs share an SM (98 KB shared memory, 256 of 512 TMEM columns each), so one tile's
 // epilogue overlaps the other tile's loads and MMAs with no hand-written warp specialisation.
 //
 // Epilogue in two phases over a staging tile that re-uses the operand stages: (1) thread = (row = TMEM lane, column half):
-// accumulators + bias -> staging row, partial LayerNorm statistics combined through shared memory; (2) every warp walks 16 rows
+// accumulators + bias -> staging row, LayerNorm statistics of the half (block-wise two-pass, Chan merge) parked in shared memory; (2) every warp walks 16 rows
 // with lanes across the columns: per-channel vectors sit in registers, residual reads and output stores are coalesced 128-bit
 // accesses.
 #include <cuda_fp16.h>
@@ -43,8 +43,8 @@ struct LinShared {
   unsigned long long acc_full;
   uint32_t tmem_base;
   alignas(16) float bias[kLinTile];
-  float part[2][kTcRows];   // per (column half, row): partial sum, then partial squared deviation
-  float mean[kTcRows], rstd[kTcRows];
+  float part[2][kTcRows], part2[2][kTcRows];   // per (column half, row): mean and sum of squared deviations of the half's columns
+  float mean[kTcRows], rstd[kTcRows];          // merged row statistics (written and read by the row's phase-2 warp)
 };
 
 // VEC: rows of `a` are 16-byte aligned with a stride that is a multiple of 4 floats (the stride then covers round_up(cin, 4))
@@ -62,6 +62,34 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
   const int c_n = min(kLinTile, P.S.cout - c0);            // real channels of this column tile
   const int kc_n = P.S.kc();
   const uint32_t acc_cols = n_sub <= 64 ? 64u : 128u;
+
+  // ---- operand loads: thread = (16-byte piece of the 128-byte K chunk, rows row_a + 32 i); three chunks in flight ----
+  const int chunk = tid & 7, row_a = tid >> 3;
+  const bool odd = (chunk & 1) != 0;
+  const uint32_t piece = (uint32_t)(odd ? 4 + (chunk >> 1) : (chunk >> 1));   // even lane stores both hi halves, odd both lo
+  const uint32_t dst0 = (uint32_t)row_a * 128u + ((piece ^ (uint32_t)(row_a & 7)) << 4);   // + 4096 i: same row & 7
+  auto load_chunk = [&](int kc, float4(&v)[4]) {
+    const int col = kc * kGemmKChunk + chunk * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = row0 + row_a + 32 * i;
+      const bool ok = r < P.rows;
+      const float* g = P.a + (ok ? r : 0) * P.a_stride + col;
+      if (VEC) {
+        v[i] = ldg_pred_f4_na(g, ok && col < P.cin);
+      } else {
+        v[i].x = ldg_pred_f1(g, ok && col < P.cin);
+        v[i].y = ldg_pred_f1(g + 1, ok && col + 1 < P.cin);
+        v[i].z = ldg_pred_f1(g + 2, ok && col + 2 < P.cin);
+        v[i].w = ldg_pred_f1(g + 3, ok && col + 3 < P.cin);
+      }
+    }
+  };
+  // the first two chunks are requested before anything else: their latency covers the barrier / tensor-memory set-up below
+  float4 q0[4], q1[4], q2[4];   // static register sets: chunk kc lives in q[kc % 3]
+  load_chunk(0, q0);
+  if (kc_n > 1) load_chunk(1, q1);
+  if (kc_n > 2) load_chunk(2, q2);
 
   // FSFB_GEMM_TIMERS=1 (tools/gemm_role_timers.py): thread 0 of the CTAs 1000..1147 (steady state of a large grid) records
   // the clocks of its phases: [16] prologue, [17] main loop, [18] wait for the last MMA, [19] phase 1, [20] statistics,
@@ -86,7 +114,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid < kLinTile) sh->bias[tid] = (E.bias && tid < c_n) ? __ldg(E.bias + c0 + tid) : 0.f;
+  const float bias_r = (E.bias && tid < c_n) ? __ldg(E.bias + c0 + tid) : 0.f;   // parked in shared memory after the set-up barrier
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -108,28 +136,6 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
   if (tid == 0)
     for (int j = 0; j < min(kLinWStages, kc_n); ++j) issue_w(j);
 
-  // ---- operand loads: thread = (16-byte piece of the 128-byte K chunk, rows row_a + 32 i); two chunks in flight ----
-  const int chunk = tid & 7, row_a = tid >> 3;
-  const bool odd = (chunk & 1) != 0;
-  const uint32_t piece = (uint32_t)(odd ? 4 + (chunk >> 1) : (chunk >> 1));   // even lane stores both hi halves, odd both lo
-  const uint32_t dst0 = (uint32_t)row_a * 128u + ((piece ^ (uint32_t)(row_a & 7)) << 4);   // + 4096 i: same row & 7
-  auto load_chunk = [&](int kc, float4(&v)[4]) {
-    const int col = kc * kGemmKChunk + chunk * 4;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t r = row0 + row_a + 32 * i;
-      const bool ok = r < P.rows;
-      const float* g = P.a + (ok ? r : 0) * P.a_stride + col;
-      if (VEC) {
-        v[i] = ldg_pred_f4_na(g, ok && col < P.cin);
-      } else {
-        v[i].x = ldg_pred_f1(g, ok && col < P.cin);
-        v[i].y = ldg_pred_f1(g + 1, ok && col + 1 < P.cin);
-        v[i].z = ldg_pred_f1(g + 2, ok && col + 2 < P.cin);
-        v[i].w = ldg_pred_f1(g + 3, ok && col + 3 < P.cin);
-      }
-    }
-  };
   __half2 ovf = __floats2half2_rn(0.f, 0.f);
   auto store_chunk = [&](int kc, uint32_t slot, const float4(&v)[4]) {
     const int nv = P.cin - (kc * kGemmKChunk + chunk * 4);   // real columns in this thread's piece
@@ -156,17 +162,18 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
     }
   };
 
+  if (tid < kLinTile) sh->bias[tid] = bias_r;   // read in phase 1, behind the main loop's barriers
   LIN_T(0);
   // ---- main loop over the K chunks ----
   const uint32_t idesc = make_idesc_f16(n_sub);
   constexpr uint64_t kDescHi = (uint64_t)0x40004040u << 32;   // SBO = 1024, version 1, SWIZZLE_128B
-  auto step = [&](int kc, float4(&v)[4]) {   // v holds chunk kc on entry and chunk kc + 2 on exit
+  auto step = [&](int kc, float4(&v)[4]) {   // v holds chunk kc on entry and chunk kc + 3 on exit
     const int s = kc & 1;
     const uint32_t use = (uint32_t)kc >> 1;   // earlier uses of this A stage
     if (use > 0) mbar_wait(smem_u32(&sh->a_empty[s]), (use - 1u) & 1u);   // the MMAs of chunk kc - 2 have read the stage
     store_chunk(kc, s_a + (uint32_t)s * kLinASlot, v);
     fence_proxy_async();   // generic-proxy stores before the tensor core's async-proxy reads
-    if (kc + 2 < kc_n) load_chunk(kc + 2, v);   // in flight across two barriers
+    if (kc + 3 < kc_n) load_chunk(kc + 3, v);   // in flight across three barriers
     if (tid == 0 && kc + 2 >= kLinWStages && kc + 2 < kc_n) issue_w(kc + 2);
     __syncthreads();
     if (warp == 0) {
@@ -196,14 +203,10 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
       __syncwarp();
     }
   };
-  {
-    float4 q0[4], q1[4];   // static register sets: chunk kc lives in q[kc & 1]
-    load_chunk(0, q0);
-    if (kc_n > 1) load_chunk(1, q1);
-    for (int kc = 0; kc < kc_n; kc += 2) {
-      step(kc, q0);
-      if (kc + 1 < kc_n) step(kc + 1, q1);
-    }
+  for (int kc = 0; kc < kc_n; kc += 3) {
+    step(kc, q0);
+    if (kc + 1 < kc_n) step(kc + 1, q1);
+    if (kc + 2 < kc_n) step(kc + 2, q2);
   }
   {  // overflow report: any converted magnitude that became +Inf
     const __half2 gt = __hgt2(ovf, __floats2half2_rn(65504.f, 65504.f));
@@ -225,7 +228,10 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
   const uint32_t t_row = tmem_d + ((uint32_t)(quad * 32) << 16);
   const uint32_t my_row = base + (uint32_t)row_l * (uint32_t)kLinStageStride * 4u;
   const uint32_t s_bias = smem_u32(sh->bias);
-  float sum = 0.f;
+  const bool ln = E.norm == FSFB_NORM_LAYERNORM;
+  // LayerNorm statistics of this thread's columns: per 32-column block an exact two-pass (mean, sum of squared deviations)
+  // on the registers, blocks and halves merged with Chan's update — no second pass over shared memory, no extra barrier
+  float cnt = 0.f, mean_h = 0.f, m2_h = 0.f;
 #pragma unroll 1
   for (int cb = cb_lo; cb < cb_hi; cb += 32) {   // warp-uniform
     float x[32], c2[32];
@@ -234,50 +240,75 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 bb = lds_f4(s_bias + (uint32_t)(cb + j) * 4u);
-      float4 y;
-      y.x = fmaf(c2[j], 1.f / kF16LoScale, x[j]) + bb.x;
-      y.y = fmaf(c2[j + 1], 1.f / kF16LoScale, x[j + 1]) + bb.y;
-      y.z = fmaf(c2[j + 2], 1.f / kF16LoScale, x[j + 2]) + bb.z;
-      y.w = fmaf(c2[j + 3], 1.f / kF16LoScale, x[j + 3]) + bb.w;
+      x[j] = fmaf(c2[j], 1.f / kF16LoScale, x[j]) + bb.x;
+      x[j + 1] = fmaf(c2[j + 1], 1.f / kF16LoScale, x[j + 1]) + bb.y;
+      x[j + 2] = fmaf(c2[j + 2], 1.f / kF16LoScale, x[j + 2]) + bb.z;
+      x[j + 3] = fmaf(c2[j + 3], 1.f / kF16LoScale, x[j + 3]) + bb.w;
       // columns in [c_n, n_sub) are exact zeros (zero weight rows, bias 0); past the half's end the 32-column load holds
       // the other half's (or stale) columns
-      if (cb + j < cb_hi) {
-        sum += (y.x + y.y) + (y.z + y.w);
-        sts_f4(my_row + (uint32_t)(cb + j) * 4u, y);
+      if (cb + j < cb_hi) sts_f4(my_row + (uint32_t)(cb + j) * 4u, make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]));
+    }
+    if (ln) {
+      const int nb = max(0, min(32, min(c_n, cb_hi) - cb));   // real columns of this block
+      if (nb > 0) {
+        float sb = 0.f, qb = 0.f, mb;
+        if (nb == 32) {   // whole block (every block of a 128-wide layer): no per-column predicates
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s4[j & 3] += x[j];
+          mb = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 32.f);
+          float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = x[j] - mb;
+            q4[j & 3] = fmaf(d, d, q4[j & 3]);
+          }
+          qb = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sb += j < nb ? x[j] : 0.f;
+          mb = sb / (float)nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = x[j] - mb;
+            qb += j < nb ? d * d : 0.f;
+          }
+        }
+        const float tot = cnt + (float)nb, delta = mb - mean_h;
+        mean_h += delta * ((float)nb / tot);
+        m2_h += qb + delta * delta * (cnt * (float)nb / tot);
+        cnt = tot;
       }
     }
   }
   tc_fence_before();
   LIN_T(3);
-  if (E.norm == FSFB_NORM_LAYERNORM) {   // kernel-uniform
-    sh->part[half][row_l] = sum;
-    __syncthreads();
-    const float mean = (sh->part[0][row_l] + sh->part[1][row_l]) / (float)c_n;
-    float qq = 0.f;
-    const int c_hi = min(cb_hi, c_n);
-#pragma unroll 4
-    for (int c = cb_lo; c < c_hi; c += 4) {
-      const float4 x = lds_f4(my_row + (uint32_t)c * 4u);
-      const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
-      qq += d0 * d0 + (c + 1 < c_n ? d1 * d1 : 0.f) + (c + 2 < c_n ? d2 * d2 : 0.f) + (c + 3 < c_n ? d3 * d3 : 0.f);
-    }
-    __syncthreads();   // every thread has read both partial sums
-    sh->part[half][row_l] = qq;
-    __syncthreads();
-    if (half == 0) {
-      sh->mean[row_l] = mean;
-      sh->rstd[row_l] = 1.f / sqrtf((sh->part[0][row_l] + sh->part[1][row_l]) / (float)c_n + E.eps);
-    }
+  if (ln) {   // kernel-uniform
+    sh->part[half][row_l] = mean_h;
+    sh->part2[half][row_l] = m2_h;
   }
   __syncthreads();   // the staging tile (and the row statistics) are complete
   LIN_T(4);
 
   // ---- epilogue phase 2: warp = 16 rows, lanes across the columns ----
-  const bool ln = E.norm == FSFB_NORM_LAYERNORM;
   const bool res_vec = !E.residual || (((uintptr_t)E.residual % 16 == 0) && (E.residual_stride % 4 == 0));
   const bool vec = (c_n & 3) == 0 && P.out_vec && res_vec;
   constexpr int kRowsPerWarp = kTcRows / (kLinThreads / 32);
   const int rl0 = warp * kRowsPerWarp;
+  const float n0 = (float)min(c_n, split), n1 = (float)(c_n - min(c_n, split));
+  // lane i < 16 merges the two halves' (mean, M2) of row rl0 + i once; the rows are this warp's own, so a warp barrier orders
+  // the broadcast reads of the row walk below
+  if (ln) {
+    if (lane < kRowsPerWarp) {
+      const int rl = rl0 + lane;
+      const float m0 = sh->part[0][rl], m1 = sh->part[1][rl];
+      const float delta = m1 - m0;
+      sh->mean[rl] = m0 + delta * (n1 / (float)c_n);
+      const float m2 = sh->part2[0][rl] + sh->part2[1][rl] + delta * delta * (n0 * n1 / (float)c_n);
+      sh->rstd[rl] = 1.f / sqrtf(m2 / (float)c_n + E.eps);
+    }
+    __syncwarp();
+  }
   if (vec) {
     const int c = 4 * lane;
     const bool on = c < c_n;
