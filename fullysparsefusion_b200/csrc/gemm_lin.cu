@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
 int launch_linear_ss(TcParams& P, bool a_vec, cudaStream_t st) {
   static const int mode = [] { const char* e = getenv("FSFB_GEMM_LIN"); return e ? atoi(e) : 1; }();
   if (!mode || !gemm_f16_enabled()) return 1;
-  static const int64_t min_rows = [] { const char* e = getenv("FSFB_GEMM_LIN_MIN_ROWS"); return e ? atoll(e) : 8192ll; }();
+  static const int64_t min_rows = [] { const char* e = getenv("FSFB_GEMM_LIN_MIN_ROWS"); return e ? atoll(e) : 1024ll; }();
   const int n_pad = P.S.n_pad();
   if (P.nbr || P.row_order || P.koff != 1 || P.rows < min_rows) return 1;
   if (n_pad > kLinTile && P.E.norm == FSFB_NORM_LAYERNORM) return 1;   // row statistics across column tiles

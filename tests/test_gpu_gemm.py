@@ -195,7 +195,7 @@ def test_epilogue_vectors_not_cached_by_address(cuda):
     (12345, 181, 128, "ln", None, True, True),
 ])
 def test_linear_row_tile_kernel(cuda, rows, cin, cout, norm, act, res, post):
-    """Dense Linear over >= 8192 rows runs csrc/gemm_lin.cu (one CTA per 128-row tile); same oracle, same tolerance."""
+    """Dense Linear over >= 1024 rows runs csrc/gemm_lin.cu (one CTA per 128-row tile); same oracle, same tolerance."""
     rng = np.random.default_rng(rows + 7 * cin + cout)
     a = rng.standard_normal((rows, cin)).astype(np.float32)
     w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
