@@ -283,63 +283,65 @@ __global__ void __launch_bounds__(kNmsReduceWarps * 32)
   }
 }
 
-// kept rows → outputs (order of `kept_idx`: class-major, score descending).  When more than max_num survive, the output is the
-// max_num best by (score desc, emitted position asc): a counting rank, P x P compares.  A CTA ranks 32 candidates; its 8 warps
-// each take one eighth of every 256-entry shared-memory tile (broadcast 128-bit reads, four independent counters).
-constexpr int kNmsEmitWarps = 8;
-constexpr int kNmsEmitTile = 2048;   // scores per shared-memory tile
-__global__ void __launch_bounds__(kNmsEmitWarps * 32)
+// kept rows → outputs (order of `kept_idx`: class-major, score descending, ties by box index).  When more than max_num survive,
+// the output is the max_num best by (score desc, emitted position asc).  The kept list is one descending run per class, so a
+// candidate's rank is its index inside its own class plus, for every other class, the number of entries that beat it — a binary
+// search per class over the compacted scores (ties: earlier classes win, later classes lose), instead of P x P compares.
+__global__ void __launch_bounds__(256)
+    k_nms_kept_scores(const int32_t* __restrict__ kept_idx, int64_t P, const float* __restrict__ sorted_score,
+                      float* __restrict__ kept_score) {
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < P; t += (int64_t)gridDim.x * 256) kept_score[t] = sorted_score[kept_idx[t]];
+}
+
+constexpr int kNmsMaxClasses = 64;
+__global__ void __launch_bounds__(256)
     k_nms_emit(const int32_t* __restrict__ kept_idx, int64_t P, const int32_t* __restrict__ sorted_box,
-               const int32_t* __restrict__ sorted_cls, const float* __restrict__ sorted_score, const float* __restrict__ boxes,
-               int64_t box_stride, int box_dim, int64_t max_num, float* __restrict__ out_boxes, float* __restrict__ out_scores,
-               long long* __restrict__ out_labels, int32_t* __restrict__ out_box_idx) {
-  __shared__ __align__(16) float s_tile[kNmsEmitTile];
-  __shared__ int s_rank[kNmsEmitWarps][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int64_t t0 = (int64_t)blockIdx.x * 32; t0 < P; t0 += (int64_t)gridDim.x * 32) {   // block-uniform
-    const int64_t t = t0 + lane;
-    const bool live = t < P;
-    const int r = live ? kept_idx[t] : 0;
-    const float s = live ? sorted_score[r] : 0.f;
-    int64_t dst = t;
-    if (P > max_num) {
-      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-      for (int64_t u0 = 0; u0 < P; u0 += kNmsEmitTile) {
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < kNmsEmitTile / (kNmsEmitWarps * 32); ++e) {   // independent gathers: one latency per tile
-          const int64_t u = u0 + e * (kNmsEmitWarps * 32) + threadIdx.x;
-          s_tile[e * (kNmsEmitWarps * 32) + threadIdx.x] = u < P ? sorted_score[kept_idx[u]] : -INFINITY;   // never counts
-        }
-        __syncthreads();
-        constexpr int kPer = kNmsEmitTile / kNmsEmitWarps;   // this warp's share of the tile
-        const int64_t xb = u0 + warp * kPer;
-#pragma unroll 4
-        for (int x = 0; x < kPer; x += 4) {
-          const float4 su = *reinterpret_cast<const float4*>(&s_tile[warp * kPer + x]);
-          r0 += (su.x > s) | ((su.x == s) & (xb + x < t));
-          r1 += (su.y > s) | ((su.y == s) & (xb + x + 1 < t));
-          r2 += (su.z > s) | ((su.z == s) & (xb + x + 2 < t));
-          r3 += (su.w > s) | ((su.w == s) & (xb + x + 3 < t));
-        }
+               const int32_t* __restrict__ sorted_cls, const float* __restrict__ sorted_score, const float* __restrict__ kept_score,
+               const float* __restrict__ boxes, int64_t box_stride, int box_dim, int64_t max_num, float* __restrict__ out_boxes,
+               float* __restrict__ out_scores, long long* __restrict__ out_labels, int32_t* __restrict__ out_box_idx) {
+  __shared__ int s_kb[kNmsMaxClasses + 1];   // class c occupies [s_kb[c], s_kb[c + 1]) of the kept list
+  const bool select = P > max_num;
+  if (select) {
+    if (threadIdx.x <= kNmsMaxClasses) {
+      const int c = threadIdx.x;
+      int lo = 0, hi = (int)P;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sorted_cls[kept_idx[mid]] < c) lo = mid + 1;
+        else hi = mid;
       }
-      s_rank[warp][lane] = (r0 + r1) + (r2 + r3);
-      __syncthreads();
-      int rank = 0;
-#pragma unroll
-      for (int w = 0; w < kNmsEmitWarps; ++w) rank += s_rank[w][lane];
-      __syncthreads();
+      s_kb[c] = lo;
+    }
+    __syncthreads();
+  }
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < P; t += (int64_t)gridDim.x * 256) {
+    const int r = kept_idx[t];
+    const float s = sorted_score[r];
+    const int ct = sorted_cls[r];
+    int64_t dst = t;
+    if (select) {
+      int rank = (int)t - s_kb[ct];
+      for (int c = 0; c < kNmsMaxClasses && rank < max_num; ++c) {
+        const int beg = s_kb[c], end = s_kb[c + 1];
+        if (beg == end || c == ct) continue;
+        int lo = beg, hi = end;   // first entry of the class that does not beat (s, position t)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const float v = kept_score[mid];
+          const bool beats = c < ct ? (v >= s) : (v > s);
+          if (beats) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += lo - beg;
+      }
+      if (rank >= max_num) continue;
       dst = rank;
     }
-    if (!live || (P > max_num && dst >= max_num)) continue;
-    // warp w writes the fields d = w, w + 8, ... of the 32 candidates
     const float* b = boxes + (int64_t)sorted_box[r] * box_stride;
-    for (int d = warp; d < box_dim; d += kNmsEmitWarps) out_boxes[dst * box_dim + d] = b[d];
-    if (warp == 0) {
-      out_scores[dst] = s;
-      out_labels[dst] = sorted_cls[r];
-      if (out_box_idx) out_box_idx[dst] = sorted_box[r];
-    }
+    for (int d = 0; d < box_dim; ++d) out_boxes[dst * box_dim + d] = b[d];
+    out_scores[dst] = s;
+    out_labels[dst] = ct;
+    if (out_box_idx) out_box_idx[dst] = sorted_box[r];
   }
 }
 
@@ -425,14 +427,18 @@ int fsfb_nms_emit(const float* boxes, int64_t box_stride, int box_dim, const int
   int32_t* sorted_box = ws.take<int32_t>(candidates);
   int32_t* sorted_cls = ws.take<int32_t>(candidates);
   float* sorted_score = ws.take<float>(candidates);
-  ws.take<unsigned long long>((size_t)candidates * words);
+  unsigned long long* mask_mem = ws.take<unsigned long long>((size_t)candidates * words);
   if (!ws.ok()) {
     set_error("nms_emit: workspace does not match the one given to nms_suppress");
     return FSFB_ERR_CAPACITY;
   }
-  const int grid = (int)std::min<int64_t>(ceil_div(kept, 32), (int64_t)kNumSMs * 8);
-  FSFB_LAUNCH(k_nms_emit, grid, kNmsEmitWarps * 32, 0, (cudaStream_t)stream, kept_idx, kept, sorted_box, sorted_cls, sorted_score, boxes, box_stride,
-              box_dim, max_num, out_boxes, out_scores, out_labels, out_box_idx);
+  // the suppression matrix is dead by now: its memory holds the compacted scores of the kept list
+  float* kept_score = reinterpret_cast<float*>(mask_mem);
+  const int grid = (int)std::min<int64_t>(ceil_div(kept, 256), (int64_t)kNumSMs * 8);
+  if (kept > max_num)
+    FSFB_LAUNCH(k_nms_kept_scores, grid, 256, 0, (cudaStream_t)stream, kept_idx, kept, sorted_score, kept_score);
+  FSFB_LAUNCH(k_nms_emit, grid, 256, 0, (cudaStream_t)stream, kept_idx, kept, sorted_box, sorted_cls, sorted_score, kept_score, boxes,
+              box_stride, box_dim, max_num, out_boxes, out_scores, out_labels, out_box_idx);
   return FSFB_OK;
 }
 

@@ -517,6 +517,28 @@ def split_rows(a: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_SPLITS_AUTO = os.environ.get("FSFB_GEMM_AUTO_SPLITS", "1") != "0"
+
+
+def _pick_splits(rows: int, cpad: int, koff: int, kc: int) -> int:
+    """Offset splits of a convolution on a level with few row tiles.  The persistent kernel runs ceil(units / 148) waves of
+    (128-row, 128-column) units; splitting the offsets s ways makes the units s times shorter, so the last wave wastes less, at the
+    price of the partial sums' round trip and one more launch.  Model: a unit costs ~0.62 us per (visited offset, K chunk) stage
+    (1.2 k clk measured, ~60 % of the offsets visited on the deep levels); the split epilogue ~20 us + its traffic at 5 TB/s."""
+    if koff < 6 or cpad > 1024 or koff * kc < 32:
+        return 1
+    units = ((rows + 127) // 128) * (cpad // 128)
+    t_unit = koff * kc * 0.6 * 0.62e-6
+    best_s, best_t = 1, -(-units // 148) * t_unit
+    if not _SPLITS_AUTO:   # the round-1 rule: only when half the SMs would idle
+        return max(1, min(koff // 3, 148 // units)) if units * 2 <= 148 else 1
+    for s in range(2, min(koff // 3, 9) + 1):
+        t = -(-units * s // 148) * t_unit / s + 20e-6 + 2.0 * rows * cpad * 4 * s / 5e12
+        if t < 0.9 * best_t:
+            best_s, best_t = s, t
+    return best_s
+
+
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
                 out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False,
@@ -567,10 +589,7 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
     cpad = (w.cout + 127) // 128 * 128
     tileable = w.cout <= 128 or (((w.cout + 15) // 16 * 16) % 128 == 0 and norm != "layernorm" and norm != "ln")
     if splits is None:
-        splits = 1
-        units = ((rows + 127) // 128) * (cpad // 128)
-        if tileable and w.koff >= 6 and cpad <= 1024 and units * 2 <= 148 and w.koff * ((w.cin + 31) // 32) >= 32:
-            splits = max(1, min(w.koff // 3, 148 // units))
+        splits = _pick_splits(rows, cpad, w.koff, (w.cin + 31) // 32) if tileable else 1
     # 27-offset convolutions: every input row is gathered by ~6 offsets, so the fp32 → fp16-split conversion is done once per
     # row up front (fsfb_split_rows) and the kernel's gather is pure data movement (include/fsf_b200.h)
     if (_SPLIT_ON and nbr is not None and w.koff > 1 and w.koff <= 27 and w.cin % 32 == 0 and tileable and a.data_ptr() % 16 == 0
