@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--scope", default="full", choices=["hot", "full"],
                     help="full (default): FSF.simple_test = segment → combine + query refinement + final boxes (decode + rotated "
                          "NMS) on both arms; hot: segment → combine only (the scope of the round-1 numbers)")
+    ap.add_argument("--train", action="store_true",
+                    help="training step of the segmentation stage (fullysparsefusion_b200/train.py: forward, focal + vote loss, backward "
+                         "through the tcgen05 gather-GEMM / fsfb_conv_wgrad, bucketed NCCL gradient all-reduce overlapped with backward, "
+                         "AdamW) instead of the inference frame; one frame per GPU per step, synthetic labels")
     return ap.parse_args()
 
 
@@ -318,10 +322,136 @@ def resolve(v):
     return v
 
 
+def synth_labels(points, num_classes: int = 10):
+    """Deterministic point labels for the training bench: returns above the ground inside 40 m take the class of their azimuth
+    sector, everything else is background (= num_classes); vote target = offset to the sector's anchor at 20 m."""
+    import math
+
+    import torch
+
+    x, y, z = points[:, 0], points[:, 1], points[:, 2]
+    az = torch.atan2(y, x)
+    sector = ((az + math.pi) / (2 * math.pi) * num_classes).long().clamp(0, num_classes - 1)
+    fg = (z > -1.3) & (x * x + y * y < 1600.0)
+    labels = torch.where(fg, sector, torch.full_like(sector, num_classes))
+    ang = (sector.float() + 0.5) / num_classes * 2 * math.pi - math.pi
+    anchor = torch.stack([20 * torch.cos(ang), 20 * torch.sin(ang), torch.zeros_like(ang)], 1)
+    return labels, (anchor - points[:, :3]).clamp(-3, 3)
+
+
+def main_train(args):
+    """`--train`: segmentation-stage training step, one frame per GPU per step."""
+    import torch
+    import torch.distributed as dist
+
+    from fullysparsefusion_b200 import _capi
+    from fullysparsefusion_b200 import dist as fdist
+    from fullysparsefusion_b200.train import SegmentorTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --train: no CUDA device")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _capi.load()
+    from fullysparsefusion_b200 import synth
+    n_frames = 3
+    frames = []
+    for i in range(n_frames):
+        pts = torch.from_numpy(synth.ring_points(args.points, sweeps=args.sweeps, seed=fdist.frame_seed(rank, i))).to(dev)
+        lab, vote = synth_labels(pts)
+        frames.append((pts, lab, vote))
+    torch.manual_seed(0)   # identical initial weights on every rank
+    model = make_model(config=args.config).to(dev)
+    trainer = SegmentorTrainer(model)
+    n_params = sum(p.numel() for p in trainer.params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses, exposed = [], []
+
+    def step(i):
+        out = trainer.step(*frames[i % n_frames])
+        return out
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+        losses.append(out["loss"])
+        if trainer.reducer is not None:
+            exposed.append(trainer.reducer._events)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    exp_ms = [a.elapsed_time(b) for a, b in exposed]
+    # phase split of one more (untimed) step: forward+loss / backward / reducer wait / optimizer
+    ph = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    trainer.opt.zero_grad(set_to_none=True)
+    if trainer.reducer is not None:
+        trainer.reducer.begin()
+    ph[0].record()
+    loss, _ = trainer.forward_loss(*frames[0])
+    ph[1].record()
+    loss.backward()
+    ph[2].record()
+    if trainer.reducer is not None:
+        trainer.reducer.finish()
+    ph[3].record()
+    trainer.opt.step()
+    ph[4].record()
+    torch.cuda.synchronize()
+    phases = {n: round(ph[j].elapsed_time(ph[j + 1]), 3) for j, n in enumerate(["forward_loss", "backward", "allreduce_wait", "optimizer"])}
+    if rank == 0:
+        ls = [float(v) for v in losses]
+        line = {"metric": "nuScenes 10-sweep TRAIN frames/sec, segmentation stage (VoteSegmentor: VFE + sparse U-Net + seg head)",
+                "value": world * args.steps / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "mode": "train",
+                "config": {"workload": f"FSF_nuScenes_config {args.sweeps}-sweep frame: {args.points} pts, segmentation stage only, synthetic labels, "
+                                       "one frame per GPU per step", "points": args.points, "sweeps": args.sweeps,
+                           "optimizer": "AdamW", "norm": "naiveSyncBN1d (one differentiable [2C] all-reduce per layer when n_gpus > 1)"},
+                "parameters": n_params, "grad_bytes_per_step": 4 * n_params,
+                "buckets": len(trainer.reducer.buckets) if trainer.reducer is not None else 0,
+                "allreduce_exposed_ms": round(sum(exp_ms) / len(exp_ms), 3) if exp_ms else 0.0,
+                "allreduce_share_of_step": round(sum(exp_ms) / ms, 4) if exp_ms else 0.0,
+                "phases_ms": phases, "loss_first_last": [ls[0], ls[-1]], "gpu_launches": int(launches), "clocks": clocks}
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return main_reference(args)
+    if args.train:
+        return main_train(args)
 
     import torch
     import torch.distributed as dist

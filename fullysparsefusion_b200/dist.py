@@ -64,6 +64,23 @@ def reduce_means(values: List[torch.Tensor]) -> List[torch.Tensor]:
     return [flat[i].to(values[i].dtype) for i in range(len(values))]
 
 
+class _AllReduceSum(torch.autograd.Function):
+    """Differentiable sum all-reduce: the gradient of a sum over ranks is the sum over ranks of the gradients (detectron2's
+    differentiable AllReduce, which NaiveSyncBatchNorm relies on)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g
+
+
 def naive_sync_bn_stats(x: torch.Tensor):
     """Batch statistics of `naiveSyncBN1d` in training mode [UPSTREAM-RECALL: the fork's class is detectron2's NaiveSyncBatchNorm for
     1-d inputs]: per-rank mean and mean of squares concatenated into ONE [2C] vector, all-reduced, divided by the world size (ranks
@@ -74,7 +91,6 @@ def naive_sync_bn_stats(x: torch.Tensor):
     vec = torch.cat([x.mean(0), (x * x).mean(0)])
     w = _world()
     if w > 1:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-        vec = vec / w
+        vec = _AllReduceSum.apply(vec) / w   # differentiable: the statistics are part of the training graph
     mean, meansq = vec[:c], vec[c:]
     return mean, meansq - mean * mean

@@ -781,6 +781,27 @@ def add_(x, y):
     return x
 
 
+def conv_wgrad(a: torch.Tensor, dy: torch.Tensor, nbr: Optional[torch.Tensor], koff: int) -> torch.Tensor:
+    """Weight gradient of the gather-GEMM: dw[k][co][ci] = sum_r dy[r][co] * a[nbr[k][r]][ci]  → [koff, cout, cin] f32
+    (include/fsf_b200.h; nbr None = Linear)."""
+    dev = _need_cuda(a, dy)
+    assert a.dim() == 2 and dy.dim() == 2 and a.dtype == torch.float32 and dy.dtype == torch.float32
+    assert a.stride(1) == 1 and dy.stride(1) == 1
+    if nbr is not None:
+        assert nbr.dtype == torch.int32 and nbr.dim() == 2 and nbr.size(0) == koff and nbr.size(1) == dy.size(0) and nbr.is_contiguous()
+    cin, cout, rows = a.size(1), dy.size(1), dy.size(0)
+    dw = torch.empty((koff, cout, cin), dtype=torch.float32, device=dev)
+    lib = load()
+    need = C.c_size_t()
+    check(lib.fsfb_conv_wgrad_workspace_bytes(rows, koff, cin, cout, C.byref(need)), "fsfb_conv_wgrad_workspace_bytes")
+    ws = _ws(need.value, dev)
+    with _Prof("conv_wgrad", 4 * (a.size(0) * cin + rows * cout + koff * cin * cout)):
+        check(lib.fsfb_conv_wgrad(_ptr(a), a.size(0), cin, a.stride(0) if a.size(0) else cin, _ptr(dy), rows, cout,
+                                  dy.stride(0) if rows else cout, _ptr(nbr), koff, _ptr(dw), _ptr(ws), ws.numel(), _stream(dev)),
+              "fsfb_conv_wgrad")
+    return dw
+
+
 def reduce_channel(x, out_channels: int):
     dev = _need_cuda(x)
     assert x.dim() == 2 and x.stride(1) == 1

@@ -547,6 +547,21 @@ int fsfb_nms_emit(const float* boxes, int64_t box_stride, int box_dim, const int
                   int max_class, int64_t max_num, float* out_boxes, float* out_scores, long long* out_labels, int32_t* out_box_idx,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* -------------------------------------------------------------------------
+ * Weight gradient of the gather-GEMM (training)
+ * Replaces: the weight-gradient half of the backward of spconv's SubMConv3d / SparseConv3d / SparseInverseConv3d (un-vendored;
+ * the layers of SimpleSparseUNet, projects/configs/FSF_nuScenes_config.py:58-70) and of nn.Linear inside build_mlp
+ * (projects/mmdet3d_plugin/ops/sst_ops.py:808-833), as run by tools/train.py:244-251.
+ *   dw[k][co][ci] = sum over output rows r with 0 <= nbr[k][r] < a_rows of dy[r][co] * a[nbr[k][r]][ci]
+ *   a dev [a_rows, cin] f32 (row stride a_stride), dy dev [rows, cout] f32 (row stride dy_stride), nbr dev [koff][rows] i32 or
+ *   null with koff == 1 (Linear: every row pairs with itself), dw dev [koff][cout][cin] f32, overwritten.
+ *   Deterministic: pairs are summed in ascending row order inside fixed row splits, splits in order (no atomics).
+ * ------------------------------------------------------------------------- */
+int fsfb_conv_wgrad_workspace_bytes(int64_t rows, int koff, int cin, int cout, size_t* bytes);
+int fsfb_conv_wgrad(const float* a, int64_t a_rows, int cin, int64_t a_stride, const float* dy, int64_t rows, int cout,
+                    int64_t dy_stride, const int32_t* nbr, int koff, float* dw, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

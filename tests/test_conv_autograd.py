@@ -72,12 +72,60 @@ def _check(device, rtol, atol):
     assert w1.grad is not None and w1.grad.shape == w.shape
 
 
+def _wgrad_reference(a, dy, nbr, koff, dtype=torch.float64):
+    """dw[k] = dy[rows_k].T @ a[nbr[k][rows_k]] (the 27 matmuls the native kernel replaced), float64 unless told otherwise."""
+    a64, g64 = a.to(dtype), dy.to(dtype)
+    dw = torch.zeros(koff, dy.size(1), a.size(1), dtype=dtype, device=a.device)
+    for k in range(koff):
+        if nbr is None:
+            dw[k] = g64.t() @ a64
+        else:
+            rows = torch.nonzero((nbr[k] >= 0) & (nbr[k] < a.size(0)))[:, 0]
+            if rows.numel():
+                dw[k] = g64[rows].t() @ a64[nbr[k][rows].long()]
+    return dw
+
+
 def test_backward_glue_on_cpu(monkeypatch):
     monkeypatch.setattr(ops, "gemm_prepack", lambda w, keep_raw=False: types.SimpleNamespace(raw=w if w.dim() == 3 else w[None]))
     monkeypatch.setattr(ops, "gather_gemm", lambda a, pw, nbr=None, **kw: _reference(a, pw.raw, nbr))
+    monkeypatch.setattr(ops, "conv_wgrad", lambda a, dy, nbr, koff: _wgrad_reference(a, dy, nbr, koff, torch.float32))
     _check("cpu", 1e-5, 1e-5)
 
 
 @pytest.mark.gpu
 def test_backward_on_device(cuda):
     _check("cuda:0", 1e-4, 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_in,n_out,cin,cout,koff,density", [
+    (5000, 5000, 128, 128, 27, 0.2),     # a submanifold level: several row splits
+    (40000, 40000, 64, 128, 27, 0.2),
+    (3000, 900, 128, 256, 27, 0.3),      # strided: fewer outputs than inputs, four cout tiles
+    (900, 3000, 256, 128, 8, 0.5),       # inverse
+    (700, 700, 33, 11, 27, 0.3),         # odd widths, partial tiles
+    (10000, 10000, 131, 128, 1, 1.0),    # Linear through a table
+    (20000, 20000, 133, 64, 0, 1.0),     # Linear, no table
+    (1, 1, 16, 16, 27, 1.0),
+])
+def test_conv_wgrad_kernel(cuda, n_in, n_out, cin, cout, koff, density):
+    """csrc/conv_wgrad.cu against per-offset float64 matmuls; twice the same bits (deterministic: no atomics)."""
+    g = torch.Generator().manual_seed(n_in + cin + koff)
+    a = torch.randn(n_in, cin, generator=g).to(cuda)
+    dy = torch.randn(n_out, cout, generator=g).to(cuda)
+    nbr = None
+    if koff:
+        nbr = torch.randint(0, n_in, (koff, n_out), generator=g, dtype=torch.int32)
+        nbr[torch.rand(koff, n_out, generator=g) >= density] = -1
+        nbr = nbr.to(cuda)
+    k = max(koff, 1)
+    got = ops.conv_wgrad(a, dy, nbr, k)
+    want = _wgrad_reference(a, dy, nbr, k)
+    scale = want.abs().max().clamp(min=1e-6)
+    assert float((got.double() - want).abs().max() / scale) < 2e-5
+    assert torch.equal(got, ops.conv_wgrad(a, dy, nbr, k))
+    # strided operands (a row slice of a wider buffer)
+    wide = torch.zeros(n_in, cin + 7, device=cuda)
+    wide[:, :cin] = a
+    assert torch.equal(got, ops.conv_wgrad(wide[:, :cin], dy, nbr, k))

@@ -73,3 +73,62 @@ def test_single_process_is_identity():
     mu, var = fdist.naive_sync_bn_stats(x)
     assert mu.tolist() == [2.0, 4.0] and var.tolist() == [1.0, 4.0]
     assert fdist.coalesced_all_reduce([x])[0] is x
+
+
+def _train_worker(rank, world, port, out):
+    """Bucketed gradient reducer + differentiable sync-BN statistics on gloo: every rank ends with the rank-mean gradient."""
+    import torch.nn as nn
+
+    from fullysparsefusion_b200.train import BucketedReducer
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(6, 8), nn.ReLU(), nn.Linear(8, 4), nn.ReLU(), nn.Linear(4, 2))
+    unused = nn.Parameter(torch.ones(3))                    # a parameter that gets no gradient: reduced as zeros
+    params = list(net.parameters()) + [unused]
+    red = BucketedReducer(params, bucket_mb=200 / (1 << 20))   # 50 floats per bucket: several buckets
+    x = torch.arange(30, dtype=torch.float32).view(5, 6) * (rank + 1) / 10
+    local = []
+    for step in range(2):                                   # two steps: the buckets are reusable
+        for p in params:
+            p.grad = None
+        red.begin()
+        net(x).pow(2).sum().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        red.finish()
+    grads = [p.grad.clone() for p in net.parameters()]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [g.tolist() for g in local])
+    # differentiable statistics: d/dx of sum(mean over ranks) = 1 / (rows * world) per element... times world (sum of all ranks' losses)
+    y = (torch.ones(3, 2) * (rank + 1)).requires_grad_(True)
+    mu, var = fdist.naive_sync_bn_stats(y)
+    (mu.sum() + var.sum()).backward()
+    if rank == 0:
+        out.put(dict(n_buckets=len(red.buckets), grads=[g.tolist() for g in grads], local=gathered, unused=unused.grad.tolist(),
+                     dy=y.grad.tolist(), mu=mu.tolist(), var=var.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_reducer_and_differentiable_sync_bn():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["n_buckets"] >= 2
+    for i, g in enumerate(res["grads"]):                      # reduced gradient = mean of the two ranks' local gradients
+        want = (torch.tensor(res["local"][0][i]) + torch.tensor(res["local"][1][i])) / 2
+        assert torch.allclose(torch.tensor(g), want, rtol=1e-6, atol=1e-6)
+    assert res["unused"] == [0.0, 0.0, 0.0]
+    # ranks hold constant rows 1 and 2: mean 1.5, E[x^2] 2.5, var 0.25
+    assert res["mu"] == [1.5, 1.5] and all(abs(v - 0.25) < 1e-6 for v in res["var"])
+    # loss_r = sum(mu) + sum(var) on both ranks; d(mu)/dy = 1/(3*2); d(var)/dy = (2 y - 2 mu)/(3*2); both ranks' losses flow back
+    # through the all-reduce: total = 2 * (1/6 + (2*1 - 3)/6) = 0 for rank 0's rows
+    assert all(abs(v) < 1e-6 for row in res["dy"] for v in row)
