@@ -7,84 +7,122 @@
 // tools/train.py:244-251.  The restatement is the definition above; tests compare with per-offset torch.matmul in fp64.
 //
 // fp32 CUDA-core kernel, deterministic (no atomics): the reduction dimension is the PAIR list of an offset, which is sparse in
-// the rows (~20 % of the rows have a given neighbour), so a CTA first compacts the valid (row, source) pairs of a 256-row block
-// into shared memory and then runs 32-pair chunks: dy rows and gathered a rows staged as [32][64] tiles, 256 threads with a 4 x 4
-// register tile each (two 128-bit shared-memory reads per 16 FMAs).  Grid = (row splits, cout tiles x cin tiles, offsets); the
+// the rows (~20 % of the rows have a given neighbour), so a CTA first compacts the valid (row, source) pairs of a 1024-row block
+// into shared memory and then runs 32-pair chunks: dy rows and gathered a rows staged as [32][128] tiles (the next chunk's rows
+// are in flight in registers meanwhile), 256 threads with an 8 x 8 register tile each (four 128-bit shared-memory reads per 64
+// FMAs; 64 x 64 tiles / 4 x 4 per thread for narrow layers).  Grid = (row splits, cout tiles x cin tiles, offsets); the
 // splits write partial tiles that a second kernel sums in a fixed order.  A tcgen05 version needs MN-major operand tiles (the
 // reduction runs over rows, which are the slow dimension of both operands); not built — DESIGN.md section 8.
 #include "common.cuh"
 
 namespace fsfb {
 
-constexpr int kWgTile = 64;      // cout tile = cin tile
-constexpr int kWgChunk = 32;     // pairs per FMA chunk
-constexpr int kWgBlockRows = 256;
+constexpr int kWgChunk = 32;        // pairs per FMA chunk
+constexpr int kWgBlockRows = 1024;  // rows compacted at a time (four per thread)
 
-__global__ void __launch_bounds__(256)
+// T x T outputs per thread, 16 x 16 threads: tiles of 64 x 64 (T = 4) or 128 x 128 (T = 8) weights.
+// VEC: both operands allow 128-bit loads (16-byte aligned bases, strides and widths that are multiples of 4).
+template <int T, bool VEC>
+__global__ void __launch_bounds__(256, T == 8 ? 2 : 4)
     k_conv_wgrad(const float* __restrict__ a, int64_t a_rows, int cin, int64_t a_stride, const float* __restrict__ dy, int64_t rows,
                  int cout, int64_t dy_stride, const int32_t* __restrict__ nbr, int ci_tiles, int64_t rows_per_split,
                  float* __restrict__ part) {
-  __shared__ __align__(16) float s_dy[kWgChunk][kWgTile + 4];
-  __shared__ __align__(16) float s_a[kWgChunk][kWgTile + 4];
+  constexpr int kTile = 16 * T;
+  constexpr int kV = kTile / 32;   // float4 pieces per thread, operand and chunk (32 pairs x kTile floats / 256 threads / 4)
+  __shared__ __align__(16) float s_dy[kWgChunk][kTile + 4];
+  __shared__ __align__(16) float s_a[kWgChunk][kTile + 4];
   __shared__ int s_row[kWgBlockRows], s_src[kWgBlockRows];
   __shared__ int s_warp[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = blockIdx.z, split = blockIdx.x;
-  const int co0 = (blockIdx.y / ci_tiles) * kWgTile, ci0 = (blockIdx.y % ci_tiles) * kWgTile;
-  const int ty = tid >> 4, tx = tid & 15;   // 4 x 4 outputs: co = co0 + 4 ty + i, ci = ci0 + 4 tx + j
-  float acc[4][4];
+  const int co0 = (blockIdx.y / ci_tiles) * kTile, ci0 = (blockIdx.y % ci_tiles) * kTile;
+  // outputs of a thread: co = co0 + 4 ty + (i & 3) + 64 (i >> 2), ci likewise with tx — groups of four 64 apart, so that the
+  // sixteen tx lanes of a 128-bit shared-memory read touch 256 contiguous bytes (no bank conflicts)
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[T][T];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < T; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
+  // staging: thread = (pair p = tid / 8, float4 pieces (tid % 8) + 8 v of the pair's two tile rows)
+  const int sp = tid >> 3, sq = tid & 7;
+  float4 rd[kV], ra[kV];
+  auto fetch = [&](int64_t rb, int p0, int total) {   // chunk [p0, p0 + 32) of the compacted pairs → registers
+    const bool live = p0 + sp < total;
+    const float* dr = dy + (rb + (live ? s_row[p0 + sp] : 0)) * dy_stride + co0;
+    const float* ar = a + (int64_t)(live ? s_src[p0 + sp] : 0) * a_stride + ci0;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const int c = 4 * (sq + 8 * v);
+      if (VEC) {
+        rd[v] = (live && co0 + c < cout) ? __ldg(reinterpret_cast<const float4*>(dr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ra[v] = (live && ci0 + c < cin) ? __ldg(reinterpret_cast<const float4*>(ar + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        rd[v].x = (live && co0 + c < cout) ? __ldg(dr + c) : 0.f;
+        rd[v].y = (live && co0 + c + 1 < cout) ? __ldg(dr + c + 1) : 0.f;
+        rd[v].z = (live && co0 + c + 2 < cout) ? __ldg(dr + c + 2) : 0.f;
+        rd[v].w = (live && co0 + c + 3 < cout) ? __ldg(dr + c + 3) : 0.f;
+        ra[v].x = (live && ci0 + c < cin) ? __ldg(ar + c) : 0.f;
+        ra[v].y = (live && ci0 + c + 1 < cin) ? __ldg(ar + c + 1) : 0.f;
+        ra[v].z = (live && ci0 + c + 2 < cin) ? __ldg(ar + c + 2) : 0.f;
+        ra[v].w = (live && ci0 + c + 3 < cin) ? __ldg(ar + c + 3) : 0.f;
+      }
+    }
+  };
   const int64_t r_beg = (int64_t)split * rows_per_split, r_end = min(rows, r_beg + rows_per_split);
   for (int64_t rb = r_beg; rb < r_end; rb += kWgBlockRows) {
-    // ---- compact the valid pairs of this 256-row block (ascending rows: a fixed summation order) ----
-    const int64_t r = rb + tid;
-    int src = -1;
-    if (r < r_end) src = nbr ? __ldg(nbr + (int64_t)k * rows + r) : (int)r;
-    const bool ok = src >= 0 && src < a_rows;
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) s_warp[warp] = __popc(bal);
-    __syncthreads();   // (also: the previous block's chunks are done with s_row / s_src)
-    int before = 0, total = 0;
+    // ---- compact the valid pairs of this row block (ascending rows: a fixed summation order) ----
+    int total = 0;
+    __syncthreads();   // the previous block's chunks are done with s_row / s_src
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const int c = s_warp[w];
-      before += w < warp ? c : 0;
-      total += c;
+    for (int pass = 0; pass < kWgBlockRows / 256; ++pass) {
+      const int64_t r = rb + pass * 256 + tid;
+      int src = -1;
+      if (r < r_end) src = nbr ? __ldg(nbr + (int64_t)k * rows + r) : (int)r;
+      const bool ok = src >= 0 && src < a_rows;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_warp[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, here = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int c = s_warp[w];
+        before += w < warp ? c : 0;
+        here += c;
+      }
+      if (ok) {
+        const int pos = total + before + __popc(bal & ((1u << lane) - 1u));
+        s_row[pos] = pass * 256 + tid;
+        s_src[pos] = src;
+      }
+      total += here;
+      __syncthreads();
     }
-    if (ok) {
-      const int pos = before + __popc(bal & ((1u << lane) - 1u));
-      s_row[pos] = (int)(r - rb);
-      s_src[pos] = src;
-    }
-    __syncthreads();
-    // ---- 32-pair chunks ----
+    // ---- 32-pair chunks; the next chunk's rows are in flight while this one multiplies ----
+    if (total > 0) fetch(rb, 0, total);
     for (int p0 = 0; p0 < total; p0 += kWgChunk) {
-      const int np = min(kWgChunk, total - p0);
-      // stage dy[row][co0 .. co0+63] and a[src][ci0 .. ci0+63]: thread = (pair p = tid / 8, 8 floats at 8 (tid % 8))
-      {
-        const int p = tid >> 3, q = (tid & 7) * 8;
-        const bool live = p < np;
-        const float* dr = dy + (rb + (live ? s_row[p0 + p] : 0)) * dy_stride + co0 + q;
-        const float* ar = a + (int64_t)(live ? s_src[p0 + p] : 0) * a_stride + ci0 + q;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          s_dy[p][q + e] = (live && co0 + q + e < cout) ? __ldg(dr + e) : 0.f;
-          s_a[p][q + e] = (live && ci0 + q + e < cin) ? __ldg(ar + e) : 0.f;
-        }
+      for (int v = 0; v < kV; ++v) {
+        const int c = 4 * (sq + 8 * v);
+        *reinterpret_cast<float4*>(&s_dy[sp][c]) = rd[v];
+        *reinterpret_cast<float4*>(&s_a[sp][c]) = ra[v];
       }
       __syncthreads();
-#pragma unroll 8
+      if (p0 + kWgChunk < total) fetch(rb, p0 + kWgChunk, total);
+#pragma unroll 4
       for (int p = 0; p < kWgChunk; ++p) {
-        const float4 d4 = *reinterpret_cast<const float4*>(&s_dy[p][4 * ty]);
-        const float4 a4 = *reinterpret_cast<const float4*>(&s_a[p][4 * tx]);
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+        float d[T], av[T];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < T; i += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(&s_dy[p][4 * ty + 16 * i]);
+          const float4 a4 = *reinterpret_cast<const float4*>(&s_a[p][4 * tx + 16 * i]);
+          d[i] = d4.x; d[i + 1] = d4.y; d[i + 2] = d4.z; d[i + 3] = d4.w;
+          av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(d[i], av[j], acc[i][j]);
+        for (int i = 0; i < T; ++i)
+#pragma unroll
+          for (int j = 0; j < T; ++j) acc[i][j] = fmaf(d[i], av[j], acc[i][j]);
       }
       __syncthreads();
     }
@@ -92,12 +130,12 @@ __global__ void __launch_bounds__(256)
   // partial tile of this split: part[split][k][cout][cin]
   float* out = part + ((int64_t)split * gridDim.z + k) * cout * cin;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int co = co0 + 4 * ty + i;
+  for (int i = 0; i < T; ++i) {
+    const int co = co0 + 4 * ty + (i & 3) + 64 * (i >> 2);
     if (co >= cout) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ci = ci0 + 4 * tx + j;
+    for (int j = 0; j < T; ++j) {
+      const int ci = ci0 + 4 * tx + (j & 3) + 64 * (j >> 2);
       if (ci < cin) out[(int64_t)co * cin + ci] = acc[i][j];
     }
   }
@@ -112,8 +150,9 @@ __global__ void __launch_bounds__(256) k_conv_wgrad_reduce(const float* __restri
   }
 }
 
+static int wgrad_tile(int cin, int cout) { return (cin >= 96 && cout >= 96) ? 128 : 64; }
 static int wgrad_splits(int64_t rows, int koff, int tiles) {
-  const int64_t by_rows = std::max<int64_t>(1, rows / 2048);                          // at least eight row blocks per split
+  const int64_t by_rows = std::max<int64_t>(1, rows / (2 * kWgBlockRows));            // at least two row blocks per split
   const int64_t want = std::max<int64_t>(1, ceil_div((int64_t)kNumSMs * 4, (int64_t)koff * tiles));
   return (int)std::min<int64_t>(std::min(by_rows, want), 64);
 }
@@ -125,7 +164,8 @@ extern "C" {
 int fsfb_conv_wgrad_workspace_bytes(int64_t rows, int koff, int cin, int cout, size_t* bytes) {
   using namespace fsfb;
   FSFB_CHECK_ARG(bytes && rows >= 0 && koff >= 1 && cin >= 1 && cout >= 1, "conv_wgrad_workspace_bytes: bad argument");
-  const int tiles = (int)(ceil_div(cout, kWgTile) * ceil_div(cin, kWgTile));
+  const int tile = wgrad_tile(cin, cout);
+  const int tiles = (int)(ceil_div(cout, tile) * ceil_div(cin, tile));
   const int splits = wgrad_splits(rows, koff, tiles);
   Workspace ws(nullptr, 0);
   if (splits > 1) ws.take<float>((size_t)splits * koff * cout * cin);
@@ -151,8 +191,9 @@ int fsfb_conv_wgrad(const float* a, int64_t a_rows, int cin, int64_t a_stride, c
     return FSFB_OK;
   }
   FSFB_CHECK_ARG(a && dy, "conv_wgrad: null pointer");
-  const int ci_tiles = (int)ceil_div(cin, kWgTile);
-  const int tiles = (int)ceil_div(cout, kWgTile) * ci_tiles;
+  const int tile = wgrad_tile(cin, cout);
+  const int ci_tiles = (int)ceil_div(cin, tile);
+  const int tiles = (int)ceil_div(cout, tile) * ci_tiles;
   const int splits = wgrad_splits(rows, koff, tiles);
   float* part = dw;
   if (splits > 1) {
@@ -165,7 +206,16 @@ int fsfb_conv_wgrad(const float* a, int64_t a_rows, int cin, int64_t a_stride, c
   }
   const int64_t rows_per_split = ceil_div(ceil_div(rows, splits), kWgBlockRows) * kWgBlockRows;
   const dim3 grid((unsigned)splits, (unsigned)tiles, (unsigned)koff);
-  FSFB_LAUNCH(k_conv_wgrad, grid, 256, 0, st, a, a_rows, cin, a_stride, dy, rows, cout, dy_stride, nbr, ci_tiles, rows_per_split, part);
+  const bool vec = ((uintptr_t)a % 16 == 0) && ((uintptr_t)dy % 16 == 0) && a_stride % 4 == 0 && dy_stride % 4 == 0 && cin % 4 == 0 &&
+                   cout % 4 == 0;
+#define WG_LAUNCH(T, V) \
+  FSFB_LAUNCH((k_conv_wgrad<T, V>), grid, 256, 0, st, a, a_rows, cin, a_stride, dy, rows, cout, dy_stride, nbr, ci_tiles, rows_per_split, part)
+  if (tile == 128) {
+    if (vec) WG_LAUNCH(8, true); else WG_LAUNCH(8, false);
+  } else {
+    if (vec) WG_LAUNCH(4, true); else WG_LAUNCH(4, false);
+  }
+#undef WG_LAUNCH
   if (splits > 1) {
     const int rgrid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
     FSFB_LAUNCH(k_conv_wgrad_reduce, rgrid, 256, 0, st, part, n, splits, dw);
