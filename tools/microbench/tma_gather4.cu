@@ -81,13 +81,15 @@ __global__ void __launch_bounds__(64) k_tma(const __grid_constant__ CUtensorMap 
 }
 
 // ---- the same gather with 16-byte cp.async copies (4 producer warps, thread = (piece, rows r0 + 16 i)), as k_gather_gemm_ss<3> ----
-__global__ void __launch_bounds__(160) k_cpasync(const unsigned char* __restrict__ a, int64_t rows, int row_bytes, const int* __restrict__ idx,
+template <int PW, bool ZST = false, int ARR = 1>   // ARR: one of ARR lanes arrives on the slot barrier (timing experiment only when > 1)
+   // producer warps: 4 (as k_gather_gemm_ss<3>) or 8 / 16; ZST: missing rows zeroed by a plain store instead of a zero-size cp.async
+__global__ void __launch_bounds__(PW * 32 + 32) k_cpasync(const unsigned char* __restrict__ a, int64_t rows, int row_bytes, const int* __restrict__ idx,
                                                  int64_t n_stages, int col_pieces, unsigned long long* clk, int slots) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long full[kSlots], empty[kSlots];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&full[s]), 128); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(smem_u32(&full[s]), PW * 32 / ARR); mbar_init(smem_u32(&empty[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   int* s_idx = reinterpret_cast<int*>(smem + (size_t)kSlots * kRows * kRowBytes);
@@ -100,20 +102,27 @@ __global__ void __launch_bounds__(160) k_cpasync(const unsigned char* __restrict
   int ls = 0;
   for (int64_t st = blockIdx.x; st < n_stages; st += gridDim.x, ++ls) {
     const uint32_t slot = smem_u32(smem) + (uint32_t)s * kRows * kRowBytes;
-    if (warp < 4) {
+    if (warp < PW) {
       if (lane == 0) mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
       __syncwarp();
       const int piece = tid & 7, r0 = tid >> 3;
       const int col = (int)(st % col_pieces) * kRowBytes + piece * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = r0 + 16 * i;
+      for (int i = 0; i < 32 / PW; ++i) {
+        const int row = r0 + 4 * PW * i;
         const int src = s_idx[ls * kRows + row];
         const bool ok = (unsigned)src < (unsigned)rows;
         const unsigned char* g = a + (size_t)(ok ? src : 0) * row_bytes + col;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot + (uint32_t)row * kRowBytes + (uint32_t)((piece ^ (row & 7)) << 4)), "l"(g), "r"(ok ? 16 : 0) : "memory");
+        const uint32_t dst = slot + (uint32_t)row * kRowBytes + (uint32_t)((piece ^ (row & 7)) << 4);
+        if (ZST) {
+          if (ok) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+          else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0) : "memory");
+        } else {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(g), "r"(ok ? 16 : 0) : "memory");
+        }
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+      if (ZST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (ARR == 1 || (tid % ARR) == 0) asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
     } else {
       if (lane == 0) mbar_wait(smem_u32(&full[s]), ph);
       __syncwarp();
@@ -125,10 +134,11 @@ __global__ void __launch_bounds__(160) k_cpasync(const unsigned char* __restrict
   }
   const long long t1 = clock64();
   if (acc == 0x12345678u && clk == nullptr) printf("x");
-  if (tid == 128) clk[blockIdx.x] = (unsigned long long)(t1 - t0);
+  if (tid == PW * 32) clk[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const int zero_pct = argc > 1 ? atoi(argv[1]) : 40;   // share of "no neighbour" rows
   const int64_t M = 160000;            // rows of the operand matrix (the frame's level-0 voxels)
   const int row_bytes = 512;           // 128 channels, pre-split format
   const int col_pieces = row_bytes / kRowBytes;
@@ -137,7 +147,7 @@ int main() {
   for (size_t i = 0; i < h.size(); ++i) h[i] = (unsigned char)((i * 2654435761u) >> 13);
   std::vector<int> hidx((size_t)n_stages * kRows);
   uint32_t seed = 12345;
-  for (auto& v : hidx) { seed = seed * 1664525u + 1013904223u; v = (seed >> 8) % 10 < 4 ? -1 : (int)((seed >> 4) % M); }   // 40 % "no neighbour"
+  for (auto& v : hidx) { seed = seed * 1664525u + 1013904223u; v = (int)((seed >> 8) % 100) < zero_pct ? -1 : (int)((seed >> 4) % M); }
   unsigned char* d_a; int* d_idx; unsigned long long* d_clk; uint32_t* d_check;
   CK(cudaMalloc(&d_a, h.size())); CK(cudaMemcpy(d_a, h.data(), h.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_idx, hidx.size() * 4)); CK(cudaMemcpy(d_idx, hidx.data(), hidx.size() * 4, cudaMemcpyHostToDevice));
@@ -195,20 +205,32 @@ int main() {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     CK(cudaMemcpy(clk.data(), d_clk, 148 * 8, cudaMemcpyDeviceToHost));
     double mx = 0; for (auto c : clk) mx = c > mx ? c : mx;
-    const double bytes = (double)n_stages * kRows * kRowBytes * 0.6;   // 40 % of the rows are zero fill
+    const double bytes = (double)n_stages * kRows * kRowBytes * (1.0 - zero_pct / 100.0);
     printf("TMA gather4 (1 issuing warp, %d slots): %.3f ms, %.1f B/clk/SM of real rows (%.0f clk per 128-row stage)\n", slots, ms, bytes / 148 / mx,
            mx / (n_stages / 148.0));
-    CK(cudaFuncSetAttribute(k_cpasync, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlots * kRows * kRowBytes + kStagesPerCta * kRows * 4));
-    for (int rep = 0; rep < 2; ++rep) {
-      CK(cudaEventRecord(e0));
-      k_cpasync<<<148, 160, kSlots * kRows * kRowBytes + kStagesPerCta * kRows * 4>>>(d_a, M, row_bytes, d_idx, n_stages, col_pieces, d_clk, slots);
-      CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
-    }
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    CK(cudaMemcpy(clk.data(), d_clk, 148 * 8, cudaMemcpyDeviceToHost));
-    mx = 0; for (auto c : clk) mx = c > mx ? c : mx;
-    printf("cp.async 16 B  (4 issuing warps, %d slots): %.3f ms, %.1f B/clk/SM of real rows (%.0f clk per 128-row stage)\n", slots, ms, bytes / 148 / mx,
-           mx / (n_stages / 148.0));
+    auto run_cp = [&](auto kern, int pw) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSlots * kRows * kRowBytes + kStagesPerCta * kRows * 4));
+      for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(e0));
+        kern<<<148, pw * 32 + 32, kSlots * kRows * kRowBytes + kStagesPerCta * kRows * 4>>>(d_a, M, row_bytes, d_idx, n_stages, col_pieces, d_clk, slots);
+        CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
+      }
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      CK(cudaMemcpy(clk.data(), d_clk, 148 * 8, cudaMemcpyDeviceToHost));
+      mx = 0; for (auto c : clk) mx = c > mx ? c : mx;
+      printf("cp.async 16 B  (%d issuing warps, %d slots, %d %% zero fill): %.3f ms, %.0f clk per 128-row stage\n", pw, slots, zero_pct, ms,
+             mx / (n_stages / 148.0));
+    };
+    run_cp(k_cpasync<4>, 4);
+    run_cp(k_cpasync<8>, 8);
+    run_cp(k_cpasync<16>, 16);
+    printf("  missing rows by plain zero stores:\n");
+    run_cp(k_cpasync<4, true>, 4);
+    run_cp(k_cpasync<8, true>, 8);
+    printf("  one arrival per 8 / 32 lanes (completion of the other lanes' copies NOT tracked: timing only):\n");
+    run_cp(k_cpasync<4, false, 8>, 4);
+    run_cp(k_cpasync<4, false, 32>, 4);
+    run_cp(k_cpasync<8, false, 32>, 8);
   }
   return 0;
 }
