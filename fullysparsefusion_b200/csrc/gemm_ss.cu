@@ -583,6 +583,14 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
             if (lane == 0) mbar_wait(smem_u32(&sh->tbl_empty[tb]), ((seq >> 1) + 1u) & 1u);
             __syncwarp();
           }
+          if (P.nbr_ro) {   // table permuted into the row order, padded to whole tiles: 27 contiguous 512-byte runs
+            const int64_t stride = (P.rows + kTcRows - 1) / kTcRows * kTcRows;
+            const int32_t* src = P.nbr + U.row0 + 4 * lane;
+            for (int k = 0; k < P.koff; ++k)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(nb + (uint32_t)(k * kTcRows + 4 * lane) * 4u),
+                           "l"(src + (int64_t)k * stride)
+                           : "memory");
+          } else {
           int64_t r[4];
 #pragma unroll
           for (int rq = 0; rq < 4; ++rq) {
@@ -601,6 +609,7 @@ __global__ void __launch_bounds__(kSsThreads, 1) k_gather_gemm_ss(const __grid_c
             } else {
               for (int k = 0; k < P.koff; ++k) sts_i32(nb + (uint32_t)(k * kTcRows + r_l) * 4u, -1);
             }
+          }
           }
           asm volatile("cp.async.wait_all;" ::: "memory");
           __syncwarp();

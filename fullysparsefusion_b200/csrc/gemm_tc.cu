@@ -281,6 +281,9 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
                             const float* residual, int64_t residual_stride, int act, float* out,
                             int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, const float* host_bias,
                             const float* host_norm_w, const float* host_norm_b, void* stream, bool a_split = false) {
+  const bool nbr_ro = (act & FSFB_NBR_ROW_ORDERED) != 0;   // include/fsf_b200.h: the table is permuted into the row order
+  act &= ~FSFB_NBR_ROW_ORDERED;
+  FSFB_CHECK_ARG(!nbr_ro || (a_split && nbr && row_order), "gather_gemm: FSFB_NBR_ROW_ORDERED needs fsfb_gather_gemm_split with a row order");
   int rc = check_epilogue(cout, bias, norm, norm_w, norm_b, act, "gather_gemm");
   if (rc != FSFB_OK) return rc;
   FSFB_CHECK_ARG(rows >= 0 && a_rows >= 0 && a_rows < (1ll << 31) && cin >= 1 && a_stride >= cin &&
@@ -302,6 +305,7 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
   P.a_stride = a_stride;
   P.nbr = nbr;
   P.row_order = row_order;
+  P.nbr_ro = nbr_ro ? 1 : 0;
   P.koff = koff;
   P.rows = rows;
   P.w_packed = (const unsigned char*)w_packed;

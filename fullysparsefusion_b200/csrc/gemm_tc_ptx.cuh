@@ -170,6 +170,7 @@ struct TcParams {
   // offsets of the regions behind the A / W rings
   int ss_a_stages, ss_w_stages, ss_tile_w, ss_acc_cols, ss_bufs, ss_stage_stride;
   uint32_t ss_w_slot, ss_off_w, ss_off_nbr, ss_off_stage, ss_off_vec, ss_off_sh;
+  int nbr_ro;                 // nbr is permuted into the row order, row stride round_up(rows, 128) (FSFB_NBR_ROW_ORDERED)
   unsigned int* ss_overflow;  // device counter: launches that saw an input outside fp16 range (|a| >= 65504)
 };
 

@@ -428,7 +428,7 @@ class SIR(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class Rulebook:
     """Neighbour table of one indice_key plus the mask-sorted row order the gather-GEMM tiles walk."""
-    __slots__ = ("nbr", "order")
+    __slots__ = ("nbr", "order", "nbr_ro")
 
     def __init__(self, nbr: torch.Tensor, sort_rows: bool = True):
         self.nbr = nbr
@@ -436,6 +436,8 @@ class Rulebook:
         # its rows has (21 → ~11 of 27 offsets per tile on LiDAR voxel sets); results do not depend on the order
         # (the sort is ~12 small launches: only worth it for the big levels)
         self.order = ops.rulebook_row_order(nbr) if sort_rows and nbr.size(0) > 1 and nbr.size(1) >= 50000 else None
+        # the table once more in that order (tile tables become contiguous runs for the kernel's scheduler warp)
+        self.nbr_ro = ops.permute_rulebook(nbr, self.order) if self.order is not None else None
 
 
 class SparseConvModule(nn.Module):
@@ -457,7 +459,7 @@ class SparseConvModule(nn.Module):
         self._pack = None
 
     def forward(self, feats, rb, out=None, residual=None, residual_post=False):
-        nbr, order = (rb.nbr, rb.order) if isinstance(rb, Rulebook) else (rb, None)
+        nbr, order, nbr_ro = (rb.nbr, rb.order, rb.nbr_ro) if isinstance(rb, Rulebook) else (rb, None, None)
         if self._pack is None:
             n = self.bn
             scale = n.weight.detach().float() / torch.sqrt(n.running_var.float() + n.eps)
@@ -465,7 +467,7 @@ class SparseConvModule(nn.Module):
             self._pack = (ops.gemm_prepack(self.weight.detach().float()), scale.contiguous(), shift.contiguous())
         w, scale, shift = self._pack
         return ops.gather_gemm(feats, w, nbr=nbr, norm="affine", norm_w=scale, norm_b=shift, residual=residual,
-                               act=self.act, out=out, residual_post=residual_post, row_order=order)
+                               act=self.act, out=out, residual_post=residual_post, row_order=order, nbr_ro=nbr_ro)
 
 
 class SparseBasicBlock(nn.Module):

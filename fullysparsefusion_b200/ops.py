@@ -542,7 +542,8 @@ def _pick_splits(rows: int, cpad: int, koff: int, kc: int) -> int:
 def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = None, rows: Optional[int] = None,
                 bias=None, norm=None, norm_w=None, norm_b=None, eps: float = 1e-5, residual=None, act=None,
                 out: Optional[torch.Tensor] = None, simt: bool = False, residual_post: bool = False,
-                row_order: Optional[torch.Tensor] = None, splits: Optional[int] = None) -> torch.Tensor:
+                row_order: Optional[torch.Tensor] = None, splits: Optional[int] = None,
+                nbr_ro: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r] = act(norm(sum_k a[nbr[k][r]] @ w[k].T + bias) + residual)  (include/fsf_b200.h).
 
     splits: offset ranges run as independent work units (fsfb_gather_gemm_splitk); None picks it from the shape
@@ -597,6 +598,10 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
         a_s = split_rows(a)
         ws = torch.empty(splits * rows * cpad, dtype=torch.float32, device=dev) if splits > 1 else None
         hv = w.cout <= 128 and splits == 1
+        if nbr_ro is not None and row_order is not None:   # the table permuted into the row order (permute_rulebook): contiguous tile tables
+            assert nbr_ro.dtype == torch.int32 and nbr_ro.is_contiguous() and tuple(nbr_ro.shape) == (w.koff, (rows + 127) // 128 * 128)
+            nbr = nbr_ro
+            tail = tail[:8] + (tail[8] | 0x200,) + tail[9:]   # FSFB_NBR_ROW_ORDERED rides in `act`
         with prof:
             check(lib.fsfb_gather_gemm_split(_ptr(a_s), a.size(0), w.cin, _ptr(nbr), _ptr(row_order), w.koff, rows, _ptr(w.data), *tail[:-1],
                                              splits, _ptr(ws), ws.numel() * 4 if ws is not None else 0,
@@ -1016,6 +1021,15 @@ def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers,
                                         h1, h2, _ptr(w1), _ptr(g1), _ptr(b1), _ptr(w2), _ptr(g2), _ptr(b2), _ptr(w3), _ptr(g3),
                                         _ptr(b3), float(eps), _ACTS[act], _ptr(out), out.stride(0) if n else c, _stream(dev))
     check(rc, "fsfb_sir_gate_input")
+    return out
+
+
+def permute_rulebook(nbr: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
+    """nbr [koff, rows] and a row order → the table in that order, padded to whole 128-row tiles with -1
+    ([koff, round_up(rows, 128)] i32): what FSFB_NBR_ROW_ORDERED expects (include/fsf_b200.h).  Once per rulebook."""
+    koff, rows = nbr.shape
+    out = torch.full((koff, (rows + 127) // 128 * 128), -1, dtype=torch.int32, device=nbr.device)
+    out[:, :rows].copy_(nbr.index_select(1, order.long()))
     return out
 
 

@@ -38,6 +38,11 @@ extern "C" {
 #define FSFB_ACT_RELU 1
 #define FSFB_ACT_GELU 2
 #define FSFB_RESIDUAL_POST 0x100 /* OR into `act`: y = act(norm(x + bias)) + residual (default adds before act) */
+/* OR into `act` (fsfb_gather_gemm_split with a row_order only): `nbr` is already permuted into the row order and padded —
+ * nbr[k][i] = neighbour of output row row_order[i], row stride round_up(rows, 128), padding = -1 — so that a tile's table is
+ * 27 contiguous 512-byte runs instead of 27 x 128 scattered words (the scattered form cost as much load/store-unit time as the
+ * operand gather itself: profiles/r2_ncu_summary.md section 2). */
+#define FSFB_NBR_ROW_ORDERED 0x200
 
 #define FSFB_NORM_NONE 0
 #define FSFB_NORM_LAYERNORM 1 /* per-row LN over channels (mmcv 'LN')            */

@@ -133,6 +133,18 @@ def test_gather_gemm_large_vs_simt(cuda):
     assert torch.equal(torch.sort(order.long())[0], torch.arange(m, device=cuda))
     got2 = ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order)
     torch.testing.assert_close(got2, want, rtol=1e-4, atol=1e-4)
+    # the table permuted into that order and padded to whole tiles (FSFB_NBR_ROW_ORDERED): bit-identical results
+    nbr_ro = ops.permute_rulebook(nbr, order)
+    assert nbr_ro.shape == (koff, (m + 127) // 128 * 128) and bool((nbr_ro[:, m:] == -1).all())
+    got3 = ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order, nbr_ro=nbr_ro)
+    assert torch.equal(got3, got2)
+    m2 = 70_001                                  # a ragged last tile and a sparse table: padding rows stay without neighbours
+    nbr2 = torch.randint(0, m2, (koff, m2), device=cuda, generator=g, dtype=torch.int32)
+    nbr2[torch.rand(koff, m2, device=cuda, generator=g) > 0.2] = -1
+    a2 = torch.randn(m2, c, device=cuda, generator=g)
+    order2 = ops.rulebook_row_order(nbr2)
+    ref2 = ops.gather_gemm(a2, pw, nbr=nbr2, act="relu", row_order=order2)
+    assert torch.equal(ops.gather_gemm(a2, pw, nbr=nbr2, act="relu", row_order=order2, nbr_ro=ops.permute_rulebook(nbr2, order2)), ref2)
 
 
 @pytest.mark.parametrize("rows,a_rows,koff,cin,cout,splits,density", [(300, 300, 27, 64, 256, 3, 0.4), (1100, 900, 27, 256, 512, 4, 0.3),

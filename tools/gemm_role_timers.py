@@ -16,6 +16,7 @@ c4 = F.pad(ops.voxelize(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, floor_mode=0), 
 plan = M.ScatterPlan(c4, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], want_index=True)
 nbr = ops.conv_rulebook(plan.new_coors, plan.index, 3, 1, 1)
 order = ops.rulebook_row_order(nbr)
+nbr_ro = ops.permute_rulebook(nbr, order)
 a = torch.randn(plan.m, 128, device=dev, generator=g)
 a133 = ops.empty_rows(plan.m, 133, dev); a133.copy_(torch.randn(plan.m, 133, device=dev, generator=g))
 w = ops.gemm_prepack(torch.randn(27, 128, 128, device=dev, generator=g) * 0.03)
@@ -28,7 +29,7 @@ names = ["p_empty", "p_conv", "p_fetch", "p_stages", "mma_open", "mma_w", "mma_a
          "epi_out", "epi_units"]
 print("rows", plan.m, "pairs/row", float((nbr >= 0).sum()) / plan.m)
 for label, fn in (("split_rows only (timers below are stale)", lambda: ops.split_rows(a)),
-                  ("conv sorted 128x128", lambda: ops.gather_gemm(a, w, nbr=nbr, act="relu", row_order=order)),
+                  ("conv sorted 128x128", lambda: ops.gather_gemm(a, w, nbr=nbr, act="relu", row_order=order, nbr_ro=nbr_ro)),
                   ("conv natural 128x128", lambda: ops.gather_gemm(a, w, nbr=nbr, act="relu")),
                   ("linear 128x128 bias relu", lambda: ops.gather_gemm(a, lin_w, bias=bias, act="relu")),
                   ("linear 128x128 plain", lambda: ops.gather_gemm(a, lin_w)),
