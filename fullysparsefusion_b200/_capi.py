@@ -62,6 +62,7 @@ SIGNATURES = {
     "fsfb_nms_emit": (_i, [_p, _i64, _i, _p, _i64, _i64, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "fsfb_decode_boxes": (_i, [_p, _i64, _i, _i64, _p, _i64, _p, _i64, _p, _p]),
     "fsfb_dynamic_point_pool_workspace_bytes": (_i, [_i64, _i, _p]),
+    "fsfb_permute_rulebook": (_i, [_p, _i, _i64, _p, _p, _p]),
     "fsfb_conv_wgrad_workspace_bytes": (_i, [_i64, _i, _i, _i, _p]),
     "fsfb_conv_wgrad": (_i, [_p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i, _p, _p, _sz, _p]),
     "fsfb_dynamic_point_pool": (_i, [_p, _i64, _p, _i64, _i64, _p, _i, _i64, _p, _p, _p, _p, _p, _sz, _p]),

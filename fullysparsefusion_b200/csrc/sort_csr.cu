@@ -346,6 +346,17 @@ static int csr_build_impl(const void* index, int index_i64, int64_t n, int64_t m
 
 }  // namespace fsfb
 
+namespace fsfb {
+__global__ void __launch_bounds__(256)
+    k_permute_rulebook(const int32_t* __restrict__ nbr, int koff, int64_t rows, int64_t stride, const int32_t* __restrict__ order,
+                       int32_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < stride; i += (int64_t)gridDim.x * 256) {
+    const int64_t src = i < rows ? (int64_t)__ldg(order + i) : -1;
+    for (int k = 0; k < koff; ++k) out[(int64_t)k * stride + i] = src >= 0 ? __ldg(nbr + (int64_t)k * rows + src) : -1;
+  }
+}
+}  // namespace fsfb
+
 extern "C" {
 
 int fsfb_csr_workspace_bytes(int64_t n, int64_t m, size_t* bytes) {
@@ -400,6 +411,19 @@ int fsfb_rulebook_row_order(const int32_t* nbr, int koff, int64_t rows, int32_t*
   FSFB_LAUNCH(k_rulebook_masks, grid, 256, 0, st, nbr, koff, rows, mask, mode);
   // stable LSD sort of the keys: rows with the same set of neighbour offsets become adjacent, fewest offsets first
   return radix_sort_index<int>(mask, rows, rulebook_key((1u << koff) - 1u, koff, mode), keys, (uint32_t*)order, tk, tv, hist, st);
+}
+
+/* out[k][i] = nbr[k][order[i]] for i < rows, -1 for rows <= i < stride = round_up(rows, 128): the neighbour table in the row order,
+ * padded to whole tiles (FSFB_NBR_ROW_ORDERED, include/fsf_b200.h). */
+int fsfb_permute_rulebook(const int32_t* nbr, int koff, int64_t rows, const int32_t* order, int32_t* out, void* stream) {
+  using namespace fsfb;
+  FSFB_CHECK_ARG(rows >= 0 && rows < (1ll << 31) && koff >= 1 && koff <= 32, "permute_rulebook: bad argument");
+  if (rows == 0) return FSFB_OK;
+  FSFB_CHECK_ARG(nbr && order && out, "permute_rulebook: null pointer");
+  const int64_t stride = ceil_div(rows, 128) * 128;
+  const int grid = (int)std::min<int64_t>(ceil_div(stride, 256), (int64_t)kNumSMs * 8);
+  FSFB_LAUNCH(k_permute_rulebook, grid, 256, 0, (cudaStream_t)stream, nbr, koff, rows, stride, order, out);
+  return FSFB_OK;
 }
 
 int fsfb_ingroup_workspace_bytes(int64_t n, int64_t m, size_t* bytes) {

@@ -1027,9 +1027,11 @@ def sir_gate_input(features, f_cluster, rel_dist_scaler, xyz_normalizer, layers,
 def permute_rulebook(nbr: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
     """nbr [koff, rows] and a row order → the table in that order, padded to whole 128-row tiles with -1
     ([koff, round_up(rows, 128)] i32): what FSFB_NBR_ROW_ORDERED expects (include/fsf_b200.h).  Once per rulebook."""
+    dev = _need_cuda(nbr, order)
+    assert nbr.dtype == torch.int32 and nbr.dim() == 2 and nbr.is_contiguous() and order.dtype == torch.int32 and order.numel() == nbr.size(1)
     koff, rows = nbr.shape
-    out = torch.full((koff, (rows + 127) // 128 * 128), -1, dtype=torch.int32, device=nbr.device)
-    out[:, :rows].copy_(nbr.index_select(1, order.long()))
+    out = torch.empty((koff, (rows + 127) // 128 * 128), dtype=torch.int32, device=dev)
+    check(load().fsfb_permute_rulebook(_ptr(nbr), koff, rows, _ptr(order), _ptr(out), _stream(dev)), "fsfb_permute_rulebook")
     return out
 
 

@@ -552,6 +552,10 @@ int fsfb_nms_emit(const float* boxes, int64_t box_stride, int box_dim, const int
                   int max_class, int64_t max_num, float* out_boxes, float* out_scores, long long* out_labels, int32_t* out_box_idx,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* The neighbour table in the row order of fsfb_rulebook_row_order, padded with -1 to round_up(rows, 128) columns: the form
+ * FSFB_NBR_ROW_ORDERED expects.  out dev [koff][round_up(rows, 128)] i32.  (No reference counterpart: spconv keeps pair lists.) */
+int fsfb_permute_rulebook(const int32_t* nbr, int koff, int64_t rows, const int32_t* order, int32_t* out, void* stream);
+
 /* -------------------------------------------------------------------------
  * Weight gradient of the gather-GEMM (training)
  * Replaces: the weight-gradient half of the backward of spconv's SubMConv3d / SparseConv3d / SparseInverseConv3d (un-vendored;
