@@ -31,30 +31,42 @@ def transpose_rulebook(nbr: torch.Tensor, n_in: int) -> torch.Tensor:
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, w, nbr):
-        ctx.save_for_backward(a, w, nbr)
-        return ops.gather_gemm(a.contiguous(), ops.gemm_prepack(w.detach()), nbr=nbr)
+    def forward(ctx, a, w, nbr, order, nbr_ro, symmetric):
+        ctx.save_for_backward(a, w, nbr, order, nbr_ro)
+        ctx.symmetric = bool(symmetric)
+        return ops.gather_gemm(a.contiguous(), ops.gemm_prepack(w.detach()), nbr=nbr, row_order=order, nbr_ro=nbr_ro)
 
     @staticmethod
     def backward(ctx, grad_out):
-        a, w, nbr = ctx.saved_tensors
+        a, w, nbr, order, nbr_ro = ctx.saved_tensors
         w3 = w if w.dim() == 3 else w[None]
         g = grad_out.contiguous()
         grad_a = grad_w = None
         if ctx.needs_input_grad[0]:
             wt = w3.detach().transpose(1, 2).contiguous()                  # [koff, cin, cout]: the "weights" of the transposed conv
-            inv = transpose_rulebook(nbr, a.size(0)) if nbr is not None else None
-            grad_a = ops.gather_gemm(g, ops.gemm_prepack(wt), nbr=inv)
+            if nbr is not None and ctx.symmetric:
+                # submanifold rulebook: offset k of output r reads input j exactly when offset koff-1-k of output j reads input r,
+                # so the transposed rulebook is the rulebook itself with the offsets reversed — its row order and row-ordered
+                # table are reused and no transposition runs
+                grad_a = ops.gather_gemm(g, ops.gemm_prepack(wt.flip(0).contiguous()), nbr=nbr, row_order=order, nbr_ro=nbr_ro)
+            else:
+                inv = transpose_rulebook(nbr, a.size(0)) if nbr is not None else None
+                grad_a = ops.gather_gemm(g, ops.gemm_prepack(wt), nbr=inv)
             if grad_a.size(0) != a.size(0):                                # Linear: rows == a rows by construction
                 raise RuntimeError("sparse_conv backward: input gradient has the wrong number of rows")
             grad_a = grad_a[:, : a.size(1)]
         if ctx.needs_input_grad[1]:   # native: csrc/conv_wgrad.cu (pairs compacted per row block, deterministic row splits)
             grad_w = ops.conv_wgrad(a.contiguous(), g, nbr, w3.size(0)).view_as(w)
-        return grad_a, grad_w, None
+        return grad_a, grad_w, None, None, None, None
 
 
-def sparse_conv(a: torch.Tensor, w: torch.Tensor, nbr: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Differentiable gather-GEMM: a [n_in, cin] f32, w [koff, cout, cin] (or [cout, cin] with nbr None), nbr [koff, n_out] i32."""
+def sparse_conv(a: torch.Tensor, w: torch.Tensor, nbr: Optional[torch.Tensor] = None, order: Optional[torch.Tensor] = None,
+                nbr_ro: Optional[torch.Tensor] = None, symmetric: bool = False) -> torch.Tensor:
+    """Differentiable gather-GEMM: a [n_in, cin] f32, w [koff, cout, cin] (or [cout, cin] with nbr None), nbr [koff, n_out] i32.
+    order / nbr_ro: the rulebook's row order and row-ordered table (modules.Rulebook); symmetric: the rulebook is a submanifold
+    one (n_out == n_in, offsets in mirrored order), whose transpose is itself with the offsets reversed."""
     if nbr is None and w.dim() == 3 and w.size(0) != 1:
         raise ValueError("a weight with several offsets needs a rulebook")
-    return _SparseConv.apply(a, w, nbr)
+    if symmetric and (nbr is None or nbr.size(1) != a.size(0)):
+        raise ValueError("a symmetric (submanifold) rulebook has as many outputs as inputs")
+    return _SparseConv.apply(a, w, nbr, order, nbr_ro, symmetric)

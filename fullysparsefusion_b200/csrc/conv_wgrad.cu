@@ -141,6 +141,118 @@ __global__ void __launch_bounds__(256, T == 8 ? 2 : 4)
   }
 }
 
+// The same tiles with the operand chunks copied global -> shared memory by 16-byte cp.async into a double buffer (no staging
+// registers: the 8 x 8 register tile plus a prefetched chunk did not fit 128 registers).  Needs 128-bit aligned operands.
+template <int T>
+__global__ void __launch_bounds__(256, 2)
+    k_conv_wgrad_async(const float* __restrict__ a, int64_t a_rows, int cin, int64_t a_stride, const float* __restrict__ dy, int64_t rows,
+                       int cout, int64_t dy_stride, const int32_t* __restrict__ nbr, int ci_tiles, int64_t rows_per_split,
+                       float* __restrict__ part) {
+  constexpr int kTile = 16 * T;
+  constexpr int kV = kTile / 32;
+  constexpr int kLd = kTile + 4;                       // floats per staged row
+  constexpr int kBuf = 2 * kWgChunk * kLd;             // floats per buffer: dy rows, then a rows
+  extern __shared__ __align__(16) float s_dyn[];       // [2][kBuf] | s_row[1024] | s_src[1024]
+  int* s_row = reinterpret_cast<int*>(s_dyn + 2 * kBuf);
+  int* s_src = s_row + kWgBlockRows;
+  __shared__ int s_warp[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.z, split = blockIdx.x;
+  const int co0 = (blockIdx.y / ci_tiles) * kTile, ci0 = (blockIdx.y % ci_tiles) * kTile;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[T][T];
+#pragma unroll
+  for (int i = 0; i < T; ++i)
+#pragma unroll
+    for (int j = 0; j < T; ++j) acc[i][j] = 0.f;
+  const int sp = tid >> 3, sq = tid & 7;
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_dyn);
+  auto issue = [&](int64_t rb, int p0, int total, int buf) {   // chunk [p0, p0 + 32) → buffer `buf`, one commit group
+    const bool live = p0 + sp < total;
+    const float* dr = dy + (rb + (live ? s_row[p0 + sp] : 0)) * dy_stride + co0;
+    const float* ar = a + (int64_t)(live ? s_src[p0 + sp] : 0) * a_stride + ci0;
+    const uint32_t d_dst = s_base + (uint32_t)(buf * kBuf + sp * kLd) * 4u;
+    const uint32_t a_dst = d_dst + (uint32_t)(kWgChunk * kLd) * 4u;
+#pragma unroll
+    for (int v = 0; v < kV; ++v) {
+      const int c = 4 * (sq + 8 * v);
+      const bool okd = live && co0 + c < cout, oka = live && ci0 + c < cin;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d_dst + (uint32_t)c * 4u), "l"(okd ? dr + c : dy), "r"(okd ? 16 : 0) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_dst + (uint32_t)c * 4u), "l"(oka ? ar + c : a), "r"(oka ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t r_beg = (int64_t)split * rows_per_split, r_end = min(rows, r_beg + rows_per_split);
+  for (int64_t rb = r_beg; rb < r_end; rb += kWgBlockRows) {
+    int total = 0;
+    __syncthreads();   // the previous block's chunks are done with s_row / s_src and both buffers
+#pragma unroll
+    for (int pass = 0; pass < kWgBlockRows / 256; ++pass) {
+      const int64_t r = rb + pass * 256 + tid;
+      int src = -1;
+      if (r < r_end) src = nbr ? __ldg(nbr + (int64_t)k * rows + r) : (int)r;
+      const bool ok = src >= 0 && src < a_rows;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_warp[warp] = __popc(bal);
+      __syncthreads();
+      int before = 0, here = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int c = s_warp[w];
+        before += w < warp ? c : 0;
+        here += c;
+      }
+      if (ok) {
+        const int pos = total + before + __popc(bal & ((1u << lane) - 1u));
+        s_row[pos] = pass * 256 + tid;
+        s_src[pos] = src;
+      }
+      total += here;
+      __syncthreads();
+    }
+    if (total > 0) issue(rb, 0, total, 0);
+    int buf = 0;
+    for (int p0 = 0; p0 < total; p0 += kWgChunk, buf ^= 1) {
+      if (p0 + kWgChunk < total) {
+        issue(rb, p0 + kWgChunk, total, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();   // every thread's copies of this chunk have landed
+      const float* bd = s_dyn + buf * kBuf;
+      const float* ba = bd + kWgChunk * kLd;
+#pragma unroll 4
+      for (int p = 0; p < kWgChunk; ++p) {
+        float d[T], av[T];
+#pragma unroll
+        for (int i = 0; i < T; i += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(bd + p * kLd + 4 * ty + 16 * i);
+          const float4 a4 = *reinterpret_cast<const float4*>(ba + p * kLd + 4 * tx + 16 * i);
+          d[i] = d4.x; d[i + 1] = d4.y; d[i + 2] = d4.z; d[i + 3] = d4.w;
+          av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < T; ++i)
+#pragma unroll
+          for (int j = 0; j < T; ++j) acc[i][j] = fmaf(d[i], av[j], acc[i][j]);
+      }
+      __syncthreads();   // the buffer may be overwritten by the copies of the chunk after next
+    }
+  }
+  float* out = part + ((int64_t)split * gridDim.z + k) * cout * cin;
+#pragma unroll
+  for (int i = 0; i < T; ++i) {
+    const int co = co0 + 4 * ty + (i & 3) + 64 * (i >> 2);
+    if (co >= cout) continue;
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      const int ci = ci0 + 4 * tx + (j & 3) + 64 * (j >> 2);
+      if (ci < cin) out[(int64_t)co * cin + ci] = acc[i][j];
+    }
+  }
+}
+
 // dw[e] = sum over the splits, in split order
 __global__ void __launch_bounds__(256) k_conv_wgrad_reduce(const float* __restrict__ part, int64_t n, int splits, float* __restrict__ dw) {
   for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256) {
@@ -210,8 +322,17 @@ int fsfb_conv_wgrad(const float* a, int64_t a_rows, int cin, int64_t a_stride, c
                    cout % 4 == 0;
 #define WG_LAUNCH(T, V) \
   FSFB_LAUNCH((k_conv_wgrad<T, V>), grid, 256, 0, st, a, a_rows, cin, a_stride, dy, rows, cout, dy_stride, nbr, ci_tiles, rows_per_split, part)
-  if (tile == 128) {
-    if (vec) WG_LAUNCH(8, true); else WG_LAUNCH(8, false);
+  if (tile == 128 && vec) {   // the wide tiles of the convolution layers: cp.async double buffer
+    constexpr size_t smem = (size_t)(2 * 2 * kWgChunk * (128 + 4)) * 4 + (size_t)2 * kWgBlockRows * 4;
+    static bool attr = false;
+    if (!attr) {
+      FSFB_CUDA(cudaFuncSetAttribute(k_conv_wgrad_async<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    FSFB_LAUNCH(k_conv_wgrad_async<8>, grid, 256, smem, st, a, a_rows, cin, a_stride, dy, rows, cout, dy_stride, nbr, ci_tiles,
+                rows_per_split, part);
+  } else if (tile == 128) {
+    WG_LAUNCH(8, false);
   } else {
     if (vec) WG_LAUNCH(4, true); else WG_LAUNCH(4, false);
   }

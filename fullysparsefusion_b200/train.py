@@ -72,8 +72,11 @@ def vfe_train(vfe: M.DynamicScatterVFE, features: torch.Tensor, coors: torch.Ten
 
 def conv_train(m: M.SparseConvModule, x: torch.Tensor, rb, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """conv → BN → (+ residual) → ReLU, the block `SparseConvModule` folds into one epilogue at inference."""
-    nbr = rb.nbr if isinstance(rb, M.Rulebook) else rb
-    y = m.bn(AG.sparse_conv(x, m.weight, nbr))
+    if isinstance(rb, M.Rulebook):
+        y = AG.sparse_conv(x, m.weight, rb.nbr, rb.order, rb.nbr_ro, symmetric=m.conv_type == "SubMConv3d")
+    else:
+        y = AG.sparse_conv(x, m.weight, rb)
+    y = m.bn(y)
     if residual is not None:
         y = y + residual
     return F.relu(y) if m.act else y

@@ -72,3 +72,29 @@ def test_training_step_updates_every_parameter_and_lowers_the_loss(cuda):
         x = model.backbone_unet.conv_input.weight
         pack = ops.gemm_prepack(x.detach().float())
         assert model.backbone_unet.conv_input._pack is None or model.backbone_unet.conv_input._pack[0].data.shape == pack.data.shape
+
+
+def test_submanifold_input_gradient_reuses_the_rulebook(cuda):
+    """A submanifold rulebook transposed is itself with the offsets reversed: the input gradient through that shortcut (row order
+    and row-ordered table reused) equals the one through the explicit transposition."""
+    from fullysparsefusion_b200 import autograd as AG
+
+    pts = torch.from_numpy(synth.ring_points(120000, sweeps=4, seed=5)).to(cuda)
+    coors4 = F.pad(ops.voxelize(pts, synth.NUSC_VOXEL, synth.NUSC_RANGE, floor_mode=0), (1, 0), value=0)
+    plan = M.ScatterPlan(coors4, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], want_index=True)
+    rb = M.Rulebook(ops.conv_rulebook(plan.new_coors, plan.index, 3, 1, 1))
+    assert rb.order is not None and rb.nbr_ro is not None      # big enough for the row order
+    g = torch.Generator(device=cuda).manual_seed(1)
+    a = torch.randn(plan.m, 64, device=cuda, generator=g)
+    w = torch.randn(27, 32, 64, device=cuda, generator=g) / 40
+    coef = torch.randn(plan.m, 32, device=cuda, generator=g)
+    grads = []
+    for sym in (True, False):
+        a1, w1 = a.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = AG.sparse_conv(a1, w1, rb.nbr, rb.order, rb.nbr_ro, symmetric=sym)
+        (y * coef).sum().backward()
+        grads.append((y.detach(), a1.grad, w1.grad))
+    assert torch.equal(grads[0][0], grads[1][0])
+    scale = float(grads[1][1].abs().max())      # two summation orders of the same fp32 sums
+    assert float((grads[0][1] - grads[1][1]).abs().max()) <= 2e-5 * scale, float((grads[0][1] - grads[1][1]).abs().max()) / scale
+    assert torch.equal(grads[0][2], grads[1][2])
