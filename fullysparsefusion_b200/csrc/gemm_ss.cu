@@ -1062,7 +1062,8 @@ int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspac
   const size_t budget = 227 * 1024;
   const int kc_n = P.S.kc();
   // ring depths: W first (a Linear layer keeps all its K chunks resident when they fit), then as many A slots as remain
-  int w_stages = std::min(kSsMaxW, std::max(2, std::min(kc_n * P.koff, kSsMaxW)));
+  static const int w_cap = [] { const char* e = getenv("FSFB_SS_W_STAGES"); return e ? std::max(2, std::min(atoi(e), kSsMaxW)) : kSsMaxW; }();
+  int w_stages = std::min(w_cap, std::max(2, std::min(kc_n * P.koff, kSsMaxW)));
   int a_stages = 0;
   for (;; --w_stages) {
     const size_t fixed = (size_t)w_stages * P.ss_w_slot + nbr_bytes + staging + vec + sizeof(SsShared) + 64;
