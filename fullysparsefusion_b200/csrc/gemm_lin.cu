@@ -55,12 +55,25 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t s_a = base, s_w = base + kLinAStages * kLinASlot;
   LinShared* sh = reinterpret_cast<LinShared*>(smem_raw + kLinOperandBytes);
-  const Epilogue& E = P.E;
+  // K split (P.splits > 1, few row tiles x deep K: the 1024-wide refinement heads): CTA z handles the K chunks [kc_lo, kc_hi) and
+  // stores raw partial sums to P.partial[z][row][cpad]; k_splitk_epilogue sums the slabs and applies the epilogue
+  const bool raw = P.splits > 1;
+  Epilogue E = P.E;
+  if (raw) {
+    E.bias = nullptr;
+    E.norm = FSFB_NORM_NONE;
+    E.act = FSFB_ACT_NONE;
+    E.residual = nullptr;
+  }
   const int64_t row0 = (int64_t)blockIdx.x * kTcRows;
+  float* const out_base = raw ? P.partial + (int64_t)blockIdx.z * P.rows * P.cpad : P.out;
+  const int64_t out_ld = raw ? (int64_t)P.cpad : P.out_stride;
   const int c0 = blockIdx.y * kLinTile;
   const int n_sub = min(kLinTile, P.S.n_pad() - c0);       // MMA N (multiple of 16)
-  const int c_n = min(kLinTile, P.S.cout - c0);            // real channels of this column tile
-  const int kc_n = P.S.kc();
+  const int c_n = raw ? kLinTile : min(kLinTile, P.S.cout - c0);   // real channels of this column tile (raw slabs: the padded tile)
+  const int kc_all = P.S.kc();
+  const int kc_lo = raw ? (int)((int64_t)kc_all * blockIdx.z / P.splits) : 0;
+  const int kc_n = (raw ? (int)((int64_t)kc_all * (blockIdx.z + 1) / P.splits) : kc_all) - kc_lo;   // chunks of this CTA: kc_lo + [0, kc_n)
   const uint32_t acc_cols = n_sub <= 64 ? 64u : 128u;
 
   // ---- operand loads: thread = (16-byte piece of the 128-byte K chunk, rows row_a + 32 i); three chunks in flight ----
@@ -69,7 +82,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
   const uint32_t piece = (uint32_t)(odd ? 4 + (chunk >> 1) : (chunk >> 1));   // even lane stores both hi halves, odd both lo
   const uint32_t dst0 = (uint32_t)row_a * 128u + ((piece ^ (uint32_t)(row_a & 7)) << 4);   // + 4096 i: same row & 7
   auto load_chunk = [&](int kc, float4(&v)[4]) {
-    const int col = kc * kGemmKChunk + chunk * 4;
+    const int col = (kc_lo + kc) * kGemmKChunk + chunk * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int64_t r = row0 + row_a + 32 * i;
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
     const uint32_t use = (uint32_t)j / kLinWStages;
     if (use > 0) mbar_wait(smem_u32(&sh->w_empty[ws]), (use - 1u) & 1u);   // the MMAs of chunk j - 4 have read the slot
     mbar_expect_tx(smem_u32(&sh->w_full[ws]), w_bytes);
-    bulk_g2s(s_w + (uint32_t)ws * kLinWSlot, w_unit + (size_t)j * blk_bytes, w_bytes, smem_u32(&sh->w_full[ws]));
+    bulk_g2s(s_w + (uint32_t)ws * kLinWSlot, w_unit + (size_t)(kc_lo + j) * blk_bytes, w_bytes, smem_u32(&sh->w_full[ws]));
     mbar_arrive(smem_u32(&sh->w_full[ws]));
   };
   if (tid == 0)
@@ -138,7 +151,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
 
   __half2 ovf = __floats2half2_rn(0.f, 0.f);
   auto store_chunk = [&](int kc, uint32_t slot, const float4(&v)[4]) {
-    const int nv = P.cin - (kc * kGemmKChunk + chunk * 4);   // real columns in this thread's piece
+    const int nv = P.cin - ((kc_lo + kc) * kGemmKChunk + chunk * 4);   // real columns in this thread's piece
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 x = v[i];
@@ -186,7 +199,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
       if (elected) {
         const uint32_t a_d = (((s_a + (uint32_t)s * kLinASlot) & 0x3FFFFu) >> 4) | 0x10000u;
         const uint32_t w_d = (((s_w + (uint32_t)ws * kLinWSlot) & 0x3FFFFu) >> 4) | 0x10000u;
-        const int ksteps = (min(kGemmKChunk, P.cin - kc * kGemmKChunk) + 15) >> 4;
+        const int ksteps = (min(kGemmKChunk, P.cin - (kc_lo + kc) * kGemmKChunk) + 15) >> 4;
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk) {
           if (kk < ksteps) {   // 16-byte units inside the 128-byte row: K step +2, lo half +4
@@ -281,6 +294,10 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
       }
     }
   }
+  if (raw) {   // the slab is cpad wide: columns past n_sub of this tile are zeros
+    const int z_lo = max(half ? split : 0, n_sub), z_hi = half ? kLinTile : split;
+    for (int c = z_lo; c < z_hi; c += 4) sts_f4(my_row + (uint32_t)c * 4u, make_float4(0.f, 0.f, 0.f, 0.f));
+  }
   tc_fence_before();
   LIN_T(3);
   if (ln) {   // kernel-uniform
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
         } else {
           y.x = apply_act(y.x + g.x, act); y.y = apply_act(y.y + g.y, act); y.z = apply_act(y.z + g.z, act); y.w = apply_act(y.w + g.w, act);
         }
-        *reinterpret_cast<float4*>(P.out + r * P.out_stride + c0 + c) = y;
+        *reinterpret_cast<float4*>(out_base + r * out_ld + c0 + c) = y;
       }
     }
   } else {   // odd widths / unaligned rows: the same walk, one column per lane and trip
@@ -363,7 +380,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
           else if (E.norm == FSFB_NORM_AFFINE) y = fmaf(y, w1[j], h1[j]);
           const float g = E.residual ? __ldg(E.residual + r * E.residual_stride + c0 + c) : 0.f;
           y = post ? apply_act(y, act) + g : apply_act(y + g, act);
-          P.out[r * P.out_stride + c0 + c] = y;
+          out_base[r * out_ld + c0 + c] = y;
         }
       }
     }
@@ -378,13 +395,13 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_linear_ss(const __grid_const
 }
 
 // 0 = launched, 1 = shape not served here (the persistent kernels take it), otherwise an error code
-int launch_linear_ss(TcParams& P, bool a_vec, cudaStream_t st) {
+int launch_linear_ss(TcParams& P, bool a_vec, int ksplits, float* workspace, size_t workspace_bytes, cudaStream_t st) {
   static const int mode = [] { const char* e = getenv("FSFB_GEMM_LIN"); return e ? atoi(e) : 1; }();
   if (!mode || !gemm_f16_enabled()) return 1;
   static const int64_t min_rows = [] { const char* e = getenv("FSFB_GEMM_LIN_MIN_ROWS"); return e ? atoll(e) : 1024ll; }();
   const int n_pad = P.S.n_pad();
   if (P.nbr || P.row_order || P.koff != 1 || P.rows < min_rows) return 1;
-  if (n_pad > kLinTile && P.E.norm == FSFB_NORM_LAYERNORM) return 1;   // row statistics across column tiles
+  if (n_pad > kLinTile && P.E.norm == FSFB_NORM_LAYERNORM && ksplits <= 1) return 1;   // row statistics across column tiles
   if (P.a_rows < P.rows) return 1;
   {
     const int rc = ss_overflow_counter(&P.ss_overflow);
@@ -401,9 +418,24 @@ int launch_linear_ss(TcParams& P, bool a_vec, cudaStream_t st) {
     FSFB_CUDA(cudaFuncSetAttribute(k_linear_ss<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  const dim3 grid((unsigned)ceil_div(P.rows, kTcRows), (unsigned)ceil_div(n_pad, kLinTile));
+  // K split: raw slabs [ksplits][rows][cpad] + the split epilogue kernel (bias / norm / activation / residual)
+  P.splits = 1;
+  P.partial = nullptr;
+  P.cpad = (n_pad + 127) & ~127;
+  if (ksplits > 1) {
+    const size_t need = (size_t)ksplits * (size_t)P.rows * P.cpad * sizeof(float);
+    if (ksplits > P.S.kc() || P.cpad > 1024 || !workspace || workspace_bytes < need) {
+      set_error("gather_gemm: K split %d needs 1 < splits <= %d K chunks, cout <= 1024 and %zu bytes of workspace (%zu given)", ksplits,
+                P.S.kc(), need, workspace_bytes);
+      return FSFB_ERR_CAPACITY;
+    }
+    P.splits = ksplits;
+    P.partial = workspace;
+  }
+  const dim3 grid((unsigned)ceil_div(P.rows, kTcRows), (unsigned)ceil_div(n_pad, kLinTile), (unsigned)P.splits);
   if (a_vec) FSFB_LAUNCH(k_linear_ss<true>, grid, kLinThreads, smem, st, P);
   else FSFB_LAUNCH(k_linear_ss<false>, grid, kLinThreads, smem, st, P);
+  if (P.splits > 1) return launch_splitk_epilogue(P, st);
   return FSFB_OK;
 }
 

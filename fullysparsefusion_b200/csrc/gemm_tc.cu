@@ -292,7 +292,7 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
                  (long long)a_rows, cin, cout);
   FSFB_CHECK_ARG(koff >= 1 && koff <= kTcMaxOff, "gather_gemm: koff=%d unsupported (1..%d)", koff, kTcMaxOff);
   FSFB_CHECK_ARG(nbr || koff == 1, "gather_gemm: koff > 1 needs a neighbour table");
-  FSFB_CHECK_ARG(norm != FSFB_NORM_LAYERNORM || cout <= kGemmNTile,
+  FSFB_CHECK_ARG(norm != FSFB_NORM_LAYERNORM || cout <= kGemmNTile || (koff == 1 && !nbr && splits > 1 && cout <= 1024),
                  "gather_gemm: fused LayerNorm needs cout <= %d (use fsfb_rownorm_act after the GEMM)",
                  kGemmNTile);
   if (rows == 0) return FSFB_OK;
@@ -325,9 +325,11 @@ static int gather_gemm_impl(const float* a, int64_t a_rows, int cin, int64_t a_s
     // channels; the kernel below remains for widths like 131 / 144 (one 256-wide tile) and fused LayerNorms wider
     // than 128.  FSFB_GEMM_TS=0 forces the kernel below (A/B experiments).
     static const int ss_mode = [] { const char* e = getenv("FSFB_GEMM_SS"); return e ? atoi(e) : 1; }();
-    if (ss_mode && !a_split && splits <= 1) {  // dense Linear over many rows: one CTA per row tile (gemm_lin.cu)
-      const int rc_lin = launch_linear_ss(P, a_vec, (cudaStream_t)stream);
+    if (ss_mode && !a_split && (splits <= 1 || (koff == 1 && !nbr))) {  // dense Linear: one CTA per row tile (gemm_lin.cu)
+      // (a Linear layer has one "offset": splits > 1 there means K-chunk ranges, which only this kernel implements)
+      const int rc_lin = launch_linear_ss(P, a_vec, splits, (float*)workspace, workspace_bytes, (cudaStream_t)stream);
       if (rc_lin != 1) return rc_lin;
+      FSFB_CHECK_ARG(splits <= 1, "gather_gemm: K split of a Linear layer needs the row-tile kernel (rows >= 1024, FSFB_GEMM_LIN != 0)");
     }
     if (ss_mode) {  // fp16-split operands from shared memory (gemm_ss.cu); 1 = shape not served there
       const int rc_ss = launch_gather_gemm_ss(P, a_vec, a_split, (float*)workspace, workspace_bytes, splits, host_bias, host_norm_w,
@@ -408,7 +410,8 @@ extern "C" int fsfb_gather_gemm_splitk(const float* a, int64_t a_rows, int cin, 
                                        const float* residual, int64_t residual_stride, int act, float* out,
                                        int64_t out_stride, int splits, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace fsfb;
-  FSFB_CHECK_ARG(splits >= 1 && splits <= koff, "gather_gemm_splitk: splits=%d must be in 1..koff", splits);
+  FSFB_CHECK_ARG(splits >= 1 && (splits <= koff || (koff == 1 && !nbr && splits <= (cin + 31) / 32)),
+                 "gather_gemm_splitk: splits=%d must be in 1..koff (Linear: 1..K chunks)", splits);
   FSFB_CHECK_ARG(splits == 1 || ((uintptr_t)workspace & 15) == 0, "gather_gemm_splitk: workspace must be 16-byte aligned");
   return gather_gemm_impl(a, a_rows, cin, a_stride, nbr, row_order, koff, rows, w_packed, cout, bias, norm, norm_w, norm_b, eps,
                           residual, residual_stride, act, out, out_stride, splits, workspace, workspace_bytes, nullptr, nullptr, nullptr, stream);

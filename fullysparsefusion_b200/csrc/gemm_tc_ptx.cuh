@@ -288,7 +288,7 @@ int launch_gather_gemm_ss(TcParams& P, bool a_vec, bool a_split, float* workspac
 // gemm_ts.cu
 int launch_splitk_epilogue(const TcParams& P, cudaStream_t st);
 // gemm_lin.cu: dense Linear layers over many rows, one CTA per 128-row tile (0 = launched, 1 = shape not served there)
-int launch_linear_ss(TcParams& P, bool a_vec, cudaStream_t st);
+int launch_linear_ss(TcParams& P, bool a_vec, int ksplits, float* workspace, size_t workspace_bytes, cudaStream_t st);
 int ss_overflow_counter(unsigned int** out);
 int ss_timers_buffer(uint32_t** out, cudaStream_t st);
 int launch_gather_gemm_ts(TcParams& P, bool a_vec, float* workspace, size_t workspace_bytes, int splits, const float* host_bias,

@@ -145,6 +145,10 @@ class FusedLinear:
         if self._pack is None:
             self._prepare()
         p = self._pack
+        if p["wide_ln"] and ops.linear_k_splits(x.size(0), self.linear.in_features, self.linear.out_features) > 1 and self.linear.out_features <= 1024:
+            # K-split GEMM: its split epilogue sees whole rows, so the wide LayerNorm is fused there (one launch less)
+            return ops.gather_gemm(x, p["w"], bias=p["bias"], norm="ln", norm_w=p["norm_w"], norm_b=p["norm_b"], eps=p["eps"],
+                                   residual=residual, act=self.act, out=out)
         if p["wide_ln"]:  # LayerNorm wider than one accumulator tile: GEMM, then the row kernel
             y = ops.gather_gemm(x, p["w"])
             return ops.rownorm_act(y, bias=p["bias"], norm="ln", norm_w=p["norm_w"], norm_b=p["norm_b"], eps=p["eps"],

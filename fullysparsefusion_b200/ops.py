@@ -518,6 +518,20 @@ def split_rows(a: torch.Tensor) -> torch.Tensor:
 
 
 _SPLITS_AUTO = os.environ.get("FSFB_GEMM_AUTO_SPLITS", "1") != "0"
+_LIN_KSPLIT = os.environ.get("FSFB_GEMM_LIN_KSPLIT", "1") != "0" and os.environ.get("FSFB_GEMM_LIN", "1") != "0" and "FSFB_GEMM_LIN_MIN_ROWS" not in os.environ
+
+
+def linear_k_splits(rows: int, cin: int, cout: int) -> int:
+    """K-chunk splits of a dense Linear layer whose (row tile, column tile) grid leaves most SMs idle while each tile walks a deep
+    K (the 768 / 896 / 1024-wide refinement heads over a few thousand queries): the row-tile kernel (csrc/gemm_lin.cu) runs the K
+    ranges as separate CTAs and `k_splitk_epilogue` sums the slabs and applies the epilogue (any LayerNorm width up to 1024)."""
+    kc = (cin + 31) // 32
+    if not _LIN_KSPLIT or rows < 1024 or rows > 16384 or kc < 8 or cout > 1024:
+        return 1
+    tiles = ((rows + 127) // 128) * ((cout + 127) // 128)
+    return max(1, min(kc // 4, 8, 296 // tiles))
+
+
 
 
 def _pick_splits(rows: int, cpad: int, koff: int, kc: int) -> int:
@@ -590,7 +604,10 @@ def gather_gemm(a: torch.Tensor, w: PackedWeight, nbr: Optional[torch.Tensor] = 
     cpad = (w.cout + 127) // 128 * 128
     tileable = w.cout <= 128 or (((w.cout + 15) // 16 * 16) % 128 == 0 and norm != "layernorm" and norm != "ln")
     if splits is None:
-        splits = _pick_splits(rows, cpad, w.koff, (w.cin + 31) // 32) if tileable else 1
+        if nbr is None:
+            splits = linear_k_splits(rows, w.cin, w.cout)
+        else:
+            splits = _pick_splits(rows, cpad, w.koff, (w.cin + 31) // 32) if tileable else 1
     # 27-offset convolutions: every input row is gathered by ~6 offsets, so the fp32 → fp16-split conversion is done once per
     # row up front (fsfb_split_rows) and the kernel's gather is pure data movement (include/fsf_b200.h)
     if (_SPLIT_ON and nbr is not None and w.koff > 1 and w.koff <= 27 and w.cin % 32 == 0 and tileable and a.data_ptr() % 16 == 0

@@ -231,3 +231,32 @@ def test_linear_row_tile_kernel(cuda, rows, cin, cout, norm, act, res, post):
         ops.gather_gemm(wide[:, :cin], pw, out=out[:, :cout], **kw)
         np.testing.assert_allclose(out[:, :cout].cpu().numpy(), want, rtol=RTOL, atol=ATOL)
         assert float(out[:, cout:].min()) == -7.0 and float(out[:, cout:].max()) == -7.0   # nothing written past the row
+
+
+@pytest.mark.parametrize("rows,cin,cout,norm,act,res", [
+    (3782, 1024, 128, "ln", "gelu", False),     # the refinement heads: 30 row tiles, 32 K chunks -> 8 K ranges
+    (3000, 768, 128, "affine", "relu", True),
+    (1500, 1000, 33, None, None, False),        # partial last chunk, odd width
+    (2048, 1024, 384, "ln", "gelu", True),      # LayerNorm wider than a column tile: fused in the split epilogue
+    (1200, 512, 1024, "ln", None, False),       # 1024-wide LayerNorm, two K ranges
+])
+def test_linear_k_split(cuda, rows, cin, cout, norm, act, res):
+    """Few row tiles x deep K: csrc/gemm_lin.cu runs K ranges as separate CTAs, k_splitk_epilogue sums the slabs (fixed order)."""
+    assert ops.linear_k_splits(rows, cin, cout) > 1
+    rng = np.random.default_rng(rows + cin + cout)
+    a = rng.standard_normal((rows, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    nw = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    nb = rng.standard_normal(cout).astype(np.float32)
+    r = rng.standard_normal((rows, cout)).astype(np.float32) if res else None
+    want = O.gather_gemm(a, w, bias=b, norm=norm, norm_w=nw, norm_b=nb, eps=1e-3, residual=r, act=act)
+    pw = ops.gemm_prepack(T(w, cuda), keep_raw=True)
+    kw = dict(bias=T(b, cuda), norm=norm, norm_w=T(nw, cuda) if norm else None, norm_b=T(nb, cuda) if norm else None, eps=1e-3,
+              residual=T(r, cuda) if res else None, act=act)
+    got = ops.gather_gemm(T(a, cuda), pw, **kw)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    assert torch.equal(got, ops.gather_gemm(T(a, cuda), pw, **kw))                 # deterministic
+    one = ops.gather_gemm(T(a, cuda), pw, splits=1, **kw) if cout <= 256 or norm != "ln" else None
+    if one is not None:
+        np.testing.assert_allclose(one.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
