@@ -400,7 +400,9 @@ int launch_linear_ss(TcParams& P, bool a_vec, int ksplits, float* workspace, siz
   if (!mode || !gemm_f16_enabled()) return 1;
   static const int64_t min_rows = [] { const char* e = getenv("FSFB_GEMM_LIN_MIN_ROWS"); return e ? atoll(e) : 1024ll; }();
   const int n_pad = P.S.n_pad();
-  if (P.nbr || P.row_order || P.koff != 1 || P.rows < min_rows) return 1;
+  // below min_rows only narrow layers come here (cout <= 256: a handful of CTAs beat the persistent kernel's fixed cost — 43 -> 20 us
+  // for 248 x 1024 -> 128 — while 1024-wide outputs over two row tiles do not)
+  if (P.nbr || P.row_order || P.koff != 1 || (P.rows < min_rows && n_pad > 256)) return 1;
   if (n_pad > kLinTile && P.E.norm == FSFB_NORM_LAYERNORM && ksplits <= 1) return 1;   // row statistics across column tiles
   if (P.a_rows < P.rows) return 1;
   {

@@ -518,7 +518,8 @@ def split_rows(a: torch.Tensor) -> torch.Tensor:
 
 
 _SPLITS_AUTO = os.environ.get("FSFB_GEMM_AUTO_SPLITS", "1") != "0"
-_LIN_KSPLIT = os.environ.get("FSFB_GEMM_LIN_KSPLIT", "1") != "0" and os.environ.get("FSFB_GEMM_LIN", "1") != "0" and "FSFB_GEMM_LIN_MIN_ROWS" not in os.environ
+_LIN_KSPLIT = os.environ.get("FSFB_GEMM_LIN_KSPLIT", "1") != "0" and os.environ.get("FSFB_GEMM_LIN", "1") != "0"
+_LIN_MIN_ROWS = int(os.environ.get("FSFB_GEMM_LIN_MIN_ROWS", "1024"))   # the same default as csrc/gemm_lin.cu
 
 
 def linear_k_splits(rows: int, cin: int, cout: int) -> int:
@@ -526,7 +527,7 @@ def linear_k_splits(rows: int, cin: int, cout: int) -> int:
     K (the 768 / 896 / 1024-wide refinement heads over a few thousand queries): the row-tile kernel (csrc/gemm_lin.cu) runs the K
     ranges as separate CTAs and `k_splitk_epilogue` sums the slabs and applies the epilogue (any LayerNorm width up to 1024)."""
     kc = (cin + 31) // 32
-    if not _LIN_KSPLIT or rows < 1024 or rows > 16384 or kc < 8 or cout > 1024:
+    if not _LIN_KSPLIT or (rows < _LIN_MIN_ROWS and cout > 256) or rows > 16384 or kc < 8 or cout > 1024:
         return 1
     tiles = ((rows + 127) // 128) * ((cout + 127) // 128)
     return max(1, min(kc // 4, 8, 296 // tiles))

@@ -239,6 +239,7 @@ def test_linear_row_tile_kernel(cuda, rows, cin, cout, norm, act, res, post):
     (1500, 1000, 33, None, None, False),        # partial last chunk, odd width
     (2048, 1024, 384, "ln", "gelu", True),      # LayerNorm wider than a column tile: fused in the split epilogue
     (1200, 512, 1024, "ln", None, False),       # 1024-wide LayerNorm, two K ranges
+    (248, 1024, 128, "ln", "gelu", False),      # the frustum heads: two row tiles
 ])
 def test_linear_k_split(cuda, rows, cin, cout, norm, act, res):
     """Few row tiles x deep K: csrc/gemm_lin.cu runs K ranges as separate CTAs, k_splitk_epilogue sums the slabs (fixed order)."""
