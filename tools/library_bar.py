@@ -113,6 +113,7 @@ def run(points: int = 300000, dev=None):
     index = M.ScatterPlan(c4, lo=[0, 0, 0, 0], ext=[1, 40, 512, 512], want_index=True)
     nbr = ops.conv_rulebook(index.new_coors, index.index, 3, 1, 1)
     order = ops.rulebook_row_order(nbr)
+    nbr_ro = ops.permute_rulebook(nbr, order)   # built once per rulebook, as modules.Rulebook does (not timed, like the rulebook)
     m = index.m
     a = torch.randn(m, 128, device=dev, generator=g)
     w = torch.randn(27, 128, 128, device=dev, generator=g) * 0.03
@@ -127,7 +128,7 @@ def run(points: int = 300000, dev=None):
                 o.index_add_(0, dst, a.index_select(0, src) @ w[k].t())
         return torch.relu(o)
 
-    rec(f"SubMConv3d 27x128->128 [{m} voxels]", _time(lib_conv, reps=3, warm=1), _time(lambda: ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order)))
+    rec(f"SubMConv3d 27x128->128 [{m} voxels]", _time(lib_conv, reps=3, warm=1), _time(lambda: ops.gather_gemm(a, pw, nbr=nbr, act="relu", row_order=order, nbr_ro=nbr_ro)))
     # ---- Linear -> LayerNorm -> GELU over the points ----
     x = torch.randn(n, 128, device=dev, generator=g)
     lw = torch.randn(128, 128, device=dev, generator=g) * 0.05
