@@ -189,3 +189,24 @@ def test_hwc16_projection_matches_planar(cuda, gold):
         got = ops.project_sample_select_hwc(xyz, l2i, hwc, 10, want_overlap=True, anno=anno)
         for w, g in zip(want, got):
             assert torch.equal(w, g)
+
+
+def test_split_heuristics_stay_inside_what_the_kernels_accept():
+    """Host-side split selection (ops._pick_splits / ops.linear_k_splits): the C entry points reject splits outside
+    1..koff (convolutions) and 1..K chunks (Linear), and a K range must not be empty."""
+    from fullysparsefusion_b200 import ops
+
+    for rows in (1, 127, 248, 1024, 1400, 3782, 11000, 16384, 16385, 75000, 300000):
+        for cin in (3, 16, 32, 128, 256, 512, 768, 896, 1000, 1024):
+            for cout in (2, 11, 33, 128, 256, 384, 1024, 1025):
+                s = ops.linear_k_splits(rows, cin, cout)
+                kc = (cin + 31) // 32
+                assert 1 <= s <= max(1, kc // 4) and s <= 8
+                if s > 1:   # only shapes the row-tile kernel serves with a split epilogue
+                    assert cout <= 1024 and rows <= 16384 and (rows >= 1024 or cout <= 256)
+        for koff in (1, 8, 27):
+            for kc in (1, 2, 4, 8, 16, 32):
+                for cpad in (128, 256, 512, 1024, 2048):
+                    s = ops._pick_splits(rows, cpad, koff, kc)
+                    assert 1 <= s <= max(1, koff // 3)
+    assert ops.linear_k_splits(3782, 1024, 128) == 8 and ops.linear_k_splits(300000, 128, 128) == 1
